@@ -1,0 +1,274 @@
+"""ctypes binding of the C ABI in include/cwr.h (libcwr_b200.so, hand-written sm_100a CUDA).
+
+There is deliberately no CPU fallback: if the shared library is missing or no CUDA
+device is present, construction raises.  Everything crosses the boundary as plain
+pointers and sizes in the reference's cell / edge numbering.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+_LIB_NAME = "libcwr_b200.so"
+_lib = None
+
+CWR_OK, CWR_EINVAL, CWR_ECUDA, CWR_ENOTCONVERGED, CWR_EBREAKDOWN, CWR_ENAN, CWR_ESINGULAR, CWR_ENOMEM = 0, -1, -2, -3, -4, -5, -6, -7
+STATUS_NAMES = {0: "CWR_OK", -1: "CWR_EINVAL", -2: "CWR_ECUDA", -3: "CWR_ENOTCONVERGED", -4: "CWR_EBREAKDOWN",
+                -5: "CWR_ENAN", -6: "CWR_ESINGULAR", -7: "CWR_ENOMEM"}
+
+
+class CwrOptions(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("max_iter", C.c_int), ("reorder", C.c_int), ("keep_history", C.c_int),
+                ("hydro_capacity", C.c_int), ("mass_flux", C.c_int), ("solver_path", C.c_int),
+                ("use_graph", C.c_int), ("check_every", C.c_int), ("reserved", C.c_int * 7)]
+
+
+class CwrStepInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("restarts", C.c_int), ("status", C.c_int),
+                ("max_relres", C.c_double), ("n_launches", C.c_int)]
+
+
+class CwrMassTotals(C.Structure):
+    _fields_ = [("vol_start", C.c_double), ("mass_start", C.c_double), ("vol_end", C.c_double), ("mass_end", C.c_double)]
+
+
+class CwrError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"{STATUS_NAMES.get(status, status)}: {message}")
+        self.status = status
+
+
+class SolverWarning(UserWarning):
+    """The iterative solve ended without meeting rtol (results are stored, like scipy's
+    MatrixRankWarning path in the reference, transport.py:249)."""
+
+
+def library_path() -> Path:
+    return Path(__file__).resolve().parent / _LIB_NAME
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("CWR_B200_LIB", library_path()))
+    if not path.is_file():
+        raise RuntimeError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  clearwater_riverine_b200 has no CPU fallback.")
+    lib = C.CDLL(str(path))
+    H = C.c_void_p
+    dp, fp, ip = C.POINTER(C.c_double), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    sigs = {
+        "cwr_default_options": ([C.POINTER(CwrOptions)], C.c_int),
+        "cwr_create": ([C.POINTER(H), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_double,
+                        C.POINTER(CwrOptions)], C.c_int),
+        "cwr_destroy": ([H], None),
+        "cwr_last_error": ([H], C.c_char_p),
+        "cwr_set_hydro": ([H, C.c_int, C.c_int, fp, dp, fp, fp, dp], C.c_int),
+        "cwr_set_geometry": ([H, dp, dp], C.c_int),
+        "cwr_set_hydro_raw": ([H, C.c_int, C.c_int, fp, fp, fp, dp], C.c_int),
+        "cwr_set_inputs": ([H, C.c_int, dp], C.c_int),
+        "cwr_set_state": ([H, C.c_int, C.c_int, dp], C.c_int),
+        "cwr_set_state_all": ([H, C.c_int, dp, C.POINTER(C.c_uint8)], C.c_int),
+        "cwr_step": ([H, C.c_int, C.POINTER(CwrStepInfo)], C.c_int),
+        "cwr_run": ([H, C.c_int, C.c_int, C.POINTER(CwrStepInfo)], C.c_int),
+        "cwr_get_state": ([H, C.c_int, C.c_int, dp], C.c_int),
+        "cwr_get_state_all": ([H, C.c_int, dp], C.c_int),
+        "cwr_get_mass_flux": ([H, C.c_int, C.c_int, dp, dp, dp], C.c_int),
+        "cwr_mass_totals_at": ([H, C.c_int, C.c_int, C.c_int, C.POINTER(CwrMassTotals)], C.c_int),
+        "cwr_get_flux_sums": ([H, C.c_int, dp, dp, dp], C.c_int),
+        "cwr_get_lhs": ([H, C.POINTER(C.c_int64), ip, ip, dp], C.c_int),
+        "cwr_get_rhs": ([H, C.c_int, dp], C.c_int),
+        "cwr_get_permutation": ([H, ip], C.c_int),
+        "cwr_stream": ([H, C.POINTER(C.c_void_p)], C.c_int),
+        "cwr_counters": ([H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
+        "cwr_time_spmm": ([H, C.c_int, dp, dp], C.c_int),
+    }
+    for name, (argtypes, restype) in sigs.items():
+        fn = getattr(lib, name)      # AttributeError here = the .so does not export what cwr.h declares
+        fn.argtypes, fn.restype = argtypes, restype
+    lib._cwr_symbols = tuple(sigs)
+    _lib = lib
+    return lib
+
+
+def _ptr(a: Optional[np.ndarray], ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _arr(a, dtype, shape=None, name="array") -> np.ndarray:
+    out = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None and tuple(out.shape) != tuple(shape):
+        raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(out.shape)}")
+    return out
+
+
+class TransportBackend:
+    """One model on one GPU: fixed topology, K constituents, T time slices."""
+
+    def __init__(self, f1, f2, n_face: int, n_time: int, n_constituents: int, diffusion_coefficient: float,
+                 device: int = 0, **options):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
+        self.n_edge = int(f1.shape[0]); self.n_face = int(n_face); self.n_time = int(n_time)
+        self.n_real = int(f1.max()) + 1            # reference: nreal = max(edges_face1)  (io/hdf.py:268-269)
+        self.K = int(n_constituents)
+        self.diffusion_coefficient = float(diffusion_coefficient)
+        opt = CwrOptions()
+        self._lib.cwr_default_options(C.byref(opt))
+        for key, val in options.items():
+            if not hasattr(opt, key):
+                raise TypeError(f"unknown option {key!r}")
+            setattr(opt, key, val)
+        self.options = opt
+        rc = self._lib.cwr_create(C.byref(self._h), device, self.n_real, self.n_face, self.n_edge, self.n_time, self.K,
+                                  _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), self.diffusion_coefficient, C.byref(opt))
+        if rc != CWR_OK:
+            msg = self._lib.cwr_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise CwrError(rc, msg)
+        self.last_info = CwrStepInfo()
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc: int, allow_solver_status: bool = False) -> int:
+        if rc == CWR_OK:
+            return rc
+        if allow_solver_status and rc in (CWR_ENOTCONVERGED, CWR_EBREAKDOWN, CWR_ENAN, CWR_ESINGULAR):
+            return rc
+        raise CwrError(rc, self._lib.cwr_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.cwr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- inputs ----------------------------------------------------------------------------------
+    def set_hydro(self, t0: int, adv, cdiff, vel, vol, dt):
+        adv = _arr(adv, np.float32); nt = adv.shape[0] if adv.ndim == 2 else 1
+        adv = adv.reshape(nt, self.n_edge)
+        cdiff = _arr(cdiff, np.float64).reshape(nt, self.n_edge)
+        vel = _arr(vel, np.float32).reshape(nt, self.n_edge)
+        vol = _arr(vol, np.float32).reshape(nt, self.n_face)
+        dt = _arr(dt, np.float64).reshape(nt)
+        self._check(self._lib.cwr_set_hydro(self._h, t0, nt, _ptr(adv, C.c_float), _ptr(cdiff, C.c_double),
+                                            _ptr(vel, C.c_float), _ptr(vol, C.c_float), _ptr(dt, C.c_double)))
+
+    def set_geometry(self, face_x, face_y):
+        fx = _arr(face_x, np.float64, (self.n_face,), "face_x"); fy = _arr(face_y, np.float64, (self.n_face,), "face_y")
+        self._check(self._lib.cwr_set_geometry(self._h, _ptr(fx, C.c_double), _ptr(fy, C.c_double)))
+
+    def set_hydro_raw(self, t0: int, face_flow, edge_velocity, volume, dt):
+        q = _arr(face_flow, np.float32); nt = q.shape[0] if q.ndim == 2 else 1
+        q = q.reshape(nt, self.n_edge)
+        u = _arr(edge_velocity, np.float32).reshape(nt, self.n_edge)
+        v = _arr(volume, np.float32).reshape(nt, self.n_face)
+        dt = _arr(dt, np.float64).reshape(nt)
+        self._check(self._lib.cwr_set_hydro_raw(self._h, t0, nt, _ptr(q, C.c_float), _ptr(u, C.c_float),
+                                                _ptr(v, C.c_float), _ptr(dt, C.c_double)))
+
+    def set_inputs(self, k: int, input_array):
+        a = _arr(input_array, np.float64, (self.n_time, self.n_face), "input_array")
+        self._check(self._lib.cwr_set_inputs(self._h, k, _ptr(a, C.c_double)))
+
+    def set_state(self, k: int, t: int, c):
+        a = _arr(np.asarray(c)[: self.n_real], np.float64, (self.n_real,), "c")
+        self._check(self._lib.cwr_set_state(self._h, k, t, _ptr(a, C.c_double)))
+
+    def set_state_all(self, t: int, c, mask: Optional[Sequence[bool]] = None):
+        a = _arr(c, np.float64, (self.K, self.n_real), "c")
+        m = None if mask is None else _arr(mask, np.uint8, (self.K,), "mask")
+        self._check(self._lib.cwr_set_state_all(self._h, t, _ptr(a, C.c_double), _ptr(m, C.c_uint8)))
+
+    # -- stepping ----------------------------------------------------------------------------------
+    def step(self, t: int) -> CwrStepInfo:
+        info = CwrStepInfo()
+        self._check(self._lib.cwr_step(self._h, t, C.byref(info)), allow_solver_status=True)
+        self.last_info = info
+        return info
+
+    def run(self, t_begin: int, t_end: int) -> CwrStepInfo:
+        info = CwrStepInfo()
+        self._check(self._lib.cwr_run(self._h, t_begin, t_end, C.byref(info)), allow_solver_status=True)
+        self.last_info = info
+        return info
+
+    # -- outputs -----------------------------------------------------------------------------------
+    def get_state(self, k: int, t: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty(self.n_face) if out is None else out
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.n_face,)
+        self._check(self._lib.cwr_get_state(self._h, k, t, _ptr(out, C.c_double)))
+        return out
+
+    def get_state_all(self, t: int, out: Optional[np.ndarray] = None) -> np.ndarray:
+        out = np.empty((self.K, self.n_real)) if out is None else out
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.K, self.n_real)
+        self._check(self._lib.cwr_get_state_all(self._h, t, _ptr(out, C.c_double)))
+        return out
+
+    def get_mass_flux(self, k: int, t: int, advection=None, diffusion=None, total=None):
+        outs = []
+        for a in (advection, diffusion, total):
+            if a is None:
+                a = np.empty(self.n_edge)
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.shape == (self.n_edge,)
+            outs.append(a)
+        self._check(self._lib.cwr_get_mass_flux(self._h, k, t, *[_ptr(a, C.c_double) for a in outs]))
+        return tuple(outs)
+
+    def flux_sums(self, k: int):
+        outs = [np.empty(self.n_edge) for _ in range(3)]
+        self._check(self._lib.cwr_get_flux_sums(self._h, k, *[_ptr(a, C.c_double) for a in outs]))
+        return tuple(outs)
+
+    def mass_totals(self, k: int, t_start: int, t_end: int) -> CwrMassTotals:
+        m = CwrMassTotals()
+        self._check(self._lib.cwr_mass_totals_at(self._h, k, t_start, t_end, C.byref(m)))
+        return m
+
+    # -- introspection ---------------------------------------------------------------------------------
+    def get_lhs(self):
+        """scipy CSR of A(t) as last assembled, reference numbering."""
+        from scipy.sparse import csr_matrix
+        nnz = C.c_int64()
+        self._check(self._lib.cwr_get_lhs(self._h, C.byref(nnz), None, None, None))
+        indptr = np.empty(self.n_real + 1, np.int32); indices = np.empty(nnz.value, np.int32); data = np.empty(nnz.value)
+        self._check(self._lib.cwr_get_lhs(self._h, C.byref(nnz), _ptr(indptr, C.c_int32), _ptr(indices, C.c_int32),
+                                          _ptr(data, C.c_double)))
+        return csr_matrix((data, indices, indptr), shape=(self.n_real, self.n_real))
+
+    def get_rhs(self, k: int) -> np.ndarray:
+        b = np.empty(self.n_real)
+        self._check(self._lib.cwr_get_rhs(self._h, k, _ptr(b, C.c_double)))
+        return b
+
+    def permutation(self) -> np.ndarray:
+        p = np.empty(self.n_real, np.int32)
+        self._check(self._lib.cwr_get_permutation(self._h, _ptr(p, C.c_int32)))
+        return p
+
+    def counters(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._lib.cwr_counters(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._check(self._lib.cwr_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    def time_spmm(self, reps: int = 20):
+        ms, nbytes = C.c_double(), C.c_double()
+        self._check(self._lib.cwr_time_spmm(self._h, reps, C.byref(ms), C.byref(nbytes)))
+        return ms.value, nbytes.value

@@ -1,0 +1,820 @@
+// C ABI (include/cwr.h) over the sm_100a kernels in cwr_kernels.cuh.
+// Host logic only: buffers, per-step parameter block, launch order, the solver driver loop.
+#include "../../include/cwr.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "cwr_kernels.cuh"
+#include "cwr_topology.h"
+
+using namespace cwr;
+
+static thread_local std::string g_create_error;
+
+struct cwr_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cwr_options opt{};
+    Topology topo;
+    int n = 0, F = 0, E = 0, K = 0, T = 0, G = 0;
+    int C = 0;                       // hydro slices resident
+    int KC = 1;                      // lanes per row
+    int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0;
+    DeviceModel M{};
+    // device buffers
+    int32_t *d_rowptr = nullptr, *d_col = nullptr, *d_slot = nullptr, *d_f1p = nullptr, *d_f2p = nullptr;
+    int32_t *d_bcell = nullptr, *d_bptr = nullptr, *d_bedge = nullptr, *d_eperm = nullptr, *d_einv = nullptr;
+    int32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr, *d_f1 = nullptr, *d_f2 = nullptr;
+    float *d_adv = nullptr, *d_velg = nullptr, *d_vol = nullptr;   // (C,E), (C,E_g), (C,n)
+    double* d_cdiff = nullptr;                                    // (C,E)
+    double* d_bc = nullptr;                                       // (T,G,K)
+    double* d_state = nullptr;                                    // (S,n,K)
+    double* d_dist = nullptr;                                     // (E) reference order
+    void* d_stage = nullptr; size_t stage_bytes = 0;
+    StepParams* d_sp = nullptr;
+    SolverCtl* h_ctl = nullptr;                                   // pinned
+    double* h_sc = nullptr; int* h_flags = nullptr; int* h_iters = nullptr;   // pinned
+    int n_state_slots = 0;
+    std::vector<double> dt;
+    std::vector<int> slot_time;
+    std::vector<std::vector<double>> initial_row;                 // per constituent (F)
+    std::vector<uint8_t> inputs_set;
+    std::vector<std::map<int, std::vector<std::pair<int32_t, double>>>> real_overrides;   // [k][t] -> (device cell, value)
+    int computed_upto = 0;           // c[t] valid for t <= computed_upto
+    int flux_step = -1;              // step whose mass fluxes are on the device
+    int lhs_step = -1;
+    bool have_geometry = false;
+    int64_t launches = 0, iterations = 0;
+    std::string err;
+    std::vector<void*> allocs;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+            return CWR_ECUDA;                                                                      \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(code, msg) do { h->err = (msg); return (code); } while (0)
+
+template <typename T>
+static cudaError_t dalloc(cwr_handle* h, T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e == cudaSuccess) h->allocs.push_back(*p);
+    return e;
+}
+
+template <typename T>
+static cudaError_t upload(cwr_handle* h, T** p, const std::vector<T>& v) {
+    cudaError_t e = dalloc(h, p, v.size());
+    if (e != cudaSuccess) return e;
+    if (!v.empty()) e = cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+    return e;
+}
+
+static inline int grid_for(int64_t items, int per_block, int max_grid) {
+    int64_t g = (items + per_block - 1) / per_block;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, max_grid));
+}
+
+static int ensure_stage(cwr_handle* h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return CWR_OK;
+    if (h->d_stage) { CK(cudaStreamSynchronize(h->stream)); CK(cudaFree(h->d_stage)); h->d_stage = nullptr; h->stage_bytes = 0; }
+    CK(cudaMalloc(&h->d_stage, bytes));
+    h->stage_bytes = bytes;
+    return CWR_OK;
+}
+
+#define KC_DISPATCH(KCV, ...)                  \
+    switch (KCV) {                             \
+        case 1: { constexpr int KC = 1; __VA_ARGS__; break; }   \
+        case 2: { constexpr int KC = 2; __VA_ARGS__; break; }   \
+        case 4: { constexpr int KC = 4; __VA_ARGS__; break; }   \
+        case 8: { constexpr int KC = 8; __VA_ARGS__; break; }   \
+        case 16: { constexpr int KC = 16; __VA_ARGS__; break; } \
+        default: { constexpr int KC = 32; __VA_ARGS__; break; } \
+    }
+
+extern "C" {
+
+int cwr_default_options(cwr_options* o) {
+    if (!o) return CWR_EINVAL;
+    std::memset(o, 0, sizeof(*o));
+    o->rtol = 1e-13;
+    o->max_iter = 500;
+    o->reorder = 1;
+    o->keep_history = 1;
+    o->hydro_capacity = 0;
+    o->mass_flux = 1;
+    o->solver_path = 0;
+    o->use_graph = 1;
+    o->check_every = 4;
+    return CWR_OK;
+}
+
+const char* cwr_last_error(const cwr_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+void cwr_destroy(cwr_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->h_sc) cudaFreeHost(h->h_sc);
+    if (h->h_flags) cudaFreeHost(h->h_flags);
+    if (h->h_iters) cudaFreeHost(h->h_iters);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
+                       const int32_t* f1, const int32_t* f2, double D, const cwr_options* opt) {
+    if (!f1 || !f2) FAIL(CWR_EINVAL, "f1/f2 must not be NULL");
+    if (n_time < 2) FAIL(CWR_EINVAL, "n_time must be >= 2");
+    if (n_const < 1 || n_const > kMaxK) FAIL(CWR_EINVAL, "n_const must be in [1, 128]");
+    if (opt) h->opt = *opt; else cwr_default_options(&h->opt);
+    if (!(h->opt.rtol > 0)) h->opt.rtol = 1e-13;
+    if (h->opt.max_iter <= 0) h->opt.max_iter = 500;
+    if (h->opt.check_every <= 0) h->opt.check_every = 4;
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (ndev == 0) FAIL(CWR_ECUDA, "no CUDA device: this library has no CPU fallback");
+    if (device < 0 || device >= ndev) FAIL(CWR_EINVAL, "device index out of range");
+    h->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+
+    std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0, h->topo);
+    if (!terr.empty()) FAIL(CWR_EINVAL, terr);
+    const Topology& tp = h->topo;
+    h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
+    const int n = h->n, E = h->E, K = h->K, T = h->T;
+    h->C = (h->opt.hydro_capacity <= 0 || h->opt.hydro_capacity > T) ? T : std::max(2, h->opt.hydro_capacity);
+    int kc = 1;
+    while (kc < K && kc < 32) kc <<= 1;
+    h->KC = kc;
+    h->max_grid = h->num_sms * 8;
+    h->grid_rows = grid_for(n, kThreads / kc, h->max_grid);
+    h->grid_edges = grid_for(E, kThreads / kc, h->max_grid);
+    h->grid_b = grid_for((int64_t)tp.bcell.size(), kThreads / kc, h->max_grid);
+
+    // topology -> device
+    CK(upload(h, &h->d_rowptr, tp.rowptr)); CK(upload(h, &h->d_col, tp.col)); CK(upload(h, &h->d_slot, tp.slot_edge));
+    CK(upload(h, &h->d_f1p, tp.f1p)); CK(upload(h, &h->d_f2p, tp.f2p));
+    CK(upload(h, &h->d_bcell, tp.bcell)); CK(upload(h, &h->d_bptr, tp.bptr)); CK(upload(h, &h->d_bedge, tp.bedge));
+    CK(upload(h, &h->d_eperm, tp.eperm));
+    std::vector<int32_t> einv(E);
+    for (int ep = 0; ep < E; ++ep) einv[tp.eperm[ep]] = ep;
+    CK(upload(h, &h->d_einv, einv));
+    CK(upload(h, &h->d_new_of_old, tp.new_of_old)); CK(upload(h, &h->d_old_of_new, tp.old_of_new));
+    {
+        std::vector<int32_t> a(f1, f1 + E), b(f2, f2 + E);
+        CK(upload(h, &h->d_f1, a)); CK(upload(h, &h->d_f2, b));
+        CK(cudaStreamSynchronize(h->stream));   // the vectors above die here
+    }
+
+    // hydro window, inputs, state, work vectors
+    const size_t nK = (size_t)n * K;
+    CK(dalloc(h, &h->d_adv, (size_t)h->C * E)); CK(dalloc(h, &h->d_cdiff, (size_t)h->C * E));
+    CK(dalloc(h, &h->d_velg, (size_t)h->C * std::max(1, tp.E_g))); CK(dalloc(h, &h->d_vol, (size_t)h->C * n));
+    CK(dalloc(h, &h->d_bc, (size_t)T * std::max(1, h->G) * K));
+    CK(cudaMemsetAsync(h->d_bc, 0, (size_t)T * std::max(1, h->G) * K * sizeof(double), h->stream));
+    h->n_state_slots = h->opt.keep_history ? T : 2;
+    if (cudaMalloc((void**)&h->d_state, (size_t)h->n_state_slots * nK * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        FAIL(CWR_ENOMEM, "not enough device memory for the concentration history; set keep_history = 0");
+    }
+    h->allocs.push_back(h->d_state);
+    CK(cudaMemsetAsync(h->d_state, 0, (size_t)h->n_state_slots * nK * sizeof(double), h->stream));
+
+    DeviceModel& M = h->M;
+    M.n = n; M.K = K; M.E = E; M.E_int = tp.E_int; M.E_g = tp.E_g; M.G = h->G; M.nb = (int)tp.bcell.size();
+    M.rowptr = h->d_rowptr; M.col = h->d_col; M.slot_edge = h->d_slot; M.f1p = h->d_f1p; M.f2p = h->d_f2p;
+    M.bcell = h->d_bcell; M.bptr = h->d_bptr; M.bedge = h->d_bedge;
+    CK(dalloc(h, &M.val, (size_t)tp.nnz)); CK(dalloc(h, &M.diag, (size_t)n)); CK(dalloc(h, &M.gdiag, (size_t)n));
+    CK(cudaMemsetAsync(M.gdiag, 0, (size_t)n * sizeof(double), h->stream));
+    double* ic = nullptr;
+    CK(dalloc(h, &ic, nK)); CK(cudaMemsetAsync(ic, 0, nK * sizeof(double), h->stream));
+    M.ic = ic;
+    CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
+    CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
+    CK(dalloc(h, &M.partials, (size_t)h->max_grid * kMaxDots * K));
+    CK(dalloc(h, &M.sc, (size_t)SC_ROWS * K));
+    CK(dalloc(h, &M.colflags, (size_t)K)); CK(dalloc(h, &M.coliters, (size_t)K));
+    CK(cudaMemsetAsync(M.colflags, 0, K * sizeof(int), h->stream));
+    CK(cudaMemsetAsync(M.coliters, 0, K * sizeof(int), h->stream));
+    CK(dalloc(h, &M.ctl, 1)); CK(cudaMemsetAsync(M.ctl, 0, sizeof(SolverCtl), h->stream));
+    CK(dalloc(h, &h->d_sp, 1)); CK(cudaMemsetAsync(h->d_sp, 0, sizeof(StepParams), h->stream));
+    M.sp = h->d_sp;
+    M.want_flux = h->opt.mass_flux;
+    if (M.want_flux) {
+        CK(dalloc(h, &M.flux, (size_t)3 * E * K));
+        CK(dalloc(h, &M.bsum, (size_t)3 * std::max(1, tp.E_g) * K));
+        CK(cudaMemsetAsync(M.bsum, 0, (size_t)3 * std::max(1, tp.E_g) * K * sizeof(double), h->stream));
+    }
+    M.tol2 = h->opt.rtol * h->opt.rtol;
+    M.diffusion_coefficient = D;
+    M.max_iter = h->opt.max_iter;
+
+    CK(cudaMallocHost((void**)&h->h_ctl, sizeof(SolverCtl)));
+    CK(cudaMallocHost((void**)&h->h_sc, (size_t)SC_ROWS * K * sizeof(double)));
+    CK(cudaMallocHost((void**)&h->h_flags, K * sizeof(int)));
+    CK(cudaMallocHost((void**)&h->h_iters, K * sizeof(int)));
+    h->dt.assign(T, NAN);
+    h->slot_time.assign(h->C, -1);
+    h->initial_row.assign(K, std::vector<double>());
+    h->inputs_set.assign(K, 0);
+    h->real_overrides.resize(K);
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+int cwr_create(cwr_handle** out, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
+               const int32_t* f1, const int32_t* f2, double D, const cwr_options* opt) {
+    if (!out) return CWR_EINVAL;
+    *out = nullptr;
+    cwr_handle* h = new cwr_handle();
+    int rc = create_impl(h, device, n_real, n_face, n_edge, n_time, n_const, f1, f2, D, opt);
+    if (rc != CWR_OK) {
+        g_create_error = h->err;
+        cwr_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return CWR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// inputs
+// ------------------------------------------------------------------------------------------------
+static int check_slices(cwr_handle* h, int t0, int nt) {
+    if (t0 < 0 || nt <= 0 || t0 + nt > h->T) FAIL(CWR_EINVAL, "time slice range outside [0, n_time)");
+    if (nt > h->C) FAIL(CWR_EINVAL, "more slices than hydro_capacity in one call");
+    return CWR_OK;
+}
+
+int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double* cdiff, const float* vel,
+                  const float* vol, const double* dt) {
+    if (!h) return CWR_EINVAL;
+    if (!adv || !cdiff || !vel || !vol || !dt) FAIL(CWR_EINVAL, "NULL array");
+    int rc = check_slices(h, t0, nt);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
+    // staging: adv f32 (E) | vel f32 (E) | vol f32 (F) | cdiff f64 (E)
+    const size_t off_vel = (size_t)E * 4, off_vol = off_vel + (size_t)E * 4, off_cd = (off_vol + (size_t)F * 4 + 7) & ~(size_t)7;
+    rc = ensure_stage(h, off_cd + (size_t)E * 8);
+    if (rc) return rc;
+    char* st = (char*)h->d_stage;
+    const int g = grid_for(E, kThreads, h->max_grid);
+    for (int s = 0; s < nt; ++s) {
+        const int t = t0 + s, slot = t % h->C;
+        CK(cudaMemcpyAsync(st, adv + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(st + off_vel, vel + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(st + off_vol, vol + (size_t)s * F, (size_t)F * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(st + off_cd, cdiff + (size_t)s * E, (size_t)E * 8, cudaMemcpyHostToDevice, h->stream));
+        k_gather<float><<<g, kThreads, 0, h->stream>>>(h->d_adv + (size_t)slot * E, (const float*)st, h->d_eperm, E);
+        k_gather<double><<<g, kThreads, 0, h->stream>>>(h->d_cdiff + (size_t)slot * E, (const double*)(st + off_cd), h->d_eperm, E);
+        if (Eg > 0)
+            k_gather<float><<<grid_for(Eg, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+                h->d_velg + (size_t)slot * Eg, (const float*)(st + off_vel), h->d_eperm + Ei, Eg);
+        k_gather<float><<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+            h->d_vol + (size_t)slot * n, (const float*)(st + off_vol), h->d_old_of_new, n);
+        h->launches += 4;
+        h->dt[t] = dt[s];
+        h->slot_time[slot] = t;
+    }
+    CK(cudaGetLastError());
+    return CWR_OK;
+}
+
+int cwr_set_geometry(cwr_handle* h, const double* face_x, const double* face_y) {
+    if (!h) return CWR_EINVAL;
+    if (!face_x || !face_y) FAIL(CWR_EINVAL, "NULL array");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_stage(h, (size_t)2 * h->F * 8);
+    if (rc) return rc;
+    double* fx = (double*)h->d_stage; double* fy = fx + h->F;
+    CK(cudaMemcpyAsync(fx, face_x, (size_t)h->F * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(fy, face_y, (size_t)h->F * 8, cudaMemcpyHostToDevice, h->stream));
+    if (!h->d_dist) CK(dalloc(h, &h->d_dist, (size_t)h->E));
+    k_dist<<<grid_for(h->E, kThreads, h->max_grid), kThreads, 0, h->stream>>>(h->d_dist, fx, fy, h->d_f1, h->d_f2, h->E);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    h->have_geometry = true;
+    return CWR_OK;
+}
+
+int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
+                      const float* volume, const double* dt) {
+    if (!h) return CWR_EINVAL;
+    if (!face_flow || !edge_velocity || !volume || !dt) FAIL(CWR_EINVAL, "NULL array");
+    if (!h->have_geometry) FAIL(CWR_EINVAL, "cwr_set_geometry must be called before cwr_set_hydro_raw");
+    int rc = check_slices(h, t0, nt);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
+    const size_t off_vel = (size_t)E * 4, off_vol = off_vel + (size_t)E * 4;
+    rc = ensure_stage(h, off_vol + (size_t)F * 4);
+    if (rc) return rc;
+    char* st = (char*)h->d_stage;
+    for (int s = 0; s < nt; ++s) {
+        const int t = t0 + s, slot = t % h->C;
+        CK(cudaMemcpyAsync(st, face_flow + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(st + off_vel, edge_velocity + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(st + off_vol, volume + (size_t)s * F, (size_t)F * 4, cudaMemcpyHostToDevice, h->stream));
+        k_derive<<<grid_for(E, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+            h->d_adv + (size_t)slot * E, h->d_cdiff + (size_t)slot * E, h->d_velg + (size_t)slot * std::max(1, Eg),
+            (const float*)st, (const float*)(st + off_vel), h->d_dist, h->d_eperm, E, Ei, (float)h->M.diffusion_coefficient);
+        k_gather<float><<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+            h->d_vol + (size_t)slot * n, (const float*)(st + off_vol), h->d_old_of_new, n);
+        h->launches += 2;
+        h->dt[t] = dt[s];
+        h->slot_time[slot] = t;
+    }
+    CK(cudaGetLastError());
+    return CWR_OK;
+}
+
+int cwr_set_inputs(cwr_handle* h, int k, const double* input) {
+    if (!h) return CWR_EINVAL;
+    if (!input) FAIL(CWR_EINVAL, "NULL array");
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n, F = h->F, G = h->G, T = h->T, K = h->K;
+    // host: initial row (constituents.py:94-98) and BC block packed (T,G)
+    std::vector<double>& row0 = h->initial_row[k];
+    row0.assign(F, 0.0);
+    std::copy(input, input + n, row0.begin());
+    std::vector<double> pack((size_t)T * std::max(1, G));
+    for (int t = 0; t < T; ++t) std::copy(input + (size_t)t * F + n, input + (size_t)t * F + F, pack.begin() + (size_t)t * G);
+    // real-cell entries at t >= 1 that are non-zero override c~ (linalg.py:199-200); rare
+    auto& ov = h->real_overrides[k];
+    ov.clear();
+    for (int t = 1; t < T; ++t) {
+        const double* r = input + (size_t)t * F;
+        for (int i = 0; i < n; ++i)
+            if (r[i] != 0.0) ov[t].emplace_back(h->topo.new_of_old[i], r[i]);
+    }
+    int rc = ensure_stage(h, std::max(pack.size(), (size_t)n) * 8 + (size_t)n * 8);
+    if (rc) return rc;
+    double* st = (double*)h->d_stage;
+    CK(cudaMemcpyAsync(st, input, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    const int g = grid_for(n, kThreads, h->max_grid);
+    k_scatter_column<<<g, kThreads, 0, h->stream>>>((double*)h->M.ic, st, h->d_old_of_new, n, K, k);
+    k_scatter_column<<<g, kThreads, 0, h->stream>>>(h->d_state, st, h->d_old_of_new, n, K, k);   // c[0]
+    h->launches += 2;
+    CK(cudaStreamSynchronize(h->stream));
+    if (G > 0) {
+        CK(cudaMemcpyAsync(st, pack.data(), pack.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        // input layout seen by the kernel: (T, G) with "F" = G and n = 0
+        k_scatter_bc<<<grid_for((int64_t)T * G, kThreads, h->max_grid), kThreads, 0, h->stream>>>(h->d_bc, st, T, G, 0, G, K, k);
+        h->launches += 1;
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    CK(cudaGetLastError());
+    h->inputs_set[k] = 1;
+    return CWR_OK;
+}
+
+static inline double* state_slot(cwr_handle* h, int t) {
+    const int s = h->opt.keep_history ? t : (t & 1);
+    return h->d_state + (size_t)s * h->n * h->K;
+}
+
+static int state_available(cwr_handle* h, int t) {
+    if (t < 0 || t >= h->T) FAIL(CWR_EINVAL, "time index out of range");
+    if (t > h->computed_upto) FAIL(CWR_EINVAL, "state at this time index has not been computed yet");
+    if (!h->opt.keep_history && t < h->computed_upto - 1) FAIL(CWR_EINVAL, "state no longer on the device (keep_history = 0)");
+    return CWR_OK;
+}
+
+int cwr_set_state(cwr_handle* h, int k, int t, const double* c) {
+    if (!h) return CWR_EINVAL;
+    if (!c) FAIL(CWR_EINVAL, "NULL array");
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    int rc = state_available(h, t);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = ensure_stage(h, (size_t)h->n * 8);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->d_stage, c, (size_t)h->n * 8, cudaMemcpyHostToDevice, h->stream));
+    k_scatter_column<<<grid_for(h->n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+        state_slot(h, t), (const double*)h->d_stage, h->d_old_of_new, h->n, h->K, k);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+int cwr_set_state_all(cwr_handle* h, int t, const double* c, const uint8_t* mask) {
+    if (!h) return CWR_EINVAL;
+    if (!c) FAIL(CWR_EINVAL, "NULL array");
+    int rc = state_available(h, t);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t nK = (size_t)h->n * h->K;
+    rc = ensure_stage(h, nK * 8 + 256);
+    if (rc) return rc;
+    uint8_t* dmask = nullptr;
+    CK(cudaMemcpyAsync(h->d_stage, c, nK * 8, cudaMemcpyHostToDevice, h->stream));
+    if (mask) {
+        dmask = (uint8_t*)h->d_stage + nK * 8;
+        CK(cudaMemcpyAsync(dmask, mask, h->K, cudaMemcpyHostToDevice, h->stream));
+    }
+    k_scatter_all<<<grid_for((int64_t)nK, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+        state_slot(h, t), (const double*)h->d_stage, dmask, h->d_new_of_old, h->n, h->K);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one step
+// ------------------------------------------------------------------------------------------------
+static int poll(cwr_handle* h) {
+    CK(cudaMemcpyAsync(h->h_ctl, h->M.ctl, sizeof(SolverCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+static int launch_iteration(cwr_handle* h) {
+    const int g = h->grid_rows;
+    DeviceModel& M = h->M;
+    KC_DISPATCH(h->KC,
+        (k_spmm<KC, 1><<<g, kThreads, 0, h->stream>>>(M, M.p, nullptr));
+        (k_update_s<KC><<<g, kThreads, 0, h->stream>>>(M));
+        (k_spmm<KC, 2><<<g, kThreads, 0, h->stream>>>(M, M.r, nullptr));
+        (k_update_xrp<KC><<<g, kThreads, 0, h->stream>>>(M)));
+    h->launches += 4;
+    return CWR_OK;
+}
+
+static int solve(cwr_handle* h, cwr_step_info* info) {
+    DeviceModel& M = h->M;
+    const int g = h->grid_rows;
+    int restarts = 0;
+    int total_iter = 0;
+    for (;;) {
+        KC_DISPATCH(h->KC, (k_spmm<KC, 0><<<g, kThreads, 0, h->stream>>>(M, nullptr, nullptr)));
+        h->launches += 1;
+        int rc = poll(h);
+        if (rc) return rc;
+        while (!h->h_ctl->all_done) {
+            for (int i = 0; i < h->opt.check_every; ++i) launch_iteration(h);
+            rc = poll(h);
+            if (rc) return rc;
+        }
+        total_iter += h->h_ctl->iter;
+        const bool breakdown = (h->h_ctl->flags_or & FL_BREAKDOWN) != 0;
+        if (breakdown && restarts < 3 && !h->h_ctl->hit_max_iter) {
+            // restart from the current iterate: new shadow residual (standard cure for rho ~ 0)
+            ++restarts;
+            CK(cudaMemsetAsync(&M.ctl->all_done, 0, 2 * sizeof(int), h->stream));   // all_done, iter
+            continue;
+        }
+        break;
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_sc, M.sc, (size_t)SC_ROWS * h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_flags, M.colflags, h->K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->iterations += total_iter;
+    int status = CWR_OK;
+    double worst = 0.0;
+    for (int k = 0; k < h->K; ++k) {
+        const double bb = h->h_sc[SC_BNORM2 * h->K + k], rr = h->h_sc[SC_RNORM2 * h->K + k];
+        const double rel = bb > 0 ? std::sqrt(rr / bb) : (rr > 0 ? INFINITY : 0.0);
+        if (rel == rel) worst = std::max(worst, rel);
+        const int f = h->h_flags[k];
+        if (f & FL_NAN) status = CWR_ENAN;
+        else if ((f & FL_BREAKDOWN) && !(f & FL_CONVERGED) && status == CWR_OK) status = CWR_EBREAKDOWN;
+        else if (!(f & FL_CONVERGED) && status == CWR_OK) status = CWR_ENOTCONVERGED;
+    }
+    if (h->h_ctl->singular) status = CWR_ESINGULAR;
+    if (info) { info->iterations = total_iter; info->restarts = restarts; info->status = status; info->max_relres = worst; }
+    return status;
+}
+
+static int find_slot(cwr_handle* h, int t) {
+    const int s = t % h->C;
+    return h->slot_time[s] == t ? s : -1;
+}
+
+int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
+    if (!h) return CWR_EINVAL;
+    if (t < 0 || t + 1 >= h->T) FAIL(CWR_EINVAL, "cwr_step: t must satisfy 0 <= t < n_time - 1 (dt[n_time-1] is NaN)");
+    if (t > h->computed_upto) FAIL(CWR_EINVAL, "cwr_step: c[t] has not been computed yet");
+    if (!h->opt.keep_history && t < h->computed_upto - 1) FAIL(CWR_EINVAL, "cwr_step: c[t] no longer on the device");
+    for (int k = 0; k < h->K; ++k)
+        if (!h->inputs_set[k]) FAIL(CWR_EINVAL, "cwr_set_inputs has not been called for every constituent");
+    const int s0 = find_slot(h, t), s1 = find_slot(h, t + 1);
+    if (s0 < 0 || s1 < 0) FAIL(CWR_EINVAL, "hydrodynamic slices t and t+1 are not resident; call cwr_set_hydro");
+    CK(cudaSetDevice(h->device));
+    const int64_t launches0 = h->launches;
+    const int n = h->n, E = h->E, K = h->K, Eg = std::max(1, h->topo.E_g), G = std::max(1, h->G);
+    StepParams p;
+    p.adv_t = h->d_adv + (size_t)s0 * E; p.cdiff_t = h->d_cdiff + (size_t)s0 * E;
+    p.vol_t = h->d_vol + (size_t)s0 * n; p.vol_t1 = h->d_vol + (size_t)s1 * n;
+    p.adv_t1 = h->d_adv + (size_t)s1 * E; p.cdiff_t1 = h->d_cdiff + (size_t)s1 * E;
+    p.velg_t1 = h->d_velg + (size_t)s1 * Eg;
+    p.bc_t1 = h->d_bc + (size_t)(t + 1) * G * K;
+    p.state_t = state_slot(h, t); p.state_t1 = state_slot(h, t + 1);
+    p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
+    DeviceModel& M = h->M;
+    k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl);
+    if (M.nb > 0) k_boundary_diag<<<grid_for(M.nb, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+    k_assemble<<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+    KC_DISPATCH(h->KC, (k_rhs<KC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
+    h->launches += 3 + (M.nb > 0);
+    // sparse real-cell overrides of c~ (input_array[t][real cell] != 0 at t >= 1): recompute those rows
+    for (int k = 0; k < K; ++k) {
+        auto it = h->real_overrides[k].find(t);
+        if (it == h->real_overrides[k].end()) continue;
+        // applied through the state + a second k_rhs pass restricted by value: simplest faithful form is to
+        // patch c~ in place on a scratch copy of c[t]; since c[t] itself must stay untouched (the reference
+        // only patches its temporary `solver` array), patch state_t1 and b directly on the host side values.
+        std::vector<double> conc(1), dummy;
+        for (auto& cv : it->second) {
+            const size_t idx = (size_t)cv.first * K + k;
+            float vol; double diag;
+            CK(cudaMemcpyAsync(&vol, p.vol_t + cv.first, 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(&diag, M.diag + cv.first, 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            const double b = ((double)vol * cv.second / p.dt) / diag;
+            CK(cudaMemcpyAsync(M.b + idx, &b, 8, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaMemcpyAsync(p.state_t1 + idx, &cv.second, 8, cudaMemcpyHostToDevice, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+        }
+    }
+    if (M.nb > 0) {
+        KC_DISPATCH(h->KC, (k_boundary_rhs<KC><<<h->grid_b, kThreads, 0, h->stream>>>(M)));
+        h->launches += 1;
+    }
+    h->lhs_step = t;
+    cwr_step_info local;
+    int status = solve(h, &local);
+    if (status == CWR_ECUDA) return status;
+    if (M.want_flux) {
+        KC_DISPATCH(h->KC, (k_mass_flux<KC><<<h->grid_edges, kThreads, 0, h->stream>>>(M)));
+        h->launches += 1;
+        h->flux_step = t;
+    }
+    CK(cudaGetLastError());
+    h->computed_upto = std::max(h->computed_upto, t + 1);
+    if (!h->opt.keep_history) h->computed_upto = t + 1;
+    local.n_launches = (int)(h->launches - launches0);
+    if (info) *info = local;
+    if (status != CWR_OK) {
+        char buf[160];
+        std::snprintf(buf, sizeof buf, "step %d: solver status %d after %d iterations (max relres %.3e)", t, status,
+                      local.iterations, local.max_relres);
+        h->err = buf;
+    }
+    return status;
+}
+
+int cwr_run(cwr_handle* h, int t_begin, int t_end, cwr_step_info* worst) {
+    if (!h) return CWR_EINVAL;
+    cwr_step_info w{}; w.status = CWR_OK;
+    int rc_final = CWR_OK;
+    for (int t = t_begin; t < t_end; ++t) {
+        cwr_step_info i{};
+        int rc = cwr_step(h, t, &i);
+        if (rc == CWR_EINVAL || rc == CWR_ECUDA) return rc;
+        if (rc != CWR_OK && rc_final == CWR_OK) rc_final = rc;
+        w.iterations = std::max(w.iterations, i.iterations);
+        w.restarts = std::max(w.restarts, i.restarts);
+        w.max_relres = std::max(w.max_relres, i.max_relres);
+        w.n_launches += i.n_launches;
+        if (i.status != CWR_OK) w.status = i.status;
+    }
+    if (worst) *worst = w;
+    return rc_final;
+}
+
+// ------------------------------------------------------------------------------------------------
+// outputs
+// ------------------------------------------------------------------------------------------------
+int cwr_get_state(cwr_handle* h, int k, int t, double* out) {
+    if (!h) return CWR_EINVAL;
+    if (!out) FAIL(CWR_EINVAL, "NULL array");
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    int rc = state_available(h, t);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    rc = ensure_stage(h, (size_t)h->F * 8);
+    if (rc) return rc;
+    const double* bc_t = (t >= 1 && h->G > 0) ? h->d_bc + (size_t)t * h->G * h->K : nullptr;
+    k_extract_state<<<grid_for(h->F, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+        (double*)h->d_stage, state_slot(h, t), bc_t, h->d_new_of_old, h->n, h->F, h->K, k);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->d_stage, (size_t)h->F * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (t == 0 && !h->initial_row[k].empty())   // row 0 = the IC row: zeros (not NaN) where unset
+        std::copy(h->initial_row[k].begin() + h->n, h->initial_row[k].end(), out + h->n);
+    return CWR_OK;
+}
+
+int cwr_get_state_all(cwr_handle* h, int t, double* out) {
+    if (!h) return CWR_EINVAL;
+    if (!out) FAIL(CWR_EINVAL, "NULL array");
+    int rc = state_available(h, t);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t nK = (size_t)h->n * h->K;
+    rc = ensure_stage(h, nK * 8);
+    if (rc) return rc;
+    k_extract_all<<<grid_for((int64_t)nK, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+        (double*)h->d_stage, state_slot(h, t), h->d_new_of_old, h->n, h->K);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->d_stage, nK * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+int cwr_get_mass_flux(cwr_handle* h, int k, int t, double* adv, double* diff, double* tot) {
+    if (!h) return CWR_EINVAL;
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    if (!h->M.want_flux) FAIL(CWR_EINVAL, "mass flux disabled (options.mass_flux = 0)");
+    if (t != h->flux_step) FAIL(CWR_EINVAL, "only the most recent step's mass fluxes are on the device");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_stage(h, (size_t)h->E * 8);
+    if (rc) return rc;
+    double* outs[3] = {adv, diff, tot};
+    for (int w = 0; w < 3; ++w) {
+        if (!outs[w]) continue;
+        k_extract_flux<<<grid_for(h->E, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+            (double*)h->d_stage, h->M.flux + (size_t)w * h->E * h->K, h->d_einv, h->E, h->K, k);
+        h->launches += 1;
+        CK(cudaMemcpyAsync(outs[w], h->d_stage, (size_t)h->E * 8, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    CK(cudaGetLastError());
+    return CWR_OK;
+}
+
+int cwr_get_flux_sums(cwr_handle* h, int k, double* total_sum, double* in_sum, double* out_sum) {
+    if (!h) return CWR_EINVAL;
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    if (!h->M.want_flux) FAIL(CWR_EINVAL, "mass flux disabled (options.mass_flux = 0)");
+    CK(cudaSetDevice(h->device));
+    const int Eg = h->topo.E_g, Ei = h->topo.E_int, K = h->K;
+    std::vector<double> host((size_t)3 * std::max(1, Eg) * K);
+    CK(cudaMemcpyAsync(host.data(), h->M.bsum, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double* outs[3] = {total_sum, in_sum, out_sum};
+    for (int w = 0; w < 3; ++w) {
+        if (!outs[w]) continue;
+        std::fill(outs[w], outs[w] + h->E, 0.0);
+        for (int g = 0; g < Eg; ++g) outs[w][h->topo.eperm[Ei + g]] = host[((size_t)w * Eg + g) * K + k];
+    }
+    return CWR_OK;
+}
+
+int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_totals* out) {
+    if (!h) return CWR_EINVAL;
+    if (!out) FAIL(CWR_EINVAL, "NULL output");
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    CK(cudaSetDevice(h->device));
+    int ts[2] = {t_start, t_end};
+    double res[2][2];
+    int rc = ensure_stage(h, 64);
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        rc = state_available(h, ts[i]);
+        if (rc) return rc;
+        const int s = find_slot(h, ts[i]);
+        if (s < 0) FAIL(CWR_EINVAL, "volume slice not resident for mass totals");
+        k_mass_total<<<1, kThreads, 0, h->stream>>>(h->d_vol + (size_t)s * h->n, state_slot(h, ts[i]), h->n, h->K, k, (double*)h->d_stage);
+        h->launches += 1;
+        CK(cudaMemcpyAsync(res[i], h->d_stage, 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    out->vol_start = res[0][0]; out->mass_start = res[0][1]; out->vol_end = res[1][0]; out->mass_end = res[1][1];
+    return CWR_OK;
+}
+
+int cwr_get_lhs(cwr_handle* h, int64_t* nnz, int32_t* indptr, int32_t* indices, double* data) {
+    if (!h) return CWR_EINVAL;
+    const Topology& tp = h->topo;
+    // merged pattern size (duplicate (row, col) pairs collapse, as csr_matrix sums them)
+    const int n = h->n;
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> rows(n);   // reference row -> (reference col, slot or -1 for diag)
+    for (int i = 0; i < n; ++i) {
+        auto& r = rows[tp.old_of_new[i]];
+        r.emplace_back(tp.old_of_new[i], -1 - i);
+        for (int j = tp.rowptr[i]; j < tp.rowptr[i + 1]; ++j) r.emplace_back(tp.old_of_new[tp.col[j]], j);
+    }
+    int64_t total = 0;
+    for (auto& r : rows) {
+        std::sort(r.begin(), r.end());
+        int32_t last = -1;
+        for (auto& pr : r) if (pr.first != last) { ++total; last = pr.first; }
+    }
+    if (nnz) *nnz = total;
+    if (!indptr || !indices || !data) return CWR_OK;
+    if (h->lhs_step < 0) FAIL(CWR_EINVAL, "no LHS assembled yet");
+    CK(cudaSetDevice(h->device));
+    std::vector<double> val((size_t)tp.nnz), diag(n);
+    CK(cudaMemcpyAsync(val.data(), h->M.val, val.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(diag.data(), h->M.diag, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int64_t pos = 0;
+    for (int r0 = 0; r0 < n; ++r0) {
+        indptr[r0] = (int32_t)pos;
+        const int i = tp.new_of_old[r0];
+        int32_t last = -1;
+        for (auto& pr : rows[r0]) {
+            const double v = pr.second < 0 ? diag[i] : val[pr.second] * diag[i];
+            if (pr.first == last) data[pos - 1] += v;
+            else { indices[pos] = pr.first; data[pos] = v; ++pos; last = pr.first; }
+        }
+    }
+    indptr[n] = (int32_t)pos;
+    return CWR_OK;
+}
+
+int cwr_get_rhs(cwr_handle* h, int k, double* b) {
+    if (!h) return CWR_EINVAL;
+    if (!b) FAIL(CWR_EINVAL, "NULL array");
+    if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");
+    if (h->lhs_step < 0) FAIL(CWR_EINVAL, "no step taken yet");
+    CK(cudaSetDevice(h->device));
+    const int n = h->n, K = h->K;
+    std::vector<double> bs((size_t)n * K), diag(n);
+    CK(cudaMemcpyAsync(bs.data(), h->M.b, bs.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(diag.data(), h->M.diag, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int r0 = 0; r0 < n; ++r0) {
+        const int i = h->topo.new_of_old[r0];
+        b[r0] = bs[(size_t)i * K + k] * diag[i];
+    }
+    return CWR_OK;
+}
+
+int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old) {
+    if (!h) return CWR_EINVAL;
+    if (!new_of_old) FAIL(CWR_EINVAL, "NULL array");
+    std::copy(h->topo.new_of_old.begin(), h->topo.new_of_old.end(), new_of_old);
+    return CWR_OK;
+}
+
+int cwr_stream(cwr_handle* h, void** s) {
+    if (!h || !s) return CWR_EINVAL;
+    *s = (void*)h->stream;
+    return CWR_OK;
+}
+
+int cwr_counters(cwr_handle* h, int64_t* launches, int64_t* iterations) {
+    if (!h) return CWR_EINVAL;
+    if (launches) *launches = h->launches;
+    if (iterations) *iterations = h->iterations;
+    return CWR_OK;
+}
+
+int cwr_time_spmm(cwr_handle* h, int reps, double* ms_per_launch, double* algorithmic_bytes) {
+    if (!h) return CWR_EINVAL;
+    if (reps <= 0) FAIL(CWR_EINVAL, "reps must be positive");
+    if (h->lhs_step < 0) FAIL(CWR_EINVAL, "assemble a LHS (take a step) before timing the product");
+    CK(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    DeviceModel& M = h->M;
+    // x = p (left by the last solve), y = v ; both are scratch between steps
+    for (int w = 0; w < 3; ++w) { KC_DISPATCH(h->KC, (k_spmm<KC, 3><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, M.v))); }
+    CK(cudaEventRecord(e0, h->stream));
+    for (int r = 0; r < reps; ++r) { KC_DISPATCH(h->KC, (k_spmm<KC, 3><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, M.v))); }
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaEventSynchronize(e1));
+    h->launches += reps + 3;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+    if (ms_per_launch) *ms_per_launch = (double)ms / reps;
+    if (algorithmic_bytes)
+        *algorithmic_bytes = 12.0 * (double)h->topo.nnz + 4.0 * (h->n + 1.0) + 16.0 * (double)h->n * h->K;
+    return CWR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,566 @@
+// sm_100a kernels of the transport step.  fp64 throughout; HBM-bound gather/stream work, so the
+// design rules are coalescing (constituents interleaved: x[row*K + k], one 128 B line per row at
+// K = 16), persistent grids sized from the SM count, fused dot products with a deterministic
+// two-level reduction (no floating-point atomics anywhere), and per-step parameters read from a
+// device-resident struct so that the whole step can be replayed as one CUDA graph.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cwr {
+
+constexpr int kThreads = 256;
+constexpr int kMaxK = 128;      // constituents per handle
+constexpr int kMaxDots = 5;
+
+// Per-step pointers/values; written by k_set_step (a graph node whose parameters are the only
+// thing that changes between steps) and read by every kernel of the step.
+struct StepParams {
+    const float* adv_t;      // (E)  advection_coeff[t]       device edge order
+    const double* cdiff_t;   // (E)  coeff_to_diffusion[t]
+    const float* vol_t;      // (n)  volume[t]   real cells, device cell order
+    const float* vol_t1;     // (n)  volume[t+1]
+    const float* adv_t1;     // (E)  advection_coeff[t+1]
+    const double* cdiff_t1;  // (E)  coeff_to_diffusion[t+1]
+    const float* velg_t1;    // (E_g) edge_velocity[t+1] of ghost edges
+    const double* bc_t1;     // (G,K) input_array[t+1][ghost cells]
+    const double* state_t;   // (n,K) c[t]
+    double* state_t1;        // (n,K) c[t+1]  (the solver iterates in place on it)
+    double dt;               // dt[t]
+    int t;
+    int apply_ic;            // t == 0: input_array[0] overrides c~ where non-zero (linalg.py:199-200)
+};
+
+enum ScalarRow { SC_RHO = 0, SC_ALPHA, SC_OMEGA, SC_BETA, SC_BNORM2, SC_RNORM2, SC_RHATV, SC_ROWS };
+enum ColFlag { FL_CONVERGED = 1, FL_BREAKDOWN = 2, FL_NAN = 4, FL_ZERO_RHS = 8, FL_PENDING = 16 };
+
+struct SolverCtl {
+    int all_done;       // every column converged / failed / fixed
+    int iter;           // BiCGSTAB iterations done in this solve
+    int flags_or;       // OR of column flags that matter to the host (breakdown, nan)
+    int singular;       // a zero diagonal was met during assembly
+    int hit_max_iter;
+    int pad[3];
+    unsigned ticket[4]; // last-block tickets (one per kernel family)
+};
+
+struct DeviceModel {
+    int n, K, E, E_int, E_g, G, nb;
+    const int32_t* rowptr; const int32_t* col; const int32_t* slot_edge;
+    const int32_t* f1p; const int32_t* f2p;
+    const int32_t* bcell; const int32_t* bptr; const int32_t* bedge;
+    double* val;        // (nnz) off-diagonals of D^-1 A
+    double* diag;       // (n)   D
+    double* gdiag;      // (n)   ghost-edge diagonal terms (boundary cells only, 0 elsewhere)
+    const double* ic;   // (n,K) input_array[0][0:n]
+    double *b, *r, *rhat, *p, *v, *tt;   // (n,K) work vectors (b is the row-scaled RHS)
+    double* partials;   // (grid, kMaxDots, K)
+    double* sc;         // (SC_ROWS, K) per-column scalars
+    int* colflags;      // (K)
+    int* coliters;      // (K)
+    SolverCtl* ctl;
+    const StepParams* sp;
+    double* flux;       // (3, E, K) advection / diffusion / total mass flux of the last step
+    double* bsum;       // (3, E_g, K) running total / in / out sums on ghost edges
+    double tol2;        // rtol^2
+    double diffusion_coefficient;
+    int max_iter;
+    int want_flux;
+};
+
+__global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl) {
+    *dst = p;
+    ctl->all_done = 0; ctl->iter = 0; ctl->flags_or = 0; ctl->hit_max_iter = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// upload helpers: reference order -> device order
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_gather(T* __restrict__ dst, const T* __restrict__ src, const int32_t* __restrict__ idx, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+
+// dst[(i)*K + k] = src[old_of_new[i]]   (one constituent's real-cell vector into the interleaved state)
+__global__ void k_scatter_column(double* __restrict__ dst, const double* __restrict__ src,
+                                 const int32_t* __restrict__ old_of_new, int n, int K, int k) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[(size_t)i * K + k] = src[old_of_new[i]];
+}
+
+// bc[(t*G + g)*K + k] = input[t*F + n + g]
+__global__ void k_scatter_bc(double* __restrict__ bc, const double* __restrict__ input, int T, int F, int n, int G, int K, int k) {
+    size_t total = (size_t)T * G;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        size_t t = i / G, g = i % G;
+        bc[i * K + k] = input[t * F + n + g];
+    }
+}
+
+// out[F]: real cells from the interleaved state (reference order), ghost cells: BC value or NaN
+__global__ void k_extract_state(double* __restrict__ out, const double* __restrict__ state, const double* __restrict__ bc_t,
+                                const int32_t* __restrict__ new_of_old, int n, int F, int K, int k) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < F; j += gridDim.x * blockDim.x) {
+        double v;
+        if (j < n) v = state[(size_t)new_of_old[j] * K + k];
+        else {
+            v = bc_t ? bc_t[(size_t)(j - n) * K + k] : 0.0;
+            if (v == 0.0) v = __longlong_as_double(0x7ff8000000000000LL);   // transport.py:258-264: unset ghost cells stay NaN
+        }
+        out[j] = v;
+    }
+}
+
+// out[(k, j)] for all constituents, real cells only, reference order
+__global__ void k_extract_all(double* __restrict__ out, const double* __restrict__ state,
+                              const int32_t* __restrict__ new_of_old, int n, int K) {
+    size_t total = (size_t)n * K;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int k = (int)(i / n), j = (int)(i % n);
+        out[i] = state[(size_t)new_of_old[j] * K + k];
+    }
+}
+
+__global__ void k_scatter_all(double* __restrict__ state, const double* __restrict__ src, const uint8_t* __restrict__ mask,
+                              const int32_t* __restrict__ new_of_old, int n, int K) {
+    size_t total = (size_t)n * K;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int k = (int)(i / n), j = (int)(i % n);
+        if (mask == nullptr || mask[k]) state[(size_t)new_of_old[j] * K + k] = src[i];
+    }
+}
+
+// out[e] (reference edge order) = flux[which][e'][k]
+__global__ void k_extract_flux(double* __restrict__ out, const double* __restrict__ flux, const int32_t* __restrict__ einv,
+                               int E, int K, int k) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x)
+        out[e] = flux[(size_t)einv[e] * K + k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// "next" row N1: derive adv / cdiff from the raw HEC-RAS arrays (reference utilities.py:513-541)
+//   adv = face_flow * sign(|vel|)  (f32);  area = adv / vel, NaN -> 0 (f32);
+//   cdiff = f64(f32(area * D)) / dist
+// input in reference edge order, output in device edge order.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_derive(float* __restrict__ adv, double* __restrict__ cdiff, float* __restrict__ velg,
+                         const float* __restrict__ flow, const float* __restrict__ vel, const double* __restrict__ dist,
+                         const int32_t* __restrict__ eperm, int E, int E_int, float Df) {
+    for (int ep = blockIdx.x * blockDim.x + threadIdx.x; ep < E; ep += gridDim.x * blockDim.x) {
+        int e = eperm[ep];
+        float q = flow[e], u = vel[e];
+        float au = fabsf(u);
+        float sg = (au > 0.f) ? 1.f : ((au == 0.f) ? 0.f : au);     // sign(|u|); NaN stays NaN
+        float a = __fmul_rn(q, sg);
+        float area = __fdiv_rn(a, u);
+        if (area != area) area = 0.f;                                // fillna(0)
+        float ad = __fmul_rn(area, Df);
+        adv[ep] = a;
+        cdiff[ep] = (double)ad / dist[e];
+        if (ep >= E_int) velg[ep - E_int] = u;
+    }
+}
+
+__global__ void k_dist(double* __restrict__ dist, const double* __restrict__ fx, const double* __restrict__ fy,
+                       const int32_t* __restrict__ f1, const int32_t* __restrict__ f2, int E) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+        double dx = fx[f1[e]] - fx[f2[e]], dy = fy[f1[e]] - fy[f2[e]];
+        dist[e] = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));   // no fma contraction: matches numpy
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LHS assembly  (reference linalg.py:34-156 + transport.py:215-218)
+// ---------------------------------------------------------------------------------------------
+// ghost-edge diagonal terms: sum over a boundary cell's ghost edges of cdiff + max(adv, 0)
+// (linalg.py:92-97 and 113-115 applied to ghost edges).
+__global__ void k_boundary_diag(DeviceModel M) {
+    const StepParams& sp = *M.sp;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < M.nb; b += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int j = M.bptr[b]; j < M.bptr[b + 1]; ++j) {
+            int e = M.bedge[j];
+            s += sp.cdiff_t[e] + fmax((double)sp.adv_t[e], 0.0);
+        }
+        M.gdiag[M.bcell[b]] = s;
+    }
+}
+
+// One thread per row: diagonal D_i and the row's off-diagonals, written once into their fixed
+// slots, already divided by D_i (row-scaled system D^-1 A, unit diagonal implied).
+//   internal edge e = (P = f1, N = f2), a = adv[t,e], d = cdiff[t,e]:
+//     A[P,N] = -d + min(a,0)   A[N,P] = -d - max(a,0)
+//     A[P,P] += d + max(a,0)   A[N,N] += d - min(a,0)
+//   A[i,i] += vol[t+1,i]/dt[t]  (+1 if vol[t+1,i] == 0, linalg.py:66,77-81)
+__global__ void __launch_bounds__(kThreads) k_assemble(DeviceModel M) {
+    const StepParams& sp = *M.sp;
+    const double dt = sp.dt;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += gridDim.x * blockDim.x) {
+        const float vol = sp.vol_t1[i];
+        double diag = (vol == 0.f ? 1.0 : 0.0) + (double)vol / dt + M.gdiag[i];
+        const int s = M.rowptr[i], e = M.rowptr[i + 1];
+        for (int j = s; j < e; ++j) {
+            const int code = M.slot_edge[j];
+            const double a = (double)sp.adv_t[code >> 1];
+            const double d = sp.cdiff_t[code >> 1];
+            diag += (code & 1) ? (d - fmin(a, 0.0)) : (d + fmax(a, 0.0));
+        }
+        const double inv = 1.0 / diag;
+        for (int j = s; j < e; ++j) {
+            const int code = M.slot_edge[j];
+            const double a = (double)sp.adv_t[code >> 1];
+            const double d = sp.cdiff_t[code >> 1];
+            const double off = (code & 1) ? (-d - fmax(a, 0.0)) : (-d + fmin(a, 0.0));
+            M.val[j] = off * inv;
+        }
+        M.diag[i] = diag;
+        if (diag == 0.0) M.ctl->singular = 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RHS  (reference linalg.py:177-275, 354-406), K constituents at once, row-scaled by 1/D
+// thread mapping used by all (row, column) kernels: KC lanes per row, lane = column
+// ---------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(kThreads) k_rhs(DeviceModel M) {
+    const StepParams& sp = *M.sp;
+    const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const double dt = sp.dt;
+    for (int c = lane; c < K; c += KC)
+        for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+            const size_t idx = (size_t)i * K + c;
+            double conc = sp.state_t[idx];
+            if (sp.apply_ic) { const double ic = M.ic[idx]; if (ic != 0.0) conc = ic; }
+            const double load = (double)sp.vol_t[i] * conc / dt;      // linalg.py:239
+            M.b[idx] = load / M.diag[i];
+            sp.state_t1[idx] = conc;                                 // warm start x0 = c~[t]
+        }
+}
+
+// Boundary cells: b_i = load + ghost_in + ghost_out with the reference's selection and
+// last-edge-wins assignment (linalg.py:349-351, 372-378, 390).
+template <int KC>
+__global__ void __launch_bounds__(kThreads) k_boundary_rhs(DeviceModel M) {
+    const StepParams& sp = *M.sp;
+    const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const double dt = sp.dt;
+    const bool has_diffusion = M.diffusion_coefficient != 0.0;
+    for (int c = lane; c < K; c += KC)
+        for (int b = blockIdx.x * GPB + group; b < M.nb; b += gridDim.x * GPB) {
+            const int i = M.bcell[b];
+            double m_in = 0.0, ca_in = 0.0, cd_in = 0.0, m_out = 0.0, cd_out = 0.0;
+            for (int j = M.bptr[b]; j < M.bptr[b + 1]; ++j) {
+                const int e = M.bedge[j];
+                const float u = sp.velg_t1[e - M.E_int];
+                const double bc = sp.bc_t1[(size_t)(M.f2p[e] - M.n) * K + c];
+                const double cd = has_diffusion ? fabs(sp.cdiff_t1[e]) : 0.0;
+                if (u < 0.f) { m_in = bc; ca_in = fabs((double)sp.adv_t1[e]); cd_in = cd; }
+                if (u > 0.f) { m_out = bc; cd_out = cd; }
+            }
+            const size_t idx = (size_t)i * K + c;
+            const double conc = sp.state_t1[idx];                    // c~ written by k_rhs
+            const double load = (double)sp.vol_t[i] * conc / dt;
+            const double rhs = load + (ca_in + cd_in) * m_in + cd_out * m_out;
+            M.b[idx] = rhs / M.diag[i];
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic block / grid reduction of per-column dot products
+// ---------------------------------------------------------------------------------------------
+template <int ND, int KC>
+__device__ __forceinline__ void block_dots(double (&acc)[ND], double* smem, double* block_out, int K, int chunk) {
+#pragma unroll
+    for (int off = KC; off < 32; off <<= 1)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], off);
+    const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = kThreads / 32;
+    if (wl < KC)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) smem[(warp * ND + d) * KC + wl] = acc[d];
+    __syncthreads();
+    if (threadIdx.x < ND * KC) {
+        const int d = threadIdx.x / KC, l = threadIdx.x % KC;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += smem[(w * ND + d) * KC + l];
+        const int c = chunk * KC + l;
+        if (c < K) block_out[d * K + c] = s;
+    }
+    __syncthreads();
+}
+
+// true in exactly one block: the last one to arrive.  All of the grid's partials are visible to it.
+__device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+        if (is_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last != 0;
+}
+
+// sum the grid's partials in block order -> tot[d*K + k] (shared memory)
+template <int ND>
+__device__ __forceinline__ void grid_totals(const double* partials, double* tot, int K) {
+    for (int idx = threadIdx.x; idx < ND * K; idx += blockDim.x) {
+        const int d = idx / K, k = idx % K;
+        double s = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[((size_t)b * kMaxDots + d) * K + k]);
+        tot[idx] = s;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
+    // thread 0 of the last block: are all columns finished?
+    int done = 1, flags = 0;
+    for (int k = 0; k < K; ++k) {
+        const int f = M.colflags[k];
+        flags |= f;
+        if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN)) || (f & FL_PENDING)) done = 0;
+    }
+    M.ctl->flags_or = flags;
+    if (M.ctl->iter >= M.max_iter && !done) { M.ctl->hit_max_iter = 1; done = 1; }
+    M.ctl->all_done = done;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMM  y = (I + offdiag) x  for all K columns, fused with the BiCGSTAB step that consumes it
+//   MODE 0: r = b - A x0 ; rhat = p = r ; dots (r,r), (b,b)
+//   MODE 1: v = A p      ; dot (rhat, v)              -> alpha = rho / (rhat,v)
+//   MODE 2: t = A s      ; dots (t,s),(t,t),(rhat,t),(rhat,s) -> omega, rho', beta
+//   MODE 3: y = A x      (plain product, used for timing and tests)
+// ---------------------------------------------------------------------------------------------
+template <int KC, int MODE>
+__global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* __restrict__ xin, double* __restrict__ yout) {
+    constexpr int ND = MODE == 0 ? 2 : MODE == 1 ? 1 : MODE == 2 ? 4 : 1;
+    __shared__ double smem[(kThreads / 32) * kMaxDots * 32];
+    __shared__ double tot[kMaxDots * kMaxK];
+    if (MODE == 1 || MODE == 2) { if (M.ctl->all_done) return; }
+    const int K = M.K, n = M.n, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const int32_t* __restrict__ rowptr = M.rowptr;
+    const int32_t* __restrict__ col = M.col;
+    const double* __restrict__ val = M.val;
+    if (MODE == 0) xin = M.sp->state_t1;
+    const int nchunk = (K + KC - 1) / KC;
+    for (int chunk = 0; chunk < nchunk; ++chunk) {
+        const int c = chunk * KC + lane;
+        const bool active = c < K;
+        double acc[ND];
+#pragma unroll
+        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+        if (active)
+            for (int i = blockIdx.x * GPB + group; i < n; i += gridDim.x * GPB) {
+                const int s = rowptr[i], e = rowptr[i + 1];
+                const size_t idx = (size_t)i * K + c;
+                const double xi = xin[idx];
+                double y = xi;
+                for (int j = s; j < e; j += 4) {
+                    int cj[4]; double vj[4], xj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const bool ok = j + u < e;
+                        cj[u] = ok ? col[j + u] : i;
+                        vj[u] = ok ? val[j + u] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) xj[u] = xin[(size_t)cj[u] * K + c];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) y = fma(vj[u], xj[u], y);
+                }
+                if (MODE == 0) {
+                    const double bi = M.b[idx];
+                    const double r = bi - y;
+                    M.r[idx] = r; M.rhat[idx] = r; M.p[idx] = r;
+                    acc[0] = fma(r, r, acc[0]); acc[1] = fma(bi, bi, acc[1]);
+                } else if (MODE == 1) {
+                    M.v[idx] = y;
+                    acc[0] = fma(M.rhat[idx], y, acc[0]);
+                } else if (MODE == 2) {
+                    M.tt[idx] = y;
+                    const double rh = M.rhat[idx];
+                    acc[0] = fma(y, xi, acc[0]); acc[1] = fma(y, y, acc[1]);
+                    acc[2] = fma(rh, y, acc[2]); acc[3] = fma(rh, xi, acc[3]);
+                } else {
+                    yout[idx] = y;
+                }
+            }
+        if (MODE != 3) block_dots<ND, KC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
+    }
+    if (MODE == 3) return;
+    if (!last_block_arrives(&M.ctl->ticket[MODE])) return;
+    grid_totals<ND>(M.partials, tot, K);
+    double* sc = M.sc;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        int f = M.colflags[k];
+        if (MODE == 0) {
+            const double rr = tot[0 * K + k], bb = tot[1 * K + k];
+            sc[SC_RHO * K + k] = rr; sc[SC_BNORM2 * K + k] = bb; sc[SC_RNORM2 * K + k] = rr;
+            sc[SC_ALPHA * K + k] = 0.0; sc[SC_OMEGA * K + k] = 0.0; sc[SC_BETA * K + k] = 0.0;
+            f &= ~(FL_CONVERGED | FL_BREAKDOWN | FL_PENDING | FL_ZERO_RHS | FL_NAN);
+            if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) f |= FL_NAN | FL_PENDING;
+            else if (bb == 0.0 && rr != 0.0) f |= FL_ZERO_RHS | FL_PENDING;     // b == 0  =>  x = 0
+            else if (rr <= M.tol2 * bb) { f |= FL_CONVERGED; M.coliters[k] = M.ctl->iter; }
+        } else if (MODE == 1) {
+            const double rv = tot[k];
+            sc[SC_RHATV * K + k] = rv;
+            double alpha = 0.0;
+            if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING))) {
+                if (rv == 0.0 || !(rv == rv)) f |= FL_BREAKDOWN;
+                else alpha = sc[SC_RHO * K + k] / rv;
+            }
+            sc[SC_ALPHA * K + k] = alpha;
+        } else {
+            const double ts = tot[0 * K + k], t2 = tot[1 * K + k], rt = tot[2 * K + k], rs = tot[3 * K + k];
+            double omega = 0.0, beta = 0.0;
+            if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING))) {
+                const double rho = sc[SC_RHO * K + k], alpha = sc[SC_ALPHA * K + k];
+                omega = t2 > 0.0 ? ts / t2 : 0.0;
+                const double rho_new = rs - omega * rt;          // (rhat, s - omega t)
+                if (omega != 0.0 && rho != 0.0) beta = (rho_new / rho) * (alpha / omega);
+                else if (t2 > 0.0) f |= FL_BREAKDOWN;            // omega == 0 with s != 0: stagnation
+                if (!(beta == beta) || isinf(beta)) { beta = 0.0; f |= FL_BREAKDOWN; }
+                sc[SC_RHO * K + k] = rho_new;
+            }
+            sc[SC_OMEGA * K + k] = omega; sc[SC_BETA * K + k] = beta;
+        }
+        M.colflags[k] = f;
+    }
+    __syncthreads();
+    if (MODE == 0 && threadIdx.x == 0) publish_done(M, K);
+}
+
+// s = r - alpha v  (in place on r)
+template <int KC>
+__global__ void __launch_bounds__(kThreads) k_update_s(DeviceModel M) {
+    if (M.ctl->all_done) return;
+    const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    for (int c = lane; c < K; c += KC) {
+        const double alpha = M.sc[SC_ALPHA * K + c];
+        if (alpha == 0.0) continue;        // frozen column: s = r
+        for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+            const size_t idx = (size_t)i * K + c;
+            M.r[idx] = fma(-alpha, M.v[idx], M.r[idx]);
+        }
+    }
+}
+
+// x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; dot (r,r); convergence
+template <int KC>
+__global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M) {
+    __shared__ double smem[(kThreads / 32) * kMaxDots * 32];
+    __shared__ double tot[kMaxDots * kMaxK];
+    if (M.ctl->all_done) return;
+    const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    double* __restrict__ x = M.sp->state_t1;
+    const int nchunk = (K + KC - 1) / KC;
+    for (int chunk = 0; chunk < nchunk; ++chunk) {
+        const int c = chunk * KC + lane;
+        double acc[1] = {0.0};
+        if (c < K) {
+            const int f = M.colflags[c];
+            const double alpha = M.sc[SC_ALPHA * K + c], omega = M.sc[SC_OMEGA * K + c], beta = M.sc[SC_BETA * K + c];
+            if (f & FL_PENDING) {
+                const double fill = (f & FL_NAN) ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
+                for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+                    const size_t idx = (size_t)i * K + c;
+                    x[idx] = fill; M.r[idx] = 0.0; M.p[idx] = 0.0;
+                }
+            } else if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN))) {
+                for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+                    const size_t idx = (size_t)i * K + c;
+                    const double s = M.r[idx], tv = M.tt[idx], pv = M.p[idx], vv = M.v[idx];
+                    x[idx] = fma(omega, s, fma(alpha, pv, x[idx]));
+                    const double rn = fma(-omega, tv, s);
+                    M.r[idx] = rn;
+                    M.p[idx] = fma(beta, fma(-omega, vv, pv), rn);
+                    acc[0] = fma(rn, rn, acc[0]);
+                }
+            }
+        }
+        block_dots<1, KC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
+    }
+    if (!last_block_arrives(&M.ctl->ticket[3])) return;
+    grid_totals<1>(M.partials, tot, K);
+    if (threadIdx.x == 0) M.ctl->iter += 1;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        int f = M.colflags[k];
+        if (f & FL_PENDING) {
+            f &= ~FL_PENDING;
+            if (f & FL_ZERO_RHS) { f |= FL_CONVERGED; M.sc[SC_RNORM2 * K + k] = 0.0; M.coliters[k] = M.ctl->iter; }
+        } else if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN))) {
+            const double rr = tot[k];
+            M.sc[SC_RNORM2 * K + k] = rr;
+            if (!(rr == rr) || isinf(rr)) f |= FL_NAN;
+            else if (rr <= M.tol2 * M.sc[SC_BNORM2 * K + k]) { f |= FL_CONVERGED; M.coliters[k] = M.ctl->iter; }
+        }
+        M.colflags[k] = f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) publish_done(M, K);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mass flux across every edge  (reference transport.py:406-429) + running boundary sums
+// (postproc_util.py:100-143).  c[t+1] of a ghost cell = its BC value, NaN when unset.
+// ---------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
+    const StepParams& sp = *M.sp;
+    const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const double dt = sp.dt;
+    const double* __restrict__ x = sp.state_t1;
+    const size_t EK = (size_t)M.E * K, GK = (size_t)M.E_g * K;
+    for (int c = lane; c < K; c += KC)
+        for (int e = blockIdx.x * GPB + group; e < M.E; e += gridDim.x * GPB) {
+            const int P = M.f1p[e], N = M.f2p[e];
+            const double a = (double)sp.adv_t[e], d = sp.cdiff_t[e];
+            const double cP = x[(size_t)P * K + c];
+            double cN;
+            if (N < M.n) cN = x[(size_t)N * K + c];
+            else {
+                cN = sp.bc_t1[(size_t)(N - M.n) * K + c];
+                if (cN == 0.0) cN = __longlong_as_double(0x7ff8000000000000LL);
+            }
+            const double fa = __dmul_rn((a < 0.0 ? __dmul_rn(a, cN) : __dmul_rn(a, cP)), dt);
+            const double fd = __dmul_rn(__dmul_rn(d, cN - cP), dt);
+            const double ft = fa + fd;
+            const size_t o = (size_t)e * K + c;
+            M.flux[o] = fa; M.flux[EK + o] = fd; M.flux[2 * EK + o] = ft;
+            if (e >= M.E_int) {
+                const size_t g = (size_t)(e - M.E_int) * K + c;
+                M.bsum[g] += ft;
+                M.bsum[GK + g] += (ft <= 0.0) ? ft : ft * 0.0;
+                M.bsum[2 * GK + g] += (ft >= 0.0) ? ft : ft * 0.0;
+            }
+        }
+}
+
+// sum_i vol[i] * c[i,k]  -> out[k]   (single block, deterministic; postproc_util.py:36-59)
+__global__ void k_mass_total(const float* __restrict__ vol, const double* __restrict__ state, int n, int K, int k,
+                             double* __restrict__ out /* [2]: volume, mass */) {
+    __shared__ double sv[kThreads], sm[kThreads];
+    double v = 0.0, m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double vi = (double)vol[i];
+        v += vi; m = fma(vi, state[(size_t)i * K + k], m);
+    }
+    sv[threadIdx.x] = v; sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) { sv[threadIdx.x] += sv[threadIdx.x + s]; sm[threadIdx.x] += sm[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sv[0]; out[1] = sm[0]; }
+}
+
+}  // namespace cwr

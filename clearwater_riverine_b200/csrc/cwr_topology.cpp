@@ -1,0 +1,194 @@
+#include "cwr_topology.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace cwr {
+namespace {
+
+// Breadth-first level structure from `start` inside the unvisited component; returns the last
+// level's minimum-degree node and the number of levels.  `mark` is scratch (stamp-based).
+struct Bfs {
+    const std::vector<int32_t>& ptr;
+    const std::vector<int32_t>& adj;
+    std::vector<int32_t> stamp;
+    std::vector<int32_t> queue;
+    int32_t cur = 0;
+    Bfs(const std::vector<int32_t>& p, const std::vector<int32_t>& a, int n) : ptr(p), adj(a), stamp(n, 0) { queue.reserve(n); }
+
+    int levels(int32_t start, int32_t& far_node) {
+        ++cur;
+        queue.clear();
+        queue.push_back(start);
+        stamp[start] = cur;
+        size_t head = 0;
+        int nlev = 0;
+        size_t level_begin = 0;
+        while (head < queue.size()) {
+            size_t level_end = queue.size();
+            level_begin = head;
+            for (; head < level_end; ++head) {
+                int32_t u = queue[head];
+                for (int32_t j = ptr[u]; j < ptr[u + 1]; ++j) {
+                    int32_t v = adj[j];
+                    if (stamp[v] != cur) { stamp[v] = cur; queue.push_back(v); }
+                }
+            }
+            ++nlev;
+        }
+        far_node = queue[level_begin];
+        int32_t best = ptr[far_node + 1] - ptr[far_node];
+        for (size_t i = level_begin; i < queue.size(); ++i) {
+            int32_t d = ptr[queue[i] + 1] - ptr[queue[i]];
+            if (d < best) { best = d; far_node = queue[i]; }
+        }
+        return nlev;
+    }
+};
+
+}  // namespace
+
+std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
+                           bool rcm, Topology& T) {
+    if (n_real <= 0 || n_face < n_real || n_edge <= 0) return "n_real, n_face, n_edge must be positive and n_face >= n_real";
+    const int n = n_real, F = n_face, E = n_edge;
+    int32_t max_f1 = -1;
+    int E_int = 0;
+    for (int e = 0; e < E; ++e) {
+        if (f1[e] < 0 || f1[e] >= n) return "edges_face1 must be a real cell (the reference defines nreal = max(edges_face1))";
+        if (f2[e] < 0 || f2[e] >= F) return "edges_face2 out of range";
+        if (f1[e] == f2[e]) return "edge connects a cell to itself";
+        max_f1 = std::max(max_f1, f1[e]);
+        if (f2[e] < n) ++E_int;
+    }
+    if (max_f1 != n - 1) return "n_real must equal max(edges_face1) + 1 (reference io/hdf.py:268-269)";
+    T.n = n; T.F = F; T.E = E; T.E_int = E_int; T.E_g = E - E_int; T.G = F - n;
+    T.nnz = 2 * (int64_t)E_int;
+    if (T.nnz > 0x7fffffffLL) return "too many non-zeros for 32-bit indices";
+    if ((int64_t)E > 0x3fffffffLL) return "too many edges";
+
+    // ---- adjacency of real cells (both directions of every internal edge) --------------------
+    std::vector<int32_t> aptr(n + 1, 0), adj(T.nnz);
+    for (int e = 0; e < E; ++e)
+        if (f2[e] < n) { ++aptr[f1[e] + 1]; ++aptr[f2[e] + 1]; }
+    for (int i = 0; i < n; ++i) aptr[i + 1] += aptr[i];
+    {
+        std::vector<int32_t> fill(aptr.begin(), aptr.end() - 1);
+        for (int e = 0; e < E; ++e)
+            if (f2[e] < n) { adj[fill[f1[e]]++] = f2[e]; adj[fill[f2[e]]++] = f1[e]; }
+    }
+
+    // ---- reverse Cuthill-McKee -------------------------------------------------------------------
+    T.old_of_new.resize(n);
+    T.new_of_old.resize(n);
+    if (!rcm) {
+        std::iota(T.old_of_new.begin(), T.old_of_new.end(), 0);
+    } else {
+        std::vector<int32_t> by_degree(n);
+        std::iota(by_degree.begin(), by_degree.end(), 0);
+        auto deg = [&](int32_t u) { return aptr[u + 1] - aptr[u]; };
+        std::stable_sort(by_degree.begin(), by_degree.end(), [&](int32_t a, int32_t b) { return deg(a) < deg(b); });
+        std::vector<uint8_t> visited(n, 0);
+        std::vector<int32_t> order;
+        order.reserve(n);
+        Bfs bfs(aptr, adj, n);
+        std::vector<int32_t> nbrs;
+        for (int32_t s0 : by_degree) {
+            if (visited[s0]) continue;
+            // pseudo-peripheral start (George-Liu): walk to the far end while the level count grows
+            int32_t start = s0, far = s0;
+            int nlev = bfs.levels(start, far);
+            for (int it = 0; it < 4; ++it) {
+                int32_t far2;
+                int nlev2 = bfs.levels(far, far2);
+                if (nlev2 <= nlev) break;
+                start = far; far = far2; nlev = nlev2;
+            }
+            size_t head = order.size();
+            order.push_back(start);
+            visited[start] = 1;
+            while (head < order.size()) {
+                int32_t u = order[head++];
+                nbrs.clear();
+                for (int32_t j = aptr[u]; j < aptr[u + 1]; ++j) {
+                    int32_t v = adj[j];
+                    if (!visited[v]) { visited[v] = 1; nbrs.push_back(v); }
+                }
+                std::sort(nbrs.begin(), nbrs.end(), [&](int32_t a, int32_t b) {
+                    int da = deg(a), db = deg(b);
+                    return da != db ? da < db : a < b;
+                });
+                order.insert(order.end(), nbrs.begin(), nbrs.end());
+            }
+        }
+        for (int i = 0; i < n; ++i) T.old_of_new[i] = order[n - 1 - i];
+    }
+    for (int i = 0; i < n; ++i) T.new_of_old[T.old_of_new[i]] = i;
+
+    // ---- edge renumbering ---------------------------------------------------------------------------
+    // internal edges: sort by (min new cell, max new cell, original id); ghost edges: by (new cell, original id)
+    std::vector<int32_t> internal, ghost;
+    internal.reserve(E_int); ghost.reserve(T.E_g);
+    for (int e = 0; e < E; ++e) (f2[e] < n ? internal : ghost).push_back(e);
+    auto lo = [&](int32_t e) { return std::min(T.new_of_old[f1[e]], T.new_of_old[f2[e]]); };
+    auto hi = [&](int32_t e) { return std::max(T.new_of_old[f1[e]], T.new_of_old[f2[e]]); };
+    std::sort(internal.begin(), internal.end(), [&](int32_t a, int32_t b) {
+        int32_t la = lo(a), lb = lo(b);
+        if (la != lb) return la < lb;
+        int32_t ha = hi(a), hb = hi(b);
+        if (ha != hb) return ha < hb;
+        return a < b;
+    });
+    std::sort(ghost.begin(), ghost.end(), [&](int32_t a, int32_t b) {
+        int32_t ca = T.new_of_old[f1[a]], cb = T.new_of_old[f1[b]];
+        return ca != cb ? ca < cb : a < b;
+    });
+    T.eperm.resize(E); T.f1p.resize(E); T.f2p.resize(E);
+    for (int i = 0; i < E_int; ++i) T.eperm[i] = internal[i];
+    for (int i = 0; i < T.E_g; ++i) T.eperm[E_int + i] = ghost[i];
+    for (int ep = 0; ep < E; ++ep) {
+        int32_t e = T.eperm[ep];
+        T.f1p[ep] = T.new_of_old[f1[e]];
+        T.f2p[ep] = f2[e] < n ? T.new_of_old[f2[e]] : f2[e];   // ghost cells keep their id (>= n)
+    }
+
+    // ---- off-diagonal CSR with slot -> (edge, side) --------------------------------------------------
+    T.rowptr.assign(n + 1, 0);
+    for (int ep = 0; ep < E_int; ++ep) { ++T.rowptr[T.f1p[ep] + 1]; ++T.rowptr[T.f2p[ep] + 1]; }
+    for (int i = 0; i < n; ++i) T.rowptr[i + 1] += T.rowptr[i];
+    T.col.resize(T.nnz); T.slot_edge.resize(T.nnz);
+    {
+        // (col, slot code) pairs per row, then sort each row by column
+        std::vector<int32_t> fill(T.rowptr.begin(), T.rowptr.end() - 1);
+        for (int ep = 0; ep < E_int; ++ep) {
+            int32_t P = T.f1p[ep], N = T.f2p[ep];
+            int32_t a = fill[P]++; T.col[a] = N; T.slot_edge[a] = (ep << 1) | 0;   // A[P,N]
+            int32_t b = fill[N]++; T.col[b] = P; T.slot_edge[b] = (ep << 1) | 1;   // A[N,P]
+        }
+        std::vector<std::pair<int32_t, int32_t>> tmp;
+        T.max_row_len = 0; T.bandwidth = 0;
+        for (int i = 0; i < n; ++i) {
+            int32_t s = T.rowptr[i], e = T.rowptr[i + 1];
+            T.max_row_len = std::max(T.max_row_len, e - s);
+            tmp.clear();
+            for (int32_t j = s; j < e; ++j) tmp.emplace_back(T.col[j], T.slot_edge[j]);
+            std::sort(tmp.begin(), tmp.end());
+            for (int32_t j = s; j < e; ++j) {
+                T.col[j] = tmp[j - s].first; T.slot_edge[j] = tmp[j - s].second;
+                T.bandwidth = std::max<int64_t>(T.bandwidth, std::abs((int64_t)T.col[j] - i));
+            }
+        }
+    }
+
+    // ---- boundary cells ----------------------------------------------------------------------------------
+    T.bcell.clear(); T.bptr.clear(); T.bedge.resize(T.E_g);
+    for (int i = 0; i < T.E_g; ++i) {
+        int ep = E_int + i;
+        if (i == 0 || T.f1p[ep] != T.f1p[ep - 1]) { T.bcell.push_back(T.f1p[ep]); T.bptr.push_back(i); }
+        T.bedge[i] = ep;
+    }
+    T.bptr.push_back(T.E_g);
+    return "";
+}
+
+}  // namespace cwr

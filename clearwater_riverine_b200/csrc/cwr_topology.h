@@ -1,0 +1,50 @@
+// Host-side, once-per-model topology preprocessing.
+//
+// Replaces what the reference recomputes every step: LHS.__init__ index sets
+// (reference linalg.py:28-32), the per-step COO row/col lists (linalg.py:69-156) and the
+// COO->CSR conversion with duplicate summation (transport.py:215-218).  Because the sparsity
+// pattern of A(t) is time-invariant (n + 2*E_int entries), it is built once:
+//   * real cells are renumbered by reverse Cuthill-McKee (optional),
+//   * edges are renumbered: internal edges first, sorted by their lower cell; ghost edges after,
+//     grouped by cell in ascending ORIGINAL edge id (the order the reference's last-write-wins
+//     ghost scatter depends on, linalg.py:349-351, 377-378),
+//   * off-diagonal CSR (rowptr, col) with a slot->(edge, side) map: every slot is owned by exactly
+//     one (edge, side) pair, so assembly writes each value once with no atomics,
+//   * the list of boundary cells with their ghost edges.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace cwr {
+
+struct Topology {
+    int n = 0;        // real cells = matrix order (reference: nreal + 1)
+    int F = 0;        // real + ghost cells
+    int E = 0;        // edges
+    int E_int = 0;    // internal edges (both cells real)
+    int E_g = 0;      // ghost edges
+    int G = 0;        // ghost cells = F - n
+    int64_t nnz = 0;  // off-diagonal entries = 2 * E_int
+
+    std::vector<int32_t> new_of_old;  // (n)  device cell id of reference cell
+    std::vector<int32_t> old_of_new;  // (n)
+    std::vector<int32_t> eperm;       // (E)  reference edge id of device edge e'
+    std::vector<int32_t> f1p, f2p;    // (E)  device cell ids of device edge e'; ghost: n + (f2 - n)
+
+    std::vector<int32_t> rowptr;      // (n+1) off-diagonal CSR
+    std::vector<int32_t> col;         // (nnz)
+    std::vector<int32_t> slot_edge;   // (nnz) (e' << 1) | side ; side 0: row == f1 of the edge, 1: row == f2
+
+    std::vector<int32_t> bcell;       // (nb)   device ids of cells that own ghost edges
+    std::vector<int32_t> bptr;        // (nb+1) ranges into bedge
+    std::vector<int32_t> bedge;       // (E_g)  device edge ids, ascending original id within a cell
+    int max_row_len = 0;
+    int64_t bandwidth = 0;            // max |row - col| after reordering (diagnostic)
+};
+
+// Returns an empty string on success, else an error message.
+std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
+                           bool rcm, Topology& out);
+
+}  // namespace cwr

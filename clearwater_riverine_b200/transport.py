@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's stepping interface, backed by the CUDA library.
+
+Same names, argument meaning and per-step behaviour as the reference's
+`ClearwaterRiverine` (reference: src/clearwater_riverine/transport.py:68-276) and
+`Constituent` (constituents.py:17-76) for the hot path -- `update()` advances every
+constituent one timestep -- so code written against the reference's loop
+
+    for _ in range(n): model.update(update_concentration)
+
+runs unchanged.  The mesh container is a plain dict of numpy arrays under the reference's
+variable names (variables.py) instead of an xarray Dataset; xarray is not a dependency.
+All arithmetic happens on the GPU through `TransportBackend` (no CPU fallback).
+"""
+from __future__ import annotations
+
+import warnings
+from pathlib import Path
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+
+from .backend import CWR_OK, STATUS_NAMES, SolverWarning, TransportBackend
+
+# reference variables.py names
+ADVECTION_COEFFICIENT = "advection_coeff"
+COEFFICIENT_TO_DIFFUSION_TERM = "coeff_to_diffusion"
+EDGES_FACE1 = "edges_face1"
+EDGES_FACE2 = "edges_face2"
+EDGE_VELOCITY = "edge_velocity"
+VOLUME = "volume"
+CHANGE_IN_TIME = "dt"
+FLOW_ACROSS_FACE = "face_flow"
+NUMBER_OF_REAL_CELLS = "nreal"
+
+
+class ModelMesh(dict):
+    """dict of numpy arrays + `.attrs`; `mesh.nreal`, `mesh.diffusion_coefficient` work as in the reference."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.attrs: Dict[str, Any] = {}
+
+    def __getattr__(self, item):
+        if item.startswith("__"):
+            raise AttributeError(item)
+        if item in self:
+            return self[item]
+        attrs = self.__dict__.get("attrs", {})
+        if item in attrs:
+            return attrs[item]
+        raise AttributeError(item)
+
+
+class Constituent:
+    """Array contract of reference constituents.py:19-76."""
+
+    def __init__(self, name: str, mesh: ModelMesh, input_array: np.ndarray, units: str = "Unknown",
+                 store_mass_flux: bool = True):
+        T, F, E = len(mesh["time"]), mesh.attrs["n_face"], len(mesh[EDGES_FACE1])
+        self.name = name
+        self.units = units
+        self.input_array = np.ascontiguousarray(input_array, dtype=np.float64)
+        if self.input_array.shape != (T, F):
+            raise ValueError(f"input_array for {name!r}: expected {(T, F)}, got {self.input_array.shape}")
+        if store_mass_flux:
+            self.advection_mass_flux = np.zeros((T, E))
+            self.diffusion_mass_flux = np.zeros((T, E))
+            self.total_mass_flux = np.zeros((T, E))
+        else:
+            self.advection_mass_flux = self.diffusion_mass_flux = self.total_mass_flux = None
+        n = mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
+        out = np.full((T, F), np.nan)                    # constituents.py:39-48
+        out[0] = 0.0
+        out[0, :n] = self.input_array[0, :n]             # constituents.py:94-98 (IC row; BCs are merged later)
+        mesh[name] = out
+
+
+class ClearwaterRiverine:
+    """Drop-in for the reference class on the stepping path.
+
+    Construct either like the reference (HEC-RAS file + constituent CSVs, or a YAML config),
+    or from arrays with `ClearwaterRiverine.from_arrays(...)`.
+    """
+
+    def __init__(
+        self,
+        flow_field_file_path: Optional[str | Path] = None,
+        diffusion_coefficient_input: Optional[float] = None,
+        constituent_dict: Optional[Dict[str, Dict[str, Any]]] = None,
+        config_filepath: Optional[str] = None,
+        verbose: Optional[bool] = False,
+        datetime_range: Optional[Tuple[int, int]] = None,
+        mesh_file_path: Optional[str | Path] = None,
+        **backend_options,
+    ) -> None:
+        from .io import ras
+        if mesh_file_path:
+            raise NotImplementedError("loading saved zarr/netCDF meshes is outside the transport-step scope")
+        if config_filepath:                                        # reference io/config.py:33-47
+            import yaml
+            with open(config_filepath) as fh:
+                cfg = yaml.safe_load(fh)
+            for key in ("diffusion_coefficient", "flow_field_filepath", "constituents"):
+                if key not in cfg:
+                    raise ValueError(f"Missing required key in model config: {key}")
+            if diffusion_coefficient_input is None:
+                diffusion_coefficient_input = cfg["diffusion_coefficient"]
+            if not flow_field_file_path:
+                flow_field_file_path = cfg["flow_field_filepath"]
+            constituent_dict = cfg["constituents"]
+        if not flow_field_file_path or not isinstance(constituent_dict, dict):
+            raise TypeError("Missing a `config_filepath` or a `constituent_dict` and `flow_field_file_path` to run the model.")
+        plan = ras.read_ras_plan(flow_field_file_path, datetime_range)
+        if verbose:
+            print("Populating Model Mesh...")
+        inputs, units = {}, {}
+        for name, cfg_c in constituent_dict.items():
+            inputs[name] = ras.build_input_array(len(plan.time), len(plan.face_x), plan.time, plan.f2, plan.boundary_data,
+                                                 cfg_c["initial_conditions"], cfg_c["boundary_conditions"])
+            units[name] = cfg_c.get("units", "Unknown")
+        self._setup(plan.f1, plan.f2, plan.face_x, plan.face_y, plan.time_seconds, plan.face_flow, plan.edge_velocity,
+                    plan.volume, float(diffusion_coefficient_input), inputs, units, time=plan.time,
+                    backend_options=backend_options)
+        self.boundary_data = plan.boundary_data
+        self.mesh.attrs["boundary_data"] = plan.boundary_data
+
+    @classmethod
+    def from_arrays(cls, f1, f2, face_x, face_y, time_seconds, face_flow, edge_velocity, volume,
+                    diffusion_coefficient: float, inputs: Dict[str, np.ndarray], units: Optional[Dict[str, str]] = None,
+                    **backend_options) -> "ClearwaterRiverine":
+        self = cls.__new__(cls)
+        self._setup(f1, f2, face_x, face_y, time_seconds, face_flow, edge_velocity, volume, float(diffusion_coefficient),
+                    inputs, units or {}, time=None, backend_options=backend_options)
+        self.boundary_data = None
+        return self
+
+    # ------------------------------------------------------------------------------------------
+    def _setup(self, f1, f2, face_x, face_y, time_seconds, face_flow, edge_velocity, volume, D, inputs, units, time,
+               backend_options):
+        store_mass_flux = backend_options.pop("store_mass_flux", True)
+        self.output = backend_options.pop("output", "eager")      # 'eager': copy results to host every update()
+        device = backend_options.pop("device", 0)
+        T, F = volume.shape
+        mesh = ModelMesh()
+        mesh.attrs.update({"diffusion_coefficient": D, NUMBER_OF_REAL_CELLS: int(np.max(f1)), "n_face": F})
+        mesh[EDGES_FACE1] = np.ascontiguousarray(f1, dtype=np.int32)
+        mesh[EDGES_FACE2] = np.ascontiguousarray(f2, dtype=np.int32)
+        mesh["face_x"], mesh["face_y"] = np.asarray(face_x, np.float64), np.asarray(face_y, np.float64)
+        mesh["time"] = np.asarray(time_seconds, np.float64) if time is None else np.asarray(time)
+        mesh[FLOW_ACROSS_FACE] = np.ascontiguousarray(face_flow, np.float32)
+        mesh[EDGE_VELOCITY] = np.ascontiguousarray(edge_velocity, np.float32)
+        mesh[VOLUME] = np.ascontiguousarray(volume, np.float32)
+        tsec = np.asarray(time_seconds, np.float64)
+        mesh[CHANGE_IN_TIME] = np.append(np.diff(tsec), np.nan)    # utilities.py:537-541
+        self.mesh = mesh
+        self.time_step = 0
+        self.constituents = list(inputs.keys())
+        self.constituent_dict = {name: Constituent(name, mesh, arr, units.get(name, "Unknown"), store_mass_flux)
+                                 for name, arr in inputs.items()}
+        self.backend = TransportBackend(mesh[EDGES_FACE1], mesh[EDGES_FACE2], F, T, len(inputs), D, device=device,
+                                        **backend_options)
+        # derived coefficients (utilities.py:513-541) are computed on the device from the raw arrays
+        self.backend.set_geometry(mesh["face_x"], mesh["face_y"])
+        chunk = max(1, min(T, (64 << 20) // max(1, 4 * len(f1))))
+        for t0 in range(0, T, chunk):
+            t1 = min(T, t0 + chunk)
+            self.backend.set_hydro_raw(t0, mesh[FLOW_ACROSS_FACE][t0:t1], mesh[EDGE_VELOCITY][t0:t1], mesh[VOLUME][t0:t1],
+                                       mesh[CHANGE_IN_TIME][t0:t1])
+        for k, name in enumerate(self.constituents):
+            self.backend.set_inputs(k, self.constituent_dict[name].input_array)
+        self._index = {name: k for k, name in enumerate(self.constituents)}
+        self.solver_info = []
+
+    # ------------------------------------------------------------------------------------------
+    def update(self, update_concentration: Optional[Dict[str, np.ndarray]] = None):
+        """Update a single timestep (reference transport.py:201-276)."""
+        t = self.time_step
+        n = self.mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
+        if isinstance(update_concentration, dict):
+            for name, values in update_concentration.items():
+                if name not in self.constituent_dict:        # transport.py:223-229
+                    print(f"WARNING: {name} is not being used in the model.")
+                    print("Please review the constituent names in the update dictionary")
+                    continue
+                values = np.asarray(getattr(values, "values", values), dtype=np.float64)[0:n]
+                self.mesh[name][t][0:n] = values             # transport.py:233-236: history at t is overwritten too
+                self.backend.set_state(self._index[name], t, values)
+        info = self.backend.step(t)
+        self.solver_info.append((info.iterations, info.max_relres, info.status))
+        if info.status != CWR_OK:
+            warnings.warn(f"step {t}: {STATUS_NAMES.get(info.status, info.status)} "
+                          f"({info.iterations} iterations, relres {info.max_relres:.3e})", SolverWarning)
+        if self.output == "eager":
+            self._fetch(t + 1)
+        self.time_step += 1                                   # transport.py:276
+
+    def _fetch(self, t1: int):
+        for name, k in self._index.items():
+            self.backend.get_state(k, t1, self.mesh[name][t1])
+            c = self.constituent_dict[name]
+            if c.total_mass_flux is not None and self.backend.options.mass_flux:
+                self.backend.get_mass_flux(k, t1 - 1, c.advection_mass_flux[t1 - 1], c.diffusion_mass_flux[t1 - 1],
+                                           c.total_mass_flux[t1 - 1])
+
+    def run(self, n_steps: Optional[int] = None):
+        """`n_steps` updates back to back on the device, then one bulk copy of the concentrations
+        (mass-flux history is only recorded by `update()`, which reads it back every step)."""
+        T = len(self.mesh["time"])
+        t0 = self.time_step
+        t1 = T - 1 if n_steps is None else min(T - 1, t0 + n_steps)
+        info = self.backend.run(t0, t1)
+        self.time_step = t1
+        if self.output == "eager" and self.backend.options.keep_history:
+            for t in range(t0 + 1, t1 + 1):
+                for name, k in self._index.items():
+                    self.backend.get_state(k, t, self.mesh[name][t])
+        return info
+
+    def finalize(self):
+        self.backend.close()

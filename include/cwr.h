@@ -1,0 +1,139 @@
+/*
+ * cwr.h -- C ABI of the B200-native ClearWater-Riverine transport step.
+ *
+ * The reference (EcohydrologyTeam/ClearWater-riverine, pure Python) has no FFI; the
+ * seam this library drops into is the body of
+ *     ClearwaterRiverine.update()            src/clearwater_riverine/transport.py:201-276
+ * and the state it touches.  Each entry point below names the reference lines it
+ * replaces.  All arrays are caller-owned, contiguous, row-major, in the REFERENCE's
+ * cell / edge numbering (the library's internal RCM ordering never crosses the ABI);
+ * every set_* call copies its input.  One handle = one device + one stream; a handle
+ * is not thread-safe, distinct handles may be driven from distinct host threads.
+ *
+ * Return value: 0 (CWR_OK) or a negative cwr_status; cwr_last_error() gives the text.
+ * No exceptions or C++ types cross this boundary.
+ */
+#ifndef CWR_H
+#define CWR_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cwr_handle cwr_handle;
+
+typedef enum {
+    CWR_OK = 0,
+    CWR_EINVAL = -1,        /* bad argument / state not available */
+    CWR_ECUDA = -2,         /* CUDA runtime error */
+    CWR_ENOTCONVERGED = -3, /* BiCGSTAB hit max_iter (results are still stored) */
+    CWR_EBREAKDOWN = -4,    /* BiCGSTAB breakdown that restarts could not cure */
+    CWR_ENAN = -5,          /* non-finite residual (NaN/Inf in the inputs, e.g. a NaN boundary value) */
+    CWR_ESINGULAR = -6,     /* zero diagonal: the reference's spsolve would warn MatrixRankWarning */
+    CWR_ENOMEM = -7
+} cwr_status;
+
+typedef struct {
+    double rtol;            /* stop when ||r||_2 <= rtol * ||b||_2 (row-scaled system); default 1e-13 */
+    int max_iter;           /* BiCGSTAB iterations per solve; default 500 */
+    int reorder;            /* 0 = keep cell order, 1 = reverse Cuthill-McKee (default) */
+    int keep_history;       /* 1 = keep every c[t] on the device (default), 0 = only c[t], c[t+1] */
+    int hydro_capacity;     /* time slices resident on the device; 0 = all n_time (default) */
+    int mass_flux;          /* 1 = compute the three per-edge mass-flux arrays every step (default, as the
+                               reference does, transport.py:267-273), 0 = skip */
+    int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = single-CTA persistent solve (small meshes) */
+    int use_graph;          /* 1 = device-side iteration loop in a CUDA graph (default), 0 = host-polled loop */
+    int check_every;        /* host-polled loop: iterations launched per convergence poll; default 4 */
+    int reserved[7];
+} cwr_options;
+
+typedef struct {
+    int iterations;         /* max over constituents */
+    int restarts;
+    int status;             /* cwr_status of the solve */
+    double max_relres;      /* max over constituents of ||r|| / ||b|| at exit */
+    int n_launches;         /* kernels this step launched */
+} cwr_step_info;
+
+typedef struct {
+    double vol_start, mass_start, vol_end, mass_end;   /* postproc_util.py:36-59 */
+} cwr_mass_totals;
+
+/* defaults for every field of cwr_options */
+int cwr_default_options(cwr_options* opt);
+
+/* Replaces LHS.__init__ / RHS.__init__ (linalg.py:18-32, 159-175) and the per-step COO->CSR
+ * rebuild (transport.py:215-218): builds the fixed CSR pattern, the slot->edge map and the
+ * boundary-cell lists once.  n_real = nreal + 1 = max(f1) + 1 (io/hdf.py:268-269). */
+int cwr_create(cwr_handle** h, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
+               const int32_t* f1, const int32_t* f2, double diffusion_coefficient, const cwr_options* opt);
+void cwr_destroy(cwr_handle* h);
+const char* cwr_last_error(const cwr_handle* h);   /* h may be NULL: error of the last failed cwr_create */
+
+/* The mesh variables the step reads (linalg.py:61-66,89,225,372; produced by utilities.py:513-541):
+ * slices [t0, t0+nt) of advection_coeff (nt,E) f32, coeff_to_diffusion (nt,E) f64,
+ * edge_velocity (nt,E) f32, volume (nt,F) f32, dt (nt,) f64. */
+int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double* cdiff, const float* vel,
+                  const float* vol, const double* dt);
+
+/* "Next" row N1: the same, derived on the device from the raw HEC-RAS arrays as
+ * WQVariableCalculator.calculate does (utilities.py:513-541).  cwr_set_geometry gives the cell
+ * centres (face_x, face_y: (F,)) from which face_to_face_dist is computed (utilities.py:261-280). */
+int cwr_set_geometry(cwr_handle* h, const double* face_x, const double* face_y);
+int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
+                      const float* volume, const double* dt);
+
+/* Constituent.input_array (constituents.py:31,93,164): (T,F) f64, IC in row 0, BC values in
+ * ghost-cell columns, 0 = "not set".  Also initialises c[0] as set_initial_conditions does. */
+int cwr_set_inputs(cwr_handle* h, int k, const double* input_array);
+
+/* update_concentration override (transport.py:233-236): overwrite c_k[t, 0:n]. */
+int cwr_set_state(cwr_handle* h, int k, int t, const double* c);
+
+/* One ClearwaterRiverine.update() (transport.py:201-276) for all constituents: LHS(t) assembly,
+ * RHS per constituent, solve, store c[t+1] with BC re-imposition, mass flux.  info may be NULL. */
+int cwr_step(cwr_handle* h, int t, cwr_step_info* info);
+
+/* for (t = t_begin; t < t_end; ++t) cwr_step(h, t) without host round trips between steps
+ * (the loop the reference's users write, examples/01_getting_started_riverine.ipynb cell 26). */
+int cwr_run(cwr_handle* h, int t_begin, int t_end, cwr_step_info* worst);
+
+/* mesh[name][t] (transport.py:252-264): (F,) f64 -- real cells, BC ghost values, NaN elsewhere. */
+int cwr_get_state(cwr_handle* h, int k, int t, double* c_out);
+/* All constituents at once, real cells only: (K, n) f64 (what a coupling loop reads each step). */
+int cwr_get_state_all(cwr_handle* h, int t, double* c_out);
+/* All overrides at once: (K, n) f64; mask[k] != 0 selects the constituents to overwrite. */
+int cwr_set_state_all(cwr_handle* h, int t, const double* c, const uint8_t* mask);
+
+/* Constituent.{advection,diffusion,total}_mass_flux[t] (transport.py:406-429): (E,) f64 each; any
+ * pointer may be NULL.  Only the most recent step's fluxes are held on the device. */
+int cwr_get_mass_flux(cwr_handle* h, int k, int t, double* advection, double* diffusion, double* total);
+
+/* "Next" row N2 (postproc_util.py:36-59): sum(V*c) over real cells at t_start and t_end. */
+int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_totals* out);
+/* Per-edge running sums of total_mass_flux over the steps taken so far, split as the reference's
+ * mass balance does (postproc_util.py:100-143): in = sum of entries <= 0, out = sum of entries >= 0.
+ * (E,) f64 each, any may be NULL.  Enabled when options.mass_flux != 0. */
+int cwr_get_flux_sums(cwr_handle* h, int k, double* total_sum, double* in_sum, double* out_sum);
+
+/* --- introspection used by the parity tests -------------------------------------------------- */
+/* CSR of A(t) as last assembled, reference numbering, diagonal included, columns sorted:
+ * call with NULL arrays to get nnz. */
+int cwr_get_lhs(cwr_handle* h, int64_t* nnz, int32_t* indptr, int32_t* indices, double* data);
+int cwr_get_rhs(cwr_handle* h, int k, double* b);           /* (n,) f64, unscaled */
+int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old); /* (n,) */
+int cwr_stream(cwr_handle* h, void** cuda_stream);           /* the handle's cudaStream_t */
+int cwr_counters(cwr_handle* h, int64_t* kernel_launches, int64_t* solver_iterations);
+
+/* --- device timing of the dominant kernel (bench.py roofline) -------------------------------- */
+/* Time `reps` launches of the SpMM/SpMV kernel (y = A x over all K columns) with CUDA events on
+ * the handle's stream; returns average milliseconds per launch and the algorithmic bytes of one
+ * launch (12*nnz_off + 4*(n+1) + 16*n*K). */
+int cwr_time_spmm(cwr_handle* h, int reps, double* ms_per_launch, double* algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CWR_H */

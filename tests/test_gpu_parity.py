@@ -1,0 +1,300 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle and the
+golden vectors of the unmodified reference.  Tolerance (BASELINE.json north_star): concentrations
+within rtol 1e-9 per step of the reference's spsolve path on the same inputs."""
+import numpy as np
+import pytest
+
+from oracle import reference_step as ref
+from tests.helpers import GOLDEN_CASES, golden_mesh, golden_overrides, load_golden
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+
+
+def close(got, want, rtol=RTOL, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    nan_g, nan_w = np.isnan(got), np.isnan(want)
+    assert np.array_equal(nan_g, nan_w), f"{what}: NaN pattern differs"
+    fin = ~nan_w
+    if not fin.any():
+        return 0.0
+    scale = np.abs(want[fin]).max()
+    err = np.abs(got[fin] - want[fin]).max()
+    assert err <= rtol * max(scale, 1e-300), f"{what}: max abs err {err:.3e} vs scale {scale:.3e}"
+    return err / max(scale, 1e-300)
+
+
+def make_backend(mesh, inputs, **opt):
+    from clearwater_riverine_b200 import TransportBackend
+    be = TransportBackend(mesh.f1, mesh.f2, mesh.n_face, mesh.n_time, len(inputs), mesh.diffusion_coefficient, **opt)
+    be.set_hydro(0, mesh.adv, mesh.cdiff, mesh.vel, mesh.vol, mesh.dt)
+    for k, a in enumerate(inputs):
+        be.set_inputs(k, a)
+    return be
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("reorder", [1, 0])
+def test_golden_free_running(case, reorder):
+    """Whole trajectory against what the unmodified reference produced (tests/golden)."""
+    g = load_golden(case)
+    mesh = golden_mesh(g)
+    names = [str(c) for c in g["constituents"]]
+    be = make_backend(mesh, [g[f"input_{c}"] for c in names], reorder=reorder)
+    overrides = golden_overrides(g)
+    snaps = set(int(s) for s in g["snapshot_steps"])
+    n = mesh.n
+    from scipy.sparse import csr_matrix
+    for t in range(mesh.n_time - 1):
+        for c, v in overrides.get(t, {}).items():
+            be.set_state(names.index(c), t, v)
+        info = be.step(t)
+        assert info.status == 0, (t, info.status, info.max_relres)
+        if t in snaps:
+            A = be.get_lhs()
+            Ag = csr_matrix((g[f"A_data_{t}"], g[f"A_indices_{t}"], g[f"A_indptr_{t}"]), shape=(n, n))
+            assert np.array_equal(A.indptr, Ag.indptr) and np.array_equal(A.indices, Ag.indices)
+            close(A.data, Ag.data, 1e-14, f"LHS step {t}")
+            for k, c in enumerate(names):
+                close(be.get_rhs(k), g[f"b_{c}_{t}"], 1e-13, f"RHS {c} step {t}")
+        for k, c in enumerate(names):
+            close(be.get_state(k, t + 1), g[f"conc_{c}"][t + 1], RTOL, f"{case} c[{t + 1}] {c}")
+            fa, fd, ft = be.get_mass_flux(k, t)
+            close(fa, g[f"advflux_{c}"][t], RTOL, f"adv flux {t}")
+            close(fd, g[f"diffflux_{c}"][t], 1e-7, f"diff flux {t}")     # differences of nearly equal c: cancellation
+            close(ft, g[f"totflux_{c}"][t], RTOL, f"total flux {t}")
+    # row 0 and overridden history rows are reported like the reference's Dataset
+    for k, c in enumerate(names):
+        close(be.get_state(k, 0), g[f"conc_{c}"][0], 1e-15, "row 0")
+    be.close()
+
+
+@pytest.mark.parametrize("case", ["p01_random_two", "p02_uniform100"])
+def test_golden_teacher_forced_per_step(case):
+    """Per-step parity on the same inputs: start every step from the reference's own c[t]."""
+    g = load_golden(case)
+    mesh = golden_mesh(g)
+    names = [str(c) for c in g["constituents"]]
+    be = make_backend(mesh, [g[f"input_{c}"] for c in names])
+    overrides = golden_overrides(g)
+    n = mesh.n
+    for t in range(mesh.n_time - 1):
+        for k, c in enumerate(names):
+            state = g[f"conc_{c}"][t][:n].copy()
+            if t in overrides and c in overrides[t]:
+                state = overrides[t][c]
+            be.set_state(k, t, state)
+        assert be.step(t).status == 0
+        for k, c in enumerate(names):
+            close(be.get_state(k, t + 1)[:n], g[f"conc_{c}"][t + 1][:n], RTOL, f"{case} step {t} {c}")
+    be.close()
+
+
+def test_raw_inputs_derived_on_device_match_reference_coefficients():
+    """N1: adv / cdiff computed by the device from Face Flow / Face Velocity / coordinates
+    (utilities.py:513-541) give the same trajectory as the reference-derived arrays."""
+    from clearwater_riverine_b200 import TransportBackend
+    g = load_golden("p01_random_two")
+    mesh = golden_mesh(g)
+    names = [str(c) for c in g["constituents"]]
+    be = TransportBackend(mesh.f1, mesh.f2, mesh.n_face, mesh.n_time, len(names), mesh.diffusion_coefficient)
+    be.set_geometry(g["face_x"], g["face_y"])
+    be.set_hydro_raw(0, g["face_flow"], g["edge_velocity"], g["volume"], g["dt"])
+    for k, c in enumerate(names):
+        be.set_inputs(k, g[f"input_{c}"])
+    for t in range(60):
+        assert be.step(t).status == 0
+        if t == 0:
+            from scipy.sparse import csr_matrix
+            Ag = csr_matrix((g["A_data_0"], g["A_indices_0"], g["A_indptr_0"]), shape=(mesh.n, mesh.n))
+            close(be.get_lhs().data, Ag.data, 1e-14, "LHS from raw inputs")
+        if t == 7 or t == 120:
+            break
+        for k, c in enumerate(names):
+            close(be.get_state(k, t + 1), g[f"conc_{c}"][t + 1], RTOL, f"raw-input path c[{t + 1}]")
+    be.close()
+
+
+def synthetic_case(nx, ny, T, K, seed, D=0.1, **kw):
+    from clearwater_riverine_b200 import synthetic
+    plan = synthetic.make_plan(nx, ny, T, seed=seed, **kw)
+    adv, _, _, cdiff, dt = ref.derive_coefficients(plan.face_flow, plan.edge_velocity, plan.face_x, plan.face_y,
+                                                   plan.f1, plan.f2, D, plan.time_seconds)
+    mesh = ref.HydroMesh(plan.f1, plan.f2, plan.n_face, adv, cdiff, plan.edge_velocity, plan.volume, dt, D)
+    inputs = synthetic.make_inputs(plan, K, seed=seed)
+    return plan, mesh, inputs
+
+
+def run_against_oracle(mesh, inputs, steps, rtol=RTOL, **opt):
+    K = len(inputs)
+    be = make_backend(mesh, list(inputs), **opt)
+    oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(K)})
+    worst = 0.0
+    for t in range(steps):
+        info = be.step(t)
+        assert info.status == 0, (t, info.status, info.iterations, info.max_relres)
+        oracle.update()
+        for k in range(K):
+            con = oracle.constituent_dict[f"c{k}"]
+            worst = max(worst, close(be.get_state(k, t + 1), con.concentration[t + 1], rtol, f"step {t} k {k}"))
+            _, _, ft = be.get_mass_flux(k, t)
+            close(ft, con.total_mass_flux[t], 1e-8, f"total flux step {t} k {k}")
+    be.close()
+    return worst
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 16, 33])
+def test_synthetic_mesh_all_column_widths(K):
+    """Quad-dominant shuffled mesh with dry cells; every lanes-per-row instantiation of the kernels."""
+    _, mesh, inputs = synthetic_case(40, 25, 8, K, seed=K, dry_fraction=0.02)
+    run_against_oracle(mesh, inputs, 7)
+
+
+@pytest.mark.parametrize("opts", [dict(reorder=0), dict(keep_history=0), dict(mass_flux=1, check_every=1),
+                                  dict(hydro_capacity=2)])
+def test_option_variants(opts):
+    plan, mesh, inputs = synthetic_case(30, 30, 6, 4, seed=5, dry_fraction=0.01)
+    if "hydro_capacity" in opts:
+        from clearwater_riverine_b200 import TransportBackend
+        be = TransportBackend(mesh.f1, mesh.f2, mesh.n_face, mesh.n_time, 4, mesh.diffusion_coefficient, **opts)
+        for k in range(4):
+            be.set_inputs(k, inputs[k])
+        oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(4)})
+        be.set_hydro(0, mesh.adv[0:1], mesh.cdiff[0:1], mesh.vel[0:1], mesh.vol[0:1], mesh.dt[0:1])
+        for t in range(5):     # stream one slice ahead, two resident
+            be.set_hydro(t + 1, mesh.adv[t + 1:t + 2], mesh.cdiff[t + 1:t + 2], mesh.vel[t + 1:t + 2],
+                         mesh.vol[t + 1:t + 2], mesh.dt[t + 1:t + 2])
+            assert be.step(t).status == 0
+            oracle.update()
+            for k in range(4):
+                close(be.get_state(k, t + 1), oracle.constituent_dict[f"c{k}"].concentration[t + 1], RTOL, "streamed")
+        be.close()
+    else:
+        run_against_oracle(mesh, inputs, 5, **opts)
+
+
+def test_adversarial_boundary_semantics():
+    """Reference quirks: several inflowing ghost edges on one cell (last edge wins on the
+    RHS while the LHS sums), zero BC = unset (ghost stays NaN), NaN BC propagates, velocity / flow sign
+    disagreement on a ghost edge, D == 0."""
+    plan, mesh, inputs = synthetic_case(12, 9, 6, 3, seed=21, tri_fraction=0.3)
+    n = mesh.n
+    ghost = np.nonzero(mesh.f2 >= n)[0]
+    rng = np.random.default_rng(0)
+    # make every ghost edge carry flow, with random direction per time step -> corner cells get 2 active edges
+    mesh.adv[:, ghost] = (rng.random((mesh.n_time, len(ghost))) - 0.4).astype(np.float32) * 3
+    mesh.vel[:, ghost] = mesh.adv[:, ghost] / 20.0
+    flip = ghost[:: 5]
+    mesh.vel[:, flip] *= -1                        # sign(vel) != sign(adv): LHS follows adv, RHS follows vel
+    mesh.cdiff[:, ghost] = np.abs(mesh.adv[:, ghost]) * 0.01 + 0.003
+    inputs[1][:, mesh.f2[ghost[::3]]] = 0.0        # unset BCs
+    inputs[2][3:, mesh.f2[ghost[1]]] = np.nan      # a boundary that starts late (merge_asof NaN)
+    be = make_backend(mesh, list(inputs))
+    oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(3)})
+    for t in range(5):
+        info = be.step(t)
+        oracle.update()
+        for k in range(2):
+            close(be.get_state(k, t + 1), oracle.constituent_dict[f"c{k}"].concentration[t + 1], RTOL, f"adv k{k} t{t}")
+        want = oracle.constituent_dict["c2"].concentration[t + 1]
+        got = be.get_state(2, t + 1)
+        if np.isnan(want[:n]).any():
+            assert info.status == -5               # CWR_ENAN, and the column is NaN like spsolve's result
+            assert np.isnan(got[:n]).all()
+        else:
+            close(got, want, RTOL, f"adv k2 t{t}")
+    be.close()
+
+
+def test_zero_diffusion_and_zero_rhs():
+    plan, mesh, inputs = synthetic_case(16, 10, 5, 2, seed=3)
+    mesh.diffusion_coefficient = 0.0
+    mesh.cdiff[:] = 0.0
+    inputs[1][:] = 0.0                              # nothing set at all: b == 0 -> c == 0
+    run_against_oracle(mesh, inputs, 4)
+
+
+def test_uniform_concentration_is_preserved_on_steady_flow():
+    """The invariant behind the reference's tests/test_final_mass.py (IC == BC == 100)."""
+    plan, mesh, _ = synthetic_case(50, 30, 12, 1, seed=9, unsteady=0.0, tidal=0.0, dry_fraction=0.0)
+    n = mesh.n
+    inp = np.zeros((mesh.n_time, mesh.n_face)); inp[0, :n] = 100.0; inp[:, n:] = 100.0
+    be = make_backend(mesh, [inp])
+    for t in range(11):
+        assert be.step(t).status == 0
+    c = be.get_state(0, 11)[:n]
+    assert np.abs(c - 100.0).max() < 1e-3          # float32 continuity error of the hydrodynamics only
+    m = be.mass_totals(0, 0, 11)
+    assert abs(m.mass_end - 100.0 * m.vol_end) / m.mass_end < 1e-5
+    be.close()
+
+
+def test_host_mirror_update_loop_matches_oracle():
+    """ClearwaterRiverine.update() with update_concentration, as a coupling loop drives it
+    (examples/03_01_coupling_riverine_modules_nsm.ipynb cell 47)."""
+    from clearwater_riverine_b200 import ClearwaterRiverine
+    plan, mesh, inputs = synthetic_case(20, 14, 7, 2, seed=4)
+    model = ClearwaterRiverine.from_arrays(plan.f1, plan.f2, plan.face_x, plan.face_y, plan.time_seconds, plan.face_flow,
+                                           plan.edge_velocity, plan.volume, 0.1, {"a": inputs[0], "b": inputs[1]})
+    oracle = ref.OracleRiverine(mesh, {"a": inputs[0], "b": inputs[1]})
+    n = mesh.n
+    rng = np.random.default_rng(1)
+    for t in range(6):
+        upd = {"b": 50.0 + rng.random(n)} if t in (2, 4) else None
+        model.update(upd)
+        oracle.update(upd)
+        assert model.time_step == oracle.time_step
+        for name in ("a", "b"):
+            close(model.mesh[name][t + 1], oracle.constituent_dict[name].concentration[t + 1], RTOL, f"{name} {t}")
+            close(model.mesh[name][t], oracle.constituent_dict[name].concentration[t], RTOL, f"{name} history {t}")
+            close(model.constituent_dict[name].total_mass_flux[t], oracle.constituent_dict[name].total_mass_flux[t], 1e-8, "flux")
+    model.finalize()
+
+
+def test_bitwise_repeatable():
+    """Deterministic reductions: two runs give identical bits."""
+    _, mesh, inputs = synthetic_case(40, 40, 5, 4, seed=8)
+    outs = []
+    for _ in range(2):
+        be = make_backend(mesh, list(inputs))
+        for t in range(4):
+            be.step(t)
+        outs.append(be.get_state_all(4).copy())
+        be.close()
+    assert np.array_equal(outs[0], outs[1])
+
+
+def test_large_mesh_properties():
+    """Size-independent properties at a size the oracle cannot run quickly (250k cells x 4):
+    A x = b residual through an independent product, and the column-sum conservation identity."""
+    from clearwater_riverine_b200 import synthetic
+    plan = synthetic.make_plan(500, 450, 4, seed=13, dry_fraction=0.02)
+    D = 0.1
+    adv, _, _, cdiff, dt = ref.derive_coefficients(plan.face_flow, plan.edge_velocity, plan.face_x, plan.face_y,
+                                                   plan.f1, plan.f2, D, plan.time_seconds)
+    mesh = ref.HydroMesh(plan.f1, plan.f2, plan.n_face, adv, cdiff, plan.edge_velocity, plan.volume, dt, D)
+    inputs = synthetic.make_inputs(plan, 4, seed=13)
+    be = make_backend(mesh, list(inputs))
+    n = mesh.n
+    info = be.step(0)
+    assert info.status == 0
+    A = be.get_lhs()
+    # conservation: column j sums to vol[t+1,j]/dt (+1 if dry) + ghost-edge terms  
+    colsum = np.asarray(A.sum(axis=0)).ravel()
+    expect = mesh.vol[1][:n].astype(np.float64) / dt[0] + (mesh.vol[1][:n] == 0)
+    gh = np.nonzero(mesh.f2 >= n)[0]
+    np.add.at(expect, mesh.f1[gh], cdiff[0][gh] + np.maximum(adv[0][gh].astype(np.float64), 0.0))
+    assert np.abs(colsum - expect).max() <= 1e-12 * np.abs(expect).max()
+    for k in range(4):
+        x = be.get_state(k, 1)[:n]
+        b = be.get_rhs(k)
+        r = A @ x - b
+        assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(b)
+    # the oracle's own assembly agrees on this mesh too
+    lhs = ref.LHS(mesh); lhs.update_values(mesh, 0)
+    Ao = lhs.to_csr(); Ao.sum_duplicates(); Ao.sort_indices()
+    assert np.array_equal(Ao.indices, A.indices)
+    assert np.abs(Ao.data - A.data).max() <= 1e-13 * np.abs(Ao.data).max()
+    be.close()
