@@ -26,6 +26,20 @@ def close(got, want, rtol=RTOL, what=""):
     return err / max(scale, 1e-300)
 
 
+def flux_close(be, k, t, mesh, c_next, want_adv, want_diff, want_tot, what):
+    """Fluxes are products of coefficients with concentrations (and, for diffusion, with a DIFFERENCE of
+    concentrations, which cancels): the error bound is rtol * |coefficient| * |c| * dt."""
+    fa, fd, ft = be.get_mass_flux(k, t)
+    cmax = np.nanmax(np.abs(c_next))
+    scale = max(np.abs(mesh.adv[t]).max(), np.abs(mesh.cdiff[t]).max()) * cmax * mesh.dt[t]
+    for got, want, nm in ((fa, want_adv, "advection"), (fd, want_diff, "diffusion"), (ft, want_tot, "total")):
+        assert np.array_equal(np.isnan(got), np.isnan(want)), f"{what}: {nm} flux NaN pattern"
+        fin = ~np.isnan(want)
+        if fin.any():
+            err = np.abs(got[fin] - want[fin]).max()
+            assert err <= RTOL * scale, f"{what}: {nm} flux err {err:.3e} vs scale {scale:.3e}"
+
+
 def make_backend(mesh, inputs, **opt):
     from clearwater_riverine_b200 import TransportBackend
     be = TransportBackend(mesh.f1, mesh.f2, mesh.n_face, mesh.n_time, len(inputs), mesh.diffusion_coefficient, **opt)
@@ -50,6 +64,9 @@ def test_golden_free_running(case, reorder):
     for t in range(mesh.n_time - 1):
         for c, v in overrides.get(t, {}).items():
             be.set_state(names.index(c), t, v)
+        if t > 0:   # row t as the reference's Dataset holds it (an override rewrites history, transport.py:233-236)
+            for k, c in enumerate(names):
+                close(be.get_state(k, t), g[f"conc_{c}"][t], RTOL, f"{case} c[{t}] {c}")
         info = be.step(t)
         assert info.status == 0, (t, info.status, info.max_relres)
         if t in snaps:
@@ -58,16 +75,13 @@ def test_golden_free_running(case, reorder):
             assert np.array_equal(A.indptr, Ag.indptr) and np.array_equal(A.indices, Ag.indices)
             close(A.data, Ag.data, 1e-14, f"LHS step {t}")
             for k, c in enumerate(names):
-                close(be.get_rhs(k), g[f"b_{c}_{t}"], 1e-13, f"RHS {c} step {t}")
+                close(be.get_rhs(k), g[f"b_{c}_{t}"], 1e-13 if t == 0 else RTOL, f"RHS {c} step {t}")
         for k, c in enumerate(names):
-            close(be.get_state(k, t + 1), g[f"conc_{c}"][t + 1], RTOL, f"{case} c[{t + 1}] {c}")
-            fa, fd, ft = be.get_mass_flux(k, t)
-            close(fa, g[f"advflux_{c}"][t], RTOL, f"adv flux {t}")
-            close(fd, g[f"diffflux_{c}"][t], 1e-7, f"diff flux {t}")     # differences of nearly equal c: cancellation
-            close(ft, g[f"totflux_{c}"][t], RTOL, f"total flux {t}")
-    # row 0 and overridden history rows are reported like the reference's Dataset
+            flux_close(be, k, t, mesh, g[f"conc_{c}"][t + 1], g[f"advflux_{c}"][t], g[f"diffflux_{c}"][t],
+                       g[f"totflux_{c}"][t], f"{case} step {t} {c}")
     for k, c in enumerate(names):
-        close(be.get_state(k, 0), g[f"conc_{c}"][0], 1e-15, "row 0")
+        close(be.get_state(k, mesh.n_time - 1), g[f"conc_{c}"][mesh.n_time - 1], RTOL, f"{case} last row {c}")
+        close(be.get_state(k, 0), g[f"conc_{c}"][0], 1e-15, "row 0")     # the IC row: zeros (not NaN) where unset
     be.close()
 
 
@@ -88,6 +102,8 @@ def test_golden_teacher_forced_per_step(case):
             be.set_state(k, t, state)
         assert be.step(t).status == 0
         for k, c in enumerate(names):
+            if (t + 1) in overrides and c in overrides[t + 1]:
+                continue               # the reference overwrote this history row with the override
             close(be.get_state(k, t + 1)[:n], g[f"conc_{c}"][t + 1][:n], RTOL, f"{case} step {t} {c}")
     be.close()
 
@@ -104,14 +120,12 @@ def test_raw_inputs_derived_on_device_match_reference_coefficients():
     be.set_hydro_raw(0, g["face_flow"], g["edge_velocity"], g["volume"], g["dt"])
     for k, c in enumerate(names):
         be.set_inputs(k, g[f"input_{c}"])
-    for t in range(60):
+    for t in range(6):                 # the golden run overrides a constituent at step 7
         assert be.step(t).status == 0
         if t == 0:
             from scipy.sparse import csr_matrix
             Ag = csr_matrix((g["A_data_0"], g["A_indices_0"], g["A_indptr_0"]), shape=(mesh.n, mesh.n))
             close(be.get_lhs().data, Ag.data, 1e-14, "LHS from raw inputs")
-        if t == 7 or t == 120:
-            break
         for k, c in enumerate(names):
             close(be.get_state(k, t + 1), g[f"conc_{c}"][t + 1], RTOL, f"raw-input path c[{t + 1}]")
     be.close()
@@ -139,8 +153,8 @@ def run_against_oracle(mesh, inputs, steps, rtol=RTOL, **opt):
         for k in range(K):
             con = oracle.constituent_dict[f"c{k}"]
             worst = max(worst, close(be.get_state(k, t + 1), con.concentration[t + 1], rtol, f"step {t} k {k}"))
-            _, _, ft = be.get_mass_flux(k, t)
-            close(ft, con.total_mass_flux[t], 1e-8, f"total flux step {t} k {k}")
+            flux_close(be, k, t, mesh, con.concentration[t + 1], con.advection_mass_flux[t], con.diffusion_mass_flux[t],
+                       con.total_mass_flux[t], f"step {t} k {k}")
     be.close()
     return worst
 
@@ -249,7 +263,7 @@ def test_host_mirror_update_loop_matches_oracle():
         for name in ("a", "b"):
             close(model.mesh[name][t + 1], oracle.constituent_dict[name].concentration[t + 1], RTOL, f"{name} {t}")
             close(model.mesh[name][t], oracle.constituent_dict[name].concentration[t], RTOL, f"{name} history {t}")
-            close(model.constituent_dict[name].total_mass_flux[t], oracle.constituent_dict[name].total_mass_flux[t], 1e-8, "flux")
+            close(model.constituent_dict[name].total_mass_flux[t], oracle.constituent_dict[name].total_mass_flux[t], 1e-7, "flux")
     model.finalize()
 
 
