@@ -88,6 +88,7 @@ def load_library():
         "cwr_stream": ([H, C.POINTER(C.c_void_p)], C.c_int),
         "cwr_counters": ([H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "cwr_time_spmm": ([H, C.c_int, dp, dp], C.c_int),
+        "cwr_profile": ([H, C.c_int, dp, C.POINTER(C.c_int64)], C.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)      # AttributeError here = the .so does not export what cwr.h declares
@@ -267,6 +268,14 @@ class TransportBackend:
         s = C.c_void_p()
         self._check(self._lib.cwr_stream(self._h, C.byref(s)))
         return s.value or 0
+
+    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux")
+
+    def profile(self, enable: int = -1):
+        """enable = 1/0 switches per-kernel-family event timing on/off; returns {family: (ms, launches)}."""
+        ms = np.zeros(len(self.PROFILE_FAMILIES)); cnt = np.zeros(len(self.PROFILE_FAMILIES), np.int64)
+        self._check(self._lib.cwr_profile(self._h, enable, _ptr(ms, C.c_double), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+        return {f: (float(ms[i]), int(cnt[i])) for i, f in enumerate(self.PROFILE_FAMILIES)}
 
     def time_spmm(self, reps: int = 20):
         ms, nbytes = C.c_double(), C.c_double()

@@ -53,6 +53,13 @@ struct cwr_handle {
     int lhs_step = -1;
     bool have_geometry = false;
     int64_t launches = 0, iterations = 0;
+    // optional per-kernel-family timing with CUDA events on the handle's stream (bench.py roofline)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_family;
+    size_t ev_used = 0;
+    double fam_ms[CWR_PROFILE_FAMILIES] = {0};
+    int64_t fam_count[CWR_PROFILE_FAMILIES] = {0};
     std::string err;
     std::vector<void*> allocs;
 };
@@ -83,6 +90,36 @@ static cudaError_t upload(cwr_handle* h, T** p, const std::vector<T>& v) {
     if (e != cudaSuccess) return e;
     if (!v.empty()) e = cudaMemcpyAsync(*p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
     return e;
+}
+
+// profiling: an event is recorded before every kernel of a step; the time between two consecutive
+// events is attributed to the kernel family launched after the first one.
+static inline void mark(cwr_handle* h, int family) {
+    if (!h->profiling) return;
+    if (h->ev_used == h->ev_pool.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        h->ev_pool.push_back(e);
+        h->ev_family.push_back(0);
+    }
+    h->ev_family[h->ev_used] = family;
+    cudaEventRecord(h->ev_pool[h->ev_used++], h->stream);
+}
+
+static void flush_profile(cwr_handle* h) {
+    if (!h->profiling || h->ev_used == 0) return;
+    mark(h, -1);
+    cudaEventSynchronize(h->ev_pool[h->ev_used - 1]);
+    for (size_t i = 0; i + 1 < h->ev_used; ++i) {
+        const int f = h->ev_family[i];
+        if (f < 0 || f >= CWR_PROFILE_FAMILIES) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]) == cudaSuccess) {
+            h->fam_ms[f] += ms;
+            h->fam_count[f] += 1;
+        }
+    }
+    h->ev_used = 0;
 }
 
 static inline int grid_for(int64_t items, int per_block, int max_grid) {
@@ -131,6 +168,7 @@ void cwr_destroy(cwr_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
@@ -460,9 +498,13 @@ static int launch_iteration(cwr_handle* h) {
     const int g = h->grid_rows;
     DeviceModel& M = h->M;
     KC_DISPATCH(h->KC,
+        mark(h, CWR_FAM_SPMM_V);
         (k_spmm<KC, 1><<<g, kThreads, 0, h->stream>>>(M, M.p, nullptr));
+        mark(h, CWR_FAM_UPDATE_S);
         (k_update_s<KC><<<g, kThreads, 0, h->stream>>>(M));
+        mark(h, CWR_FAM_SPMM_T);
         (k_spmm<KC, 2><<<g, kThreads, 0, h->stream>>>(M, M.r, nullptr));
+        mark(h, CWR_FAM_UPDATE_XRP);
         (k_update_xrp<KC><<<g, kThreads, 0, h->stream>>>(M)));
     h->launches += 4;
     return CWR_OK;
@@ -474,12 +516,15 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
     int restarts = 0;
     int total_iter = 0;
     for (;;) {
+        mark(h, CWR_FAM_SPMM_INIT);
         KC_DISPATCH(h->KC, (k_spmm<KC, 0><<<g, kThreads, 0, h->stream>>>(M, nullptr, nullptr)));
         h->launches += 1;
+        mark(h, -1);
         int rc = poll(h);
         if (rc) return rc;
         while (!h->h_ctl->all_done) {
             for (int i = 0; i < h->opt.check_every; ++i) launch_iteration(h);
+            mark(h, -1);
             rc = poll(h);
             if (rc) return rc;
         }
@@ -541,8 +586,10 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
     DeviceModel& M = h->M;
     k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl);
+    mark(h, CWR_FAM_ASSEMBLE);
     if (M.nb > 0) k_boundary_diag<<<grid_for(M.nb, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
     k_assemble<<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+    mark(h, CWR_FAM_RHS);
     KC_DISPATCH(h->KC, (k_rhs<KC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
     h->launches += 3 + (M.nb > 0);
     // sparse real-cell overrides of c~ (input_array[t][real cell] != 0 at t >= 1): recompute those rows
@@ -573,11 +620,22 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     cwr_step_info local;
     int status = solve(h, &local);
     if (status == CWR_ECUDA) return status;
+    // transport.py:258-264: non-zero input_array[t+1] entries are re-imposed on the stored row -- ghost cells
+    // are handled where they are read (k_mass_flux, k_extract_state); real cells (rare) are patched here.
+    for (int k = 0; k < K; ++k) {
+        auto it = h->real_overrides[k].find(t + 1);
+        if (it == h->real_overrides[k].end()) continue;
+        for (auto& cv : it->second)
+            CK(cudaMemcpyAsync(p.state_t1 + (size_t)cv.first * K + k, &cv.second, 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     if (M.want_flux) {
+        mark(h, CWR_FAM_MASS_FLUX);
         KC_DISPATCH(h->KC, (k_mass_flux<KC><<<h->grid_edges, kThreads, 0, h->stream>>>(M)));
         h->launches += 1;
         h->flux_step = t;
     }
+    flush_profile(h);
     CK(cudaGetLastError());
     h->computed_upto = std::max(h->computed_upto, t + 1);
     if (!h->opt.keep_history) h->computed_upto = t + 1;
@@ -790,6 +848,21 @@ int cwr_counters(cwr_handle* h, int64_t* launches, int64_t* iterations) {
     if (!h) return CWR_EINVAL;
     if (launches) *launches = h->launches;
     if (iterations) *iterations = h->iterations;
+    return CWR_OK;
+}
+
+int cwr_profile(cwr_handle* h, int enable, double* ms, int64_t* counts) {
+    if (!h) return CWR_EINVAL;
+    if (ms) std::copy(h->fam_ms, h->fam_ms + CWR_PROFILE_FAMILIES, ms);
+    if (counts) std::copy(h->fam_count, h->fam_count + CWR_PROFILE_FAMILIES, counts);
+    if (enable >= 0) {
+        if ((enable != 0) != h->profiling) {
+            std::fill(h->fam_ms, h->fam_ms + CWR_PROFILE_FAMILIES, 0.0);
+            std::fill(h->fam_count, h->fam_count + CWR_PROFILE_FAMILIES, (int64_t)0);
+        }
+        h->profiling = enable != 0;
+        h->ev_used = 0;
+    }
     return CWR_OK;
 }
 

@@ -157,19 +157,43 @@ class ClearwaterRiverine:
         self.constituents = list(inputs.keys())
         self.constituent_dict = {name: Constituent(name, mesh, arr, units.get(name, "Unknown"), store_mass_flux)
                                  for name, arr in inputs.items()}
+        # stream_hydro: keep only a few time slices on the device and upload slice t+1 inside update()
+        # (meshes whose T x E arrays exceed device memory; also what bench.py's end-to-end leg times)
+        self.stream_hydro = bool(backend_options.pop("stream_hydro", False))
+        if self.stream_hydro:
+            backend_options.setdefault("hydro_capacity", 3)
         self.backend = TransportBackend(mesh[EDGES_FACE1], mesh[EDGES_FACE2], F, T, len(inputs), D, device=device,
                                         **backend_options)
         # derived coefficients (utilities.py:513-541) are computed on the device from the raw arrays
         self.backend.set_geometry(mesh["face_x"], mesh["face_y"])
-        chunk = max(1, min(T, (64 << 20) // max(1, 4 * len(f1))))
-        for t0 in range(0, T, chunk):
-            t1 = min(T, t0 + chunk)
-            self.backend.set_hydro_raw(t0, mesh[FLOW_ACROSS_FACE][t0:t1], mesh[EDGE_VELOCITY][t0:t1], mesh[VOLUME][t0:t1],
-                                       mesh[CHANGE_IN_TIME][t0:t1])
+        self._resident = set()
+        if self.stream_hydro:
+            self._upload_slice(0)
+        else:
+            chunk = max(1, min(T, (64 << 20) // max(1, 4 * len(f1))))
+            for t0 in range(0, T, chunk):
+                t1 = min(T, t0 + chunk)
+                self.backend.set_hydro_raw(t0, mesh[FLOW_ACROSS_FACE][t0:t1], mesh[EDGE_VELOCITY][t0:t1],
+                                           mesh[VOLUME][t0:t1], mesh[CHANGE_IN_TIME][t0:t1])
         for k, name in enumerate(self.constituents):
             self.backend.set_inputs(k, self.constituent_dict[name].input_array)
         self._index = {name: k for k, name in enumerate(self.constituents)}
+        self._all = np.empty((len(inputs), int(np.max(f1)) + 1))
+        try:                                   # page-locked landing buffer for the per-step device->host copy
+            import torch
+            self._all = torch.from_numpy(self._all).pin_memory().numpy()
+        except Exception:
+            pass
         self.solver_info = []
+
+    def _upload_slice(self, t: int):
+        if t in self._resident or t >= len(self.mesh["time"]):
+            return
+        m = self.mesh
+        self.backend.set_hydro_raw(t, m[FLOW_ACROSS_FACE][t:t + 1], m[EDGE_VELOCITY][t:t + 1], m[VOLUME][t:t + 1],
+                                   m[CHANGE_IN_TIME][t:t + 1])
+        cap = self.backend.options.hydro_capacity
+        self._resident = {s for s in self._resident if s % cap != t % cap} | {t}
 
     # ------------------------------------------------------------------------------------------
     def update(self, update_concentration: Optional[Dict[str, np.ndarray]] = None):
@@ -185,6 +209,9 @@ class ClearwaterRiverine:
                 values = np.asarray(getattr(values, "values", values), dtype=np.float64)[0:n]
                 self.mesh[name][t][0:n] = values             # transport.py:233-236: history at t is overwritten too
                 self.backend.set_state(self._index[name], t, values)
+        if self.stream_hydro:
+            self._upload_slice(t)
+            self._upload_slice(t + 1)
         info = self.backend.step(t)
         self.solver_info.append((info.iterations, info.max_relres, info.status))
         if info.status != CWR_OK:
@@ -195,9 +222,16 @@ class ClearwaterRiverine:
         self.time_step += 1                                   # transport.py:276
 
     def _fetch(self, t1: int):
+        """c[t1] of every constituent in one device->host copy; ghost cells get their BC value where
+        one is set and stay NaN elsewhere (transport.py:252-264)."""
+        n = self.mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
+        self.backend.get_state_all(t1, self._all)
         for name, k in self._index.items():
-            self.backend.get_state(k, t1, self.mesh[name][t1])
+            row = self.mesh[name][t1]
+            row[:n] = self._all[k]
             c = self.constituent_dict[name]
+            bc = c.input_array[t1, n:]
+            row[n:] = np.where(bc != 0, bc, np.nan)
             if c.total_mass_flux is not None and self.backend.options.mass_flux:
                 self.backend.get_mass_flux(k, t1 - 1, c.advection_mass_flux[t1 - 1], c.diffusion_mass_flux[t1 - 1],
                                            c.total_mass_flux[t1 - 1])

@@ -128,6 +128,22 @@ int cwr_stream(cwr_handle* h, void** cuda_stream);           /* the handle's cud
 int cwr_counters(cwr_handle* h, int64_t* kernel_launches, int64_t* solver_iterations);
 
 /* --- device timing of the dominant kernel (bench.py roofline) -------------------------------- */
+/* Per-kernel-family device time inside cwr_step, measured with CUDA events recorded on the handle's
+ * stream between the launches.  cwr_profile(h, 1, NULL, NULL) switches it on (and zeroes the sums),
+ * (h, 0, ...) off, (h, -1, ms, counts) only reads: accumulated milliseconds and launch counts. */
+enum {
+    CWR_FAM_ASSEMBLE = 0,   /* k_boundary_diag + k_assemble */
+    CWR_FAM_RHS,            /* k_rhs + k_boundary_rhs */
+    CWR_FAM_SPMM_INIT,      /* r = b - A x0 */
+    CWR_FAM_SPMM_V,         /* v = A p  with (rhat, v) */
+    CWR_FAM_UPDATE_S,       /* s = r - alpha v */
+    CWR_FAM_SPMM_T,         /* t = A s  with the four dots */
+    CWR_FAM_UPDATE_XRP,     /* x, r, p updates with (r, r) */
+    CWR_FAM_MASS_FLUX,
+    CWR_PROFILE_FAMILIES
+};
+int cwr_profile(cwr_handle* h, int enable, double* ms, int64_t* counts);
+
 /* Time `reps` launches of the SpMM/SpMV kernel (y = A x over all K columns) with CUDA events on
  * the handle's stream; returns average milliseconds per launch and the algorithmic bytes of one
  * launch (12*nnz_off + 4*(n+1) + 16*n*K). */
