@@ -166,6 +166,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE",
+                    help="cwr_options override, e.g. --opt precond_steps=8 --opt rtol=1e-12")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +198,11 @@ def main():
     inputs = synthetic.make_inputs(plan, K, seed=2 + 1000 * rank, bc_scale=bc_scale)
     dt = np.append(np.diff(plan.time_seconds), np.nan)
 
-    be = TransportBackend(plan.f1, plan.f2, F, T, K, DIFFUSION, device=local)
+    opts = {}
+    for kv in args.opt:
+        key, val = kv.split("=", 1)
+        opts[key] = float(val) if key == "rtol" else int(val)
+    be = TransportBackend(plan.f1, plan.f2, F, T, K, DIFFUSION, device=local, **opts)
     be.set_geometry(plan.face_x, plan.face_y)
     chunk = max(1, (256 << 20) // (4 * E))
     for t0 in range(0, T, chunk):
@@ -278,7 +284,7 @@ def main():
         model = ClearwaterRiverine.from_arrays(
             plan.f1, plan.f2, plan.face_x, plan.face_y, plan.time_seconds, pinned(plan.face_flow),
             pinned(plan.edge_velocity), pinned(plan.volume), DIFFUSION, {f"c{k}": inputs[k] for k in range(K)},
-            device=local, stream_hydro=True, store_mass_flux=False, keep_history=0)
+            device=local, stream_hydro=True, store_mass_flux=False, keep_history=0, **opts)
         for _ in range(W):
             model.update()
         if world > 1:
@@ -314,6 +320,7 @@ def main():
                                     "16m": "synthetic 16M-cell mesh, 1 constituent, single GPU"}[args.workload],
                        "cells": n, "edges": E, "nnz_offdiag": nnz, "constituents_per_gpu": K, "dt_s": float(dt[0]),
                        "diffusion_coefficient": DIFFUSION, "rtol": be.options.rtol,
+                       "precond_steps": be.options.precond_steps,
                        "l2": "per-step working set (7 vectors x n x K x 8 B + matrix) >> 126 MB L2; no flush needed"
                              if n * K * 56 > 4 * 126e6 else "working set is L2-resident: launch/latency bound, HBM fraction not meaningful",
                        "sharding": "independent constituents/scenarios per rank, mesh replicated, no data-path collective"},

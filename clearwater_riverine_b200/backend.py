@@ -24,7 +24,7 @@ STATUS_NAMES = {0: "CWR_OK", -1: "CWR_EINVAL", -2: "CWR_ECUDA", -3: "CWR_ENOTCON
 class CwrOptions(C.Structure):
     _fields_ = [("rtol", C.c_double), ("max_iter", C.c_int), ("reorder", C.c_int), ("keep_history", C.c_int),
                 ("hydro_capacity", C.c_int), ("mass_flux", C.c_int), ("solver_path", C.c_int),
-                ("use_graph", C.c_int), ("check_every", C.c_int), ("reserved", C.c_int * 7)]
+                ("use_graph", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class CwrStepInfo(C.Structure):
@@ -269,7 +269,7 @@ class TransportBackend:
         self._check(self._lib.cwr_stream(self._h, C.byref(s)))
         return s.value or 0
 
-    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux")
+    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux", "precond")
 
     def profile(self, enable: int = -1):
         """enable = 1/0 switches per-kernel-family event timing on/off; returns {family: (ms, launches)}."""

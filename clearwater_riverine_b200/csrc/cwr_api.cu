@@ -26,11 +26,13 @@ struct cwr_handle {
     Topology topo;
     int n = 0, F = 0, E = 0, K = 0, T = 0, G = 0;
     int C = 0;                       // hydro slices resident
-    int KC = 1;                      // lanes per row
+    int KC = 1, VEC = 1;             // lanes per row, columns per lane
+    int m_steps = 1;                 // Jacobi steps of the polynomial preconditioner (1 = none)
+    int last_iters = 0;              // iterations of the previous solve (launch-ahead prediction)
     int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0;
     DeviceModel M{};
     // device buffers
-    int32_t *d_rowptr = nullptr, *d_col = nullptr, *d_slot = nullptr, *d_f1p = nullptr, *d_f2p = nullptr;
+    int32_t *d_ell_col = nullptr, *d_ell_code = nullptr, *d_f1p = nullptr, *d_f2p = nullptr;
     int32_t *d_bcell = nullptr, *d_bptr = nullptr, *d_bedge = nullptr, *d_eperm = nullptr, *d_einv = nullptr;
     int32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr, *d_f1 = nullptr, *d_f2 = nullptr;
     float *d_adv = nullptr, *d_velg = nullptr, *d_vol = nullptr;   // (C,E), (C,E_g), (C,n)
@@ -135,8 +137,8 @@ static int ensure_stage(cwr_handle* h, size_t bytes) {
     return CWR_OK;
 }
 
-#define KC_DISPATCH(KCV, ...)                  \
-    switch (KCV) {                             \
+#define KC_CASES(...)                          \
+    switch (h->KC) {                           \
         case 1: { constexpr int KC = 1; __VA_ARGS__; break; }   \
         case 2: { constexpr int KC = 2; __VA_ARGS__; break; }   \
         case 4: { constexpr int KC = 4; __VA_ARGS__; break; }   \
@@ -144,6 +146,10 @@ static int ensure_stage(cwr_handle* h, size_t bytes) {
         case 16: { constexpr int KC = 16; __VA_ARGS__; break; } \
         default: { constexpr int KC = 32; __VA_ARGS__; break; } \
     }
+// binds constexpr KC (lanes per row) and VEC (columns per lane) for the handle's K
+#define KC_DISPATCH(KCV, ...)                                           \
+    if (h->VEC == 2) { constexpr int VEC = 2; KC_CASES(__VA_ARGS__) }   \
+    else { constexpr int VEC = 1; KC_CASES(__VA_ARGS__) }
 
 extern "C" {
 
@@ -158,7 +164,8 @@ int cwr_default_options(cwr_options* o) {
     o->mass_flux = 1;
     o->solver_path = 0;
     o->use_graph = 1;
-    o->check_every = 4;
+    o->check_every = 1;
+    o->precond_steps = 4;
     return CWR_OK;
 }
 
@@ -187,7 +194,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (opt) h->opt = *opt; else cwr_default_options(&h->opt);
     if (!(h->opt.rtol > 0)) h->opt.rtol = 1e-13;
     if (h->opt.max_iter <= 0) h->opt.max_iter = 500;
-    if (h->opt.check_every <= 0) h->opt.check_every = 4;
+    if (h->opt.check_every <= 0) h->opt.check_every = 1;
+    if (h->opt.precond_steps <= 0) h->opt.precond_steps = 4;
+    h->m_steps = std::min(h->opt.precond_steps, 64);
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) FAIL(CWR_ECUDA, "no CUDA device: this library has no CPU fallback");
@@ -205,16 +214,17 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
     h->C = (h->opt.hydro_capacity <= 0 || h->opt.hydro_capacity > T) ? T : std::max(2, h->opt.hydro_capacity);
+    h->VEC = (K % 2 == 0) ? 2 : 1;
     int kc = 1;
-    while (kc < K && kc < 32) kc <<= 1;
+    while (kc * h->VEC < K && kc < 32) kc <<= 1;
     h->KC = kc;
     h->max_grid = h->num_sms * 8;
     h->grid_rows = grid_for(n, kThreads / kc, h->max_grid);
     h->grid_edges = grid_for(E, kThreads / kc, h->max_grid);
-    h->grid_b = grid_for((int64_t)tp.bcell.size(), kThreads / kc, h->max_grid);
+    h->grid_b = grid_for((int64_t)tp.bcell.size() * K, kThreads, h->max_grid);
 
     // topology -> device
-    CK(upload(h, &h->d_rowptr, tp.rowptr)); CK(upload(h, &h->d_col, tp.col)); CK(upload(h, &h->d_slot, tp.slot_edge));
+    CK(upload(h, &h->d_ell_col, tp.ell_col)); CK(upload(h, &h->d_ell_code, tp.ell_code));
     CK(upload(h, &h->d_f1p, tp.f1p)); CK(upload(h, &h->d_f2p, tp.f2p));
     CK(upload(h, &h->d_bcell, tp.bcell)); CK(upload(h, &h->d_bptr, tp.bptr)); CK(upload(h, &h->d_bedge, tp.bedge));
     CK(upload(h, &h->d_eperm, tp.eperm));
@@ -244,15 +254,16 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
 
     DeviceModel& M = h->M;
     M.n = n; M.K = K; M.E = E; M.E_int = tp.E_int; M.E_g = tp.E_g; M.G = h->G; M.nb = (int)tp.bcell.size();
-    M.rowptr = h->d_rowptr; M.col = h->d_col; M.slot_edge = h->d_slot; M.f1p = h->d_f1p; M.f2p = h->d_f2p;
+    M.W = tp.W; M.ell_col = h->d_ell_col; M.ell_code = h->d_ell_code; M.f1p = h->d_f1p; M.f2p = h->d_f2p;
     M.bcell = h->d_bcell; M.bptr = h->d_bptr; M.bedge = h->d_bedge;
-    CK(dalloc(h, &M.val, (size_t)tp.nnz)); CK(dalloc(h, &M.diag, (size_t)n)); CK(dalloc(h, &M.gdiag, (size_t)n));
+    CK(dalloc(h, &M.val, (size_t)n * tp.W)); CK(dalloc(h, &M.diag, (size_t)n)); CK(dalloc(h, &M.gdiag, (size_t)n));
     CK(cudaMemsetAsync(M.gdiag, 0, (size_t)n * sizeof(double), h->stream));
     double* ic = nullptr;
     CK(dalloc(h, &ic, nK)); CK(cudaMemsetAsync(ic, 0, nK * sizeof(double), h->stream));
     M.ic = ic;
     CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
     CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
+    if (h->m_steps > 1) { CK(dalloc(h, &M.ph, nK)); CK(dalloc(h, &M.sh, nK)); CK(dalloc(h, &M.tmp, nK)); }
     CK(dalloc(h, &M.partials, (size_t)h->max_grid * kMaxDots * K));
     CK(dalloc(h, &M.sc, (size_t)SC_ROWS * K));
     CK(dalloc(h, &M.colflags, (size_t)K)); CK(dalloc(h, &M.coliters, (size_t)K));
@@ -494,18 +505,37 @@ static int poll(cwr_handle* h) {
     return CWR_OK;
 }
 
+// m-step Jacobi polynomial preconditioner: z_1 = u + N u, z_{j+1} = u + N z_j (N = I - D^-1 A), i.e.
+// z = (I + N + ... + N^(m-1)) u.  Returns the buffer holding z (u itself when m == 1); the last step
+// always lands in `dst`, `other` is the ping-pong partner.
+static const double* precondition(cwr_handle* h, const double* u, double* dst, double* other) {
+    const int J = h->m_steps - 1;
+    if (J <= 0) return u;
+    DeviceModel& M = h->M;
+    const double* z = u;
+    for (int j = 1; j <= J; ++j) {
+        double* out = ((J - j) % 2 == 0) ? dst : other;
+        mark(h, CWR_FAM_PRECOND);
+        KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_JAC><<<h->grid_rows, kThreads, 0, h->stream>>>(M, z, u, out)));
+        h->launches += 1;
+        z = out;
+    }
+    return z;
+}
+
 static int launch_iteration(cwr_handle* h) {
     const int g = h->grid_rows;
     DeviceModel& M = h->M;
-    KC_DISPATCH(h->KC,
-        mark(h, CWR_FAM_SPMM_V);
-        (k_spmm<KC, 1><<<g, kThreads, 0, h->stream>>>(M, M.p, nullptr));
-        mark(h, CWR_FAM_UPDATE_S);
-        (k_update_s<KC><<<g, kThreads, 0, h->stream>>>(M));
-        mark(h, CWR_FAM_SPMM_T);
-        (k_spmm<KC, 2><<<g, kThreads, 0, h->stream>>>(M, M.r, nullptr));
-        mark(h, CWR_FAM_UPDATE_XRP);
-        (k_update_xrp<KC><<<g, kThreads, 0, h->stream>>>(M)));
+    const double* ph = precondition(h, M.p, M.ph, M.tmp);
+    mark(h, CWR_FAM_SPMM_V);
+    KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_AV><<<g, kThreads, 0, h->stream>>>(M, ph, nullptr, nullptr)));
+    mark(h, CWR_FAM_UPDATE_S);
+    KC_DISPATCH(h->KC, (k_update_s<KC, VEC><<<g, kThreads, 0, h->stream>>>(M)));
+    const double* sh = precondition(h, M.r, M.sh, M.tmp);
+    mark(h, CWR_FAM_SPMM_T);
+    KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_AT><<<g, kThreads, 0, h->stream>>>(M, sh, nullptr, nullptr)));
+    mark(h, CWR_FAM_UPDATE_XRP);
+    KC_DISPATCH(h->KC, (k_update_xrp<KC, VEC><<<g, kThreads, 0, h->stream>>>(M, ph, sh)));
     h->launches += 4;
     return CWR_OK;
 }
@@ -517,17 +547,24 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
     int total_iter = 0;
     for (;;) {
         mark(h, CWR_FAM_SPMM_INIT);
-        KC_DISPATCH(h->KC, (k_spmm<KC, 0><<<g, kThreads, 0, h->stream>>>(M, nullptr, nullptr)));
+        KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_INIT><<<g, kThreads, 0, h->stream>>>(M, nullptr, nullptr, nullptr)));
         h->launches += 1;
         mark(h, -1);
-        int rc = poll(h);
-        if (rc) return rc;
+        // Launch-ahead: the previous solve's iteration count predicts this one, so that many iterations
+        // (minus one) are queued before the first convergence poll; every kernel of an iteration returns
+        // at once when the device-side all_done flag is already set, so over-launching is harmless.
+        int ahead = restarts == 0 ? std::max(0, h->last_iters - 1) : 0;
+        int rc = CWR_OK;
+        if (ahead == 0) { rc = poll(h); if (rc) return rc; } else h->h_ctl->all_done = 0;
         while (!h->h_ctl->all_done) {
-            for (int i = 0; i < h->opt.check_every; ++i) launch_iteration(h);
+            const int burst = ahead > 0 ? ahead : h->opt.check_every;
+            ahead = 0;
+            for (int i = 0; i < burst; ++i) launch_iteration(h);
             mark(h, -1);
             rc = poll(h);
             if (rc) return rc;
         }
+        h->last_iters = h->h_ctl->iter;
         total_iter += h->h_ctl->iter;
         const bool breakdown = (h->h_ctl->flags_or & FL_BREAKDOWN) != 0;
         if (breakdown && restarts < 3 && !h->h_ctl->hit_max_iter) {
@@ -590,7 +627,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     if (M.nb > 0) k_boundary_diag<<<grid_for(M.nb, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
     k_assemble<<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
     mark(h, CWR_FAM_RHS);
-    KC_DISPATCH(h->KC, (k_rhs<KC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
+    KC_DISPATCH(h->KC, (k_rhs<KC, VEC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
     h->launches += 3 + (M.nb > 0);
     // sparse real-cell overrides of c~ (input_array[t][real cell] != 0 at t >= 1): recompute those rows
     for (int k = 0; k < K; ++k) {
@@ -613,7 +650,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
         }
     }
     if (M.nb > 0) {
-        KC_DISPATCH(h->KC, (k_boundary_rhs<KC><<<h->grid_b, kThreads, 0, h->stream>>>(M)));
+        k_boundary_rhs<<<h->grid_b, kThreads, 0, h->stream>>>(M);
         h->launches += 1;
     }
     h->lhs_step = t;
@@ -631,7 +668,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     }
     if (M.want_flux) {
         mark(h, CWR_FAM_MASS_FLUX);
-        KC_DISPATCH(h->KC, (k_mass_flux<KC><<<h->grid_edges, kThreads, 0, h->stream>>>(M)));
+        KC_DISPATCH(h->KC, (k_mass_flux<KC, VEC><<<h->grid_edges, kThreads, 0, h->stream>>>(M)));
         h->launches += 1;
         h->flux_step = t;
     }
@@ -782,7 +819,8 @@ int cwr_get_lhs(cwr_handle* h, int64_t* nnz, int32_t* indptr, int32_t* indices, 
     for (int i = 0; i < n; ++i) {
         auto& r = rows[tp.old_of_new[i]];
         r.emplace_back(tp.old_of_new[i], -1 - i);
-        for (int j = tp.rowptr[i]; j < tp.rowptr[i + 1]; ++j) r.emplace_back(tp.old_of_new[tp.col[j]], j);
+        for (int j = tp.rowptr[i]; j < tp.rowptr[i + 1]; ++j)      // value index = ELL position of CSR slot j
+            r.emplace_back(tp.old_of_new[tp.col[j]], (int32_t)((size_t)i * tp.W + (j - tp.rowptr[i])));
     }
     int64_t total = 0;
     for (auto& r : rows) {
@@ -794,7 +832,7 @@ int cwr_get_lhs(cwr_handle* h, int64_t* nnz, int32_t* indptr, int32_t* indices, 
     if (!indptr || !indices || !data) return CWR_OK;
     if (h->lhs_step < 0) FAIL(CWR_EINVAL, "no LHS assembled yet");
     CK(cudaSetDevice(h->device));
-    std::vector<double> val((size_t)tp.nnz), diag(n);
+    std::vector<double> val((size_t)n * tp.W), diag(n);
     CK(cudaMemcpyAsync(val.data(), h->M.val, val.size() * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(diag.data(), h->M.diag, (size_t)n * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -875,9 +913,9 @@ int cwr_time_spmm(cwr_handle* h, int reps, double* ms_per_launch, double* algori
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     DeviceModel& M = h->M;
     // x = p (left by the last solve), y = v ; both are scratch between steps
-    for (int w = 0; w < 3; ++w) { KC_DISPATCH(h->KC, (k_spmm<KC, 3><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, M.v))); }
+    for (int w = 0; w < 3; ++w) { KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_PLAIN><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, nullptr, M.v))); }
     CK(cudaEventRecord(e0, h->stream));
-    for (int r = 0; r < reps; ++r) { KC_DISPATCH(h->KC, (k_spmm<KC, 3><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, M.v))); }
+    for (int r = 0; r < reps; ++r) { KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_PLAIN><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, nullptr, M.v))); }
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     h->launches += reps + 3;
@@ -886,7 +924,7 @@ int cwr_time_spmm(cwr_handle* h, int reps, double* ms_per_launch, double* algori
     CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
     if (ms_per_launch) *ms_per_launch = (double)ms / reps;
     if (algorithmic_bytes)
-        *algorithmic_bytes = 12.0 * (double)h->topo.nnz + 4.0 * (h->n + 1.0) + 16.0 * (double)h->n * h->K;
+        *algorithmic_bytes = 12.0 * (double)h->topo.nnz + 4.0 * (h->n + 1.0) + 16.0 * (double)h->n * h->K;   /* SURVEY 8d */
     return CWR_OK;
 }
 

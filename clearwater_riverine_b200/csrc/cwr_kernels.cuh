@@ -1,8 +1,10 @@
 // sm_100a kernels of the transport step.  fp64 throughout; HBM-bound gather/stream work, so the
-// design rules are coalescing (constituents interleaved: x[row*K + k], one 128 B line per row at
-// K = 16), persistent grids sized from the SM count, fused dot products with a deterministic
-// two-level reduction (no floating-point atomics anywhere), and per-step parameters read from a
-// device-resident struct so that the whole step can be replayed as one CUDA graph.
+// design rules are: coalescing (constituents interleaved, x[row*K + k]: one 128 B line per row at
+// K = 16, moved as 128-bit double2 per lane), a fixed-width row-major ELL matrix (one int4 + two
+// double2 broadcast loads per row, no rowptr dependency in front of the gathers), persistent grids
+// sized from the SM count, fused dot products with a deterministic two-level reduction (no
+// floating-point atomics anywhere), and per-step parameters read from a device-resident struct so
+// that a step is the same launch sequence every time.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,10 +13,9 @@ namespace cwr {
 
 constexpr int kThreads = 256;
 constexpr int kMaxK = 128;      // constituents per handle
-constexpr int kMaxDots = 5;
+constexpr int kMaxDots = 4;
 
-// Per-step pointers/values; written by k_set_step (a graph node whose parameters are the only
-// thing that changes between steps) and read by every kernel of the step.
+// Per-step pointers/values; written by k_set_step and read by every kernel of the step.
 struct StepParams {
     const float* adv_t;      // (E)  advection_coeff[t]       device edge order
     const double* cdiff_t;   // (E)  coeff_to_diffusion[t]
@@ -45,15 +46,16 @@ struct SolverCtl {
 };
 
 struct DeviceModel {
-    int n, K, E, E_int, E_g, G, nb;
-    const int32_t* rowptr; const int32_t* col; const int32_t* slot_edge;
+    int n, K, E, E_int, E_g, G, nb, W;     // W = ELL width (multiple of 4)
+    const int32_t* ell_col;   // (n,W) neighbour row, padded with the row itself
+    const int32_t* ell_code;  // (n,W) (e' << 1) | side, -1 = padding
     const int32_t* f1p; const int32_t* f2p;
     const int32_t* bcell; const int32_t* bptr; const int32_t* bedge;
-    double* val;        // (nnz) off-diagonals of D^-1 A
+    double* val;        // (n,W) off-diagonals of D^-1 A
     double* diag;       // (n)   D
     double* gdiag;      // (n)   ghost-edge diagonal terms (boundary cells only, 0 elsewhere)
     const double* ic;   // (n,K) input_array[0][0:n]
-    double *b, *r, *rhat, *p, *v, *tt;   // (n,K) work vectors (b is the row-scaled RHS)
+    double *b, *r, *rhat, *p, *v, *tt, *ph, *sh, *tmp;   // (n,K) work vectors (b is the row-scaled RHS)
     double* partials;   // (grid, kMaxDots, K)
     double* sc;         // (SC_ROWS, K) per-column scalars
     int* colflags;      // (K)
@@ -81,7 +83,6 @@ __global__ void k_gather(T* __restrict__ dst, const T* __restrict__ src, const i
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[idx[i]];
 }
 
-// dst[(i)*K + k] = src[old_of_new[i]]   (one constituent's real-cell vector into the interleaved state)
 __global__ void k_scatter_column(double* __restrict__ dst, const double* __restrict__ src,
                                  const int32_t* __restrict__ old_of_new, int n, int K, int k) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -97,6 +98,8 @@ __global__ void k_scatter_bc(double* __restrict__ bc, const double* __restrict__
     }
 }
 
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
 // out[F]: real cells from the interleaved state (reference order), ghost cells: BC value or NaN
 __global__ void k_extract_state(double* __restrict__ out, const double* __restrict__ state, const double* __restrict__ bc_t,
                                 const int32_t* __restrict__ new_of_old, int n, int F, int K, int k) {
@@ -105,7 +108,7 @@ __global__ void k_extract_state(double* __restrict__ out, const double* __restri
         if (j < n) v = state[(size_t)new_of_old[j] * K + k];
         else {
             v = bc_t ? bc_t[(size_t)(j - n) * K + k] : 0.0;
-            if (v == 0.0) v = __longlong_as_double(0x7ff8000000000000LL);   // transport.py:258-264: unset ghost cells stay NaN
+            if (v == 0.0) v = qnan();   // transport.py:258-264: unset ghost cells stay NaN
         }
         out[j] = v;
     }
@@ -195,23 +198,34 @@ __global__ void k_boundary_diag(DeviceModel M) {
 __global__ void __launch_bounds__(kThreads) k_assemble(DeviceModel M) {
     const StepParams& sp = *M.sp;
     const double dt = sp.dt;
+    const int W = M.W;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += gridDim.x * blockDim.x) {
         const float vol = sp.vol_t1[i];
         double diag = (vol == 0.f ? 1.0 : 0.0) + (double)vol / dt + M.gdiag[i];
-        const int s = M.rowptr[i], e = M.rowptr[i + 1];
-        for (int j = s; j < e; ++j) {
-            const int code = M.slot_edge[j];
-            const double a = (double)sp.adv_t[code >> 1];
-            const double d = sp.cdiff_t[code >> 1];
-            diag += (code & 1) ? (d - fmin(a, 0.0)) : (d + fmax(a, 0.0));
+        const int32_t* code = M.ell_code + (size_t)i * W;
+        double* val = M.val + (size_t)i * W;
+        for (int w = 0; w < W; w += 4) {
+            const int4 c4 = *reinterpret_cast<const int4*>(code + w);
+            const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+            double off[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                off[u] = 0.0;
+                if (cs[u] >= 0) {
+                    const double a = (double)sp.adv_t[cs[u] >> 1];
+                    const double d = sp.cdiff_t[cs[u] >> 1];
+                    if (cs[u] & 1) { off[u] = -d - fmax(a, 0.0); diag += d - fmin(a, 0.0); }
+                    else           { off[u] = -d + fmin(a, 0.0); diag += d + fmax(a, 0.0); }
+                }
+            }
+            *reinterpret_cast<double2*>(val + w) = make_double2(off[0], off[1]);
+            *reinterpret_cast<double2*>(val + w + 2) = make_double2(off[2], off[3]);
         }
         const double inv = 1.0 / diag;
-        for (int j = s; j < e; ++j) {
-            const int code = M.slot_edge[j];
-            const double a = (double)sp.adv_t[code >> 1];
-            const double d = sp.cdiff_t[code >> 1];
-            const double off = (code & 1) ? (-d - fmax(a, 0.0)) : (-d + fmin(a, 0.0));
-            M.val[j] = off * inv;
+        for (int w = 0; w < W; w += 2) {
+            double2 o = *reinterpret_cast<double2*>(val + w);
+            o.x *= inv; o.y *= inv;
+            *reinterpret_cast<double2*>(val + w) = o;
         }
         M.diag[i] = diag;
         if (diag == 0.0) M.ctl->singular = 1;
@@ -219,74 +233,100 @@ __global__ void __launch_bounds__(kThreads) k_assemble(DeviceModel M) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// RHS  (reference linalg.py:177-275, 354-406), K constituents at once, row-scaled by 1/D
-// thread mapping used by all (row, column) kernels: KC lanes per row, lane = column
+// (row, column) thread mapping shared by all vector kernels: KC lanes per row, each lane owns VEC
+// adjacent columns (VEC = 2: 128-bit accesses); rows are dealt to lane groups grid-stride.
 // ---------------------------------------------------------------------------------------------
-template <int KC>
+template <int VEC> struct Vd { double a[VEC]; };
+
+template <int VEC>
+__device__ __forceinline__ Vd<VEC> ldv(const double* p) {
+    Vd<VEC> r;
+    if (VEC == 2) { const double2 t = *reinterpret_cast<const double2*>(p); r.a[0] = t.x; r.a[VEC - 1] = t.y; }
+    else r.a[0] = *p;
+    return r;
+}
+template <int VEC>
+__device__ __forceinline__ void stv(double* p, const Vd<VEC>& v) {
+    if (VEC == 2) *reinterpret_cast<double2*>(p) = make_double2(v.a[0], v.a[VEC - 1]);
+    else *p = v.a[0];
+}
+
+// RHS  (reference linalg.py:177-275), K constituents at once, row-scaled by 1/D; warm start x0 = c~
+template <int KC, int VEC>
 __global__ void __launch_bounds__(kThreads) k_rhs(DeviceModel M) {
     const StepParams& sp = *M.sp;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const double dt = sp.dt;
-    for (int c = lane; c < K; c += KC)
+    for (int c = lane * VEC; c < K; c += KC * VEC)
         for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
             const size_t idx = (size_t)i * K + c;
-            double conc = sp.state_t[idx];
-            if (sp.apply_ic) { const double ic = M.ic[idx]; if (ic != 0.0) conc = ic; }
-            const double load = (double)sp.vol_t[i] * conc / dt;      // linalg.py:239
-            M.b[idx] = load / M.diag[i];
-            sp.state_t1[idx] = conc;                                 // warm start x0 = c~[t]
+            Vd<VEC> conc = ldv<VEC>(sp.state_t + idx);
+            if (sp.apply_ic) {
+                const Vd<VEC> ic = ldv<VEC>(M.ic + idx);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) if (ic.a[q] != 0.0) conc.a[q] = ic.a[q];
+            }
+            const double vol = (double)sp.vol_t[i], dg = M.diag[i];
+            Vd<VEC> bb;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) bb.a[q] = (vol * conc.a[q] / dt) / dg;      // linalg.py:239
+            stv<VEC>(M.b + idx, bb);
+            stv<VEC>(sp.state_t1 + idx, conc);
         }
 }
 
 // Boundary cells: b_i = load + ghost_in + ghost_out with the reference's selection and
-// last-edge-wins assignment (linalg.py:349-351, 372-378, 390).
-template <int KC>
+// last-edge-wins assignment (linalg.py:349-351, 372-378, 390).  One lane per (cell, column).
 __global__ void __launch_bounds__(kThreads) k_boundary_rhs(DeviceModel M) {
     const StepParams& sp = *M.sp;
-    const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const int K = M.K;
     const double dt = sp.dt;
     const bool has_diffusion = M.diffusion_coefficient != 0.0;
-    for (int c = lane; c < K; c += KC)
-        for (int b = blockIdx.x * GPB + group; b < M.nb; b += gridDim.x * GPB) {
-            const int i = M.bcell[b];
-            double m_in = 0.0, ca_in = 0.0, cd_in = 0.0, m_out = 0.0, cd_out = 0.0;
-            for (int j = M.bptr[b]; j < M.bptr[b + 1]; ++j) {
-                const int e = M.bedge[j];
-                const float u = sp.velg_t1[e - M.E_int];
-                const double bc = sp.bc_t1[(size_t)(M.f2p[e] - M.n) * K + c];
-                const double cd = has_diffusion ? fabs(sp.cdiff_t1[e]) : 0.0;
-                if (u < 0.f) { m_in = bc; ca_in = fabs((double)sp.adv_t1[e]); cd_in = cd; }
-                if (u > 0.f) { m_out = bc; cd_out = cd; }
-            }
-            const size_t idx = (size_t)i * K + c;
-            const double conc = sp.state_t1[idx];                    // c~ written by k_rhs
-            const double load = (double)sp.vol_t[i] * conc / dt;
-            const double rhs = load + (ca_in + cd_in) * m_in + cd_out * m_out;
-            M.b[idx] = rhs / M.diag[i];
+    const size_t total = (size_t)M.nb * K;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(q / K), c = (int)(q % K);
+        const int i = M.bcell[b];
+        double m_in = 0.0, ca_in = 0.0, cd_in = 0.0, m_out = 0.0, cd_out = 0.0;
+        for (int j = M.bptr[b]; j < M.bptr[b + 1]; ++j) {
+            const int e = M.bedge[j];
+            const float u = sp.velg_t1[e - M.E_int];
+            const double bc = sp.bc_t1[(size_t)(M.f2p[e] - M.n) * K + c];
+            const double cd = has_diffusion ? fabs(sp.cdiff_t1[e]) : 0.0;
+            if (u < 0.f) { m_in = bc; ca_in = fabs((double)sp.adv_t1[e]); cd_in = cd; }
+            if (u > 0.f) { m_out = bc; cd_out = cd; }
         }
+        const size_t idx = (size_t)i * K + c;
+        const double conc = sp.state_t1[idx];                    // c~ written by k_rhs
+        const double load = (double)sp.vol_t[i] * conc / dt;
+        const double rhs = load + (ca_in + cd_in) * m_in + cd_out * m_out;
+        M.b[idx] = rhs / M.diag[i];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // deterministic block / grid reduction of per-column dot products
 // ---------------------------------------------------------------------------------------------
-template <int ND, int KC>
-__device__ __forceinline__ void block_dots(double (&acc)[ND], double* smem, double* block_out, int K, int chunk) {
+// acc[d*VEC + q]: dot d of column (chunk*KC + lane)*VEC + q.  block_out: [kMaxDots][K] of this block.
+template <int ND, int KC, int VEC>
+__device__ __forceinline__ void block_dots(double (&acc)[ND * VEC], double* smem, double* block_out, int K, int chunk) {
+    constexpr int NA = ND * VEC;
 #pragma unroll
     for (int off = KC; off < 32; off <<= 1)
 #pragma unroll
-        for (int d = 0; d < ND; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], off);
+        for (int d = 0; d < NA; ++d) acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], off);
     const int wl = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int NW = kThreads / 32;
     if (wl < KC)
 #pragma unroll
-        for (int d = 0; d < ND; ++d) smem[(warp * ND + d) * KC + wl] = acc[d];
+        for (int d = 0; d < NA; ++d) smem[(warp * NA + d) * KC + wl] = acc[d];
     __syncthreads();
-    if (threadIdx.x < ND * KC) {
-        const int d = threadIdx.x / KC, l = threadIdx.x % KC;
+    if (threadIdx.x < NA * KC) {
+        const int a = threadIdx.x / KC, l = threadIdx.x % KC;
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) s += smem[(w * ND + d) * KC + l];
-        const int c = chunk * KC + l;
+        for (int w = 0; w < NW; ++w) s += smem[(w * NA + a) * KC + l];
+        const int d = a / VEC, q = a % VEC;
+        const int c = (chunk * KC + l) * VEC + q;
         if (c < K) block_out[d * K + c] = s;
     }
     __syncthreads();
@@ -308,19 +348,33 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
 }
 
 // sum the grid's partials in block order -> tot[d*K + k] (shared memory)
+// All 256 threads take part: each (dot, column) pair is summed by a team of threads over interleaved
+// block ranges, then the team's partial sums are combined in a fixed order -> still deterministic.
 template <int ND>
 __device__ __forceinline__ void grid_totals(const double* partials, double* tot, int K) {
-    for (int idx = threadIdx.x; idx < ND * K; idx += blockDim.x) {
-        const int d = idx / K, k = idx % K;
+    __shared__ double team_sum[kThreads];
+    const int pairs = ND * K;
+    int team = 1;
+    while (team * 2 * pairs <= kThreads && team < 64) team *= 2;     // threads per pair (power of two)
+    for (int base = 0; base < pairs; base += kThreads / team) {
+        const int pair = base + threadIdx.x / team, member = threadIdx.x % team;
         double s = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[((size_t)b * kMaxDots + d) * K + k]);
-        tot[idx] = s;
+        if (pair < pairs) {
+            const int d = pair / K, k = pair % K;
+            for (unsigned b = member; b < gridDim.x; b += team) s += __ldcg(&partials[((size_t)b * kMaxDots + d) * K + k]);
+        }
+        team_sum[threadIdx.x] = s;
+        __syncthreads();
+        if (pair < pairs && member == 0) {
+            double t = 0.0;
+            for (int m = 0; m < team; ++m) t += team_sum[threadIdx.x + m];
+            tot[pair] = t;
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
 __device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
-    // thread 0 of the last block: are all columns finished?
     int done = 1, flags = 0;
     for (int k = 0; k < K; ++k) {
         const int f = M.colflags[k];
@@ -333,75 +387,106 @@ __device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// SpMM  y = (I + offdiag) x  for all K columns, fused with the BiCGSTAB step that consumes it
-//   MODE 0: r = b - A x0 ; rhat = p = r ; dots (r,r), (b,b)
-//   MODE 1: v = A p      ; dot (rhat, v)              -> alpha = rho / (rhat,v)
-//   MODE 2: t = A s      ; dots (t,s),(t,t),(rhat,t),(rhat,s) -> omega, rho', beta
-//   MODE 3: y = A x      (plain product, used for timing and tests)
+// SpMM over the row-scaled matrix  A = I + L  (L = off-diagonals in ELL; N := -L is the Jacobi
+// iteration matrix), fused with the BiCGSTAB step that consumes it.  z is gathered, u is the
+// row's own vector.
+//   INIT : r = b - (x + L x)          ; rhat = p = r ; dots (r,r), (b,b)
+//   JAC  : out = u - L z              (one step of the m-step Jacobi preconditioner: out = u + N z)
+//   AV   : v = z + L z                ; dot (rhat, v)                      -> alpha
+//   AT   : t = z + L z                ; dots (t,s),(t,t),(rhat,t),(rhat,s) -> omega, rho', beta
+//   PLAIN: y = z + L z                (timing / tests)
 // ---------------------------------------------------------------------------------------------
-template <int KC, int MODE>
-__global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* __restrict__ xin, double* __restrict__ yout) {
-    constexpr int ND = MODE == 0 ? 2 : MODE == 1 ? 1 : MODE == 2 ? 4 : 1;
-    __shared__ double smem[(kThreads / 32) * kMaxDots * 32];
-    __shared__ double tot[kMaxDots * kMaxK];
-    if (MODE == 1 || MODE == 2) { if (M.ctl->all_done) return; }
-    const int K = M.K, n = M.n, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
-    const int32_t* __restrict__ rowptr = M.rowptr;
-    const int32_t* __restrict__ col = M.col;
-    const double* __restrict__ val = M.val;
-    if (MODE == 0) xin = M.sp->state_t1;
-    const int nchunk = (K + KC - 1) / KC;
+enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_JAC = 3, MODE_PLAIN = 4 };
+
+template <int KC, int VEC, int MODE>
+__global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* __restrict__ zin,
+                                                   const double* __restrict__ uin, double* __restrict__ out) {
+    constexpr int ND = MODE == MODE_INIT ? 2 : MODE == MODE_AV ? 1 : MODE == MODE_AT ? 4 : 1;
+    constexpr bool HAS_DOTS = MODE == MODE_INIT || MODE == MODE_AV || MODE == MODE_AT;
+    __shared__ double smem[HAS_DOTS ? (kThreads / 32) * kMaxDots * 2 * 32 : 1];
+    __shared__ double tot[HAS_DOTS ? kMaxDots * kMaxK : 1];
+    if (MODE == MODE_AV || MODE == MODE_AT || MODE == MODE_JAC) { if (M.ctl->all_done) return; }
+    const int K = M.K, n = M.n, W = M.W;
+    const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const int32_t* __restrict__ ecol = M.ell_col;
+    const double* __restrict__ eval = M.val;
+    if (MODE == MODE_INIT) zin = M.sp->state_t1;
+    const int nchunk = (K + KC * VEC - 1) / (KC * VEC);
     for (int chunk = 0; chunk < nchunk; ++chunk) {
-        const int c = chunk * KC + lane;
+        const int c = (chunk * KC + lane) * VEC;
         const bool active = c < K;
-        double acc[ND];
+        double acc[ND * VEC];
 #pragma unroll
-        for (int d = 0; d < ND; ++d) acc[d] = 0.0;
+        for (int d = 0; d < ND * VEC; ++d) acc[d] = 0.0;
         if (active)
             for (int i = blockIdx.x * GPB + group; i < n; i += gridDim.x * GPB) {
-                const int s = rowptr[i], e = rowptr[i + 1];
                 const size_t idx = (size_t)i * K + c;
-                const double xi = xin[idx];
-                double y = xi;
-                for (int j = s; j < e; j += 4) {
-                    int cj[4]; double vj[4], xj[4];
+                Vd<VEC> s;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const bool ok = j + u < e;
-                        cj[u] = ok ? col[j + u] : i;
-                        vj[u] = ok ? val[j + u] : 0.0;
-                    }
+                for (int q = 0; q < VEC; ++q) s.a[q] = 0.0;
+                for (int w = 0; w < W; w += 4) {
+                    const int4 c4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+                    const double2 v01 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w);
+                    const double2 v23 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w + 2);
+                    const Vd<VEC> x0 = ldv<VEC>(zin + (size_t)c4.x * K + c);
+                    const Vd<VEC> x1 = ldv<VEC>(zin + (size_t)c4.y * K + c);
+                    const Vd<VEC> x2 = ldv<VEC>(zin + (size_t)c4.z * K + c);
+                    const Vd<VEC> x3 = ldv<VEC>(zin + (size_t)c4.w * K + c);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) xj[u] = xin[(size_t)cj[u] * K + c];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) y = fma(vj[u], xj[u], y);
+                    for (int q = 0; q < VEC; ++q)
+                        s.a[q] = fma(v23.y, x3.a[q], fma(v23.x, x2.a[q], fma(v01.y, x1.a[q], fma(v01.x, x0.a[q], s.a[q]))));
                 }
-                if (MODE == 0) {
-                    const double bi = M.b[idx];
-                    const double r = bi - y;
-                    M.r[idx] = r; M.rhat[idx] = r; M.p[idx] = r;
-                    acc[0] = fma(r, r, acc[0]); acc[1] = fma(bi, bi, acc[1]);
-                } else if (MODE == 1) {
-                    M.v[idx] = y;
-                    acc[0] = fma(M.rhat[idx], y, acc[0]);
-                } else if (MODE == 2) {
-                    M.tt[idx] = y;
-                    const double rh = M.rhat[idx];
-                    acc[0] = fma(y, xi, acc[0]); acc[1] = fma(y, y, acc[1]);
-                    acc[2] = fma(rh, y, acc[2]); acc[3] = fma(rh, xi, acc[3]);
+                if (MODE == MODE_JAC) {
+                    const Vd<VEC> u = ldv<VEC>(uin + idx);
+                    Vd<VEC> o;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) o.a[q] = u.a[q] - s.a[q];
+                    stv<VEC>(out + idx, o);
                 } else {
-                    yout[idx] = y;
+                    const Vd<VEC> zi = ldv<VEC>(zin + idx);
+                    Vd<VEC> y;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) y.a[q] = zi.a[q] + s.a[q];
+                    if (MODE == MODE_INIT) {
+                        const Vd<VEC> bi = ldv<VEC>(M.b + idx);
+                        Vd<VEC> r;
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            r.a[q] = bi.a[q] - y.a[q];
+                            acc[0 * VEC + q] = fma(r.a[q], r.a[q], acc[0 * VEC + q]);
+                            acc[1 * VEC + q] = fma(bi.a[q], bi.a[q], acc[1 * VEC + q]);
+                        }
+                        stv<VEC>(M.r + idx, r); stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r);
+                    } else if (MODE == MODE_AV) {
+                        const Vd<VEC> rh = ldv<VEC>(M.rhat + idx);
+                        stv<VEC>(M.v + idx, y);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc[q] = fma(rh.a[q], y.a[q], acc[q]);
+                    } else if (MODE == MODE_AT) {
+                        const Vd<VEC> rh = ldv<VEC>(M.rhat + idx);
+                        const Vd<VEC> sv = ldv<VEC>(M.r + idx);          // s lives in the r buffer
+                        stv<VEC>(M.tt + idx, y);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) {
+                            acc[0 * VEC + q] = fma(y.a[q], sv.a[q], acc[0 * VEC + q]);
+                            acc[1 * VEC + q] = fma(y.a[q], y.a[q], acc[1 * VEC + q]);
+                            acc[2 * VEC + q] = fma(rh.a[q], y.a[q], acc[2 * VEC + q]);
+                            acc[3 * VEC + q] = fma(rh.a[q], sv.a[q], acc[3 * VEC + q]);
+                        }
+                    } else {
+                        stv<VEC>(out + idx, y);
+                    }
                 }
             }
-        if (MODE != 3) block_dots<ND, KC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
+        if (HAS_DOTS) block_dots<ND, KC, VEC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
     }
-    if (MODE == 3) return;
+    if (!HAS_DOTS) return;
     if (!last_block_arrives(&M.ctl->ticket[MODE])) return;
     grid_totals<ND>(M.partials, tot, K);
     double* sc = M.sc;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         int f = M.colflags[k];
-        if (MODE == 0) {
+        if (MODE == MODE_INIT) {
             const double rr = tot[0 * K + k], bb = tot[1 * K + k];
             sc[SC_RHO * K + k] = rr; sc[SC_BNORM2 * K + k] = bb; sc[SC_RNORM2 * K + k] = rr;
             sc[SC_ALPHA * K + k] = 0.0; sc[SC_OMEGA * K + k] = 0.0; sc[SC_BETA * K + k] = 0.0;
@@ -409,7 +494,7 @@ __global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* 
             if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) f |= FL_NAN | FL_PENDING;
             else if (bb == 0.0 && rr != 0.0) f |= FL_ZERO_RHS | FL_PENDING;     // b == 0  =>  x = 0
             else if (rr <= M.tol2 * bb) { f |= FL_CONVERGED; M.coliters[k] = M.ctl->iter; }
-        } else if (MODE == 1) {
+        } else if (MODE == MODE_AV) {
             const double rv = tot[k];
             sc[SC_RHATV * K + k] = rv;
             double alpha = 0.0;
@@ -435,58 +520,79 @@ __global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* 
         M.colflags[k] = f;
     }
     __syncthreads();
-    if (MODE == 0 && threadIdx.x == 0) publish_done(M, K);
+    if (MODE == MODE_INIT && threadIdx.x == 0) publish_done(M, K);
 }
 
 // s = r - alpha v  (in place on r)
-template <int KC>
+template <int KC, int VEC>
 __global__ void __launch_bounds__(kThreads) k_update_s(DeviceModel M) {
     if (M.ctl->all_done) return;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
-    for (int c = lane; c < K; c += KC) {
-        const double alpha = M.sc[SC_ALPHA * K + c];
-        if (alpha == 0.0) continue;        // frozen column: s = r
+    for (int c = lane * VEC; c < K; c += KC * VEC) {
+        double alpha[VEC];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) { alpha[q] = M.sc[SC_ALPHA * K + c + q]; any |= alpha[q] != 0.0; }
+        if (!any) continue;        // frozen columns: s = r
         for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
             const size_t idx = (size_t)i * K + c;
-            M.r[idx] = fma(-alpha, M.v[idx], M.r[idx]);
+            Vd<VEC> r = ldv<VEC>(M.r + idx);
+            const Vd<VEC> v = ldv<VEC>(M.v + idx);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) r.a[q] = fma(-alpha[q], v.a[q], r.a[q]);
+            stv<VEC>(M.r + idx, r);
         }
     }
 }
 
-// x += alpha p + omega s ; r = s - omega t ; p = r + beta (p - omega v) ; dot (r,r); convergence
-template <int KC>
-__global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M) {
-    __shared__ double smem[(kThreads / 32) * kMaxDots * 32];
+// x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v) ; dot (r,r); convergence
+// (ph, sh: preconditioned p and s; equal to p and s when the preconditioner is the identity)
+template <int KC, int VEC>
+__global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const double* __restrict__ ph,
+                                                         const double* __restrict__ sh) {
+    __shared__ double smem[(kThreads / 32) * kMaxDots * 2 * 32];
     __shared__ double tot[kMaxDots * kMaxK];
     if (M.ctl->all_done) return;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     double* __restrict__ x = M.sp->state_t1;
-    const int nchunk = (K + KC - 1) / KC;
+    const int nchunk = (K + KC * VEC - 1) / (KC * VEC);
     for (int chunk = 0; chunk < nchunk; ++chunk) {
-        const int c = chunk * KC + lane;
-        double acc[1] = {0.0};
+        const int c = (chunk * KC + lane) * VEC;
+        double acc[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = 0.0;
         if (c < K) {
-            const int f = M.colflags[c];
-            const double alpha = M.sc[SC_ALPHA * K + c], omega = M.sc[SC_OMEGA * K + c], beta = M.sc[SC_BETA * K + c];
-            if (f & FL_PENDING) {
-                const double fill = (f & FL_NAN) ? __longlong_as_double(0x7ff8000000000000LL) : 0.0;
-                for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
-                    const size_t idx = (size_t)i * K + c;
-                    x[idx] = fill; M.r[idx] = 0.0; M.p[idx] = 0.0;
-                }
-            } else if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN))) {
-                for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
-                    const size_t idx = (size_t)i * K + c;
-                    const double s = M.r[idx], tv = M.tt[idx], pv = M.p[idx], vv = M.v[idx];
-                    x[idx] = fma(omega, s, fma(alpha, pv, x[idx]));
-                    const double rn = fma(-omega, tv, s);
-                    M.r[idx] = rn;
-                    M.p[idx] = fma(beta, fma(-omega, vv, pv), rn);
-                    acc[0] = fma(rn, rn, acc[0]);
-                }
+            int f[VEC]; double alpha[VEC], omega[VEC], beta[VEC];
+            bool any_pending = false, any_active = false;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                f[q] = M.colflags[c + q];
+                alpha[q] = M.sc[SC_ALPHA * K + c + q]; omega[q] = M.sc[SC_OMEGA * K + c + q]; beta[q] = M.sc[SC_BETA * K + c + q];
+                any_pending |= (f[q] & FL_PENDING) != 0;
+                any_active |= !(f[q] & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING));
             }
+            if (any_pending || any_active)
+                for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+                    const size_t idx = (size_t)i * K + c;
+                    Vd<VEC> xv = ldv<VEC>(x + idx), rv = ldv<VEC>(M.r + idx), pv = ldv<VEC>(M.p + idx);
+                    const Vd<VEC> tv = ldv<VEC>(M.tt + idx), vv = ldv<VEC>(M.v + idx);
+                    const Vd<VEC> phv = ldv<VEC>(ph + idx), shv = ldv<VEC>(sh + idx);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        if (f[q] & FL_PENDING) {
+                            xv.a[q] = (f[q] & FL_NAN) ? qnan() : 0.0; rv.a[q] = 0.0; pv.a[q] = 0.0;
+                        } else if (!(f[q] & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN))) {
+                            xv.a[q] = fma(omega[q], shv.a[q], fma(alpha[q], phv.a[q], xv.a[q]));
+                            const double rn = fma(-omega[q], tv.a[q], rv.a[q]);
+                            rv.a[q] = rn;
+                            pv.a[q] = fma(beta[q], fma(-omega[q], vv.a[q], pv.a[q]), rn);
+                            acc[q] = fma(rn, rn, acc[q]);
+                        }
+                    }
+                    stv<VEC>(x + idx, xv); stv<VEC>(M.r + idx, rv); stv<VEC>(M.p + idx, pv);
+                }
         }
-        block_dots<1, KC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
+        block_dots<1, KC, VEC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
     }
     if (!last_block_arrives(&M.ctl->ticket[3])) return;
     grid_totals<1>(M.partials, tot, K);
@@ -513,34 +619,43 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M) {
 // mass flux across every edge  (reference transport.py:406-429) + running boundary sums
 // (postproc_util.py:100-143).  c[t+1] of a ghost cell = its BC value, NaN when unset.
 // ---------------------------------------------------------------------------------------------
-template <int KC>
+template <int KC, int VEC>
 __global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
     const StepParams& sp = *M.sp;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const double dt = sp.dt;
     const double* __restrict__ x = sp.state_t1;
     const size_t EK = (size_t)M.E * K, GK = (size_t)M.E_g * K;
-    for (int c = lane; c < K; c += KC)
+    for (int c = lane * VEC; c < K; c += KC * VEC)
         for (int e = blockIdx.x * GPB + group; e < M.E; e += gridDim.x * GPB) {
             const int P = M.f1p[e], N = M.f2p[e];
             const double a = (double)sp.adv_t[e], d = sp.cdiff_t[e];
-            const double cP = x[(size_t)P * K + c];
-            double cN;
-            if (N < M.n) cN = x[(size_t)N * K + c];
+            const Vd<VEC> cP = ldv<VEC>(x + (size_t)P * K + c);
+            Vd<VEC> cN;
+            if (N < M.n) cN = ldv<VEC>(x + (size_t)N * K + c);
             else {
-                cN = sp.bc_t1[(size_t)(N - M.n) * K + c];
-                if (cN == 0.0) cN = __longlong_as_double(0x7ff8000000000000LL);
+                cN = ldv<VEC>(sp.bc_t1 + (size_t)(N - M.n) * K + c);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) if (cN.a[q] == 0.0) cN.a[q] = qnan();
             }
-            const double fa = __dmul_rn((a < 0.0 ? __dmul_rn(a, cN) : __dmul_rn(a, cP)), dt);
-            const double fd = __dmul_rn(__dmul_rn(d, cN - cP), dt);
-            const double ft = fa + fd;
+            Vd<VEC> fa, fd, ft;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) {
+                fa.a[q] = __dmul_rn((a < 0.0 ? __dmul_rn(a, cN.a[q]) : __dmul_rn(a, cP.a[q])), dt);
+                fd.a[q] = __dmul_rn(__dmul_rn(d, cN.a[q] - cP.a[q]), dt);
+                ft.a[q] = fa.a[q] + fd.a[q];
+            }
             const size_t o = (size_t)e * K + c;
-            M.flux[o] = fa; M.flux[EK + o] = fd; M.flux[2 * EK + o] = ft;
+            stv<VEC>(M.flux + o, fa); stv<VEC>(M.flux + EK + o, fd); stv<VEC>(M.flux + 2 * EK + o, ft);
             if (e >= M.E_int) {
                 const size_t g = (size_t)(e - M.E_int) * K + c;
-                M.bsum[g] += ft;
-                M.bsum[GK + g] += (ft <= 0.0) ? ft : ft * 0.0;
-                M.bsum[2 * GK + g] += (ft >= 0.0) ? ft : ft * 0.0;
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    const double f = ft.a[q];
+                    M.bsum[g + q] += f;
+                    M.bsum[GK + g + q] += (f <= 0.0) ? f : f * 0.0;
+                    M.bsum[2 * GK + g + q] += (f >= 0.0) ? f : f * 0.0;
+                }
             }
         }
 }

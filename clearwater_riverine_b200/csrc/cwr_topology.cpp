@@ -180,6 +180,19 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         }
     }
 
+    // ---- row-major ELL copy of the pattern (what the kernels read) ------------------------------------
+    T.W = std::max(4, (T.max_row_len + 3) / 4 * 4);
+    T.ell_col.assign((size_t)n * T.W, 0);
+    T.ell_code.assign((size_t)n * T.W, -1);
+    for (int i = 0; i < n; ++i) {
+        const int32_t s = T.rowptr[i], e = T.rowptr[i + 1];
+        for (int w = 0; w < T.W; ++w) {
+            const size_t o = (size_t)i * T.W + w;
+            if (s + w < e) { T.ell_col[o] = T.col[s + w]; T.ell_code[o] = T.slot_edge[s + w]; }
+            else T.ell_col[o] = i;
+        }
+    }
+
     // ---- boundary cells ----------------------------------------------------------------------------------
     T.bcell.clear(); T.bptr.clear(); T.bedge.resize(T.E_g);
     for (int i = 0; i < T.E_g; ++i) {

@@ -39,6 +39,9 @@ struct Topology {
     std::vector<int32_t> bcell;       // (nb)   device ids of cells that own ghost edges
     std::vector<int32_t> bptr;        // (nb+1) ranges into bedge
     std::vector<int32_t> bedge;       // (E_g)  device edge ids, ascending original id within a cell
+    int W = 4;                        // ELL width: max row length rounded up to a multiple of 4
+    std::vector<int32_t> ell_col;     // (n*W) row-major; padding points at the row itself
+    std::vector<int32_t> ell_code;    // (n*W) slot_edge code, -1 for padding
     int max_row_len = 0;
     int64_t bandwidth = 0;            // max |row - col| after reordering (diagnostic)
 };

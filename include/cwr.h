@@ -45,8 +45,10 @@ typedef struct {
                                reference does, transport.py:267-273), 0 = skip */
     int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = single-CTA persistent solve (small meshes) */
     int use_graph;          /* 1 = device-side iteration loop in a CUDA graph (default), 0 = host-polled loop */
-    int check_every;        /* host-polled loop: iterations launched per convergence poll; default 4 */
-    int reserved[7];
+    int check_every;        /* host-polled loop: iterations launched per convergence poll; default 1 */
+    int precond_steps;      /* m of the m-step Jacobi polynomial preconditioner (I + N + ... + N^(m-1)) D^-1,
+                               N = I - D^-1 A; 1 = plain Jacobi (diagonal) preconditioning; default 4 */
+    int reserved[6];
 } cwr_options;
 
 typedef struct {
@@ -140,6 +142,7 @@ enum {
     CWR_FAM_SPMM_T,         /* t = A s  with the four dots */
     CWR_FAM_UPDATE_XRP,     /* x, r, p updates with (r, r) */
     CWR_FAM_MASS_FLUX,
+    CWR_FAM_PRECOND,        /* Jacobi steps of the polynomial preconditioner: out = u + N z */
     CWR_PROFILE_FAMILIES
 };
 int cwr_profile(cwr_handle* h, int enable, double* ms, int64_t* counts);
