@@ -165,7 +165,7 @@ int cwr_default_options(cwr_options* o) {
     o->solver_path = 0;
     o->use_graph = 1;
     o->check_every = 1;
-    o->precond_steps = 4;
+    o->precond_steps = 8;
     return CWR_OK;
 }
 
@@ -195,7 +195,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (!(h->opt.rtol > 0)) h->opt.rtol = 1e-13;
     if (h->opt.max_iter <= 0) h->opt.max_iter = 500;
     if (h->opt.check_every <= 0) h->opt.check_every = 1;
-    if (h->opt.precond_steps <= 0) h->opt.precond_steps = 4;
+    if (h->opt.precond_steps <= 0) h->opt.precond_steps = 8;
     h->m_steps = std::min(h->opt.precond_steps, 64);
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));

@@ -14,6 +14,9 @@ namespace cwr {
 constexpr int kThreads = 256;
 constexpr int kMaxK = 128;      // constituents per handle
 constexpr int kMaxDots = 4;
+#ifndef CWR_SPMM_MIN_BLOCKS
+#define CWR_SPMM_MIN_BLOCKS 4   // resident CTAs per SM the SpMM kernels are compiled for (register cap 64)
+#endif
 
 // Per-step pointers/values; written by k_set_step and read by every kernel of the step.
 struct StepParams {
@@ -399,7 +402,7 @@ __device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
 enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_JAC = 3, MODE_PLAIN = 4 };
 
 template <int KC, int VEC, int MODE>
-__global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* __restrict__ zin,
+__global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceModel M, const double* __restrict__ zin,
                                                    const double* __restrict__ uin, double* __restrict__ out) {
     constexpr int ND = MODE == MODE_INIT ? 2 : MODE == MODE_AV ? 1 : MODE == MODE_AT ? 4 : 1;
     constexpr bool HAS_DOTS = MODE == MODE_INIT || MODE == MODE_AV || MODE == MODE_AT;
@@ -418,37 +421,66 @@ __global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* 
         double acc[ND * VEC];
 #pragma unroll
         for (int d = 0; d < ND * VEC; ++d) acc[d] = 0.0;
-        if (active)
-            for (int i = blockIdx.x * GPB + group; i < n; i += gridDim.x * GPB) {
+        if (active) {
+            // Software pipeline: the next row's column indices and values (the loads the gathers depend
+            // on) are fetched while this row's gathers are in flight, so a row costs one memory latency,
+            // not two.
+            const int stride = gridDim.x * GPB;
+            int i = blockIdx.x * GPB + group;
+            int4 c4n = make_int4(0, 0, 0, 0);
+            double2 v01n = make_double2(0.0, 0.0), v23n = v01n;
+            if (i < n) {
+                c4n = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
+                v01n = *reinterpret_cast<const double2*>(eval + (size_t)i * W);
+                v23n = *reinterpret_cast<const double2*>(eval + (size_t)i * W + 2);
+            }
+            for (; i < n; i += stride) {
                 const size_t idx = (size_t)i * K + c;
+                const int4 c4 = c4n;
+                const double2 v01 = v01n, v23 = v23n;
+                const Vd<VEC> x0 = ldv<VEC>(zin + (size_t)c4.x * K + c);
+                const Vd<VEC> x1 = ldv<VEC>(zin + (size_t)c4.y * K + c);
+                const Vd<VEC> x2 = ldv<VEC>(zin + (size_t)c4.z * K + c);
+                const Vd<VEC> x3 = ldv<VEC>(zin + (size_t)c4.w * K + c);
+                // the row's own operands are issued now as well, so nothing waits behind the gathers
+                const Vd<VEC> own = ldv<VEC>((MODE == MODE_JAC ? uin : zin) + idx);
+                Vd<VEC> aux1 = own, aux2 = own;
+                if (MODE == MODE_INIT) aux1 = ldv<VEC>(M.b + idx);
+                if (MODE == MODE_AV || MODE == MODE_AT) aux1 = ldv<VEC>(M.rhat + idx);
+                if (MODE == MODE_AT) aux2 = ldv<VEC>(M.r + idx);          // s lives in the r buffer
+                const int inext = i + stride;
+                if (inext < n) {
+                    c4n = *reinterpret_cast<const int4*>(ecol + (size_t)inext * W);
+                    v01n = *reinterpret_cast<const double2*>(eval + (size_t)inext * W);
+                    v23n = *reinterpret_cast<const double2*>(eval + (size_t)inext * W + 2);
+                }
                 Vd<VEC> s;
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) s.a[q] = 0.0;
-                for (int w = 0; w < W; w += 4) {
-                    const int4 c4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
-                    const double2 v01 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w);
-                    const double2 v23 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w + 2);
-                    const Vd<VEC> x0 = ldv<VEC>(zin + (size_t)c4.x * K + c);
-                    const Vd<VEC> x1 = ldv<VEC>(zin + (size_t)c4.y * K + c);
-                    const Vd<VEC> x2 = ldv<VEC>(zin + (size_t)c4.z * K + c);
-                    const Vd<VEC> x3 = ldv<VEC>(zin + (size_t)c4.w * K + c);
+                for (int q = 0; q < VEC; ++q)
+                    s.a[q] = fma(v23.y, x3.a[q], fma(v23.x, x2.a[q], fma(v01.y, x1.a[q], v01.x * x0.a[q])));
+                for (int w = 4; w < W; w += 4) {      // rows wider than 4 (not pipelined)
+                    const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+                    const double2 w01 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w);
+                    const double2 w23 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w + 2);
+                    const Vd<VEC> y0 = ldv<VEC>(zin + (size_t)d4.x * K + c);
+                    const Vd<VEC> y1 = ldv<VEC>(zin + (size_t)d4.y * K + c);
+                    const Vd<VEC> y2 = ldv<VEC>(zin + (size_t)d4.z * K + c);
+                    const Vd<VEC> y3 = ldv<VEC>(zin + (size_t)d4.w * K + c);
 #pragma unroll
                     for (int q = 0; q < VEC; ++q)
-                        s.a[q] = fma(v23.y, x3.a[q], fma(v23.x, x2.a[q], fma(v01.y, x1.a[q], fma(v01.x, x0.a[q], s.a[q]))));
+                        s.a[q] = fma(w23.y, y3.a[q], fma(w23.x, y2.a[q], fma(w01.y, y1.a[q], fma(w01.x, y0.a[q], s.a[q]))));
                 }
                 if (MODE == MODE_JAC) {
-                    const Vd<VEC> u = ldv<VEC>(uin + idx);
                     Vd<VEC> o;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) o.a[q] = u.a[q] - s.a[q];
+                    for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - s.a[q];
                     stv<VEC>(out + idx, o);
                 } else {
-                    const Vd<VEC> zi = ldv<VEC>(zin + idx);
                     Vd<VEC> y;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) y.a[q] = zi.a[q] + s.a[q];
+                    for (int q = 0; q < VEC; ++q) y.a[q] = own.a[q] + s.a[q];
                     if (MODE == MODE_INIT) {
-                        const Vd<VEC> bi = ldv<VEC>(M.b + idx);
+                        const Vd<VEC> bi = aux1;
                         Vd<VEC> r;
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) {
@@ -458,13 +490,12 @@ __global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* 
                         }
                         stv<VEC>(M.r + idx, r); stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r);
                     } else if (MODE == MODE_AV) {
-                        const Vd<VEC> rh = ldv<VEC>(M.rhat + idx);
+                        const Vd<VEC> rh = aux1;
                         stv<VEC>(M.v + idx, y);
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) acc[q] = fma(rh.a[q], y.a[q], acc[q]);
                     } else if (MODE == MODE_AT) {
-                        const Vd<VEC> rh = ldv<VEC>(M.rhat + idx);
-                        const Vd<VEC> sv = ldv<VEC>(M.r + idx);          // s lives in the r buffer
+                        const Vd<VEC> rh = aux1, sv = aux2;
                         stv<VEC>(M.tt + idx, y);
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) {
@@ -478,6 +509,7 @@ __global__ void __launch_bounds__(kThreads) k_spmm(DeviceModel M, const double* 
                     }
                 }
             }
+        }
         if (HAS_DOTS) block_dots<ND, KC, VEC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
     }
     if (!HAS_DOTS) return;

@@ -47,7 +47,7 @@ typedef struct {
     int use_graph;          /* 1 = device-side iteration loop in a CUDA graph (default), 0 = host-polled loop */
     int check_every;        /* host-polled loop: iterations launched per convergence poll; default 1 */
     int precond_steps;      /* m of the m-step Jacobi polynomial preconditioner (I + N + ... + N^(m-1)) D^-1,
-                               N = I - D^-1 A; 1 = plain Jacobi (diagonal) preconditioning; default 4 */
+                               N = I - D^-1 A; 1 = plain Jacobi (diagonal) preconditioning; default 8 */
     int reserved[6];
 } cwr_options;
 
