@@ -269,7 +269,7 @@ class TransportBackend:
         self._check(self._lib.cwr_stream(self._h, C.byref(s)))
         return s.value or 0
 
-    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux", "precond")
+    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux", "precond", "solve_small")
 
     def profile(self, enable: int = -1):
         """enable = 1/0 switches per-kernel-family event timing on/off; returns {family: (ms, launches)}."""

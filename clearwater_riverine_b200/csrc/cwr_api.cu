@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "cwr_kernels.cuh"
+#include "cwr_small.cuh"
 #include "cwr_topology.h"
 
 using namespace cwr;
@@ -29,6 +30,9 @@ struct cwr_handle {
     int KC = 1, VEC = 1;             // lanes per row, columns per lane
     int m_steps = 1;                 // Jacobi steps of the polynomial preconditioner (1 = none)
     int last_iters = 0;              // iterations of the previous solve (launch-ahead prediction)
+    bool small_path = false;         // one-CTA-per-column in-kernel solve (small meshes)
+    bool in_run = false;             // inside cwr_run: the small path does not synchronise per step
+    SmallStats* d_stats = nullptr; SmallStats* h_stats = nullptr;
     int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0;
     DeviceModel M{};
     // device buffers
@@ -179,6 +183,7 @@ void cwr_destroy(cwr_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_stage) cudaFree(h->d_stage);
     if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->h_stats) cudaFreeHost(h->h_stats);
     if (h->h_sc) cudaFreeHost(h->h_sc);
     if (h->h_flags) cudaFreeHost(h->h_flags);
     if (h->h_iters) cudaFreeHost(h->h_iters);
@@ -263,7 +268,15 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     M.ic = ic;
     CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
     CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
-    if (h->m_steps > 1) { CK(dalloc(h, &M.ph, nK)); CK(dalloc(h, &M.sh, nK)); CK(dalloc(h, &M.tmp, nK)); }
+    // solver path: small meshes run the whole solve of a column inside one CTA (cwr_small.cuh)
+    h->small_path = h->opt.solver_path == 2 || (h->opt.solver_path == 0 && n <= 32768);
+    if (h->m_steps > 1 || h->small_path) { CK(dalloc(h, &M.ph, nK)); CK(dalloc(h, &M.sh, nK)); CK(dalloc(h, &M.tmp, nK)); }
+    if (h->small_path) {
+        CK(dalloc(h, &M.xc, nK));
+        CK(dalloc(h, &h->d_stats, 1));
+        CK(cudaMemsetAsync(h->d_stats, 0, sizeof(SmallStats), h->stream));
+        CK(cudaMallocHost((void**)&h->h_stats, sizeof(SmallStats)));
+    }
     CK(dalloc(h, &M.partials, (size_t)h->max_grid * kMaxDots * K));
     CK(dalloc(h, &M.sc, (size_t)SC_ROWS * K));
     CK(dalloc(h, &M.colflags, (size_t)K)); CK(dalloc(h, &M.coliters, (size_t)K));
@@ -596,6 +609,39 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
     return status;
 }
 
+// Small-mesh path: the whole solve of every column is one launch; convergence is decided on the
+// device.  Inside cwr_run nothing is read back per step (statistics accumulate in d_stats).
+static int read_small_stats(cwr_handle* h, cwr_step_info* info) {
+    CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(SmallStats), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_ctl, h->M.ctl, sizeof(SolverCtl), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const SmallStats& s = *h->h_stats;
+    double rel2;
+    std::memcpy(&rel2, &s.max_relres2_bits, sizeof rel2);
+    int status = CWR_OK;
+    if (s.flags_or & FL_NAN) status = CWR_ENAN;
+    else if (s.flags_or & FL_BREAKDOWN) status = CWR_EBREAKDOWN;
+    else if (s.not_converged > 0) status = CWR_ENOTCONVERGED;
+    if (h->h_ctl->singular) status = CWR_ESINGULAR;
+    if (info) { info->iterations = s.max_iterations; info->restarts = s.restarts; info->status = status; info->max_relres = std::sqrt(rel2); }
+    return status;
+}
+
+static int solve_small(cwr_handle* h, cwr_step_info* info) {
+    if (!h->in_run) CK(cudaMemsetAsync(h->d_stats, 0, sizeof(SmallStats), h->stream));
+    mark(h, CWR_FAM_SOLVE_SMALL);
+    k_solve_small<<<h->K, kSmallThreads, 0, h->stream>>>(h->M, h->m_steps, h->d_stats);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    if (h->in_run) {
+        if (info) { info->iterations = 0; info->restarts = 0; info->status = CWR_OK; info->max_relres = 0.0; }
+        return CWR_OK;
+    }
+    int status = read_small_stats(h, info);
+    if (status != CWR_ECUDA) h->iterations += h->h_stats->max_iterations;
+    return status;
+}
+
 static int find_slot(cwr_handle* h, int t) {
     const int s = t % h->C;
     return h->slot_time[s] == t ? s : -1;
@@ -655,7 +701,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     }
     h->lhs_step = t;
     cwr_step_info local;
-    int status = solve(h, &local);
+    int status = h->small_path ? solve_small(h, &local) : solve(h, &local);
     if (status == CWR_ECUDA) return status;
     // transport.py:258-264: non-zero input_array[t+1] entries are re-imposed on the stored row -- ghost cells
     // are handled where they are read (k_mass_flux, k_extract_state); real cells (rare) are patched here.
@@ -691,6 +737,27 @@ int cwr_run(cwr_handle* h, int t_begin, int t_end, cwr_step_info* worst) {
     if (!h) return CWR_EINVAL;
     cwr_step_info w{}; w.status = CWR_OK;
     int rc_final = CWR_OK;
+    if (h->small_path) {
+        // every step is a fixed sequence of launches with the convergence loop on the device: queue all
+        // of them, synchronise once, report the worst solver statistics over the run
+        CK(cudaSetDevice(h->device));
+        CK(cudaMemsetAsync(h->d_stats, 0, sizeof(SmallStats), h->stream));
+        h->in_run = true;
+        int rc = CWR_OK;
+        for (int t = t_begin; t < t_end && rc == CWR_OK; ++t) {
+            cwr_step_info i{};
+            rc = cwr_step(h, t, &i);
+            w.n_launches += i.n_launches;
+        }
+        h->in_run = false;
+        if (rc != CWR_OK) return rc;
+        const int n_launches = w.n_launches;
+        rc = read_small_stats(h, &w);
+        w.n_launches = n_launches;
+        if (rc != CWR_ECUDA) h->iterations += (int64_t)h->h_stats->max_iterations;
+        if (worst) *worst = w;
+        return rc;
+    }
     for (int t = t_begin; t < t_end; ++t) {
         cwr_step_info i{};
         int rc = cwr_step(h, t, &i);

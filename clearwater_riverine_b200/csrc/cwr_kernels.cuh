@@ -58,7 +58,7 @@ struct DeviceModel {
     double* diag;       // (n)   D
     double* gdiag;      // (n)   ghost-edge diagonal terms (boundary cells only, 0 elsewhere)
     const double* ic;   // (n,K) input_array[0][0:n]
-    double *b, *r, *rhat, *p, *v, *tt, *ph, *sh, *tmp;   // (n,K) work vectors (b is the row-scaled RHS)
+    double *b, *r, *rhat, *p, *v, *tt, *ph, *sh, *tmp, *xc;   // (n,K) work vectors (b is the row-scaled RHS)
     double* partials;   // (grid, kMaxDots, K)
     double* sc;         // (SC_ROWS, K) per-column scalars
     int* colflags;      // (K)

@@ -1,0 +1,183 @@
+// Small-mesh solver path: one CTA per constituent / scenario runs the WHOLE preconditioned
+// BiCGSTAB solve of its column inside one kernel launch.
+//
+// Meshes like the Ohio River model (2,943 cells) are launch-latency bound: a solve is ~100 SpMVs of
+// a 140 KB matrix, and a kernel launch costs more than the SpMV it carries.  Here the iteration loop,
+// its dot products (block-level, __syncthreads-based, deterministic) and the convergence test all
+// live in the kernel; the matrix streams from L2, the work vectors are column-contiguous scratch that
+// stays in L1/L2.  Columns are independent (they only share the matrix), so an ensemble of scenarios
+// is simply gridDim.x = K CTAs with no grid-wide synchronisation, and every column stops as soon as
+// it has converged.  Same arithmetic as the multi-CTA path (same preconditioner, same recurrences).
+#pragma once
+#include "cwr_kernels.cuh"
+
+namespace cwr {
+
+constexpr int kSmallThreads = 1024;
+
+struct SmallStats {
+    int max_iterations;
+    int flags_or;
+    int restarts;
+    int not_converged;
+    unsigned long long max_relres2_bits;   // max over columns/steps of ||r||^2/||b||^2 (bit pattern of a double >= 0)
+};
+
+template <int ND>
+__device__ __forceinline__ void cta_sum(double (&v)[ND], double* smem /* [ND][32] */) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) v[d] += __shfl_xor_sync(0xffffffffu, v[d], off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();                       // smem free from the previous use
+    if (lane == 0)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) smem[d * 32 + warp] = v[d];
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double s = lane < (int)(blockDim.x >> 5) ? smem[d * 32 + lane] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) smem[d * 32] = s;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < ND; ++d) v[d] = smem[d * 32];
+}
+
+// (L z)_i for a column-contiguous z
+__device__ __forceinline__ double ell_row_dot(const DeviceModel& M, int i, const double* z) {
+    double s = 0.0;
+    const int W = M.W;
+    for (int w = 0; w < W; w += 4) {
+        const int4 c4 = __ldg(reinterpret_cast<const int4*>(M.ell_col + (size_t)i * W + w));
+        const double2 v01 = *reinterpret_cast<const double2*>(M.val + (size_t)i * W + w);
+        const double2 v23 = *reinterpret_cast<const double2*>(M.val + (size_t)i * W + w + 2);
+        s = fma(v23.y, z[c4.w], fma(v23.x, z[c4.z], fma(v01.y, z[c4.y], fma(v01.x, z[c4.x], s))));
+    }
+    return s;
+}
+
+// z = (I + N + ... + N^(m-1)) u  with N = -L; returns the buffer holding z
+__device__ __forceinline__ const double* small_precondition(const DeviceModel& M, int n, int m_steps, const double* u,
+                                                            double* dst, double* other) {
+    const int J = m_steps - 1;
+    const double* z = u;
+    for (int j = 1; j <= J; ++j) {
+        double* out = ((J - j) % 2 == 0) ? dst : other;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = u[i] - ell_row_dot(M, i, z);
+        __syncthreads();
+        z = out;
+    }
+    return z;
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M, int m_steps, SmallStats* stats) {
+    __shared__ double red[4 * 32];
+    const int k = blockIdx.x, n = M.n, K = M.K;
+    double* __restrict__ x = M.sp->state_t1 + k;          // stride K
+    const double* __restrict__ b = M.b + k;               // stride K
+    const size_t col0 = (size_t)k * n;
+    double *r = M.r + col0, *rhat = M.rhat + col0, *p = M.p + col0, *v = M.v + col0, *t = M.tt + col0;
+    double *phb = M.ph + col0, *shb = M.sh + col0, *tmp = M.tmp + col0, *xc = M.xc + col0;
+    int flags = 0, iters = 0, restarts = 0;
+    double bb = 0.0, rr = 0.0;
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xc[i] = x[(size_t)i * K];   // contiguous copy of the iterate
+    __syncthreads();
+
+    for (;;) {
+        // r = b - A x ; rhat = p = r
+        double d2[2] = {0.0, 0.0};
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double bi = b[(size_t)i * K];
+            const double ri = bi - (xc[i] + ell_row_dot(M, i, xc));
+            r[i] = ri; rhat[i] = ri; p[i] = ri;
+            d2[0] = fma(ri, ri, d2[0]); d2[1] = fma(bi, bi, d2[1]);
+        }
+        cta_sum<2>(d2, red);
+        rr = d2[0]; bb = d2[1];
+        if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) {
+            flags |= FL_NAN;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) xc[i] = qnan();
+            break;
+        }
+        if (bb == 0.0 && rr != 0.0) {                    // b == 0  =>  x = 0
+            flags |= FL_ZERO_RHS | FL_CONVERGED;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) xc[i] = 0.0;
+            rr = 0.0;
+            break;
+        }
+        if (rr <= M.tol2 * bb) { flags |= FL_CONVERGED; break; }
+        double rho = rr;
+        bool breakdown = false;
+        while (iters < M.max_iter) {
+            const double* ph = small_precondition(M, n, m_steps, p, phb, tmp);
+            double d1[1] = {0.0};
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const double y = ph[i] + ell_row_dot(M, i, ph);
+                v[i] = y;
+                d1[0] = fma(rhat[i], y, d1[0]);
+            }
+            cta_sum<1>(d1, red);
+            if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
+            const double alpha = rho / d1[0];
+            for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] = fma(-alpha, v[i], r[i]);     // s
+            __syncthreads();
+            const double* sh = small_precondition(M, n, m_steps, r, shb, tmp);
+            double d4[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const double y = sh[i] + ell_row_dot(M, i, sh);
+                t[i] = y;
+                const double si = r[i], rh = rhat[i];
+                d4[0] = fma(y, si, d4[0]); d4[1] = fma(y, y, d4[1]); d4[2] = fma(rh, y, d4[2]); d4[3] = fma(rh, si, d4[3]);
+            }
+            cta_sum<4>(d4, red);
+            const double omega = d4[1] > 0.0 ? d4[0] / d4[1] : 0.0;
+            const double rho_new = d4[3] - omega * d4[2];
+            double beta = 0.0;
+            bool stagnated = false;
+            if (omega != 0.0 && rho != 0.0) beta = (rho_new / rho) * (alpha / omega);
+            else if (d4[1] > 0.0) stagnated = true;
+            if (!(beta == beta) || isinf(beta)) { beta = 0.0; stagnated = true; }
+            double dr[1] = {0.0};
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const double si = r[i], pv = p[i];
+                xc[i] = fma(omega, sh[i], fma(alpha, ph[i], xc[i]));
+                const double rn = fma(-omega, t[i], si);
+                r[i] = rn;
+                p[i] = fma(beta, fma(-omega, v[i], pv), rn);
+                dr[0] = fma(rn, rn, dr[0]);
+            }
+            cta_sum<1>(dr, red);
+            rr = dr[0];
+            ++iters;
+            rho = rho_new;
+            if (!(rr == rr) || isinf(rr)) { flags |= FL_NAN; break; }
+            if (rr <= M.tol2 * bb) { flags |= FL_CONVERGED; break; }
+            if (stagnated) { breakdown = true; break; }
+        }
+        if ((flags & (FL_CONVERGED | FL_NAN)) || iters >= M.max_iter) break;
+        if (breakdown && restarts < 3) { ++restarts; continue; }     // new shadow residual from the current iterate
+        if (breakdown) flags |= FL_BREAKDOWN;
+        break;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) x[(size_t)i * K] = xc[i];
+    if (threadIdx.x == 0) {
+        M.colflags[k] = flags; M.coliters[k] = iters;
+        M.sc[SC_BNORM2 * K + k] = bb; M.sc[SC_RNORM2 * K + k] = rr;
+        atomicMax(&stats->max_iterations, iters);
+        atomicOr(&stats->flags_or, flags & (FL_BREAKDOWN | FL_NAN));
+        atomicMax(&stats->restarts, restarts);
+        if (!(flags & FL_CONVERGED)) atomicAdd(&stats->not_converged, 1);
+        const double rel2 = bb > 0.0 ? rr / bb : (rr > 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : 0.0);
+        if (rel2 == rel2) atomicMax(&stats->max_relres2_bits, (unsigned long long)__double_as_longlong(rel2));
+    }
+}
+
+}  // namespace cwr

@@ -143,6 +143,7 @@ enum {
     CWR_FAM_UPDATE_XRP,     /* x, r, p updates with (r, r) */
     CWR_FAM_MASS_FLUX,
     CWR_FAM_PRECOND,        /* Jacobi steps of the polynomial preconditioner: out = u + N z */
+    CWR_FAM_SOLVE_SMALL,    /* small meshes: the whole solve of every column, one CTA each (k_solve_small) */
     CWR_PROFILE_FAMILIES
 };
 int cwr_profile(cwr_handle* h, int enable, double* ms, int64_t* counts);

@@ -50,13 +50,14 @@ def make_backend(mesh, inputs, **opt):
 
 
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-@pytest.mark.parametrize("reorder", [1, 0])
-def test_golden_free_running(case, reorder):
-    """Whole trajectory against what the unmodified reference produced (tests/golden)."""
+@pytest.mark.parametrize("reorder,solver_path", [(1, 1), (0, 1), (1, 2)])
+def test_golden_free_running(case, reorder, solver_path):
+    """Whole trajectory against what the unmodified reference produced (tests/golden), through both
+    solver paths: 1 = multi-CTA kernels + host-driven iteration, 2 = one CTA per constituent."""
     g = load_golden(case)
     mesh = golden_mesh(g)
     names = [str(c) for c in g["constituents"]]
-    be = make_backend(mesh, [g[f"input_{c}"] for c in names], reorder=reorder)
+    be = make_backend(mesh, [g[f"input_{c}"] for c in names], reorder=reorder, solver_path=solver_path)
     overrides = golden_overrides(g)
     snaps = set(int(s) for s in g["snapshot_steps"])
     n = mesh.n
@@ -159,14 +160,38 @@ def run_against_oracle(mesh, inputs, steps, rtol=RTOL, **opt):
     return worst
 
 
+@pytest.mark.parametrize("solver_path", [1, 2])
 @pytest.mark.parametrize("K", [1, 2, 3, 5, 16, 33])
-def test_synthetic_mesh_all_column_widths(K):
+def test_synthetic_mesh_all_column_widths(K, solver_path):
     """Quad-dominant shuffled mesh with dry cells; every lanes-per-row instantiation of the kernels."""
     _, mesh, inputs = synthetic_case(40, 25, 8, K, seed=K, dry_fraction=0.02)
-    run_against_oracle(mesh, inputs, 7)
+    run_against_oracle(mesh, inputs, 7, solver_path=solver_path)
 
 
-@pytest.mark.parametrize("opts", [dict(reorder=0), dict(keep_history=0), dict(mass_flux=1, check_every=1),
+@pytest.mark.parametrize("m", [1, 2, 5])
+def test_preconditioner_depths(m):
+    """m-step Jacobi polynomial preconditioner: m = 1 is plain diagonal (Jacobi) preconditioning."""
+    _, mesh, inputs = synthetic_case(40, 25, 6, 4, seed=17, dry_fraction=0.02)
+    for path in (1, 2):
+        run_against_oracle(mesh, inputs, 5, solver_path=path, precond_steps=m)
+
+
+def test_run_many_steps_without_host_round_trips():
+    """cwr_run on the small path queues every step's launches and synchronises once."""
+    _, mesh, inputs = synthetic_case(30, 20, 12, 3, seed=19, dry_fraction=0.02)
+    be = make_backend(mesh, list(inputs), solver_path=2)
+    info = be.run(0, 11)
+    assert info.status == 0 and 0 < info.max_relres <= 1e-13 and info.iterations > 0
+    oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(3)})
+    for _ in range(11):
+        oracle.update()
+    for k in range(3):
+        for t in (1, 6, 11):
+            close(be.get_state(k, t), oracle.constituent_dict[f"c{k}"].concentration[t], RTOL, f"run k{k} t{t}")
+    be.close()
+
+
+@pytest.mark.parametrize("opts", [dict(reorder=0), dict(keep_history=0), dict(solver_path=1, check_every=3),
                                   dict(hydro_capacity=2)])
 def test_option_variants(opts):
     plan, mesh, inputs = synthetic_case(30, 30, 6, 4, seed=5, dry_fraction=0.01)
