@@ -180,7 +180,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from clearwater_riverine_b200 import ClearwaterRiverine, TransportBackend, synthetic
+    from clearwater_riverine_b200 import ClearwaterRiverine, TransportBackend, ensemble, synthetic
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -190,12 +190,18 @@ def main():
     W, K_steps, P = args.warmup, args.steps, args.profile_steps
     T = W + K_steps + P + 1
     plan, K = workload_plan(args.workload, T, seed=2, scale=args.scale)
-    if args.workload == "ens64":
-        K = max(1, 64 // world)              # 64 scenarios sharded over the ranks (strong in scenarios)
     n, E, F = plan.n_real, plan.n_edge, plan.n_face
-    # independent units per rank: different ICs / BC series per rank (seeded by rank)
-    bc_scale = np.exp(np.random.default_rng(100 + rank).normal(0.0, 0.5, size=K)) if args.workload == "ens64" else None
-    inputs = synthetic.make_inputs(plan, K, seed=2 + 1000 * rank, bc_scale=bc_scale)
+    n_units = K * world                      # weak scaling: every rank brings its own K constituents
+    if args.workload == "ens64":             # 64 scenarios sharded over the ranks (total work fixed)
+        n_units = 64
+        mine = ensemble.shard_units(n_units, world, rank)
+        K = len(mine)
+        scales = np.exp(np.random.default_rng(100).normal(0.0, 0.5, size=n_units))      # same table on every rank
+        base = synthetic.make_inputs(plan, 1, seed=2)[0]
+        inputs = np.stack(ensemble.scenario_inputs(base, n, scales[mine.start:mine.stop]))
+    else:                                    # independent constituents: own ICs / BC series per rank
+        mine = range(rank * K, (rank + 1) * K)
+        inputs = synthetic.make_inputs(plan, K, seed=2 + 1000 * rank)
     dt = np.append(np.diff(plan.time_seconds), np.nan)
 
     opts = {}
@@ -223,23 +229,16 @@ def main():
     l0, i0 = be.counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    worst_status, worst_relres = 0, 0.0
-    for t in range(W, W + K_steps):
-        info = be.step(t)
-        iters.append(info.iterations)
-        worst_status = info.status if info.status != 0 else worst_status
-        worst_relres = max(worst_relres, info.max_relres)
+    info = be.run(W, W + K_steps)            # cwr_run: K_steps updates, no host round trip on the small-mesh path
+    worst_status, worst_relres = info.status, info.max_relres
     e1.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
     l1, i1 = be.counters()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_total.item())
-    value = n * K * world * K_steps / (ms_total / 1e3)
+    ms_total = ensemble.max_over_ranks(e0.elapsed_time(e1), device="cuda")
+    value = n * n_units * K_steps / (ms_total / 1e3)
 
     # ---- per-kernel device time (CUDA events between launches on the handle's stream) -> roofline -------------
     be.profile(1)
@@ -272,10 +271,12 @@ def main():
                     "families_ms_per_step": {k: v[0] / P for k, v in prof.items()}}
 
     # ---- mass-balance scalars: the only collective (NCCL all-reduce over the ranks' units) ------------------------
-    mt = [be.mass_totals(k, 0, W + K_steps) for k in range(K)]
-    mass = torch.tensor([sum(m.mass_start for m in mt), sum(m.mass_end for m in mt)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(mass, op=dist.ReduceOp.SUM)
+    local_rows = {}
+    for k, unit in enumerate(mine):
+        m = be.mass_totals(k, 0, W + K_steps)
+        _, f_in, f_out = be.flux_sums(k)
+        local_rows[unit] = (m.mass_start, m.mass_end, float(np.nansum(f_in)), float(np.nansum(f_out)))
+    mass_table = ensemble.reduce_mass_balance(local_rows, n_units, device="cuda")
     be.close()
 
     # ---- end to end through the reference-facing API with host buffers -------------------------------------------
@@ -297,7 +298,7 @@ def main():
         el = torch.tensor([time.perf_counter() - t_0], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(el, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * K * world * K_steps / float(el.item()), "unit": UNIT,
+        e2e = {"value": n * n_units * K_steps / float(el.item()), "unit": UNIT,
                "h2d_bytes_per_step": 4 * E + 4 * E + 4 * F + 8, "d2h_bytes_per_step": 8 * n * K,
                "ms_per_step": float(el.item()) / K_steps * 1e3,
                "api": "ClearwaterRiverine.update() (stream_hydro: slice t+1 uploaded from pinned host arrays each step; "
@@ -323,13 +324,17 @@ def main():
                        "precond_steps": be.options.precond_steps,
                        "l2": "per-step working set (7 vectors x n x K x 8 B + matrix) >> 126 MB L2; no flush needed"
                              if n * K * 56 > 4 * 126e6 else "working set is L2-resident: launch/latency bound, HBM fraction not meaningful",
-                       "sharding": "independent constituents/scenarios per rank, mesh replicated, no data-path collective"},
+                       "sharding": "independent constituents/scenarios per rank, mesh replicated, no data-path collective",
+                       "units_per_rank": ensemble.ensemble_plan(n_units, world)},
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(l1 - l0),
             "roofline": roofline, "cpu_baseline": cpu,
-            "solver": {"bicgstab_iterations_per_step": float(np.mean(iters[W:])), "iterations_total": int(i1 - i0),
+            "solver": {"bicgstab_iterations_per_step": (i1 - i0) / K_steps, "iterations_total": int(i1 - i0),
                        "worst_status": worst_status, "max_relres": worst_relres},
-            "mass_balance": {"mass_start_all_units": float(mass[0].item()), "mass_end_all_units": float(mass[1].item()),
+            "mass_balance": {"units": n_units, "mass_start_all_units": float(mass_table[:, 0].sum()),
+                             "mass_end_all_units": float(mass_table[:, 1].sum()),
+                             "boundary_mass_in_all_units": float(mass_table[:, 2].sum()),
+                             "boundary_mass_out_all_units": float(mass_table[:, 3].sum()),
                              "reduced_with": "nccl all_reduce" if world > 1 else "single rank"},
         }
         print(json.dumps(line), flush=True)

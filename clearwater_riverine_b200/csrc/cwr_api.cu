@@ -638,7 +638,7 @@ static int solve_small(cwr_handle* h, cwr_step_info* info) {
         return CWR_OK;
     }
     int status = read_small_stats(h, info);
-    if (status != CWR_ECUDA) h->iterations += h->h_stats->max_iterations;
+    if (status != CWR_ECUDA) h->iterations += (int64_t)(h->h_stats->sum_iterations / (unsigned long long)h->K);
     return status;
 }
 
@@ -754,7 +754,7 @@ int cwr_run(cwr_handle* h, int t_begin, int t_end, cwr_step_info* worst) {
         const int n_launches = w.n_launches;
         rc = read_small_stats(h, &w);
         w.n_launches = n_launches;
-        if (rc != CWR_ECUDA) h->iterations += (int64_t)h->h_stats->max_iterations;
+        if (rc != CWR_ECUDA) h->iterations += (int64_t)(h->h_stats->sum_iterations / (unsigned long long)h->K);
         if (worst) *worst = w;
         return rc;
     }

@@ -21,6 +21,7 @@ struct SmallStats {
     int restarts;
     int not_converged;
     unsigned long long max_relres2_bits;   // max over columns/steps of ||r||^2/||b||^2 (bit pattern of a double >= 0)
+    unsigned long long sum_iterations;     // over columns and steps
 };
 
 template <int ND>
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M,
         M.colflags[k] = flags; M.coliters[k] = iters;
         M.sc[SC_BNORM2 * K + k] = bb; M.sc[SC_RNORM2 * K + k] = rr;
         atomicMax(&stats->max_iterations, iters);
+        atomicAdd(&stats->sum_iterations, (unsigned long long)iters);
         atomicOr(&stats->flags_or, flags & (FL_BREAKDOWN | FL_NAN));
         atomicMax(&stats->restarts, restarts);
         if (!(flags & FL_CONVERGED)) atomicAdd(&stats->not_converged, 1);
