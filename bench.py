@@ -246,29 +246,59 @@ def main():
         be.step(t)
     prof = be.profile(0)
     nnz = 2 * int(np.count_nonzero(plan.f2 < n))
-    fused_bytes = 12.0 * nnz + 4.0 * (n + 1) + 24.0 * n * K       # matrix + gathered vector + rhat + product written
-    sp_ms = prof["spmm_t"][0] + prof["spmm_v"][0]
-    sp_cnt = prof["spmm_t"][1] + prof["spmm_v"][1]
+    o = be.options
+    Wd = 4 * ((int(np.bincount(np.concatenate([plan.f1[plan.f2 < n], plan.f2[plan.f2 < n]]), minlength=n).max()) + 3) // 4)
+    V = 8.0 * n * K                                     # one fp64 (n, K) vector
+    sweeps = max(0, o.precond_steps - 1)
+    sb = 4 if o.precond_precision == 32 else 8          # bytes per entry of the sweep type
+    pt = sb if sweeps else 8                            # type of the preconditioned vectors the products gather
+    ell = 4.0 * n * Wd                                  # ELL column indices
+    # algorithmic bytes per launch of every kernel family (each operand counted once)
+    fam_bytes = {
+        "assemble": 2 * ell + 12.0 * nnz + 4.0 * n + 8.0 * n * Wd + (4.0 * n * Wd if sb == 4 and sweeps else 0) + 8.0 * n,
+        "rhs": 3 * V + 12.0 * n,
+        "spmm_init": ell + 8.0 * n * Wd + 5 * V,                       # x, b read; r, rhat, p written
+        "spmm_v": ell + 8.0 * n * Wd + pt * n * K + 2 * V,             # p^ gathered, rhat read, v written
+        "spmm_t": ell + 8.0 * n * Wd + pt * n * K + 3 * V,             # s^ gathered, rhat, s read, t written
+        "update_s": 3 * V,
+        "update_xrp": 8 * V + 2.0 * pt * n * K,                        # x r p t v read, x r p written, p^ s^ read
+        "mass_flux": 8.0 * E + 12.0 * E + 2 * 8.0 * E * K + 3 * 8.0 * E * K,
+    }
+    if o.precond_sweep == 1:      # one launch = all sweeps of one application: u (fp64) once, then per sweep indices+values, u, z gathered, z written
+        fam_bytes["precond"] = sweeps * (ell + sb * n * Wd + 3.0 * sb * n * K) + 8.0 * n * K
+    else:                         # one launch = one Jacobi step
+        fam_bytes["precond"] = ell + sb * n * Wd + 3.0 * sb * n * K
     peak, peak_src = measured_peak()
+    total_ms = sum(v[0] for v in prof.values())
+    kernels = {}
+    for fam, (ms, cnt) in prof.items():
+        if cnt and fam in fam_bytes:
+            per = ms / cnt
+            gbs = fam_bytes[fam] / (per * 1e-3) / 1e9
+            kernels[fam] = {"ms_per_launch": per, "launches_per_step": cnt / P, "ms_per_step": ms / P,
+                            "share_of_step": ms / total_ms if total_ms else None,
+                            "algorithmic_bytes_per_launch": fam_bytes[fam], "achieved_gbs": gbs, "frac": gbs / peak}
     roofline = None
-    if sp_cnt:
-        per_launch_ms = sp_ms / sp_cnt
-        ach = fused_bytes / (per_launch_ms * 1e-3) / 1e9
+    if kernels:
+        dom = max(kernels, key=lambda f: kernels[f]["ms_per_step"])
+        names = {"precond": ("k_precond_gs (multicolour Gauss-Seidel preconditioner: all sweeps of one application, persistent, "
+                             "one grid barrier per colour)" if o.precond_sweep == 1 else "k_sweep (one Jacobi step of the polynomial preconditioner)"),
+                 "spmm_t": "k_spmm<AT> (t = A s^ fused with four dot products)", "spmm_v": "k_spmm<AV> (v = A p^ fused with (rhat, v))",
+                 "update_xrp": "k_update_xrp", "solve_small": "k_solve_small"}
         traffic = None
-        tp = ROOT / "profiles" / "spmm_traffic.json"
+        tp = ROOT / "profiles" / "dominant_kernel_traffic.json"
         if tp.is_file():
             try:
                 tj = json.loads(tp.read_text())
-                if tj.get("workload") == args.workload and args.scale == 1.0:
+                if tj.get("workload") == args.workload and tj.get("family") == dom and args.scale == 1.0 and not args.opt:
                     traffic = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
-        total_ms = sum(v[0] for v in prof.values())
-        roofline = {"bound": "hbm", "kernel": "k_spmm<KC,1|2> (SpMM fused with the BiCGSTAB dot products)",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "peak_source": peak_src, "algorithmic_bytes_per_launch": fused_bytes,
-                    "ms_per_launch": per_launch_ms, "share_of_step": sp_ms / total_ms if total_ms else None,
-                    "families_ms_per_step": {k: v[0] / P for k, v in prof.items()}}
+        d = kernels[dom]
+        roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "family": dom, "achieved": d["achieved_gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": d["frac"], "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "ms_per_launch": d["ms_per_launch"],
+                    "share_of_step": d["share_of_step"], "kernels": kernels}
 
     # ---- mass-balance scalars: the only collective (NCCL all-reduce over the ranks' units) ------------------------
     local_rows = {}
@@ -321,7 +351,8 @@ def main():
                                     "16m": "synthetic 16M-cell mesh, 1 constituent, single GPU"}[args.workload],
                        "cells": n, "edges": E, "nnz_offdiag": nnz, "constituents_per_gpu": K, "dt_s": float(dt[0]),
                        "diffusion_coefficient": DIFFUSION, "rtol": be.options.rtol,
-                       "precond_steps": be.options.precond_steps,
+                       "precond_steps": be.options.precond_steps, "precond_sweep": be.options.precond_sweep,
+                       "precond_precision": be.options.precond_precision, "precond_colors": be.options.precond_colors,
                        "l2": "per-step working set (7 vectors x n x K x 8 B + matrix) >> 126 MB L2; no flush needed"
                              if n * K * 56 > 4 * 126e6 else "working set is L2-resident: launch/latency bound, HBM fraction not meaningful",
                        "sharding": "independent constituents/scenarios per rank, mesh replicated, no data-path collective",

@@ -24,7 +24,9 @@ STATUS_NAMES = {0: "CWR_OK", -1: "CWR_EINVAL", -2: "CWR_ECUDA", -3: "CWR_ENOTCON
 class CwrOptions(C.Structure):
     _fields_ = [("rtol", C.c_double), ("max_iter", C.c_int), ("reorder", C.c_int), ("keep_history", C.c_int),
                 ("hydro_capacity", C.c_int), ("mass_flux", C.c_int), ("solver_path", C.c_int),
-                ("use_graph", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int), ("reserved", C.c_int * 6)]
+                ("use_graph", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int),
+                ("precond_precision", C.c_int), ("precond_sweep", C.c_int), ("precond_colors", C.c_int),
+                ("reserved", C.c_int * 3)]
 
 
 class CwrStepInfo(C.Structure):
@@ -71,6 +73,7 @@ def load_library():
         "cwr_last_error": ([H], C.c_char_p),
         "cwr_set_hydro": ([H, C.c_int, C.c_int, fp, dp, fp, fp, dp], C.c_int),
         "cwr_set_geometry": ([H, dp, dp], C.c_int),
+        "cwr_set_flow_hint": ([H, fp], C.c_int),
         "cwr_set_hydro_raw": ([H, C.c_int, C.c_int, fp, fp, fp, dp], C.c_int),
         "cwr_set_inputs": ([H, C.c_int, dp], C.c_int),
         "cwr_set_state": ([H, C.c_int, C.c_int, dp], C.c_int),
@@ -85,7 +88,10 @@ def load_library():
         "cwr_get_lhs": ([H, C.POINTER(C.c_int64), ip, ip, dp], C.c_int),
         "cwr_get_rhs": ([H, C.c_int, dp], C.c_int),
         "cwr_get_permutation": ([H, ip], C.c_int),
+        "cwr_get_options": ([H, C.POINTER(CwrOptions)], C.c_int),
         "cwr_stream": ([H, C.POINTER(C.c_void_p)], C.c_int),
+        "cwr_order_cells": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, C.c_int, fp, ip, ip, C.POINTER(C.c_int),
+                             C.POINTER(C.c_int)], C.c_int),
         "cwr_counters": ([H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "cwr_time_spmm": ([H, C.c_int, dp, dp], C.c_int),
         "cwr_profile": ([H, C.c_int, dp, C.POINTER(C.c_int64)], C.c_int),
@@ -107,6 +113,21 @@ def _arr(a, dtype, shape=None, name="array") -> np.ndarray:
     if shape is not None and tuple(out.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(out.shape)}")
     return out
+
+
+def order_cells(f1, f2, n_face: int, reorder: bool = True, n_colors: int = 0, flow_hint=None):
+    """Host-only: (new_of_old, color_ptr, n_levels) of the ordering the library builds (cwr_order_cells)."""
+    lib = load_library()
+    f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
+    n = int(f1.max()) + 1
+    hint = None if flow_hint is None else _arr(flow_hint, np.float32, f1.shape, "flow_hint")
+    new_of_old = np.empty(n, np.int32); cptr = np.zeros(65, np.int32)
+    nc, nl = C.c_int(), C.c_int()
+    rc = lib.cwr_order_cells(n, int(n_face), len(f1), _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), int(reorder), int(n_colors),
+                             _ptr(hint, C.c_float), _ptr(new_of_old, C.c_int32), _ptr(cptr, C.c_int32), C.byref(nc), C.byref(nl))
+    if rc != CWR_OK:
+        raise CwrError(rc, lib.cwr_last_error(None).decode())
+    return new_of_old, cptr[: nc.value + 1].copy(), nl.value
 
 
 class TransportBackend:
@@ -134,6 +155,7 @@ class TransportBackend:
             msg = self._lib.cwr_last_error(None).decode()
             self._h = C.c_void_p()
             raise CwrError(rc, msg)
+        self._lib.cwr_get_options(self._h, C.byref(self.options))     # autos resolved
         self.last_info = CwrStepInfo()
 
     # -- plumbing ------------------------------------------------------------------------------
@@ -165,6 +187,10 @@ class TransportBackend:
         dt = _arr(dt, np.float64).reshape(nt)
         self._check(self._lib.cwr_set_hydro(self._h, t0, nt, _ptr(adv, C.c_float), _ptr(cdiff, C.c_double),
                                             _ptr(vel, C.c_float), _ptr(vol, C.c_float), _ptr(dt, C.c_double)))
+
+    def set_flow_hint(self, face_flow):
+        q = _arr(face_flow, np.float32, (self.n_edge,), "face_flow")
+        self._check(self._lib.cwr_set_flow_hint(self._h, _ptr(q, C.c_float)))
 
     def set_geometry(self, face_x, face_y):
         fx = _arr(face_x, np.float64, (self.n_face,), "face_x"); fy = _arr(face_y, np.float64, (self.n_face,), "face_y")

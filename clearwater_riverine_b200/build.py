@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libcwr_b200.so"
 SOURCES = [CSRC / "cwr_api.cu", CSRC / "cwr_topology.cpp"]
-DEPS = SOURCES + [CSRC / "cwr_kernels.cuh", CSRC / "cwr_topology.h", PKG.parent / "include" / "cwr.h"]
+DEPS = SOURCES + [CSRC / "cwr_kernels.cuh", CSRC / "cwr_small.cuh", CSRC / "cwr_topology.h", PKG.parent / "include" / "cwr.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
 

@@ -28,12 +28,19 @@ struct cwr_handle {
     int n = 0, F = 0, E = 0, K = 0, T = 0, G = 0;
     int C = 0;                       // hydro slices resident
     int KC = 1, VEC = 1;             // lanes per row, columns per lane
-    int m_steps = 1;                 // Jacobi steps of the polynomial preconditioner (1 = none)
+    int SKC = 1, SVEC = 1;           // the same for the preconditioner sweeps (128-bit lanes of the sweep type)
+    int m_steps = 1;                 // sweeps of the preconditioner + 1 (1 = diagonal scaling only)
+    bool sweep_f32 = true;           // preconditioner sweeps (and p^, s^) in fp32
+    bool gauss_seidel = false;       // multicolour Gauss-Seidel sweeps instead of Jacobi steps
+    bool hint_done = false;          // the colours have been aligned with the flow (or it is too late to)
+    int grid_sweep = 0, grid_gs = 0;
+    int32_t* d_color_ptr = nullptr;
+    std::vector<int32_t> f1_ref, f2_ref;   // the caller's connectivity (kept for the flow-aligned recolouring)
     int last_iters = 0;              // iterations of the previous solve (launch-ahead prediction)
     bool small_path = false;         // one-CTA-per-column in-kernel solve (small meshes)
     bool in_run = false;             // inside cwr_run: the small path does not synchronise per step
     SmallStats* d_stats = nullptr; SmallStats* h_stats = nullptr;
-    int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0;
+    int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0, grid_spmm = 0, grid_xrp = 0;
     DeviceModel M{};
     // device buffers
     int32_t *d_ell_col = nullptr, *d_ell_code = nullptr, *d_f1p = nullptr, *d_f2p = nullptr;
@@ -155,6 +162,78 @@ static int ensure_stage(cwr_handle* h, size_t bytes) {
     if (h->VEC == 2) { constexpr int VEC = 2; KC_CASES(__VA_ARGS__) }   \
     else { constexpr int VEC = 1; KC_CASES(__VA_ARGS__) }
 
+// ---- preconditioner ---------------------------------------------------------------------------------
+// binds ST (sweep type), SKC, SVEC for the handle
+#define SWEEP_KC_CASES(...)                    \
+    switch (h->SKC) {                          \
+        case 1: { constexpr int SKC = 1; __VA_ARGS__; break; }   \
+        case 2: { constexpr int SKC = 2; __VA_ARGS__; break; }   \
+        case 4: { constexpr int SKC = 4; __VA_ARGS__; break; }   \
+        case 8: { constexpr int SKC = 8; __VA_ARGS__; break; }   \
+        case 16: { constexpr int SKC = 16; __VA_ARGS__; break; } \
+        default: { constexpr int SKC = 32; __VA_ARGS__; break; } \
+    }
+#define SWEEP_DISPATCH(...)                                                                   \
+    if (h->sweep_f32) {                                                                       \
+        using ST = float;                                                                     \
+        if (h->SVEC == 4) { constexpr int SVEC = 4; SWEEP_KC_CASES(__VA_ARGS__) }             \
+        else if (h->SVEC == 2) { constexpr int SVEC = 2; SWEEP_KC_CASES(__VA_ARGS__) }        \
+        else { constexpr int SVEC = 1; SWEEP_KC_CASES(__VA_ARGS__) }                          \
+    } else {                                                                                  \
+        using ST = double;                                                                    \
+        if (h->SVEC == 2) { constexpr int SVEC = 2; SWEEP_KC_CASES(__VA_ARGS__) }             \
+        else { constexpr int SVEC = 1; SWEEP_KC_CASES(__VA_ARGS__) }                          \
+    }
+// binds PT: the type of the preconditioned vectors p^ / s^ the products and the update kernel read
+#define PT_DISPATCH(...)                                                                      \
+    if (h->m_steps > 1 && h->sweep_f32) { using PT = float; KC_DISPATCH(h->KC, __VA_ARGS__) } \
+    else { using PT = double; KC_DISPATCH(h->KC, __VA_ARGS__) }
+
+// copy the (re)built topology into the device arrays allocated by create_impl (sizes do not depend on
+// the ordering)
+template <typename T>
+static cudaError_t put(cwr_handle* h, T* d, const std::vector<T>& v) {
+    return v.empty() ? cudaSuccess : cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream);
+}
+
+static int upload_topology(cwr_handle* h) {
+    const Topology& tp = h->topo;
+    CK(put(h, h->d_ell_col, tp.ell_col)); CK(put(h, h->d_ell_code, tp.ell_code));
+    CK(put(h, h->d_f1p, tp.f1p)); CK(put(h, h->d_f2p, tp.f2p));
+    CK(put(h, h->d_bcell, tp.bcell)); CK(put(h, h->d_bptr, tp.bptr)); CK(put(h, h->d_bedge, tp.bedge));
+    CK(put(h, h->d_eperm, tp.eperm));
+    std::vector<int32_t> einv(tp.E);
+    for (int ep = 0; ep < tp.E; ++ep) einv[tp.eperm[ep]] = ep;
+    CK(put(h, h->d_einv, einv));
+    CK(put(h, h->d_new_of_old, tp.new_of_old)); CK(put(h, h->d_old_of_new, tp.old_of_new));
+    CK(put(h, h->d_color_ptr, tp.color_ptr));
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+// Gauss-Seidel colours follow the flow: the first hydrodynamic slices the caller uploads give the
+// direction (time mean of the face flows over the call's slices).  Only possible while nothing that
+// depends on the cell order is on the device yet (no inputs, no hydro slices, no steps).
+static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
+    if (!h->gauss_seidel || h->hint_done) return CWR_OK;
+    h->hint_done = true;
+    for (uint8_t s : h->inputs_set) if (s) return CWR_OK;
+    const int E = h->E;
+    std::vector<double> mean(E, 0.0);
+    const int stride = std::max(1, nt / 32);
+    for (int s = 0; s < nt; s += stride)
+        for (int e = 0; e < E; ++e) { const float q = flow[(size_t)s * E + e]; if (q == q) mean[e] += q; }
+    std::vector<float> hint(E);
+    for (int e = 0; e < E; ++e) hint[e] = (float)mean[e];
+    Topology t2;
+    std::string terr = build_topology(h->n, h->F, E, h->f1_ref.data(), h->f2_ref.data(), h->opt.reorder != 0,
+                                      h->opt.precond_colors, hint.data(), t2);
+    if (!terr.empty()) FAIL(CWR_EINVAL, terr);
+    if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
+    h->topo = std::move(t2);
+    return upload_topology(h);
+}
+
 extern "C" {
 
 int cwr_default_options(cwr_options* o) {
@@ -169,7 +248,10 @@ int cwr_default_options(cwr_options* o) {
     o->solver_path = 0;
     o->use_graph = 1;
     o->check_every = 1;
-    o->precond_steps = 8;
+    o->precond_steps = 0;
+    o->precond_precision = 32;
+    o->precond_sweep = 1;
+    o->precond_colors = 0;
     return CWR_OK;
 }
 
@@ -200,8 +282,21 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (!(h->opt.rtol > 0)) h->opt.rtol = 1e-13;
     if (h->opt.max_iter <= 0) h->opt.max_iter = 500;
     if (h->opt.check_every <= 0) h->opt.check_every = 1;
-    if (h->opt.precond_steps <= 0) h->opt.precond_steps = 8;
+    const bool small = h->opt.solver_path == 2 || (h->opt.solver_path == 0 && n_real <= 32768);
+    if (h->opt.precond_steps <= 0) h->opt.precond_steps = (h->opt.precond_sweep == 1 && !small) ? 5 : 8;   // auto
     h->m_steps = std::min(h->opt.precond_steps, 64);
+    if (h->opt.precond_precision != 64) h->opt.precond_precision = 32;
+    h->sweep_f32 = h->opt.precond_precision == 32;
+    // solver path: small meshes run the whole solve of a column inside one CTA (cwr_small.cuh)
+    h->small_path = small;
+    h->gauss_seidel = h->opt.precond_sweep == 1 && !h->small_path && h->m_steps > 1;
+    if (h->opt.precond_colors <= 0) {
+        // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
+        // bytes per row of one sweep = indices + values + three vectors in the sweep type
+        const double bytes = (double)n_real * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
+        h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / 20e6)));
+    }
+    h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) FAIL(CWR_ECUDA, "no CUDA device: this library has no CPU fallback");
@@ -213,7 +308,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     CK(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
 
-    std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0, h->topo);
+    h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
+    std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
+                                      h->gauss_seidel ? h->opt.precond_colors : 0, nullptr, h->topo);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     const Topology& tp = h->topo;
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
@@ -223,21 +320,49 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     int kc = 1;
     while (kc * h->VEC < K && kc < 32) kc <<= 1;
     h->KC = kc;
+    {   // sweep lanes: 128-bit packs of the sweep type
+        const int vmax = h->sweep_f32 ? 4 : 2;
+        int sv = vmax;
+        while (sv > 1 && K % sv != 0) sv >>= 1;
+        int skc = 1;
+        while (skc * sv < K && skc < 32) skc <<= 1;
+        h->SVEC = sv; h->SKC = skc;
+    }
     h->max_grid = h->num_sms * 8;
+    // persistent single-wave grids: SM count x resident CTAs per SM of the kernel that owns the grid
+    {
+        int occ_spmm = 4, occ_xrp = 3, occ_gs = 0;
+        KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmm, k_spmm<KC, VEC, MODE_AT, double>, kThreads, 0));
+        KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_xrp, k_update_xrp<KC, VEC, double>, kThreads, 0));
+        h->grid_spmm = grid_for(n, kThreads / kc, h->num_sms * std::max(1, occ_spmm));
+        h->grid_xrp = grid_for(n, kThreads / kc, h->num_sms * std::max(1, occ_xrp));
+        h->grid_sweep = grid_for(n, kThreads / h->SKC, h->num_sms * CWR_SPMM_MIN_BLOCKS);
+        if (h->gauss_seidel) {
+            SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
+            SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC>, kGsThreads, kGsSmemBytes));
+            int coop = 0;
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+            if (!coop || occ_gs < 1) FAIL(CWR_ECUDA, "cooperative launch not available: use precond_sweep = 0");
+            // every CTA must be resident (grid barrier): SM count x occupancy, and no more CTAs than the
+            // largest colour has row groups
+            h->grid_gs = grid_for((n + (int)tp.color_ptr.size() - 2) / std::max(1, (int)tp.color_ptr.size() - 1),
+                                  kGsThreads / h->SKC, h->num_sms * occ_gs);
+        }
+    }
     h->grid_rows = grid_for(n, kThreads / kc, h->max_grid);
     h->grid_edges = grid_for(E, kThreads / kc, h->max_grid);
     h->grid_b = grid_for((int64_t)tp.bcell.size() * K, kThreads, h->max_grid);
 
     // topology -> device
-    CK(upload(h, &h->d_ell_col, tp.ell_col)); CK(upload(h, &h->d_ell_code, tp.ell_code));
-    CK(upload(h, &h->d_f1p, tp.f1p)); CK(upload(h, &h->d_f2p, tp.f2p));
-    CK(upload(h, &h->d_bcell, tp.bcell)); CK(upload(h, &h->d_bptr, tp.bptr)); CK(upload(h, &h->d_bedge, tp.bedge));
-    CK(upload(h, &h->d_eperm, tp.eperm));
-    std::vector<int32_t> einv(E);
-    for (int ep = 0; ep < E; ++ep) einv[tp.eperm[ep]] = ep;
-    CK(upload(h, &h->d_einv, einv));
-    CK(upload(h, &h->d_new_of_old, tp.new_of_old)); CK(upload(h, &h->d_old_of_new, tp.old_of_new));
+    CK(dalloc(h, &h->d_ell_col, tp.ell_col.size())); CK(dalloc(h, &h->d_ell_code, tp.ell_code.size()));
+    CK(dalloc(h, &h->d_f1p, tp.f1p.size())); CK(dalloc(h, &h->d_f2p, tp.f2p.size()));
+    CK(dalloc(h, &h->d_bcell, tp.bcell.size())); CK(dalloc(h, &h->d_bptr, tp.bptr.size())); CK(dalloc(h, &h->d_bedge, tp.bedge.size()));
+    CK(dalloc(h, &h->d_eperm, (size_t)E)); CK(dalloc(h, &h->d_einv, (size_t)E));
+    CK(dalloc(h, &h->d_new_of_old, (size_t)n)); CK(dalloc(h, &h->d_old_of_new, (size_t)n));
+    CK(dalloc(h, &h->d_color_ptr, tp.color_ptr.size()));
     {
+        int rc = upload_topology(h);
+        if (rc) return rc;
         std::vector<int32_t> a(f1, f1 + E), b(f2, f2 + E);
         CK(upload(h, &h->d_f1, a)); CK(upload(h, &h->d_f2, b));
         CK(cudaStreamSynchronize(h->stream));   // the vectors above die here
@@ -261,6 +386,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     M.n = n; M.K = K; M.E = E; M.E_int = tp.E_int; M.E_g = tp.E_g; M.G = h->G; M.nb = (int)tp.bcell.size();
     M.W = tp.W; M.ell_col = h->d_ell_col; M.ell_code = h->d_ell_code; M.f1p = h->d_f1p; M.f2p = h->d_f2p;
     M.bcell = h->d_bcell; M.bptr = h->d_bptr; M.bedge = h->d_bedge;
+    M.color_ptr = h->d_color_ptr; M.n_colors = (int)tp.color_ptr.size() - 1;
     CK(dalloc(h, &M.val, (size_t)n * tp.W)); CK(dalloc(h, &M.diag, (size_t)n)); CK(dalloc(h, &M.gdiag, (size_t)n));
     CK(cudaMemsetAsync(M.gdiag, 0, (size_t)n * sizeof(double), h->stream));
     double* ic = nullptr;
@@ -268,9 +394,12 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     M.ic = ic;
     CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
     CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
-    // solver path: small meshes run the whole solve of a column inside one CTA (cwr_small.cuh)
-    h->small_path = h->opt.solver_path == 2 || (h->opt.solver_path == 0 && n <= 32768);
-    if (h->m_steps > 1 || h->small_path) { CK(dalloc(h, &M.ph, nK)); CK(dalloc(h, &M.sh, nK)); CK(dalloc(h, &M.tmp, nK)); }
+    if (h->m_steps > 1 || h->small_path) {
+        double *ph, *sh, *tmp, *us;
+        CK(dalloc(h, &ph, nK)); CK(dalloc(h, &sh, nK)); CK(dalloc(h, &tmp, nK)); CK(dalloc(h, &us, nK));
+        M.ph = ph; M.sh = sh; M.tmp = tmp; M.us = us;
+        if (h->sweep_f32 && !h->small_path) CK(dalloc(h, &M.valf, (size_t)n * tp.W));
+    }
     if (h->small_path) {
         CK(dalloc(h, &M.xc, nK));
         CK(dalloc(h, &h->d_stats, 1));
@@ -339,6 +468,8 @@ int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double*
     int rc = check_slices(h, t0, nt);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
+    rc = align_colours_with_flow(h, adv, nt);
+    if (rc) return rc;
     const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
     // staging: adv f32 (E) | vel f32 (E) | vol f32 (F) | cdiff f64 (E)
     const size_t off_vel = (size_t)E * 4, off_vol = off_vel + (size_t)E * 4, off_cd = (off_vol + (size_t)F * 4 + 7) & ~(size_t)7;
@@ -367,6 +498,15 @@ int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double*
     return CWR_OK;
 }
 
+int cwr_set_flow_hint(cwr_handle* h, const float* face_flow) {
+    if (!h) return CWR_EINVAL;
+    if (!face_flow) FAIL(CWR_EINVAL, "NULL array");
+    for (int t : h->slot_time) if (t >= 0) FAIL(CWR_EINVAL, "cwr_set_flow_hint must come before the first hydrodynamic slice");
+    for (uint8_t s : h->inputs_set) if (s) FAIL(CWR_EINVAL, "cwr_set_flow_hint must come before cwr_set_inputs");
+    CK(cudaSetDevice(h->device));
+    return align_colours_with_flow(h, face_flow, 1);
+}
+
 int cwr_set_geometry(cwr_handle* h, const double* face_x, const double* face_y) {
     if (!h) return CWR_EINVAL;
     if (!face_x || !face_y) FAIL(CWR_EINVAL, "NULL array");
@@ -392,6 +532,8 @@ int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, con
     int rc = check_slices(h, t0, nt);
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
+    rc = align_colours_with_flow(h, face_flow, nt);
+    if (rc) return rc;
     const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
     const size_t off_vel = (size_t)E * 4, off_vol = off_vel + (size_t)E * 4;
     rc = ensure_stage(h, off_vol + (size_t)F * 4);
@@ -518,18 +660,30 @@ static int poll(cwr_handle* h) {
     return CWR_OK;
 }
 
-// m-step Jacobi polynomial preconditioner: z_1 = u + N u, z_{j+1} = u + N z_j (N = I - D^-1 A), i.e.
-// z = (I + N + ... + N^(m-1)) u.  Returns the buffer holding z (u itself when m == 1); the last step
-// always lands in `dst`, `other` is the ping-pong partner.
-static const double* precondition(cwr_handle* h, const double* u, double* dst, double* other) {
+// z = M^-1 u with m - 1 sweeps, result in `dst` (sweep type); returns u itself when m == 1.
+//   Jacobi:        z_1 = u + N u, z_{j+1} = u + N z_j  (N = I - D^-1 A)  =>  z = (I + N + ... + N^(m-1)) u
+//   Gauss-Seidel:  the same first step, then m - 2 in-place multicolour sweeps (one launch per colour)
+static const void* precondition(cwr_handle* h, const double* u, void* dst, void* other) {
     const int J = h->m_steps - 1;
     if (J <= 0) return u;
     DeviceModel& M = h->M;
-    const double* z = u;
-    for (int j = 1; j <= J; ++j) {
-        double* out = ((J - j) % 2 == 0) ? dst : other;
+    const int n = h->n;
+    if (h->gauss_seidel) {
         mark(h, CWR_FAM_PRECOND);
-        KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_JAC><<<h->grid_rows, kThreads, 0, h->stream>>>(M, z, u, out)));
+        int sweeps = J;
+        void* args[] = {(void*)&M, (void*)&u, (void*)&dst, (void*)&sweeps};
+        cudaError_t e = cudaSuccess;
+        SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream));
+        if (e != cudaSuccess) h->err = std::string("k_precond_gs: ") + cudaGetErrorString(e);
+        h->launches += 1;
+        return dst;
+    }
+    const void* z = nullptr;
+    for (int j = 1; j <= J; ++j) {
+        void* out = ((J - j) % 2 == 0) ? dst : other;      // the last step always lands in dst
+        mark(h, CWR_FAM_PRECOND);
+        if (j == 1) { SWEEP_DISPATCH((k_sweep<ST, SKC, SVEC, true><<<h->grid_sweep, kThreads, 0, h->stream>>>(M, u, nullptr, (ST*)out, 0, n))); }
+        else { SWEEP_DISPATCH((k_sweep<ST, SKC, SVEC, false><<<h->grid_sweep, kThreads, 0, h->stream>>>(M, nullptr, (const ST*)z, (ST*)out, 0, n))); }
         h->launches += 1;
         z = out;
     }
@@ -539,16 +693,16 @@ static const double* precondition(cwr_handle* h, const double* u, double* dst, d
 static int launch_iteration(cwr_handle* h) {
     const int g = h->grid_rows;
     DeviceModel& M = h->M;
-    const double* ph = precondition(h, M.p, M.ph, M.tmp);
+    const void* ph = precondition(h, M.p, M.ph, M.tmp);
     mark(h, CWR_FAM_SPMM_V);
-    KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_AV><<<g, kThreads, 0, h->stream>>>(M, ph, nullptr, nullptr)));
+    PT_DISPATCH((k_spmm<KC, VEC, MODE_AV, PT><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, (const PT*)ph, nullptr)));
     mark(h, CWR_FAM_UPDATE_S);
     KC_DISPATCH(h->KC, (k_update_s<KC, VEC><<<g, kThreads, 0, h->stream>>>(M)));
-    const double* sh = precondition(h, M.r, M.sh, M.tmp);
+    const void* sh = precondition(h, M.r, M.sh, M.tmp);
     mark(h, CWR_FAM_SPMM_T);
-    KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_AT><<<g, kThreads, 0, h->stream>>>(M, sh, nullptr, nullptr)));
+    PT_DISPATCH((k_spmm<KC, VEC, MODE_AT, PT><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, (const PT*)sh, nullptr)));
     mark(h, CWR_FAM_UPDATE_XRP);
-    KC_DISPATCH(h->KC, (k_update_xrp<KC, VEC><<<g, kThreads, 0, h->stream>>>(M, ph, sh)));
+    PT_DISPATCH((k_update_xrp<KC, VEC, PT><<<h->grid_xrp, kThreads, 0, h->stream>>>(M, (const PT*)ph, (const PT*)sh)));
     h->launches += 4;
     return CWR_OK;
 }
@@ -560,7 +714,7 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
     int total_iter = 0;
     for (;;) {
         mark(h, CWR_FAM_SPMM_INIT);
-        KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_INIT><<<g, kThreads, 0, h->stream>>>(M, nullptr, nullptr, nullptr)));
+        KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_INIT, double><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, nullptr, nullptr)));
         h->launches += 1;
         mark(h, -1);
         // Launch-ahead: the previous solve's iteration count predicts this one, so that many iterations
@@ -943,6 +1097,27 @@ int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old) {
     return CWR_OK;
 }
 
+int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int reorder, int n_colors,
+                    const float* flow_hint, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out, int* n_levels) {
+    if (!f1 || !f2 || !new_of_old) return CWR_EINVAL;
+    Topology t;
+    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, reorder != 0, n_colors, flow_hint, t);
+    if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
+    std::copy(t.new_of_old.begin(), t.new_of_old.end(), new_of_old);
+    if (color_ptr) std::copy(t.color_ptr.begin(), t.color_ptr.end(), color_ptr);
+    if (n_colors_out) *n_colors_out = (int)t.color_ptr.size() - 1;
+    if (n_levels) *n_levels = t.n_levels;
+    return CWR_OK;
+}
+
+int cwr_get_options(const cwr_handle* h, cwr_options* out) {
+    if (!h || !out) return CWR_EINVAL;
+    *out = h->opt;
+    out->precond_colors = h->gauss_seidel ? (int)h->topo.color_ptr.size() - 1 : 0;
+    out->precond_sweep = h->gauss_seidel ? 1 : 0;
+    return CWR_OK;
+}
+
 int cwr_stream(cwr_handle* h, void** s) {
     if (!h || !s) return CWR_EINVAL;
     *s = (void*)h->stream;
@@ -980,9 +1155,9 @@ int cwr_time_spmm(cwr_handle* h, int reps, double* ms_per_launch, double* algori
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     DeviceModel& M = h->M;
     // x = p (left by the last solve), y = v ; both are scratch between steps
-    for (int w = 0; w < 3; ++w) { KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_PLAIN><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, nullptr, M.v))); }
+    for (int w = 0; w < 3; ++w) { KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_PLAIN, double><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, M.p, M.v))); }
     CK(cudaEventRecord(e0, h->stream));
-    for (int r = 0; r < reps; ++r) { KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_PLAIN><<<h->grid_rows, kThreads, 0, h->stream>>>(M, M.p, nullptr, M.v))); }
+    for (int r = 0; r < reps; ++r) { KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_PLAIN, double><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, M.p, M.v))); }
     CK(cudaEventRecord(e1, h->stream));
     CK(cudaEventSynchronize(e1));
     h->launches += reps + 3;

@@ -44,8 +44,10 @@ struct SolverCtl {
     int flags_or;       // OR of column flags that matter to the host (breakdown, nan)
     int singular;       // a zero diagonal was met during assembly
     int hit_max_iter;
-    int pad[3];
+    int barrier_timeout; // a grid barrier of the persistent sweep kernel gave up (never expected)
+    int pad[2];
     unsigned ticket[4]; // last-block tickets (one per kernel family)
+    unsigned gs_bar[2]; // grid barrier arrivals / exits of k_precond_gs
 };
 
 struct DeviceModel {
@@ -54,12 +56,18 @@ struct DeviceModel {
     const int32_t* ell_code;  // (n,W) (e' << 1) | side, -1 = padding
     const int32_t* f1p; const int32_t* f2p;
     const int32_t* bcell; const int32_t* bptr; const int32_t* bedge;
+    const int32_t* color_ptr; int n_colors;   // (n_colors+1) row ranges of the Gauss-Seidel colours
     double* val;        // (n,W) off-diagonals of D^-1 A
+    float* valf;        // (n,W) the same in fp32 (fp32 preconditioner sweeps), or nullptr
     double* diag;       // (n)   D
     double* gdiag;      // (n)   ghost-edge diagonal terms (boundary cells only, 0 elsewhere)
     const double* ic;   // (n,K) input_array[0][0:n]
-    double *b, *r, *rhat, *p, *v, *tt, *ph, *sh, *tmp, *xc;   // (n,K) work vectors (b is the row-scaled RHS)
-    double* partials;   // (grid, kMaxDots, K)
+    double *b, *r, *rhat, *p, *v, *tt, *xc;   // (n,K) work vectors (b is the row-scaled RHS)
+    // preconditioned vectors p^ and s^, the sweep ping-pong partner and the sweep-precision copy of the
+    // preconditioner's input: (n,K) of the SWEEP type (float by default, double with precond_precision = 64;
+    // the small-mesh path uses them as double).  Allocated 8 bytes per entry either way.
+    void *ph, *sh, *tmp, *us;
+    double* partials;   // (kMaxDots * K, grid): per-CTA partial dot products, block index fastest
     double* sc;         // (SC_ROWS, K) per-column scalars
     int* colflags;      // (K)
     int* coliters;      // (K)
@@ -229,6 +237,7 @@ __global__ void __launch_bounds__(kThreads) k_assemble(DeviceModel M) {
             double2 o = *reinterpret_cast<double2*>(val + w);
             o.x *= inv; o.y *= inv;
             *reinterpret_cast<double2*>(val + w) = o;
+            if (M.valf) *reinterpret_cast<float2*>(M.valf + (size_t)i * W + w) = make_float2((float)o.x, (float)o.y);
         }
         M.diag[i] = diag;
         if (diag == 0.0) M.ctl->singular = 1;
@@ -309,9 +318,10 @@ __global__ void __launch_bounds__(kThreads) k_boundary_rhs(DeviceModel M) {
 // ---------------------------------------------------------------------------------------------
 // deterministic block / grid reduction of per-column dot products
 // ---------------------------------------------------------------------------------------------
-// acc[d*VEC + q]: dot d of column (chunk*KC + lane)*VEC + q.  block_out: [kMaxDots][K] of this block.
+// acc[d*VEC + q]: dot d of column (chunk*KC + lane)*VEC + q.  partials layout: [(d*K + k)][block] with
+// the block index fastest, so that the final reduction reads them coalesced.
 template <int ND, int KC, int VEC>
-__device__ __forceinline__ void block_dots(double (&acc)[ND * VEC], double* smem, double* block_out, int K, int chunk) {
+__device__ __forceinline__ void block_dots(double (&acc)[ND * VEC], double* smem, double* partials, int K, int chunk) {
     constexpr int NA = ND * VEC;
 #pragma unroll
     for (int off = KC; off < 32; off <<= 1)
@@ -330,7 +340,7 @@ __device__ __forceinline__ void block_dots(double (&acc)[ND * VEC], double* smem
         for (int w = 0; w < NW; ++w) s += smem[(w * NA + a) * KC + l];
         const int d = a / VEC, q = a % VEC;
         const int c = (chunk * KC + l) * VEC + q;
-        if (c < K) block_out[d * K + c] = s;
+        if (c < K) partials[(size_t)(d * K + c) * gridDim.x + blockIdx.x] = s;
     }
     __syncthreads();
 }
@@ -350,31 +360,25 @@ __device__ __forceinline__ bool last_block_arrives(unsigned* ticket) {
     return is_last != 0;
 }
 
-// sum the grid's partials in block order -> tot[d*K + k] (shared memory)
-// All 256 threads take part: each (dot, column) pair is summed by a team of threads over interleaved
-// block ranges, then the team's partial sums are combined in a fixed order -> still deterministic.
+// Sum the grid's partials -> tot[d*K + k] (shared memory), by the last CTA.  One warp per (dot, column)
+// pair: lanes read consecutive blocks (coalesced), accumulate in a fixed order, then a fixed shuffle
+// tree combines the lanes -> bitwise deterministic for a given grid size.
 template <int ND>
 __device__ __forceinline__ void grid_totals(const double* partials, double* tot, int K) {
-    __shared__ double team_sum[kThreads];
-    const int pairs = ND * K;
-    int team = 1;
-    while (team * 2 * pairs <= kThreads && team < 64) team *= 2;     // threads per pair (power of two)
-    for (int base = 0; base < pairs; base += kThreads / team) {
-        const int pair = base + threadIdx.x / team, member = threadIdx.x % team;
-        double s = 0.0;
-        if (pair < pairs) {
-            const int d = pair / K, k = pair % K;
-            for (unsigned b = member; b < gridDim.x; b += team) s += __ldcg(&partials[((size_t)b * kMaxDots + d) * K + k]);
-        }
-        team_sum[threadIdx.x] = s;
-        __syncthreads();
-        if (pair < pairs && member == 0) {
-            double t = 0.0;
-            for (int m = 0; m < team; ++m) t += team_sum[threadIdx.x + m];
-            tot[pair] = t;
-        }
-        __syncthreads();
+    const int pairs = ND * K, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned G = gridDim.x;
+    for (int pair = warp; pair < pairs; pair += kThreads / 32) {
+        const double* src = partials + (size_t)pair * G;
+        double s0 = 0.0, s1 = 0.0;
+        unsigned b = lane;
+        for (; b + 32 < G; b += 64) { s0 += __ldcg(src + b); s1 += __ldcg(src + b + 32); }
+        if (b < G) s0 += __ldcg(src + b);
+        double s = s0 + s1;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) tot[pair] = s;
     }
+    __syncthreads();
 }
 
 __device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
@@ -390,30 +394,316 @@ __device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// SpMM over the row-scaled matrix  A = I + L  (L = off-diagonals in ELL; N := -L is the Jacobi
-// iteration matrix), fused with the BiCGSTAB step that consumes it.  z is gathered, u is the
-// row's own vector.
+// packs of V adjacent columns of type T moved with one (<= 128-bit) access
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V> struct alignas(sizeof(T) * V > 16 ? 16 : sizeof(T) * V) Pk { T a[V]; };
+template <typename T, int V>
+__device__ __forceinline__ Pk<T, V> ldk(const T* p) { return *reinterpret_cast<const Pk<T, V>*>(p); }
+template <typename T, int V>
+__device__ __forceinline__ void stk(T* p, const Pk<T, V>& v) { *reinterpret_cast<Pk<T, V>*>(p) = v; }
+// VEC columns of a ZT vector, widened (exactly) to double
+template <typename ZT, int VEC>
+__device__ __forceinline__ Vd<VEC> ldz(const ZT* p) {
+    const Pk<ZT, VEC> t = ldk<ZT, VEC>(p);
+    Vd<VEC> r;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) r.a[q] = (double)t.a[q];
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Preconditioner sweeps over the row-scaled matrix  A = I + L  (L = off-diagonals in ELL; N := -L is
+// the Jacobi iteration matrix):   out_i = u_i - (L z)_i   for rows [row_begin, row_end).
+//   * Jacobi step: z != out, whole row range; m - 1 of them give z = (I + N + ... + N^(m-1)) u.
+//   * one colour of a multicolour Gauss-Seidel sweep: z == out (in place), [row_begin, row_end) = the
+//     rows of ONE colour -- rows of a colour are not coupled, so the range is updated in parallel.
+// ST is the sweep precision: float by default.  The preconditioner only has to be a fixed linear
+// operator close to A^-1; BiCGSTAB's own vectors, products A p^ / A s^ and dot products stay fp64 (p^,
+// s^ are widened exactly), so the converged answer is the fp64 one and the sweeps move half the bytes.
+// FIRST: z = u is the solver's fp64 vector (gathered as double); the step also leaves the ST copy of
+// u in M.us for the following sweeps.
+// ---------------------------------------------------------------------------------------------
+template <typename ST, int KC, int VEC, bool FIRST>
+__global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_sweep(DeviceModel M, const double* __restrict__ u64,
+                                                                         const ST* z, ST* out, int row_begin, int row_end) {
+    if (M.ctl->all_done) return;
+    const int K = M.K, W = M.W;
+    const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
+    const int32_t* __restrict__ ecol = M.ell_col;
+    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
+    ST* us = reinterpret_cast<ST*>(M.us);
+    const int stride = gridDim.x * GPB;
+    for (int c = lane * VEC; c < K; c += KC * VEC) {
+        // software pipeline: the next row's indices / values are fetched under this row's gathers
+        int i = row_begin + blockIdx.x * GPB + group;
+        int4 c4n = make_int4(0, 0, 0, 0);
+        Pk<ST, 4> vn = {};
+        if (i < row_end) {
+            c4n = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
+            vn = ldk<ST, 4>(eval + (size_t)i * W);
+        }
+        for (; i < row_end; i += stride) {
+            const size_t idx = (size_t)i * K + c;
+            const int4 c4 = c4n;
+            const Pk<ST, 4> v = vn;
+            Pk<ST, VEC> x0, x1, x2, x3, own;
+            if (FIRST) {
+                const Pk<double, VEC> d0 = ldk<double, VEC>(u64 + (size_t)c4.x * K + c), d1 = ldk<double, VEC>(u64 + (size_t)c4.y * K + c);
+                const Pk<double, VEC> d2 = ldk<double, VEC>(u64 + (size_t)c4.z * K + c), d3 = ldk<double, VEC>(u64 + (size_t)c4.w * K + c);
+                const Pk<double, VEC> dn = ldk<double, VEC>(u64 + idx);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) {
+                    x0.a[q] = (ST)d0.a[q]; x1.a[q] = (ST)d1.a[q]; x2.a[q] = (ST)d2.a[q]; x3.a[q] = (ST)d3.a[q]; own.a[q] = (ST)dn.a[q];
+                }
+            } else {
+                x0 = ldk<ST, VEC>(z + (size_t)c4.x * K + c); x1 = ldk<ST, VEC>(z + (size_t)c4.y * K + c);
+                x2 = ldk<ST, VEC>(z + (size_t)c4.z * K + c); x3 = ldk<ST, VEC>(z + (size_t)c4.w * K + c);
+                own = ldk<ST, VEC>(us + idx);
+            }
+            const int inext = i + stride;
+            if (inext < row_end) {
+                c4n = *reinterpret_cast<const int4*>(ecol + (size_t)inext * W);
+                vn = ldk<ST, 4>(eval + (size_t)inext * W);
+            }
+            Pk<ST, VEC> o;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q)
+                o.a[q] = v.a[3] * x3.a[q] + (v.a[2] * x2.a[q] + (v.a[1] * x1.a[q] + v.a[0] * x0.a[q]));
+            for (int w = 4; w < W; w += 4) {      // rows wider than 4 (not pipelined)
+                const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+                const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
+                const int cs[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    Pk<ST, VEC> y;
+                    if (FIRST) {
+                        const Pk<double, VEC> d = ldk<double, VEC>(u64 + (size_t)cs[u] * K + c);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) y.a[q] = (ST)d.a[q];
+                    } else y = ldk<ST, VEC>(z + (size_t)cs[u] * K + c);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) o.a[q] += wv.a[u] * y.a[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - o.a[q];
+            stk<ST, VEC>(out + idx, o);
+            if (FIRST) stk<ST, VEC>(us + idx, own);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Multicolour Gauss-Seidel preconditioner, all sweeps of one application in ONE persistent kernel:
+//   z = 0;  repeat n_sweeps times:  for colour = 0 .. n_colors-1:  z_i = u_i - (L z)_i  for the rows of
+//   that colour (in place),
+// with a grid-wide barrier between colours (cooperative launch: every CTA is resident).  The colours
+// follow the flow (cwr_topology.cpp), so one sweep carries information ~n_colors cells downstream, at
+// the memory traffic of ONE Jacobi step -- the colours only cut that step into slices.  During the first
+// sweep neighbours of a later colour have not been visited yet (z = 0 there: index >= the colour's first
+// row) and u arrives as the solver's fp64 vector; its ST copy is kept in M.us for the later sweeps.
+// Gathers bypass L1 (ld.cg): the values were written by other SMs a barrier ago.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int V>
+__device__ __forceinline__ Pk<T, V> ldk_cg(const T* p) {
+    Pk<T, V> r;
+    if constexpr (sizeof(T) * V == 16) { const int4 t = __ldcg(reinterpret_cast<const int4*>(p)); r = *reinterpret_cast<const Pk<T, V>*>(&t); }
+    else if constexpr (sizeof(T) * V == 8) { const int2 t = __ldcg(reinterpret_cast<const int2*>(p)); r = *reinterpret_cast<const Pk<T, V>*>(&t); }
+    else if constexpr (sizeof(T) * V == 4) { const int t = __ldcg(reinterpret_cast<const int*>(p)); r = *reinterpret_cast<const Pk<T, V>*>(&t); }
+    else {
+#pragma unroll
+        for (int q = 0; q < V; ++q) r.a[q] = __ldcg(p + q);
+    }
+    return r;
+}
+
+__device__ __forceinline__ void grid_barrier(SolverCtl* ctl, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(&ctl->gs_bar[0], 1u);
+        unsigned spins = 0;
+        while (*reinterpret_cast<volatile unsigned*>(&ctl->gs_bar[0]) < target)
+            if (++spins > (1u << 27)) { ctl->barrier_timeout = 1; break; }      // never hang the device
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// One CTA of 1024 threads per SM (148 barrier arrivals instead of 592); every lane group owns up to two
+// rows of a colour at a time.  The loads that do not depend on other CTAs -- the rows' column indices,
+// matrix values and right-hand side -- are issued BEFORE the barrier in front of the colour; after it the
+// eight gathers of the two rows go out together as 16-byte cp.async.cg copies into per-thread shared
+// memory slots (no destination registers held while they are in flight, L1 bypassed), so a colour costs
+// one barrier plus one gather latency.  Packs narrower than 16 bytes gather into registers instead.
+constexpr int kGsThreads = 1024;
+constexpr int kGsSmemBytes = 2 * 4 * 16 * kGsThreads;
+
+__device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <typename ST, int KC, int VEC>
+__global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, const double* __restrict__ u64, ST* z, int n_sweeps) {
+    constexpr bool SMEM = sizeof(ST) * VEC == 16;
+    extern __shared__ int4 gs_land[];          // [2 rows][4 neighbours][kGsThreads] landing slots (SMEM path)
+    if (M.ctl->all_done) return;
+    const int K = M.K, W = M.W, nc = M.n_colors;
+    const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kGsThreads / KC;
+    const int32_t* __restrict__ ecol = M.ell_col;
+    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
+    ST* us = reinterpret_cast<ST*>(M.us);
+    const int TG = gridDim.x * GPB, gid = blockIdx.x * GPB + group;
+    const int c = lane * VEC;
+    const bool lane_on = c < K;
+    const int n_steps = n_sweeps * nc;
+    unsigned epoch = 0;
+    auto colour_of = [&](int step) { return step % nc; };
+    auto load_own = [&](int i, int cc, bool first_sweep) {
+        Pk<ST, VEC> own;
+        if (first_sweep) {
+            const Pk<double, VEC> d = ldk<double, VEC>(u64 + (size_t)i * K + cc);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) own.a[q] = (ST)d.a[q];
+        } else own = ldk<ST, VEC>(us + (size_t)i * K + cc);      // written by this very thread in sweep 0
+        return own;
+    };
+    // pipeline registers: the first two rows of the coming colour
+    int4 pc[2]; Pk<ST, 4> pv[2]; Pk<ST, VEC> pown[2];
+    auto prefetch = [&](int step) {
+        const int col = colour_of(step);
+        const int rb = __ldg(M.color_ptr + col), re = __ldg(M.color_ptr + col + 1);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int i = rb + gid + r * TG;
+            if (i < re) {
+                pc[r] = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
+                pv[r] = ldk<ST, 4>(eval + (size_t)i * W);
+                if (lane_on) pown[r] = load_own(i, c, step < nc);
+            }
+        }
+    };
+    // one row, columns [cc, cc + VEC), everything through registers (tail rows / extra column chunks / wide rows)
+    auto relax_tail = [&](int i, int cc, int w0, Pk<ST, VEC> acc, const Pk<ST, VEC>& own, int rb, bool first_sweep, bool finish) {
+        for (int w = w0; w < W; w += 4) {
+            const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+            const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
+            const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+            Pk<ST, VEC> y[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (first_sweep && ds[u] >= rb) {
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) y[u].a[q] = (ST)0;
+                } else y[u] = ldk_cg<ST, VEC>(z + (size_t)ds[u] * K + cc);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) acc.a[q] += wv.a[u] * y[u].a[q];
+        }
+        if (finish) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
+            stk<ST, VEC>(z + (size_t)i * K + cc, acc);
+            if (first_sweep) stk<ST, VEC>(us + (size_t)i * K + cc, own);
+        }
+        return acc;
+    };
+    Pk<ST, VEC> zero;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) zero.a[q] = (ST)0;
+
+    prefetch(0);
+    for (int step = 0; step < n_steps; ++step) {
+        const int col = colour_of(step);
+        const bool first_sweep = step < nc;
+        const int rb = __ldg(M.color_ptr + col), re = __ldg(M.color_ptr + col + 1);
+        const int i0 = rb + gid, i1 = i0 + TG;
+        const bool on[2] = {i0 < re && lane_on, i1 < re && lane_on};
+        const int row[2] = {i0, i1};
+        // ---- gathers of both pipelined rows go out together --------------------------------------------
+        Pk<ST, VEC> xr[SMEM ? 1 : 2][SMEM ? 1 : 4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!on[r]) continue;
+            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool skip = first_sweep && cs[u] >= rb;        // not visited yet in the sweep from z = 0
+                if constexpr (SMEM) {
+                    int4* slot = gs_land + (r * 4 + u) * kGsThreads + threadIdx.x;
+                    if (skip) *slot = make_int4(0, 0, 0, 0);
+                    else cp_async_cg16(slot, z + (size_t)cs[u] * K + c);
+                } else {
+                    xr[r][u] = skip ? zero : ldk_cg<ST, VEC>(z + (size_t)cs[u] * K + c);
+                }
+            }
+        }
+        if constexpr (SMEM) cp_async_wait_all();
+        // ---- update, store ------------------------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!on[r]) continue;
+            Pk<ST, VEC> o = zero;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                Pk<ST, VEC> x;
+                if constexpr (SMEM) x = *reinterpret_cast<const Pk<ST, VEC>*>(gs_land + (r * 4 + u) * kGsThreads + threadIdx.x);
+                else x = xr[r][u];
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) o.a[q] += pv[r].a[u] * x.a[q];
+            }
+            relax_tail(row[r], c, 4, o, pown[r], rb, first_sweep, true);
+        }
+        // further column chunks of the two rows (K > lanes x VEC), and colours with more than two rows per lane group
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r)
+            if (row[r] < re)
+                for (int cc = c + KC * VEC; cc < K; cc += KC * VEC)
+                    relax_tail(row[r], cc, 0, zero, load_own(row[r], cc, first_sweep), rb, first_sweep, true);
+#pragma unroll 1
+        for (int i = rb + gid + 2 * TG; i < re; i += TG)
+            for (int cc = c; cc < K; cc += KC * VEC)
+                relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), rb, first_sweep, true);
+        if (step + 1 < n_steps) {
+            prefetch(step + 1);
+            grid_barrier(M.ctl, ++epoch * gridDim.x);
+        }
+    }
+    // the last CTA to leave re-arms the barrier for the next launch
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
+        if (t == gridDim.x - 1) { M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0; __threadfence(); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// SpMM over the row-scaled matrix, fused with the BiCGSTAB step that consumes it.  z (type ZT: the
+// solver's own fp64 vector, or a preconditioned vector in the sweep precision) is gathered and widened.
 //   INIT : r = b - (x + L x)          ; rhat = p = r ; dots (r,r), (b,b)
-//   JAC  : out = u - L z              (one step of the m-step Jacobi preconditioner: out = u + N z)
 //   AV   : v = z + L z                ; dot (rhat, v)                      -> alpha
 //   AT   : t = z + L z                ; dots (t,s),(t,t),(rhat,t),(rhat,s) -> omega, rho', beta
 //   PLAIN: y = z + L z                (timing / tests)
 // ---------------------------------------------------------------------------------------------
-enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_JAC = 3, MODE_PLAIN = 4 };
+enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_PLAIN = 4 };
 
-template <int KC, int VEC, int MODE>
-__global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceModel M, const double* __restrict__ zin,
-                                                   const double* __restrict__ uin, double* __restrict__ out) {
+template <int KC, int VEC, int MODE, typename ZT>
+__global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceModel M, const ZT* __restrict__ zin,
+                                                                        double* __restrict__ out) {
     constexpr int ND = MODE == MODE_INIT ? 2 : MODE == MODE_AV ? 1 : MODE == MODE_AT ? 4 : 1;
     constexpr bool HAS_DOTS = MODE == MODE_INIT || MODE == MODE_AV || MODE == MODE_AT;
     __shared__ double smem[HAS_DOTS ? (kThreads / 32) * kMaxDots * 2 * 32 : 1];
     __shared__ double tot[HAS_DOTS ? kMaxDots * kMaxK : 1];
-    if (MODE == MODE_AV || MODE == MODE_AT || MODE == MODE_JAC) { if (M.ctl->all_done) return; }
+    if (MODE == MODE_AV || MODE == MODE_AT) { if (M.ctl->all_done) return; }
     const int K = M.K, n = M.n, W = M.W;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
     const double* __restrict__ eval = M.val;
-    if (MODE == MODE_INIT) zin = M.sp->state_t1;
+    if (MODE == MODE_INIT) zin = reinterpret_cast<const ZT*>(M.sp->state_t1);     // ZT = double
     const int nchunk = (K + KC * VEC - 1) / (KC * VEC);
     for (int chunk = 0; chunk < nchunk; ++chunk) {
         const int c = (chunk * KC + lane) * VEC;
@@ -438,12 +728,12 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
                 const size_t idx = (size_t)i * K + c;
                 const int4 c4 = c4n;
                 const double2 v01 = v01n, v23 = v23n;
-                const Vd<VEC> x0 = ldv<VEC>(zin + (size_t)c4.x * K + c);
-                const Vd<VEC> x1 = ldv<VEC>(zin + (size_t)c4.y * K + c);
-                const Vd<VEC> x2 = ldv<VEC>(zin + (size_t)c4.z * K + c);
-                const Vd<VEC> x3 = ldv<VEC>(zin + (size_t)c4.w * K + c);
+                const Vd<VEC> x0 = ldz<ZT, VEC>(zin + (size_t)c4.x * K + c);
+                const Vd<VEC> x1 = ldz<ZT, VEC>(zin + (size_t)c4.y * K + c);
+                const Vd<VEC> x2 = ldz<ZT, VEC>(zin + (size_t)c4.z * K + c);
+                const Vd<VEC> x3 = ldz<ZT, VEC>(zin + (size_t)c4.w * K + c);
                 // the row's own operands are issued now as well, so nothing waits behind the gathers
-                const Vd<VEC> own = ldv<VEC>((MODE == MODE_JAC ? uin : zin) + idx);
+                const Vd<VEC> own = ldz<ZT, VEC>(zin + idx);
                 Vd<VEC> aux1 = own, aux2 = own;
                 if (MODE == MODE_INIT) aux1 = ldv<VEC>(M.b + idx);
                 if (MODE == MODE_AV || MODE == MODE_AT) aux1 = ldv<VEC>(M.rhat + idx);
@@ -462,55 +752,48 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
                     const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
                     const double2 w01 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w);
                     const double2 w23 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w + 2);
-                    const Vd<VEC> y0 = ldv<VEC>(zin + (size_t)d4.x * K + c);
-                    const Vd<VEC> y1 = ldv<VEC>(zin + (size_t)d4.y * K + c);
-                    const Vd<VEC> y2 = ldv<VEC>(zin + (size_t)d4.z * K + c);
-                    const Vd<VEC> y3 = ldv<VEC>(zin + (size_t)d4.w * K + c);
+                    const Vd<VEC> y0 = ldz<ZT, VEC>(zin + (size_t)d4.x * K + c);
+                    const Vd<VEC> y1 = ldz<ZT, VEC>(zin + (size_t)d4.y * K + c);
+                    const Vd<VEC> y2 = ldz<ZT, VEC>(zin + (size_t)d4.z * K + c);
+                    const Vd<VEC> y3 = ldz<ZT, VEC>(zin + (size_t)d4.w * K + c);
 #pragma unroll
                     for (int q = 0; q < VEC; ++q)
                         s.a[q] = fma(w23.y, y3.a[q], fma(w23.x, y2.a[q], fma(w01.y, y1.a[q], fma(w01.x, y0.a[q], s.a[q]))));
                 }
-                if (MODE == MODE_JAC) {
-                    Vd<VEC> o;
+                Vd<VEC> y;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - s.a[q];
-                    stv<VEC>(out + idx, o);
-                } else {
-                    Vd<VEC> y;
+                for (int q = 0; q < VEC; ++q) y.a[q] = own.a[q] + s.a[q];
+                if (MODE == MODE_INIT) {
+                    const Vd<VEC> bi = aux1;
+                    Vd<VEC> r;
 #pragma unroll
-                    for (int q = 0; q < VEC; ++q) y.a[q] = own.a[q] + s.a[q];
-                    if (MODE == MODE_INIT) {
-                        const Vd<VEC> bi = aux1;
-                        Vd<VEC> r;
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) {
-                            r.a[q] = bi.a[q] - y.a[q];
-                            acc[0 * VEC + q] = fma(r.a[q], r.a[q], acc[0 * VEC + q]);
-                            acc[1 * VEC + q] = fma(bi.a[q], bi.a[q], acc[1 * VEC + q]);
-                        }
-                        stv<VEC>(M.r + idx, r); stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r);
-                    } else if (MODE == MODE_AV) {
-                        const Vd<VEC> rh = aux1;
-                        stv<VEC>(M.v + idx, y);
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) acc[q] = fma(rh.a[q], y.a[q], acc[q]);
-                    } else if (MODE == MODE_AT) {
-                        const Vd<VEC> rh = aux1, sv = aux2;
-                        stv<VEC>(M.tt + idx, y);
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) {
-                            acc[0 * VEC + q] = fma(y.a[q], sv.a[q], acc[0 * VEC + q]);
-                            acc[1 * VEC + q] = fma(y.a[q], y.a[q], acc[1 * VEC + q]);
-                            acc[2 * VEC + q] = fma(rh.a[q], y.a[q], acc[2 * VEC + q]);
-                            acc[3 * VEC + q] = fma(rh.a[q], sv.a[q], acc[3 * VEC + q]);
-                        }
-                    } else {
-                        stv<VEC>(out + idx, y);
+                    for (int q = 0; q < VEC; ++q) {
+                        r.a[q] = bi.a[q] - y.a[q];
+                        acc[0 * VEC + q] = fma(r.a[q], r.a[q], acc[0 * VEC + q]);
+                        acc[1 * VEC + q] = fma(bi.a[q], bi.a[q], acc[1 * VEC + q]);
                     }
+                    stv<VEC>(M.r + idx, r); stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r);
+                } else if (MODE == MODE_AV) {
+                    const Vd<VEC> rh = aux1;
+                    stv<VEC>(M.v + idx, y);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc[q] = fma(rh.a[q], y.a[q], acc[q]);
+                } else if (MODE == MODE_AT) {
+                    const Vd<VEC> rh = aux1, sv = aux2;
+                    stv<VEC>(M.tt + idx, y);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        acc[0 * VEC + q] = fma(y.a[q], sv.a[q], acc[0 * VEC + q]);
+                        acc[1 * VEC + q] = fma(y.a[q], y.a[q], acc[1 * VEC + q]);
+                        acc[2 * VEC + q] = fma(rh.a[q], y.a[q], acc[2 * VEC + q]);
+                        acc[3 * VEC + q] = fma(rh.a[q], sv.a[q], acc[3 * VEC + q]);
+                    }
+                } else {
+                    stv<VEC>(out + idx, y);
                 }
             }
         }
-        if (HAS_DOTS) block_dots<ND, KC, VEC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
+        if (HAS_DOTS) block_dots<ND, KC, VEC>(acc, smem, M.partials, K, chunk);
     }
     if (!HAS_DOTS) return;
     if (!last_block_arrives(&M.ctl->ticket[MODE])) return;
@@ -578,10 +861,9 @@ __global__ void __launch_bounds__(kThreads) k_update_s(DeviceModel M) {
 }
 
 // x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v) ; dot (r,r); convergence
-// (ph, sh: preconditioned p and s; equal to p and s when the preconditioner is the identity)
-template <int KC, int VEC>
-__global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const double* __restrict__ ph,
-                                                         const double* __restrict__ sh) {
+// (ph, sh: preconditioned p and s in the sweep precision PT; p and s themselves when m = 1)
+template <int KC, int VEC, typename PT>
+__global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const PT* ph, const PT* sh) {
     __shared__ double smem[(kThreads / 32) * kMaxDots * 2 * 32];
     __shared__ double tot[kMaxDots * kMaxK];
     if (M.ctl->all_done) return;
@@ -608,7 +890,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const do
                     const size_t idx = (size_t)i * K + c;
                     Vd<VEC> xv = ldv<VEC>(x + idx), rv = ldv<VEC>(M.r + idx), pv = ldv<VEC>(M.p + idx);
                     const Vd<VEC> tv = ldv<VEC>(M.tt + idx), vv = ldv<VEC>(M.v + idx);
-                    const Vd<VEC> phv = ldv<VEC>(ph + idx), shv = ldv<VEC>(sh + idx);
+                    const Vd<VEC> phv = ldz<PT, VEC>(ph + idx), shv = ldz<PT, VEC>(sh + idx);
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) {
                         if (f[q] & FL_PENDING) {
@@ -624,7 +906,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const do
                     stv<VEC>(x + idx, xv); stv<VEC>(M.r + idx, rv); stv<VEC>(M.p + idx, pv);
                 }
         }
-        block_dots<1, KC, VEC>(acc, smem, M.partials + (size_t)blockIdx.x * kMaxDots * K, K, chunk);
+        block_dots<1, KC, VEC>(acc, smem, M.partials, K, chunk);
     }
     if (!last_block_arrives(&M.ctl->ticket[3])) return;
     grid_totals<1>(M.partials, tot, K);

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M,
     const double* __restrict__ b = M.b + k;               // stride K
     const size_t col0 = (size_t)k * n;
     double *r = M.r + col0, *rhat = M.rhat + col0, *p = M.p + col0, *v = M.v + col0, *t = M.tt + col0;
-    double *phb = M.ph + col0, *shb = M.sh + col0, *tmp = M.tmp + col0, *xc = M.xc + col0;
+    double *phb = (double*)M.ph + col0, *shb = (double*)M.sh + col0, *tmp = (double*)M.tmp + col0, *xc = M.xc + col0;
     int flags = 0, iters = 0, restarts = 0;
     double bb = 0.0, rr = 0.0;
 

@@ -49,7 +49,7 @@ struct Bfs {
 }  // namespace
 
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
-                           bool rcm, Topology& T) {
+                           bool rcm, int n_colors, const float* hint, Topology& T) {
     if (n_real <= 0 || n_face < n_real || n_edge <= 0) return "n_real, n_face, n_edge must be positive and n_face >= n_real";
     const int n = n_real, F = n_face, E = n_edge;
     int32_t max_f1 = -1;
@@ -122,6 +122,88 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             }
         }
         for (int i = 0; i < n; ++i) T.old_of_new[i] = order[n - 1 - i];
+    }
+    // ---- flow-aligned multicolouring (for the Gauss-Seidel preconditioner) -------------------------------
+    // A sweep visits the colours in order and updates the rows of one colour in parallel, so colours
+    // must separate coupled rows.  Upwind advection makes the matrix nearly triangular in the downstream
+    // order: a row mostly depends on its UPSTREAM neighbours.  If colours increase along the flow, one
+    // sweep carries information across as many cells as there are colours (a row sees the values its
+    // upstream neighbours got earlier in the same sweep); colours that ignore the flow carry it ~2 cells.
+    // So: level(v) = longest downstream path to v in the flow graph of the hint (Kahn's algorithm; cycles
+    // are cut at the node that comes first in RCM order), bumped until (level mod n_colors) differs from
+    // every neighbour already coloured; colour = level mod n_colors.  Without a hint every edge is
+    // undirected and this is the greedy colouring in RCM order.  Rows are regrouped colour-major, inside
+    // a colour by (level, RCM position): one colour = one contiguous row range.
+    T.color_ptr.assign(1, 0);
+    if (n_colors > 0) {
+        int max_deg = 0;
+        for (int i = 0; i < n; ++i) max_deg = std::max(max_deg, aptr[i + 1] - aptr[i]);
+        if (max_deg + 1 > 64) return "a cell has more than 63 neighbours: multicolour sweeps not available (precond_sweep = 0)";
+        const int nc = std::min(64, std::max(n_colors, max_deg + 1));
+        std::vector<int32_t> rcm_pos(n);
+        for (int i = 0; i < n; ++i) rcm_pos[T.old_of_new[i]] = i;
+        // directed flow graph among real cells: up -> down
+        std::vector<int32_t> indeg(n, 0), optr(n + 1, 0), oadj;
+        if (hint) {
+            for (int e = 0; e < E; ++e) {
+                if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) continue;
+                const int32_t up = hint[e] > 0.f ? f1[e] : f2[e], down = hint[e] > 0.f ? f2[e] : f1[e];
+                ++optr[up + 1]; ++indeg[down];
+            }
+            for (int i = 0; i < n; ++i) optr[i + 1] += optr[i];
+            oadj.resize(optr[n]);
+            std::vector<int32_t> fill(optr.begin(), optr.end() - 1);
+            for (int e = 0; e < E; ++e) {
+                if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) continue;
+                const int32_t up = hint[e] > 0.f ? f1[e] : f2[e], down = hint[e] > 0.f ? f2[e] : f1[e];
+                oadj[fill[up]++] = down;
+            }
+        }
+        std::vector<int32_t> level(n, -1), tentative(n, 0), queue;
+        queue.reserve(n);
+        for (int i = 0; i < n; ++i) { const int32_t u = T.old_of_new[i]; if (indeg[u] == 0) queue.push_back(u); }
+        std::vector<uint8_t> queued(n, 0);
+        for (int32_t u : queue) queued[u] = 1;
+        size_t head = 0;
+        int scan = 0;                 // next RCM position to look at when a cycle blocks the queue
+        int max_level = 0;
+        for (int done = 0; done < n; ++done) {
+            if (head == queue.size()) {            // only cycles left: cut one at the first unprocessed node
+                while (queued[T.old_of_new[scan]]) ++scan;
+                const int32_t u = T.old_of_new[scan];
+                queued[u] = 1; queue.push_back(u);
+            }
+            const int32_t u = queue[head++];
+            uint64_t used = 0;
+            for (int32_t j = aptr[u]; j < aptr[u + 1]; ++j) {
+                const int32_t lv = level[adj[j]];
+                if (lv >= 0) used |= (uint64_t)1 << (lv % nc);
+            }
+            int lv = tentative[u];
+            for (int tries = 0; tries < nc && ((used >> (lv % nc)) & 1); ++tries) ++lv;   // degree < nc: always found
+            level[u] = lv;
+            max_level = std::max(max_level, lv);
+            for (int32_t j = optr[u]; j < optr[u + 1]; ++j) {
+                const int32_t v = oadj[j];
+                tentative[v] = std::max(tentative[v], lv + 1);
+                if (--indeg[v] == 0 && !queued[v]) { queued[v] = 1; queue.push_back(v); }
+            }
+        }
+        std::vector<int32_t> order(n);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            const int ca = level[a] % nc, cb = level[b] % nc;
+            if (ca != cb) return ca < cb;
+            if (level[a] != level[b]) return level[a] < level[b];
+            return rcm_pos[a] < rcm_pos[b];
+        });
+        T.color_ptr.assign(nc + 1, 0);
+        for (int i = 0; i < n; ++i) ++T.color_ptr[level[i] % nc + 1];
+        for (int c = 0; c < nc; ++c) T.color_ptr[c + 1] += T.color_ptr[c];
+        T.old_of_new.swap(order);
+        T.n_levels = max_level + 1;
+    } else {
+        T.color_ptr.push_back(n);
     }
     for (int i = 0; i < n; ++i) T.new_of_old[T.old_of_new[i]] = i;
 

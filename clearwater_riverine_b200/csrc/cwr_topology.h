@@ -42,12 +42,16 @@ struct Topology {
     int W = 4;                        // ELL width: max row length rounded up to a multiple of 4
     std::vector<int32_t> ell_col;     // (n*W) row-major; padding points at the row itself
     std::vector<int32_t> ell_code;    // (n*W) slot_edge code, -1 for padding
+    std::vector<int32_t> color_ptr;   // (n_colors+1) row ranges of the colours ({0, n} when not multicoloured)
+    int n_levels = 1;                 // downstream levels of the flow hint the colours were cut from (diagnostic)
     int max_row_len = 0;
     int64_t bandwidth = 0;            // max |row - col| after reordering (diagnostic)
 };
 
 // Returns an empty string on success, else an error message.
+// n_colors > 0: rows are regrouped into that many colours for the multicolour Gauss-Seidel sweeps; hint
+// (may be NULL): one signed flow per edge (reference order, > 0 = out of f1) the colours are aligned with.
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
-                           bool rcm, Topology& out);
+                           bool rcm, int n_colors, const float* hint, Topology& out);
 
 }  // namespace cwr

@@ -46,9 +46,19 @@ typedef struct {
     int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = single-CTA persistent solve (small meshes) */
     int use_graph;          /* 1 = device-side iteration loop in a CUDA graph (default), 0 = host-polled loop */
     int check_every;        /* host-polled loop: iterations launched per convergence poll; default 1 */
-    int precond_steps;      /* m of the m-step Jacobi polynomial preconditioner (I + N + ... + N^(m-1)) D^-1,
-                               N = I - D^-1 A; 1 = plain Jacobi (diagonal) preconditioning; default 8 */
-    int reserved[6];
+    int precond_steps;      /* m: the preconditioner applies m - 1 sweeps; 1 = diagonal (Jacobi) scaling only;
+                               0 (default) = 5 with Gauss-Seidel sweeps, 8 with Jacobi steps / the small-mesh path */
+    int precond_precision;  /* 32 (default): the sweeps and the preconditioned vectors are fp32 (half the bytes;
+                               BiCGSTAB itself, its products A p^ / A s^ and its dots stay fp64, so the converged
+                               answer is the fp64 one); 64: fp64 sweeps */
+    int precond_sweep;      /* 1 (default) = multicolour Gauss-Seidel sweeps from z = 0, all m - 1 sweeps of one
+                               application in one persistent kernel with a grid barrier per colour; the rows are
+                               regrouped colour-major and the colours follow the flow (cwr_set_flow_hint, or the
+                               first hydrodynamic slices uploaded -- upload hydro before inputs);
+                               0 = Jacobi steps, z = (I + N + ... + N^(m-1)) u with N = I - D^-1 A */
+    int precond_colors;     /* colours of the Gauss-Seidel sweeps (raised to max row degree + 1 if smaller);
+                               0 (default) = chosen from the mesh size so that one colour moves ~20 MB */
+    int reserved[3];
 } cwr_options;
 
 typedef struct {
@@ -86,6 +96,11 @@ int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double*
 int cwr_set_geometry(cwr_handle* h, const double* face_x, const double* face_y);
 int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
                       const float* volume, const double* dt);
+
+/* Optional, before any other set_* call: one representative signed face flow per edge ((E,) f32, e.g. the
+ * time mean of `Face Flow`) for the flow-aligned colouring of the Gauss-Seidel sweeps (precond_sweep = 1).
+ * Without it the first cwr_set_hydro* call's slices are used.  Affects speed only, never results beyond rtol. */
+int cwr_set_flow_hint(cwr_handle* h, const float* face_flow);
 
 /* Constituent.input_array (constituents.py:31,93,164): (T,F) f64, IC in row 0, BC values in
  * ghost-cell columns, 0 = "not set".  Also initialises c[0] as set_initial_conditions does. */
@@ -126,7 +141,14 @@ int cwr_get_flux_sums(cwr_handle* h, int k, double* total_sum, double* in_sum, d
 int cwr_get_lhs(cwr_handle* h, int64_t* nnz, int32_t* indptr, int32_t* indices, double* data);
 int cwr_get_rhs(cwr_handle* h, int k, double* b);           /* (n,) f64, unscaled */
 int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old); /* (n,) */
+int cwr_get_options(const cwr_handle* h, cwr_options* resolved); /* the options in force (autos resolved) */
 int cwr_stream(cwr_handle* h, void** cuda_stream);           /* the handle's cudaStream_t */
+/* Host only (no device needed): the cell ordering cwr_create / the first cwr_set_hydro* would build --
+ * reverse Cuthill-McKee, then (n_colors > 0) the flow-aligned multicolouring of the Gauss-Seidel sweeps.
+ * flow_hint: (E,) signed face flow (> 0 leaves f1) or NULL; new_of_old: (n_real,); color_ptr: (65,) row
+ * ranges of the colours in the new numbering (n_colors_out + 1 entries used), may be NULL. */
+int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int reorder, int n_colors,
+                    const float* flow_hint, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out, int* n_levels);
 int cwr_counters(cwr_handle* h, int64_t* kernel_launches, int64_t* solver_iterations);
 
 /* --- device timing of the dominant kernel (bench.py roofline) -------------------------------- */

@@ -33,7 +33,7 @@ def test_default_options(lib):
     from clearwater_riverine_b200.backend import CwrOptions
     o = CwrOptions()
     assert lib.cwr_default_options(ctypes.byref(o)) == 0
-    assert o.rtol == 1e-13 and o.precond_steps == 8 and o.reorder == 1 and o.mass_flux == 1 and o.keep_history == 1
+    assert o.rtol == 1e-13 and o.precond_steps == 0 and o.precond_sweep == 1 and o.precond_precision == 32 and o.reorder == 1 and o.mass_flux == 1 and o.keep_history == 1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
