@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -345,8 +346,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
             if (!coop || occ_gs < 1) FAIL(CWR_ECUDA, "cooperative launch not available: use precond_sweep = 0");
             // every CTA must be resident (grid barrier): SM count x occupancy, and no more CTAs than the
             // largest colour has row groups
-            h->grid_gs = grid_for((n + (int)tp.color_ptr.size() - 2) / std::max(1, (int)tp.color_ptr.size() - 1),
-                                  kGsThreads / h->SKC, h->num_sms * occ_gs);
+            h->grid_gs = h->num_sms * occ_gs;      // every CTA resident: the kernel synchronises grid-wide
         }
     }
     h->grid_rows = grid_for(n, kThreads / kc, h->max_grid);
@@ -1015,16 +1015,21 @@ int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_to
     CK(cudaSetDevice(h->device));
     int ts[2] = {t_start, t_end};
     double res[2][2];
-    int rc = ensure_stage(h, 64);
+    int rc = ensure_stage(h, 64 + 16 * kMassBlocks);
     if (rc) return rc;
+    double* d_out = (double*)h->d_stage;
+    unsigned* d_ticket = (unsigned*)(d_out + 2);
+    double* d_partial = d_out + 8;
+    CK(cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), h->stream));
     for (int i = 0; i < 2; ++i) {
         rc = state_available(h, ts[i]);
         if (rc) return rc;
         const int s = find_slot(h, ts[i]);
         if (s < 0) FAIL(CWR_EINVAL, "volume slice not resident for mass totals");
-        k_mass_total<<<1, kThreads, 0, h->stream>>>(h->d_vol + (size_t)s * h->n, state_slot(h, ts[i]), h->n, h->K, k, (double*)h->d_stage);
+        k_mass_total<<<grid_for(h->n, kThreads, kMassBlocks), kThreads, 0, h->stream>>>(
+            h->d_vol + (size_t)s * h->n, state_slot(h, ts[i]), h->n, h->K, k, d_partial, d_ticket, d_out);
         h->launches += 1;
-        CK(cudaMemcpyAsync(res[i], h->d_stage, 16, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(res[i], d_out, 16, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
     out->vol_start = res[0][0]; out->mass_start = res[0][1]; out->vol_end = res[1][0]; out->mass_end = res[1][1];

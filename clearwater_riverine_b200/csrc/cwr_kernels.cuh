@@ -47,7 +47,7 @@ struct SolverCtl {
     int barrier_timeout; // a grid barrier of the persistent sweep kernel gave up (never expected)
     int pad[2];
     unsigned ticket[4]; // last-block tickets (one per kernel family)
-    unsigned gs_bar[2]; // grid barrier arrivals / exits of k_precond_gs
+    unsigned gs_bar[2]; // k_precond_gs: grid barrier arrivals, exits
 };
 
 struct DeviceModel {
@@ -530,14 +530,17 @@ __device__ __forceinline__ void grid_barrier(SolverCtl* ctl, unsigned target) {
     __syncthreads();
 }
 
-// One CTA of 1024 threads per SM (148 barrier arrivals instead of 592); every lane group owns up to two
-// rows of a colour at a time.  The loads that do not depend on other CTAs -- the rows' column indices,
-// matrix values and right-hand side -- are issued BEFORE the barrier in front of the colour; after it the
-// eight gathers of the two rows go out together as 16-byte cp.async.cg copies into per-thread shared
-// memory slots (no destination registers held while they are in flight, L1 bypassed), so a colour costs
-// one barrier plus one gather latency.  Packs narrower than 16 bytes gather into registers instead.
-constexpr int kGsThreads = 1024;
-constexpr int kGsSmemBytes = 2 * 4 * 16 * kGsThreads;
+// Two CTAs of 512 threads per SM.  Every lane group owns up to kGsRows rows of a colour at a time.  The
+// loads that do not depend on other CTAs -- the rows' column indices and matrix values -- are issued
+// BEFORE the barrier in front of the colour; after it all gathers of those rows go out together as
+// 16-byte cp.async.cg copies into per-thread shared-memory slots (no destination registers held while in
+// flight, L1 bypassed), so a colour costs one barrier plus one gather latency.  Packs narrower than 16
+// bytes gather into registers.  (Measured and rejected, profiles/r01_notes.md: splitting the columns into
+// two independently synchronised halves to overlap one half's barrier with the other half's work; three
+// pipelined rows, which spill.)
+constexpr int kGsThreads = 512;
+constexpr int kGsRows = 2;
+constexpr int kGsSmemBytes = kGsRows * 4 * 16 * kGsThreads;
 
 __device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -546,21 +549,22 @@ __device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 template <typename ST, int KC, int VEC>
-__global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, const double* __restrict__ u64, ST* z, int n_sweeps) {
+__global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, const double* __restrict__ u64, ST* z, int n_sweeps) {
     constexpr bool SMEM = sizeof(ST) * VEC == 16;
-    extern __shared__ int4 gs_land[];          // [2 rows][4 neighbours][kGsThreads] landing slots (SMEM path)
+    constexpr int NR = kGsRows;
+    extern __shared__ int4 gs_land[];          // [NR rows][4 neighbours][kGsThreads] landing slots (SMEM path)
     if (M.ctl->all_done) return;
     const int K = M.K, W = M.W, nc = M.n_colors;
+    const int vb = blockIdx.x, nvb = gridDim.x, c_end = K;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kGsThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
     const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
     ST* us = reinterpret_cast<ST*>(M.us);
-    const int TG = gridDim.x * GPB, gid = blockIdx.x * GPB + group;
+    const int TG = nvb * GPB, gid = vb * GPB + group;
     const int c = lane * VEC;
-    const bool lane_on = c < K;
+    const bool lane_on = c < c_end;
     const int n_steps = n_sweeps * nc;
     unsigned epoch = 0;
-    auto colour_of = [&](int step) { return step % nc; };
     auto load_own = [&](int i, int cc, bool first_sweep) {
         Pk<ST, VEC> own;
         if (first_sweep) {
@@ -570,23 +574,22 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, con
         } else own = ldk<ST, VEC>(us + (size_t)i * K + cc);      // written by this very thread in sweep 0
         return own;
     };
-    // pipeline registers: the first two rows of the coming colour
-    int4 pc[2]; Pk<ST, 4> pv[2]; Pk<ST, VEC> pown[2];
+    // pipeline registers: indices / values of the first NR rows of the coming colour
+    int4 pc[NR]; Pk<ST, 4> pv[NR];
     auto prefetch = [&](int step) {
-        const int col = colour_of(step);
+        const int col = step % nc;
         const int rb = __ldg(M.color_ptr + col), re = __ldg(M.color_ptr + col + 1);
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < NR; ++r) {
             const int i = rb + gid + r * TG;
             if (i < re) {
                 pc[r] = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
                 pv[r] = ldk<ST, 4>(eval + (size_t)i * W);
-                if (lane_on) pown[r] = load_own(i, c, step < nc);
             }
         }
     };
-    // one row, columns [cc, cc + VEC), everything through registers (tail rows / extra column chunks / wide rows)
-    auto relax_tail = [&](int i, int cc, int w0, Pk<ST, VEC> acc, const Pk<ST, VEC>& own, int rb, bool first_sweep, bool finish) {
+    // one row, columns [cc, cc + VEC): remaining ELL blocks through registers, then the update and the store
+    auto relax_tail = [&](int i, int cc, int w0, Pk<ST, VEC> acc, const Pk<ST, VEC>& own, int rb, bool first_sweep) {
         for (int w = w0; w < W; w += 4) {
             const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
             const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
@@ -604,13 +607,10 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, con
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) acc.a[q] += wv.a[u] * y[u].a[q];
         }
-        if (finish) {
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
-            stk<ST, VEC>(z + (size_t)i * K + cc, acc);
-            if (first_sweep) stk<ST, VEC>(us + (size_t)i * K + cc, own);
-        }
-        return acc;
+        for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
+        stk<ST, VEC>(z + (size_t)i * K + cc, acc);
+        if (first_sweep) stk<ST, VEC>(us + (size_t)i * K + cc, own);
     };
     Pk<ST, VEC> zero;
 #pragma unroll
@@ -618,16 +618,16 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, con
 
     prefetch(0);
     for (int step = 0; step < n_steps; ++step) {
-        const int col = colour_of(step);
+        const int col = step % nc;
         const bool first_sweep = step < nc;
         const int rb = __ldg(M.color_ptr + col), re = __ldg(M.color_ptr + col + 1);
-        const int i0 = rb + gid, i1 = i0 + TG;
-        const bool on[2] = {i0 < re && lane_on, i1 < re && lane_on};
-        const int row[2] = {i0, i1};
-        // ---- gathers of both pipelined rows go out together --------------------------------------------
-        Pk<ST, VEC> xr[SMEM ? 1 : 2][SMEM ? 1 : 4];
+        bool on[NR]; int row[NR];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < NR; ++r) { row[r] = rb + gid + r * TG; on[r] = row[r] < re && lane_on; }
+        // ---- all gathers of the pipelined rows go out together ------------------------------------------------
+        Pk<ST, VEC> xr[SMEM ? 1 : NR][SMEM ? 1 : 4], own[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
             if (!on[r]) continue;
             const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
 #pragma unroll
@@ -641,11 +641,12 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, con
                     xr[r][u] = skip ? zero : ldk_cg<ST, VEC>(z + (size_t)cs[u] * K + c);
                 }
             }
+            own[r] = load_own(row[r], c, first_sweep);
         }
         if constexpr (SMEM) cp_async_wait_all();
         // ---- update, store ------------------------------------------------------------------------------------
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
+        for (int r = 0; r < NR; ++r) {
             if (!on[r]) continue;
             Pk<ST, VEC> o = zero;
 #pragma unroll
@@ -656,28 +657,28 @@ __global__ void __launch_bounds__(kGsThreads, 1) k_precond_gs(DeviceModel M, con
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) o.a[q] += pv[r].a[u] * x.a[q];
             }
-            relax_tail(row[r], c, 4, o, pown[r], rb, first_sweep, true);
+            relax_tail(row[r], c, 4, o, own[r], rb, first_sweep);
         }
-        // further column chunks of the two rows (K > lanes x VEC), and colours with more than two rows per lane group
+        // further column chunks of those rows (more columns than lanes x VEC), and colours with more rows per lane group
 #pragma unroll 1
-        for (int r = 0; r < 2; ++r)
+        for (int r = 0; r < NR; ++r)
             if (row[r] < re)
-                for (int cc = c + KC * VEC; cc < K; cc += KC * VEC)
-                    relax_tail(row[r], cc, 0, zero, load_own(row[r], cc, first_sweep), rb, first_sweep, true);
+                for (int cc = c + KC * VEC; cc < c_end; cc += KC * VEC)
+                    relax_tail(row[r], cc, 0, zero, load_own(row[r], cc, first_sweep), rb, first_sweep);
 #pragma unroll 1
-        for (int i = rb + gid + 2 * TG; i < re; i += TG)
-            for (int cc = c; cc < K; cc += KC * VEC)
-                relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), rb, first_sweep, true);
+        for (int i = rb + gid + NR * TG; i < re; i += TG)
+            for (int cc = c; cc < c_end; cc += KC * VEC)
+                relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), rb, first_sweep);
         if (step + 1 < n_steps) {
             prefetch(step + 1);
-            grid_barrier(M.ctl, ++epoch * gridDim.x);
+            grid_barrier(M.ctl, ++epoch * nvb);
         }
     }
     // the last CTA to leave re-arms the barrier for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
-        if (t == gridDim.x - 1) { M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0; __threadfence(); }
+        if (t == (unsigned)nvb - 1) { M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0; __threadfence(); }
     }
 }
 
@@ -974,12 +975,16 @@ __global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
         }
 }
 
-// sum_i vol[i] * c[i,k]  -> out[k]   (single block, deterministic; postproc_util.py:36-59)
-__global__ void k_mass_total(const float* __restrict__ vol, const double* __restrict__ state, int n, int K, int k,
-                             double* __restrict__ out /* [2]: volume, mass */) {
+// sum_i vol[i], sum_i vol[i] * c[i,k]   (postproc_util.py:36-59).  Deterministic two-stage reduction:
+// kMassBlocks CTAs each reduce a grid-stride slice in a fixed order into partial[b][2]; the last CTA to
+// arrive adds the partials in block order.
+constexpr int kMassBlocks = 256;
+__global__ void __launch_bounds__(kThreads) k_mass_total(const float* __restrict__ vol, const double* __restrict__ state, int n, int K, int k,
+                                                         double* __restrict__ partial /* [kMassBlocks][2] */, unsigned* ticket,
+                                                         double* __restrict__ out /* [2]: volume, mass */) {
     __shared__ double sv[kThreads], sm[kThreads];
     double v = 0.0, m = 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double vi = (double)vol[i];
         v += vi; m = fma(vi, state[(size_t)i * K + k], m);
     }
@@ -989,7 +994,13 @@ __global__ void k_mass_total(const float* __restrict__ vol, const double* __rest
         if (threadIdx.x < s) { sv[threadIdx.x] += sv[threadIdx.x + s]; sm[threadIdx.x] += sm[threadIdx.x + s]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { out[0] = sv[0]; out[1] = sm[0]; }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sv[0]; partial[2 * blockIdx.x + 1] = sm[0]; }
+    if (!last_block_arrives(ticket)) return;
+    if (threadIdx.x == 0) {
+        double tv = 0.0, tm = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) { tv += __ldcg(partial + 2 * b); tm += __ldcg(partial + 2 * b + 1); }
+        out[0] = tv; out[1] = tm;
+    }
 }
 
 }  // namespace cwr
