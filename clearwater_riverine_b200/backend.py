@@ -26,12 +26,20 @@ class CwrOptions(C.Structure):
                 ("hydro_capacity", C.c_int), ("mass_flux", C.c_int), ("solver_path", C.c_int),
                 ("use_graph", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int),
                 ("precond_precision", C.c_int), ("precond_sweep", C.c_int), ("precond_colors", C.c_int),
-                ("reserved", C.c_int * 3)]
+                ("dd_rank", C.c_int), ("dd_world", C.c_int), ("reserved", C.c_int * 1)]
 
 
 class CwrStepInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("restarts", C.c_int), ("status", C.c_int),
                 ("max_relres", C.c_double), ("n_launches", C.c_int)]
+
+
+class CwrDdInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("world", C.c_int), ("rows_owned", C.c_int), ("rows_sent", C.c_int),
+                ("neighbour_mask", C.c_int), ("n_colors", C.c_int), ("n_levels", C.c_int)]
+
+
+IPC_HANDLE_BYTES = 64
 
 
 class CwrMassTotals(C.Structure):
@@ -89,9 +97,12 @@ def load_library():
         "cwr_get_rhs": ([H, C.c_int, dp], C.c_int),
         "cwr_get_permutation": ([H, ip], C.c_int),
         "cwr_get_options": ([H, C.POINTER(CwrOptions)], C.c_int),
+        "cwr_dd_export": ([H, C.c_void_p], C.c_int),
+        "cwr_dd_attach": ([H, C.c_void_p], C.c_int),
+        "cwr_dd_layout": ([H, C.POINTER(CwrDdInfo), C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)], C.c_int),
         "cwr_stream": ([H, C.POINTER(C.c_void_p)], C.c_int),
-        "cwr_order_cells": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, C.c_int, fp, ip, ip, C.POINTER(C.c_int),
-                             C.POINTER(C.c_int)], C.c_int),
+        "cwr_order_cells": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, C.c_int, fp, C.c_int, ip, ip, C.POINTER(C.c_int),
+                             C.POINTER(C.c_int), ip, ip], C.c_int),
         "cwr_counters": ([H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "cwr_time_spmm": ([H, C.c_int, dp, dp], C.c_int),
         "cwr_profile": ([H, C.c_int, dp, C.POINTER(C.c_int64)], C.c_int),
@@ -115,19 +126,29 @@ def _arr(a, dtype, shape=None, name="array") -> np.ndarray:
     return out
 
 
-def order_cells(f1, f2, n_face: int, reorder: bool = True, n_colors: int = 0, flow_hint=None):
-    """Host-only: (new_of_old, color_ptr, n_levels) of the ordering the library builds (cwr_order_cells)."""
+def order_cells(f1, f2, n_face: int, reorder: bool = True, n_colors: int = 0, flow_hint=None, n_parts: int = 1):
+    """Host-only: the ordering the library builds (cwr_order_cells).  Returns (new_of_old, color_ptr, n_levels) for
+    n_parts == 1, with color_ptr of shape (n_colors+1,); for n_parts > 1 returns
+    (new_of_old, color_ptr (n_parts, n_colors+1), n_levels, part_ptr (n_parts+1,), n_send (n_parts,))."""
     lib = load_library()
     f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
     n = int(f1.max()) + 1
     hint = None if flow_hint is None else _arr(flow_hint, np.float32, f1.shape, "flow_hint")
-    new_of_old = np.empty(n, np.int32); cptr = np.zeros(65, np.int32)
+    new_of_old = np.empty(n, np.int32); cptr = np.zeros(8 * 65, np.int32)
+    part_ptr = np.zeros(9, np.int32); n_send = np.zeros(8, np.int32)
     nc, nl = C.c_int(), C.c_int()
     rc = lib.cwr_order_cells(n, int(n_face), len(f1), _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), int(reorder), int(n_colors),
-                             _ptr(hint, C.c_float), _ptr(new_of_old, C.c_int32), _ptr(cptr, C.c_int32), C.byref(nc), C.byref(nl))
+                             _ptr(hint, C.c_float), int(n_parts), _ptr(new_of_old, C.c_int32), _ptr(cptr, C.c_int32),
+                             C.byref(nc), C.byref(nl), _ptr(part_ptr, C.c_int32), _ptr(n_send, C.c_int32))
     if rc != CWR_OK:
         raise CwrError(rc, lib.cwr_last_error(None).decode())
-    return new_of_old, cptr[: nc.value + 1].copy(), nl.value
+    if nc.value == 0:
+        colours = np.array([0, n], np.int32) if n_parts == 1 else part_ptr[: n_parts + 1].copy()
+    else:
+        colours = cptr[: n_parts * (nc.value + 1)].reshape(n_parts, nc.value + 1).copy()
+    if n_parts == 1:
+        return new_of_old, (colours[0] if nc.value else colours), nl.value
+    return new_of_old, colours, nl.value, part_ptr[: n_parts + 1].copy(), n_send[:n_parts].copy()
 
 
 class TransportBackend:
@@ -263,6 +284,22 @@ class TransportBackend:
         m = CwrMassTotals()
         self._check(self._lib.cwr_mass_totals_at(self._h, k, t_start, t_end, C.byref(m)))
         return m
+
+    # -- domain decomposition (one TransportBackend per GPU/process; see domain.py) -----------------------
+    def dd_export(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._check(self._lib.cwr_dd_export(self._h, buf))
+        return buf.raw
+
+    def dd_attach(self, handles: bytes):
+        buf = C.create_string_buffer(handles, len(handles))
+        self._check(self._lib.cwr_dd_attach(self._h, buf))
+
+    def dd_layout(self):
+        info = CwrDdInfo()
+        cells = np.zeros(self.n_real, np.uint8); edges = np.zeros(self.n_edge, np.uint8)
+        self._check(self._lib.cwr_dd_layout(self._h, C.byref(info), _ptr(cells, C.c_uint8), _ptr(edges, C.c_uint8)))
+        return info, cells.astype(bool), edges.astype(bool)
 
     # -- introspection ---------------------------------------------------------------------------------
     def get_lhs(self):

@@ -36,6 +36,12 @@ struct cwr_handle {
     bool hint_done = false;          // the colours have been aligned with the flow (or it is too late to)
     int grid_sweep = 0, grid_gs = 0;
     int32_t* d_color_ptr = nullptr;
+    // domain decomposition (world == 1: plain single-GPU handle)
+    int rank = 0, world = 1;
+    bool attached = false;           // peers' slabs are mapped (cwr_dd_attach)
+    char* d_slab = nullptr; size_t slab_bytes = 0;     // symmetric slab: DdCtl | p^ | s^ | tmp | state slots
+    uint8_t* d_send_mask = nullptr; int32_t* d_send_rows = nullptr;
+    std::vector<void*> peer_maps;    // cudaIpcOpenMemHandle results to close
     std::vector<int32_t> f1_ref, f2_ref;   // the caller's connectivity (kept for the flow-aligned recolouring)
     int last_iters = 0;              // iterations of the previous solve (launch-ahead prediction)
     bool small_path = false;         // one-CTA-per-column in-kernel solve (small meshes)
@@ -208,8 +214,25 @@ static int upload_topology(cwr_handle* h) {
     CK(put(h, h->d_einv, einv));
     CK(put(h, h->d_new_of_old, tp.new_of_old)); CK(put(h, h->d_old_of_new, tp.old_of_new));
     CK(put(h, h->d_color_ptr, tp.color_ptr));
+    CK(put(h, h->d_send_mask, tp.send_mask)); CK(put(h, h->d_send_rows, tp.send_rows));
     CK(cudaStreamSynchronize(h->stream));
     return CWR_OK;
+}
+
+// the part of the (re)built topology this rank owns
+static void set_owned_ranges(cwr_handle* h) {
+    const Topology& tp = h->topo;
+    DeviceModel& M = h->M;
+    const int r = h->rank;
+    M.row_lo = tp.part_ptr[r]; M.row_hi = tp.part_ptr[r + 1];
+    M.ie_lo = tp.iedge_ptr[r]; M.ie_hi = tp.iedge_ptr[r + 1];
+    M.ge_lo = tp.gedge_ptr[r]; M.ge_hi = tp.gedge_ptr[r + 1];
+    M.b_lo = tp.bcell_ptr[r]; M.b_hi = tp.bcell_ptr[r + 1];
+    M.n_colors = tp.n_colors;
+    M.color_ptr = h->d_color_ptr + (size_t)r * (tp.n_colors + 1);
+    unsigned nbr = 0;
+    for (int32_t j = tp.send_ptr[r]; j < tp.send_ptr[r + 1]; ++j) nbr |= tp.send_mask[tp.send_rows[j]];
+    M.nbr_mask = nbr;        // symmetric: whoever reads my rows owns rows I read
 }
 
 // Gauss-Seidel colours follow the flow: the first hydrodynamic slices the caller uploads give the
@@ -228,11 +251,27 @@ static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
     for (int e = 0; e < E; ++e) hint[e] = (float)mean[e];
     Topology t2;
     std::string terr = build_topology(h->n, h->F, E, h->f1_ref.data(), h->f2_ref.data(), h->opt.reorder != 0,
-                                      h->opt.precond_colors, hint.data(), t2);
+                                      h->opt.precond_colors, hint.data(), h->world, t2);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
+    if (h->attached) return CWR_OK;                 // peers already rely on the current ownership
     h->topo = std::move(t2);
+    set_owned_ranges(h);
     return upload_topology(h);
+}
+
+// domain decomposition: this rank's boundary rows of a slab vector -> the ranks that read them, followed
+// by the halo barrier (k_halo_push).  No-op on a single rank.
+template <typename T>
+static int halo_push(cwr_handle* h, T* vec) {
+    if (h->world == 1) return CWR_OK;
+    if (!h->attached) FAIL(CWR_EINVAL, "domain-decomposed handle: call cwr_dd_attach before stepping");
+    const Topology& tp = h->topo;
+    const int n_send = tp.send_ptr[h->rank + 1] - tp.send_ptr[h->rank];
+    const int g = grid_for((int64_t)std::max(1, n_send) * h->K, kThreads, 64);
+    k_halo_push<T><<<g, kThreads, 0, h->stream>>>(h->M, vec, h->d_send_rows + tp.send_ptr[h->rank], n_send);
+    h->launches += 1;
+    return CWR_OK;
 }
 
 extern "C" {
@@ -262,6 +301,7 @@ void cwr_destroy(cwr_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (void* p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_stage) cudaFree(h->d_stage);
@@ -290,6 +330,10 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->sweep_f32 = h->opt.precond_precision == 32;
     // solver path: small meshes run the whole solve of a column inside one CTA (cwr_small.cuh)
     h->small_path = small;
+    h->world = std::max(1, h->opt.dd_world); h->rank = h->opt.dd_rank;
+    if (h->world > kMaxRanks || h->rank < 0 || h->rank >= h->world) FAIL(CWR_EINVAL, "dd_rank / dd_world out of range (at most 8 ranks)");
+    if (h->world > 1 && (small || h->m_steps < 2))
+        FAIL(CWR_EINVAL, "domain decomposition needs the multi-CTA solver path (solver_path = 1) and precond_steps >= 2");
     h->gauss_seidel = h->opt.precond_sweep == 1 && !h->small_path && h->m_steps > 1;
     if (h->opt.precond_colors <= 0) {
         // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
@@ -311,7 +355,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
-                                      h->gauss_seidel ? h->opt.precond_colors : 0, nullptr, h->topo);
+                                      h->gauss_seidel ? h->opt.precond_colors : 0, nullptr, h->world, h->topo);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     const Topology& tp = h->topo;
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
@@ -335,9 +379,10 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         int occ_spmm = 4, occ_xrp = 3, occ_gs = 0;
         KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmm, k_spmm<KC, VEC, MODE_AT, double>, kThreads, 0));
         KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_xrp, k_update_xrp<KC, VEC, double>, kThreads, 0));
-        h->grid_spmm = grid_for(n, kThreads / kc, h->num_sms * std::max(1, occ_spmm));
-        h->grid_xrp = grid_for(n, kThreads / kc, h->num_sms * std::max(1, occ_xrp));
-        h->grid_sweep = grid_for(n, kThreads / h->SKC, h->num_sms * CWR_SPMM_MIN_BLOCKS);
+        const int n_own = tp.part_ptr[h->rank + 1] - tp.part_ptr[h->rank];
+        h->grid_spmm = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_spmm));
+        h->grid_xrp = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_xrp));
+        h->grid_sweep = grid_for(n_own, kThreads / h->SKC, h->num_sms * CWR_SPMM_MIN_BLOCKS);
         if (h->gauss_seidel) {
             SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
             SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC>, kGsThreads, kGsSmemBytes));
@@ -349,9 +394,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
             h->grid_gs = h->num_sms * occ_gs;      // every CTA resident: the kernel synchronises grid-wide
         }
     }
-    h->grid_rows = grid_for(n, kThreads / kc, h->max_grid);
-    h->grid_edges = grid_for(E, kThreads / kc, h->max_grid);
-    h->grid_b = grid_for((int64_t)tp.bcell.size() * K, kThreads, h->max_grid);
+    h->grid_rows = grid_for(tp.part_ptr[h->rank + 1] - tp.part_ptr[h->rank], kThreads / kc, h->max_grid);
+    h->grid_edges = grid_for(E / h->world + 1, kThreads / kc, h->max_grid);
+    h->grid_b = grid_for((int64_t)(tp.bcell.size() / h->world + 1) * K, kThreads, h->max_grid);
 
     // topology -> device
     CK(dalloc(h, &h->d_ell_col, tp.ell_col.size())); CK(dalloc(h, &h->d_ell_code, tp.ell_code.size()));
@@ -360,6 +405,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     CK(dalloc(h, &h->d_eperm, (size_t)E)); CK(dalloc(h, &h->d_einv, (size_t)E));
     CK(dalloc(h, &h->d_new_of_old, (size_t)n)); CK(dalloc(h, &h->d_old_of_new, (size_t)n));
     CK(dalloc(h, &h->d_color_ptr, tp.color_ptr.size()));
+    CK(dalloc(h, &h->d_send_mask, (size_t)n)); CK(dalloc(h, &h->d_send_rows, (size_t)n));
     {
         int rc = upload_topology(h);
         if (rc) return rc;
@@ -375,18 +421,29 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     CK(dalloc(h, &h->d_bc, (size_t)T * std::max(1, h->G) * K));
     CK(cudaMemsetAsync(h->d_bc, 0, (size_t)T * std::max(1, h->G) * K * sizeof(double), h->stream));
     h->n_state_slots = h->opt.keep_history ? T : 2;
-    if (cudaMalloc((void**)&h->d_state, (size_t)h->n_state_slots * nK * sizeof(double)) != cudaSuccess) {
+    // Symmetric slab (same layout on every rank): DdCtl | p^ | s^ | tmp | state slots -- the vectors other
+    // ranks gather from.  One allocation so that one CUDA IPC handle maps all of it into the peers.
+    const bool need_precond_vectors = h->m_steps > 1 || h->small_path;
+    const size_t vec_bytes = (nK * sizeof(double) + 255) & ~(size_t)255;
+    h->slab_bytes = kDdCtlBytes + (need_precond_vectors ? 3 : 0) * vec_bytes + (size_t)h->n_state_slots * nK * sizeof(double);
+    if (cudaMalloc((void**)&h->d_slab, h->slab_bytes) != cudaSuccess) {
         cudaGetLastError();
         FAIL(CWR_ENOMEM, "not enough device memory for the concentration history; set keep_history = 0");
     }
-    h->allocs.push_back(h->d_state);
-    CK(cudaMemsetAsync(h->d_state, 0, (size_t)h->n_state_slots * nK * sizeof(double), h->stream));
+    h->allocs.push_back(h->d_slab);
+    CK(cudaMemsetAsync(h->d_slab, 0, h->slab_bytes, h->stream));
+    h->d_state = (double*)(h->d_slab + kDdCtlBytes + (need_precond_vectors ? 3 : 0) * vec_bytes);
 
     DeviceModel& M = h->M;
     M.n = n; M.K = K; M.E = E; M.E_int = tp.E_int; M.E_g = tp.E_g; M.G = h->G; M.nb = (int)tp.bcell.size();
     M.W = tp.W; M.ell_col = h->d_ell_col; M.ell_code = h->d_ell_code; M.f1p = h->d_f1p; M.f2p = h->d_f2p;
     M.bcell = h->d_bcell; M.bptr = h->d_bptr; M.bedge = h->d_bedge;
-    M.color_ptr = h->d_color_ptr; M.n_colors = (int)tp.color_ptr.size() - 1;
+    M.rank = h->rank; M.world = h->world;
+    M.send_mask = h->d_send_mask;
+    M.dd = (DdCtl*)h->d_slab; M.sym_base = h->d_slab;
+    for (int q = 0; q < kMaxRanks; ++q) M.peer_base[q] = nullptr;
+    M.peer_base[h->rank] = h->d_slab;
+    set_owned_ranges(h);
     CK(dalloc(h, &M.val, (size_t)n * tp.W)); CK(dalloc(h, &M.diag, (size_t)n)); CK(dalloc(h, &M.gdiag, (size_t)n));
     CK(cudaMemsetAsync(M.gdiag, 0, (size_t)n * sizeof(double), h->stream));
     double* ic = nullptr;
@@ -394,10 +451,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     M.ic = ic;
     CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
     CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
-    if (h->m_steps > 1 || h->small_path) {
-        double *ph, *sh, *tmp, *us;
-        CK(dalloc(h, &ph, nK)); CK(dalloc(h, &sh, nK)); CK(dalloc(h, &tmp, nK)); CK(dalloc(h, &us, nK));
-        M.ph = ph; M.sh = sh; M.tmp = tmp; M.us = us;
+    if (need_precond_vectors) {
+        double* us;
+        CK(dalloc(h, &us, nK));
+        M.ph = h->d_slab + kDdCtlBytes; M.sh = h->d_slab + kDdCtlBytes + vec_bytes; M.tmp = h->d_slab + kDdCtlBytes + 2 * vec_bytes;
+        M.us = us;
         if (h->sweep_f32 && !h->small_path) CK(dalloc(h, &M.valf, (size_t)n * tp.W));
     }
     if (h->small_path) {
@@ -667,7 +725,6 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
     const int J = h->m_steps - 1;
     if (J <= 0) return u;
     DeviceModel& M = h->M;
-    const int n = h->n;
     if (h->gauss_seidel) {
         mark(h, CWR_FAM_PRECOND);
         int sweeps = J;
@@ -682,9 +739,10 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
     for (int j = 1; j <= J; ++j) {
         void* out = ((J - j) % 2 == 0) ? dst : other;      // the last step always lands in dst
         mark(h, CWR_FAM_PRECOND);
-        if (j == 1) { SWEEP_DISPATCH((k_sweep<ST, SKC, SVEC, true><<<h->grid_sweep, kThreads, 0, h->stream>>>(M, u, nullptr, (ST*)out, 0, n))); }
-        else { SWEEP_DISPATCH((k_sweep<ST, SKC, SVEC, false><<<h->grid_sweep, kThreads, 0, h->stream>>>(M, nullptr, (const ST*)z, (ST*)out, 0, n))); }
+        if (j == 1) { SWEEP_DISPATCH((k_sweep<ST, SKC, SVEC, true><<<h->grid_sweep, kThreads, 0, h->stream>>>(M, u, nullptr, (ST*)out, M.row_lo, M.row_hi))); }
+        else { SWEEP_DISPATCH((k_sweep<ST, SKC, SVEC, false><<<h->grid_sweep, kThreads, 0, h->stream>>>(M, nullptr, (const ST*)z, (ST*)out, M.row_lo, M.row_hi))); }
         h->launches += 1;
+        if (h->world > 1) { if (h->sweep_f32) halo_push(h, (float*)out); else halo_push(h, (double*)out); }
         z = out;
     }
     return z;
@@ -759,6 +817,13 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
         else if (!(f & FL_CONVERGED) && status == CWR_OK) status = CWR_ENOTCONVERGED;
     }
     if (h->h_ctl->singular) status = CWR_ESINGULAR;
+    if (h->h_ctl->barrier_timeout) { h->err = "a grid barrier timed out"; return CWR_ECUDA; }
+    if (h->world > 1) {
+        int dd_timeout = 0;
+        CK(cudaMemcpyAsync(&dd_timeout, &h->M.dd->timeout, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (dd_timeout) { h->err = "a peer rank did not answer (halo barrier / dot-product exchange timed out)"; return CWR_ECUDA; }
+    }
     if (info) { info->iterations = total_iter; info->restarts = restarts; info->status = status; info->max_relres = worst; }
     return status;
 }
@@ -824,11 +889,13 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     DeviceModel& M = h->M;
     k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl);
     mark(h, CWR_FAM_ASSEMBLE);
-    if (M.nb > 0) k_boundary_diag<<<grid_for(M.nb, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
-    k_assemble<<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+    if (h->world > 1 && !h->attached) FAIL(CWR_EINVAL, "domain-decomposed handle: call cwr_dd_attach before stepping");
+    const int nb_own = M.b_hi - M.b_lo;
+    if (nb_own > 0) k_boundary_diag<<<grid_for(nb_own, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+    k_assemble<<<grid_for(M.row_hi - M.row_lo, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
     mark(h, CWR_FAM_RHS);
     KC_DISPATCH(h->KC, (k_rhs<KC, VEC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
-    h->launches += 3 + (M.nb > 0);
+    h->launches += 3 + (nb_own > 0);
     // sparse real-cell overrides of c~ (input_array[t][real cell] != 0 at t >= 1): recompute those rows
     for (int k = 0; k < K; ++k) {
         auto it = h->real_overrides[k].find(t);
@@ -838,6 +905,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
         // only patches its temporary `solver` array), patch state_t1 and b directly on the host side values.
         std::vector<double> conc(1), dummy;
         for (auto& cv : it->second) {
+            if (cv.first < M.row_lo || cv.first >= M.row_hi) continue;      // another rank's row
             const size_t idx = (size_t)cv.first * K + k;
             float vol; double diag;
             CK(cudaMemcpyAsync(&vol, p.vol_t + cv.first, 4, cudaMemcpyDeviceToHost, h->stream));
@@ -849,11 +917,12 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
             CK(cudaStreamSynchronize(h->stream));
         }
     }
-    if (M.nb > 0) {
+    if (nb_own > 0) {
         k_boundary_rhs<<<h->grid_b, kThreads, 0, h->stream>>>(M);
         h->launches += 1;
     }
     h->lhs_step = t;
+    { int rc = halo_push(h, p.state_t1); if (rc) return rc; }      // x0 = c~: the first residual gathers the neighbours' rows
     cwr_step_info local;
     int status = h->small_path ? solve_small(h, &local) : solve(h, &local);
     if (status == CWR_ECUDA) return status;
@@ -863,9 +932,12 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
         auto it = h->real_overrides[k].find(t + 1);
         if (it == h->real_overrides[k].end()) continue;
         for (auto& cv : it->second)
-            CK(cudaMemcpyAsync(p.state_t1 + (size_t)cv.first * K + k, &cv.second, 8, cudaMemcpyHostToDevice, h->stream));
+            if (cv.first >= M.row_lo && cv.first < M.row_hi)
+                CK(cudaMemcpyAsync(p.state_t1 + (size_t)cv.first * K + k, &cv.second, 8, cudaMemcpyHostToDevice, h->stream));
         CK(cudaStreamSynchronize(h->stream));
     }
+    // c[t+1] of the neighbours' boundary rows: the mass flux of a cut edge and the next cwr_get_state read them
+    { int rc = halo_push(h, p.state_t1); if (rc) return rc; }
     if (M.want_flux) {
         mark(h, CWR_FAM_MASS_FLUX);
         KC_DISPATCH(h->KC, (k_mass_flux<KC, VEC><<<h->grid_edges, kThreads, 0, h->stream>>>(M)));
@@ -1026,8 +1098,8 @@ int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_to
         if (rc) return rc;
         const int s = find_slot(h, ts[i]);
         if (s < 0) FAIL(CWR_EINVAL, "volume slice not resident for mass totals");
-        k_mass_total<<<grid_for(h->n, kThreads, kMassBlocks), kThreads, 0, h->stream>>>(
-            h->d_vol + (size_t)s * h->n, state_slot(h, ts[i]), h->n, h->K, k, d_partial, d_ticket, d_out);
+        k_mass_total<<<grid_for(h->M.row_hi - h->M.row_lo, kThreads, kMassBlocks), kThreads, 0, h->stream>>>(
+            h->d_vol + (size_t)s * h->n, state_slot(h, ts[i]), h->M.row_lo, h->M.row_hi, h->K, k, d_partial, d_ticket, d_out);
         h->launches += 1;
         CK(cudaMemcpyAsync(res[i], d_out, 16, cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
@@ -1103,22 +1175,78 @@ int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old) {
 }
 
 int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int reorder, int n_colors,
-                    const float* flow_hint, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out, int* n_levels) {
+                    const float* flow_hint, int n_parts, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out,
+                    int* n_levels, int32_t* part_ptr, int32_t* n_send) {
     if (!f1 || !f2 || !new_of_old) return CWR_EINVAL;
     Topology t;
-    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, reorder != 0, n_colors, flow_hint, t);
+    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, reorder != 0, n_colors, flow_hint, std::max(1, n_parts), t);
     if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
     std::copy(t.new_of_old.begin(), t.new_of_old.end(), new_of_old);
     if (color_ptr) std::copy(t.color_ptr.begin(), t.color_ptr.end(), color_ptr);
-    if (n_colors_out) *n_colors_out = (int)t.color_ptr.size() - 1;
+    if (n_colors_out) *n_colors_out = t.n_colors;
     if (n_levels) *n_levels = t.n_levels;
+    if (part_ptr) std::copy(t.part_ptr.begin(), t.part_ptr.end(), part_ptr);
+    if (n_send) for (int p = 0; p < std::max(1, n_parts); ++p) n_send[p] = t.send_ptr[p + 1] - t.send_ptr[p];
+    return CWR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// domain decomposition plumbing: one handle per GPU/process; CUDA IPC maps every rank's slab into every peer
+// ------------------------------------------------------------------------------------------------
+int cwr_dd_export(cwr_handle* h, void* ipc_handle) {
+    if (!h || !ipc_handle) return CWR_EINVAL;
+    CK(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->d_slab));
+    static_assert(sizeof(mh) == CWR_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+    std::memcpy(ipc_handle, &mh, sizeof mh);
+    return CWR_OK;
+}
+
+int cwr_dd_attach(cwr_handle* h, const void* ipc_handles) {
+    if (!h) return CWR_EINVAL;
+    if (h->world == 1) { h->attached = true; return CWR_OK; }
+    if (!ipc_handles) FAIL(CWR_EINVAL, "NULL handles");
+    if (h->attached) FAIL(CWR_EINVAL, "already attached");
+    CK(cudaSetDevice(h->device));
+    for (int q = 0; q < h->world; ++q) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t mh;
+        std::memcpy(&mh, (const char*)ipc_handles + (size_t)q * CWR_IPC_HANDLE_BYTES, sizeof mh);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+        h->peer_maps.push_back(p);
+        h->M.peer_base[q] = (char*)p;
+    }
+    h->attached = true;
+    h->hint_done = true;       // ownership is now shared knowledge: no recolouring after this point
+    return CWR_OK;
+}
+
+int cwr_dd_layout(cwr_handle* h, cwr_dd_info* out, uint8_t* owned_cells, uint8_t* owned_edges) {
+    if (!h) return CWR_EINVAL;
+    const Topology& tp = h->topo;
+    const DeviceModel& M = h->M;
+    if (out) {
+        out->rank = h->rank; out->world = h->world;
+        out->rows_owned = M.row_hi - M.row_lo;
+        out->rows_sent = tp.send_ptr[h->rank + 1] - tp.send_ptr[h->rank];
+        out->neighbour_mask = (int)M.nbr_mask;
+        out->n_colors = tp.n_colors; out->n_levels = tp.n_levels;
+    }
+    if (owned_cells) for (int i = 0; i < h->n; ++i) { const int32_t r = tp.new_of_old[i]; owned_cells[i] = r >= M.row_lo && r < M.row_hi; }
+    if (owned_edges) {
+        std::fill(owned_edges, owned_edges + h->E, (uint8_t)0);
+        for (int ep = M.ie_lo; ep < M.ie_hi; ++ep) owned_edges[tp.eperm[ep]] = 1;
+        for (int g = M.ge_lo; g < M.ge_hi; ++g) owned_edges[tp.eperm[tp.E_int + g]] = 1;
+    }
     return CWR_OK;
 }
 
 int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     if (!h || !out) return CWR_EINVAL;
     *out = h->opt;
-    out->precond_colors = h->gauss_seidel ? (int)h->topo.color_ptr.size() - 1 : 0;
+    out->precond_colors = h->gauss_seidel ? h->topo.n_colors : 0;
     out->precond_sweep = h->gauss_seidel ? 1 : 0;
     return CWR_OK;
 }

@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "cwr_topology.h"   // kColMask: ell_col bit 31 marks a neighbour visited later in a Gauss-Seidel sweep
+
 namespace cwr {
 
 constexpr int kThreads = 256;
@@ -47,12 +49,35 @@ struct SolverCtl {
     int barrier_timeout; // a grid barrier of the persistent sweep kernel gave up (never expected)
     int pad[2];
     unsigned ticket[4]; // last-block tickets (one per kernel family)
+    unsigned ticket_halo; // k_halo_push
     unsigned gs_bar[2]; // k_precond_gs: grid barrier arrivals, exits
 };
 
+constexpr int kMaxRanks = 8;
+
+// Control block of the domain-decomposed path, at the start of every rank's symmetric slab: peers write
+// their announcements straight into it over NVLink (peer-mapped stores).
+struct DdCtl {
+    unsigned long long bar_flag[kMaxRanks];   // [q]: last halo/barrier epoch rank q announced   (written by rank q)
+    unsigned long long dot_flag[kMaxRanks];   // [q]: last dot-product epoch rank q announced     (written by rank q)
+    unsigned long long bar_epoch, dot_epoch;  // this rank's own counters (local use only)
+    int timeout;                              // a bounded wait on a peer gave up (never expected)
+    int pad[27];
+    double dot_inbox[2][kMaxRanks][kMaxDots * kMaxK];   // [epoch parity][from rank][dot * K + k]
+};
+constexpr size_t kDdCtlBytes = 128 << 10;     // room reserved for DdCtl at the head of the slab
+
 struct DeviceModel {
     int n, K, E, E_int, E_g, G, nb, W;     // W = ELL width (multiple of 4)
-    const int32_t* ell_col;   // (n,W) neighbour row, padded with the row itself
+    // rows / edges / boundary cells this rank owns (everything when world == 1)
+    int row_lo, row_hi, ie_lo, ie_hi, ge_lo, ge_hi, b_lo, b_hi;
+    int rank, world;
+    unsigned nbr_mask;            // ranks this one exchanges halo rows with
+    const uint8_t* send_mask;     // (n) bit q: rank q reads this row (0 for interior rows)
+    char* peer_base[kMaxRanks];   // every rank's symmetric slab (own included): DdCtl, p^, s^, tmp, state slots
+    char* sym_base;               // == peer_base[rank]
+    DdCtl* dd;
+    const int32_t* ell_col;   // (n,W) neighbour row (& kColMask), padded with the row itself
     const int32_t* ell_code;  // (n,W) (e' << 1) | side, -1 = padding
     const int32_t* f1p; const int32_t* f2p;
     const int32_t* bcell; const int32_t* bptr; const int32_t* bedge;
@@ -190,7 +215,7 @@ __global__ void k_dist(double* __restrict__ dist, const double* __restrict__ fx,
 // (linalg.py:92-97 and 113-115 applied to ghost edges).
 __global__ void k_boundary_diag(DeviceModel M) {
     const StepParams& sp = *M.sp;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < M.nb; b += gridDim.x * blockDim.x) {
+    for (int b = M.b_lo + blockIdx.x * blockDim.x + threadIdx.x; b < M.b_hi; b += gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int j = M.bptr[b]; j < M.bptr[b + 1]; ++j) {
             int e = M.bedge[j];
@@ -210,7 +235,7 @@ __global__ void __launch_bounds__(kThreads) k_assemble(DeviceModel M) {
     const StepParams& sp = *M.sp;
     const double dt = sp.dt;
     const int W = M.W;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M.n; i += gridDim.x * blockDim.x) {
+    for (int i = M.row_lo + blockIdx.x * blockDim.x + threadIdx.x; i < M.row_hi; i += gridDim.x * blockDim.x) {
         const float vol = sp.vol_t1[i];
         double diag = (vol == 0.f ? 1.0 : 0.0) + (double)vol / dt + M.gdiag[i];
         const int32_t* code = M.ell_code + (size_t)i * W;
@@ -270,7 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_rhs(DeviceModel M) {
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const double dt = sp.dt;
     for (int c = lane * VEC; c < K; c += KC * VEC)
-        for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+        for (int i = M.row_lo + blockIdx.x * GPB + group; i < M.row_hi; i += gridDim.x * GPB) {
             const size_t idx = (size_t)i * K + c;
             Vd<VEC> conc = ldv<VEC>(sp.state_t + idx);
             if (sp.apply_ic) {
@@ -294,9 +319,9 @@ __global__ void __launch_bounds__(kThreads) k_boundary_rhs(DeviceModel M) {
     const int K = M.K;
     const double dt = sp.dt;
     const bool has_diffusion = M.diffusion_coefficient != 0.0;
-    const size_t total = (size_t)M.nb * K;
+    const size_t total = (size_t)(M.b_hi - M.b_lo) * K;
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
-        const int b = (int)(q / K), c = (int)(q % K);
+        const int b = M.b_lo + (int)(q / K), c = (int)(q % K);
         const int i = M.bcell[b];
         double m_in = 0.0, ca_in = 0.0, cd_in = 0.0, m_out = 0.0, cd_out = 0.0;
         for (int j = M.bptr[b]; j < M.bptr[b + 1]; ++j) {
@@ -381,6 +406,103 @@ __device__ __forceinline__ void grid_totals(const double* partials, double* tot,
     __syncthreads();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Domain decomposition over NVLink: one process per GPU, every rank holds the whole mesh's index space
+// (global row numbers everywhere) but computes only its rows [row_lo, row_hi).  The vectors other
+// ranks gather from (p^, s^, x) live in a symmetric slab that every rank maps from every peer (CUDA
+// IPC), so a producer kernel stores a boundary row straight into the peers that read it, and one
+// 8-byte flag store per peer announces "everything up to epoch e has been written".  Dot products are
+// all-reduced the same way: every rank writes its partial totals into every rank's inbox and adds the
+// inbox in rank order -- identical bits on every rank, so all ranks take identical decisions.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T* peer_ptr(const DeviceModel& M, int q, T* local) {
+    return reinterpret_cast<T*>(M.peer_base[q] + (reinterpret_cast<char*>(local) - M.sym_base));
+}
+__device__ __forceinline__ void st_flag(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// one thread: announce epoch e to the ranks in `mask` / wait for theirs (bounded)
+__device__ __forceinline__ void dd_signal(const DeviceModel& M, bool dots, unsigned long long e, unsigned mask) {
+    for (int q = 0; q < M.world; ++q)
+        if (q != M.rank && ((mask >> q) & 1u)) {
+            DdCtl* pd = peer_ptr(M, q, M.dd);
+            st_flag(dots ? &pd->dot_flag[M.rank] : &pd->bar_flag[M.rank], e);
+        }
+}
+__device__ __forceinline__ bool dd_arrived(const DeviceModel& M, bool dots, unsigned long long e, unsigned mask) {
+    for (int q = 0; q < M.world; ++q)
+        if (q != M.rank && ((mask >> q) & 1u))
+            if (ld_flag(dots ? &M.dd->dot_flag[q] : &M.dd->bar_flag[q]) < e) return false;
+    return true;
+}
+__device__ __forceinline__ void dd_wait(const DeviceModel& M, bool dots, unsigned long long e, unsigned mask) {
+    unsigned spins = 0;
+    if (*reinterpret_cast<volatile int*>(&M.dd->timeout)) return;     // a peer already went missing: fail fast
+    while (!dd_arrived(M, dots, e, mask))
+        if (++spins > (1u << 22)) { M.dd->timeout = 1; break; }       // never hang the device (seconds)
+    __threadfence_system();
+}
+
+// tot[0 .. pairs) (shared memory, this rank's totals, complete) -> sums over all ranks, by the whole CTA
+__device__ __forceinline__ void dd_allreduce(const DeviceModel& M, double* tot, int pairs) {
+    if (M.world == 1) return;
+    __shared__ unsigned long long e_sh;
+    if (threadIdx.x == 0) e_sh = ++M.dd->dot_epoch;
+    __syncthreads();
+    const unsigned long long e = e_sh;
+    const int buf = (int)(e & 1ull);
+    for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
+        const double v = tot[pair];
+        for (int q = 0; q < M.world; ++q) peer_ptr(M, q, M.dd)->dot_inbox[buf][M.rank][pair] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned all = (1u << M.world) - 1u;
+        dd_signal(M, true, e, all);
+        dd_wait(M, true, e, all);
+    }
+    __syncthreads();
+    for (int pair = threadIdx.x; pair < pairs; pair += blockDim.x) {
+        double s = 0.0;
+        for (int q = 0; q < M.world; ++q) s += __ldcg(&M.dd->dot_inbox[buf][q][pair]);
+        tot[pair] = s;
+    }
+    __syncthreads();
+}
+
+// boundary rows of a slab vector -> the peers that read them, then the halo barrier: when the kernel
+// has finished, every neighbour's rows have landed here as well.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_halo_push(DeviceModel M, T* vec, const int32_t* __restrict__ send_rows, int n_send) {
+    const int K = M.K;
+    const size_t total = (size_t)n_send * K;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int row = send_rows[q / K], k = (int)(q % K);
+        const T v = vec[(size_t)row * K + k];
+        unsigned m = M.send_mask[row];
+        while (m) {
+            const int r = __ffs(m) - 1;
+            m &= m - 1;
+            peer_ptr(M, r, vec)[(size_t)row * K + k] = v;
+        }
+    }
+    __threadfence_system();
+    if (!last_block_arrives(&M.ctl->ticket_halo)) return;
+    if (threadIdx.x == 0) {
+        const unsigned long long e = ++M.dd->bar_epoch;
+        __threadfence_system();
+        dd_signal(M, false, e, M.nbr_mask);
+        dd_wait(M, false, e, M.nbr_mask);
+    }
+}
+
 __device__ __forceinline__ void publish_done(DeviceModel& M, int K) {
     int done = 1, flags = 0;
     for (int k = 0; k < K; ++k) {
@@ -444,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_sweep(DeviceM
         }
         for (; i < row_end; i += stride) {
             const size_t idx = (size_t)i * K + c;
-            const int4 c4 = c4n;
+            const int4 c4 = make_int4(c4n.x & kColMask, c4n.y & kColMask, c4n.z & kColMask, c4n.w & kColMask);
             const Pk<ST, 4> v = vn;
             Pk<ST, VEC> x0, x1, x2, x3, own;
             if (FIRST) {
@@ -472,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_sweep(DeviceM
             for (int w = 4; w < W; w += 4) {      // rows wider than 4 (not pipelined)
                 const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
                 const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
-                const int cs[4] = {d4.x, d4.y, d4.z, d4.w};
+                const int cs[4] = {d4.x & kColMask, d4.y & kColMask, d4.z & kColMask, d4.w & kColMask};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     Pk<ST, VEC> y;
@@ -517,15 +639,20 @@ __device__ __forceinline__ Pk<T, V> ldk_cg(const T* p) {
     return r;
 }
 
-__device__ __forceinline__ void grid_barrier(SolverCtl* ctl, unsigned target) {
+// Grid barrier of the persistent sweep kernel.  With several ranks it is also the halo barrier: the last
+// CTA of this rank to arrive (every CTA's stores, peer stores included, are fenced before its arrival)
+// announces epoch `e` to the neighbour ranks, and every CTA also waits for the neighbours' announcements.
+__device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned target, unsigned long long e) {
+    SolverCtl* ctl = M.ctl;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&ctl->gs_bar[0], 1u);
+        if (M.world > 1) __threadfence_system(); else __threadfence();
+        const unsigned t = atomicAdd(&ctl->gs_bar[0], 1u);
+        if (M.world > 1 && t == target - 1) { __threadfence_system(); dd_signal(M, false, e, M.nbr_mask); }
         unsigned spins = 0;
         while (*reinterpret_cast<volatile unsigned*>(&ctl->gs_bar[0]) < target)
             if (++spins > (1u << 27)) { ctl->barrier_timeout = 1; break; }      // never hang the device
-        __threadfence();
+        if (M.world > 1) dd_wait(M, false, e, M.nbr_mask); else __threadfence();
     }
     __syncthreads();
 }
@@ -565,6 +692,17 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     const bool lane_on = c < c_end;
     const int n_steps = n_sweeps * nc;
     unsigned epoch = 0;
+    const bool multi = M.world > 1;
+    const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;     // halo epochs continue where the last kernel stopped
+    // a finished row also goes to the ranks that read it (NVLink peer stores)
+    auto push = [&](int i, int cc, const Pk<ST, VEC>& o) {
+        unsigned m = M.send_mask[i];
+        while (m) {
+            const int q = __ffs(m) - 1;
+            m &= m - 1;
+            stk<ST, VEC>(peer_ptr(M, q, z) + (size_t)i * K + cc, o);
+        }
+    };
     auto load_own = [&](int i, int cc, bool first_sweep) {
         Pk<ST, VEC> own;
         if (first_sweep) {
@@ -589,7 +727,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         }
     };
     // one row, columns [cc, cc + VEC): remaining ELL blocks through registers, then the update and the store
-    auto relax_tail = [&](int i, int cc, int w0, Pk<ST, VEC> acc, const Pk<ST, VEC>& own, int rb, bool first_sweep) {
+    auto relax_tail = [&](int i, int cc, int w0, Pk<ST, VEC> acc, const Pk<ST, VEC>& own, bool first_sweep) {
         for (int w = w0; w < W; w += 4) {
             const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
             const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
@@ -597,10 +735,10 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             Pk<ST, VEC> y[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (first_sweep && ds[u] >= rb) {
+                if (first_sweep && ds[u] < 0) {              // bit 31: visited later in the sweep, still 0
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) y[u].a[q] = (ST)0;
-                } else y[u] = ldk_cg<ST, VEC>(z + (size_t)ds[u] * K + cc);
+                } else y[u] = ldk_cg<ST, VEC>(z + (size_t)(ds[u] & kColMask) * K + cc);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
@@ -611,6 +749,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
         stk<ST, VEC>(z + (size_t)i * K + cc, acc);
         if (first_sweep) stk<ST, VEC>(us + (size_t)i * K + cc, own);
+        if (multi) push(i, cc, acc);
     };
     Pk<ST, VEC> zero;
 #pragma unroll
@@ -632,13 +771,13 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool skip = first_sweep && cs[u] >= rb;        // not visited yet in the sweep from z = 0
+                const bool skip = first_sweep && cs[u] < 0;          // bit 31: visited later in the sweep from z = 0
                 if constexpr (SMEM) {
                     int4* slot = gs_land + (r * 4 + u) * kGsThreads + threadIdx.x;
                     if (skip) *slot = make_int4(0, 0, 0, 0);
-                    else cp_async_cg16(slot, z + (size_t)cs[u] * K + c);
+                    else cp_async_cg16(slot, z + (size_t)(cs[u] & kColMask) * K + c);
                 } else {
-                    xr[r][u] = skip ? zero : ldk_cg<ST, VEC>(z + (size_t)cs[u] * K + c);
+                    xr[r][u] = skip ? zero : ldk_cg<ST, VEC>(z + (size_t)(cs[u] & kColMask) * K + c);
                 }
             }
             own[r] = load_own(row[r], c, first_sweep);
@@ -657,28 +796,36 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) o.a[q] += pv[r].a[u] * x.a[q];
             }
-            relax_tail(row[r], c, 4, o, own[r], rb, first_sweep);
+            relax_tail(row[r], c, 4, o, own[r], first_sweep);
         }
         // further column chunks of those rows (more columns than lanes x VEC), and colours with more rows per lane group
 #pragma unroll 1
         for (int r = 0; r < NR; ++r)
             if (row[r] < re)
                 for (int cc = c + KC * VEC; cc < c_end; cc += KC * VEC)
-                    relax_tail(row[r], cc, 0, zero, load_own(row[r], cc, first_sweep), rb, first_sweep);
+                    relax_tail(row[r], cc, 0, zero, load_own(row[r], cc, first_sweep), first_sweep);
 #pragma unroll 1
         for (int i = rb + gid + NR * TG; i < re; i += TG)
             for (int cc = c; cc < c_end; cc += KC * VEC)
-                relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), rb, first_sweep);
+                relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), first_sweep);
         if (step + 1 < n_steps) {
             prefetch(step + 1);
-            grid_barrier(M.ctl, ++epoch * nvb);
+            ++epoch;
+            grid_barrier(M, epoch * nvb, e0 + epoch);
+        } else if (multi) {       // the products that follow gather the neighbours' last colour too
+            ++epoch;
+            grid_barrier(M, epoch * nvb, e0 + epoch);
         }
     }
     // the last CTA to leave re-arms the barrier for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
-        if (t == (unsigned)nvb - 1) { M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0; __threadfence(); }
+        if (t == (unsigned)nvb - 1) {
+            M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
+            if (multi) M.dd->bar_epoch = e0 + epoch;
+            __threadfence();
+        }
     }
 }
 
@@ -700,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
     __shared__ double smem[HAS_DOTS ? (kThreads / 32) * kMaxDots * 2 * 32 : 1];
     __shared__ double tot[HAS_DOTS ? kMaxDots * kMaxK : 1];
     if (MODE == MODE_AV || MODE == MODE_AT) { if (M.ctl->all_done) return; }
-    const int K = M.K, n = M.n, W = M.W;
+    const int K = M.K, n = M.row_hi, W = M.W;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
     const double* __restrict__ eval = M.val;
@@ -717,7 +864,7 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
             // on) are fetched while this row's gathers are in flight, so a row costs one memory latency,
             // not two.
             const int stride = gridDim.x * GPB;
-            int i = blockIdx.x * GPB + group;
+            int i = M.row_lo + blockIdx.x * GPB + group;
             int4 c4n = make_int4(0, 0, 0, 0);
             double2 v01n = make_double2(0.0, 0.0), v23n = v01n;
             if (i < n) {
@@ -727,7 +874,7 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
             }
             for (; i < n; i += stride) {
                 const size_t idx = (size_t)i * K + c;
-                const int4 c4 = c4n;
+                const int4 c4 = make_int4(c4n.x & kColMask, c4n.y & kColMask, c4n.z & kColMask, c4n.w & kColMask);
                 const double2 v01 = v01n, v23 = v23n;
                 const Vd<VEC> x0 = ldz<ZT, VEC>(zin + (size_t)c4.x * K + c);
                 const Vd<VEC> x1 = ldz<ZT, VEC>(zin + (size_t)c4.y * K + c);
@@ -750,7 +897,8 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
                 for (int q = 0; q < VEC; ++q)
                     s.a[q] = fma(v23.y, x3.a[q], fma(v23.x, x2.a[q], fma(v01.y, x1.a[q], v01.x * x0.a[q])));
                 for (int w = 4; w < W; w += 4) {      // rows wider than 4 (not pipelined)
-                    const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+                    int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+                    d4.x &= kColMask; d4.y &= kColMask; d4.z &= kColMask; d4.w &= kColMask;
                     const double2 w01 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w);
                     const double2 w23 = *reinterpret_cast<const double2*>(eval + (size_t)i * W + w + 2);
                     const Vd<VEC> y0 = ldz<ZT, VEC>(zin + (size_t)d4.x * K + c);
@@ -799,6 +947,7 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceMo
     if (!HAS_DOTS) return;
     if (!last_block_arrives(&M.ctl->ticket[MODE])) return;
     grid_totals<ND>(M.partials, tot, K);
+    dd_allreduce(M, tot, ND * K);
     double* sc = M.sc;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         int f = M.colflags[k];
@@ -850,7 +999,7 @@ __global__ void __launch_bounds__(kThreads) k_update_s(DeviceModel M) {
 #pragma unroll
         for (int q = 0; q < VEC; ++q) { alpha[q] = M.sc[SC_ALPHA * K + c + q]; any |= alpha[q] != 0.0; }
         if (!any) continue;        // frozen columns: s = r
-        for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+        for (int i = M.row_lo + blockIdx.x * GPB + group; i < M.row_hi; i += gridDim.x * GPB) {
             const size_t idx = (size_t)i * K + c;
             Vd<VEC> r = ldv<VEC>(M.r + idx);
             const Vd<VEC> v = ldv<VEC>(M.v + idx);
@@ -887,7 +1036,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const PT
                 any_active |= !(f[q] & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING));
             }
             if (any_pending || any_active)
-                for (int i = blockIdx.x * GPB + group; i < M.n; i += gridDim.x * GPB) {
+                for (int i = M.row_lo + blockIdx.x * GPB + group; i < M.row_hi; i += gridDim.x * GPB) {
                     const size_t idx = (size_t)i * K + c;
                     Vd<VEC> xv = ldv<VEC>(x + idx), rv = ldv<VEC>(M.r + idx), pv = ldv<VEC>(M.p + idx);
                     const Vd<VEC> tv = ldv<VEC>(M.tt + idx), vv = ldv<VEC>(M.v + idx);
@@ -911,6 +1060,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const PT
     }
     if (!last_block_arrives(&M.ctl->ticket[3])) return;
     grid_totals<1>(M.partials, tot, K);
+    dd_allreduce(M, tot, K);
     if (threadIdx.x == 0) M.ctl->iter += 1;
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
@@ -941,8 +1091,10 @@ __global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
     const double dt = sp.dt;
     const double* __restrict__ x = sp.state_t1;
     const size_t EK = (size_t)M.E * K, GK = (size_t)M.E_g * K;
+    const int n_ie = M.ie_hi - M.ie_lo, n_own = n_ie + (M.ge_hi - M.ge_lo);     // owned internal + ghost edges
     for (int c = lane * VEC; c < K; c += KC * VEC)
-        for (int e = blockIdx.x * GPB + group; e < M.E; e += gridDim.x * GPB) {
+        for (int j = blockIdx.x * GPB + group; j < n_own; j += gridDim.x * GPB) {
+            const int e = j < n_ie ? M.ie_lo + j : M.E_int + M.ge_lo + (j - n_ie);
             const int P = M.f1p[e], N = M.f2p[e];
             const double a = (double)sp.adv_t[e], d = sp.cdiff_t[e];
             const Vd<VEC> cP = ldv<VEC>(x + (size_t)P * K + c);
@@ -979,12 +1131,12 @@ __global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
 // kMassBlocks CTAs each reduce a grid-stride slice in a fixed order into partial[b][2]; the last CTA to
 // arrive adds the partials in block order.
 constexpr int kMassBlocks = 256;
-__global__ void __launch_bounds__(kThreads) k_mass_total(const float* __restrict__ vol, const double* __restrict__ state, int n, int K, int k,
+__global__ void __launch_bounds__(kThreads) k_mass_total(const float* __restrict__ vol, const double* __restrict__ state, int lo, int n, int K, int k,
                                                          double* __restrict__ partial /* [kMassBlocks][2] */, unsigned* ticket,
                                                          double* __restrict__ out /* [2]: volume, mass */) {
     __shared__ double sv[kThreads], sm[kThreads];
     double v = 0.0, m = 0.0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double vi = (double)vol[i];
         v += vi; m = fma(vi, state[(size_t)i * K + k], m);
     }

@@ -49,7 +49,8 @@ struct Bfs {
 }  // namespace
 
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
-                           bool rcm, int n_colors, const float* hint, Topology& T) {
+                           bool rcm, int n_colors, const float* hint, int n_parts, Topology& T) {
+    if (n_parts < 1 || n_parts > 8) return "n_parts must be in [1, 8]";
     if (n_real <= 0 || n_face < n_real || n_edge <= 0) return "n_real, n_face, n_edge must be positive and n_face >= n_real";
     const int n = n_real, F = n_face, E = n_edge;
     int32_t max_f1 = -1;
@@ -189,21 +190,51 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 if (--indeg[v] == 0 && !queued[v]) { queued[v] = 1; queue.push_back(v); }
             }
         }
+        // ---- partition into n_parts strips (domain decomposition), then colour-major inside a part ------
+        // Cells are cut into equal chunks of the (level, RCM position) order when the hint gave levels
+        // (strips across the flow), else of the RCM order (strips of the RCM band): compact parts whose
+        // rows only couple to the neighbouring strips.
         std::vector<int32_t> order(n);
         std::iota(order.begin(), order.end(), 0);
+        const bool have_levels = max_level + 1 > nc;
         std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            if (have_levels && level[a] != level[b]) return level[a] < level[b];
+            return rcm_pos[a] < rcm_pos[b];
+        });
+        std::vector<int32_t> part(n);
+        for (int i = 0; i < n; ++i) part[order[i]] = (int32_t)(((int64_t)i * n_parts) / n);
+        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+            if (part[a] != part[b]) return part[a] < part[b];
             const int ca = level[a] % nc, cb = level[b] % nc;
             if (ca != cb) return ca < cb;
             if (level[a] != level[b]) return level[a] < level[b];
             return rcm_pos[a] < rcm_pos[b];
         });
-        T.color_ptr.assign(nc + 1, 0);
-        for (int i = 0; i < n; ++i) ++T.color_ptr[level[i] % nc + 1];
-        for (int c = 0; c < nc; ++c) T.color_ptr[c + 1] += T.color_ptr[c];
+        T.n_colors = nc;
+        T.color_ptr.assign((size_t)n_parts * (nc + 1), 0);
+        T.part_ptr.assign(n_parts + 1, 0);
+        {
+            std::vector<int32_t> cnt((size_t)n_parts * nc, 0);
+            for (int i = 0; i < n; ++i) ++cnt[(size_t)part[i] * nc + level[i] % nc];
+            int32_t pos = 0;
+            for (int p = 0; p < n_parts; ++p) {
+                T.part_ptr[p] = pos;
+                for (int c = 0; c < nc; ++c) { T.color_ptr[(size_t)p * (nc + 1) + c] = pos; pos += cnt[(size_t)p * nc + c]; }
+                T.color_ptr[(size_t)p * (nc + 1) + nc] = pos;
+            }
+            T.part_ptr[n_parts] = pos;
+        }
         T.old_of_new.swap(order);
         T.n_levels = max_level + 1;
+        T.color_of.resize(n);
+        for (int i = 0; i < n; ++i) T.color_of[i] = (uint8_t)(level[T.old_of_new[i]] % nc);       // by new id
     } else {
-        T.color_ptr.push_back(n);
+        // no colours: parts are equal chunks of the RCM order
+        T.n_colors = 0;
+        T.color_ptr.clear();
+        T.part_ptr.assign(n_parts + 1, 0);
+        for (int p = 0; p <= n_parts; ++p) T.part_ptr[p] = (int32_t)(((int64_t)p * n) / n_parts);
+        T.color_of.clear();
     }
     for (int i = 0; i < n; ++i) T.new_of_old[T.old_of_new[i]] = i;
 
@@ -283,6 +314,45 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         T.bedge[i] = ep;
     }
     T.bptr.push_back(T.E_g);
+
+    // ---- Gauss-Seidel: mark the ELL entries whose neighbour is visited LATER in a sweep ------------------
+    // (colour >= the row's colour; padding points at the row itself).  During the first sweep from z = 0
+    // those neighbours still hold 0.  Bit 31 of ell_col; every kernel masks it off.
+    if (T.n_colors > 0)
+        for (int i = 0; i < n; ++i)
+            for (int w = 0; w < T.W; ++w) {
+                int32_t& cj = T.ell_col[(size_t)i * T.W + w];
+                if (T.color_of[cj] >= T.color_of[i]) cj |= kLaterBit;
+            }
+
+    // ---- domain decomposition: who reads whose rows, which edges / boundary cells a part owns ----------
+    const int P = n_parts;
+    auto part_of = [&](int32_t row) { return (int)(std::upper_bound(T.part_ptr.begin(), T.part_ptr.end(), row) - T.part_ptr.begin()) - 1; };
+    T.send_mask.assign(n, 0);
+    if (P > 1)
+        for (int ep = 0; ep < E_int; ++ep) {
+            const int pa = part_of(T.f1p[ep]), pb = part_of(T.f2p[ep]);
+            if (pa != pb) { T.send_mask[T.f1p[ep]] |= (uint8_t)(1u << pb); T.send_mask[T.f2p[ep]] |= (uint8_t)(1u << pa); }
+        }
+    T.send_ptr.assign(P + 1, 0); T.send_rows.clear();
+    for (int pp = 0; pp < P; ++pp) {
+        T.send_ptr[pp] = (int32_t)T.send_rows.size();
+        for (int32_t i = T.part_ptr[pp]; i < T.part_ptr[pp + 1]; ++i) if (T.send_mask[i]) T.send_rows.push_back(i);
+    }
+    T.send_ptr[P] = (int32_t)T.send_rows.size();
+    // internal edges are sorted by their lower cell, ghost edges and boundary cells by their cell: the
+    // owner (part of the lower / the real cell) is non-decreasing along each list
+    T.iedge_ptr.assign(P + 1, E_int); T.gedge_ptr.assign(P + 1, T.E_g); T.bcell_ptr.assign(P + 1, (int32_t)T.bcell.size());
+    {
+        int ep = 0, g = 0, b = 0;
+        for (int pp = 0; pp < P; ++pp) {
+            const int32_t lo_row = T.part_ptr[pp];
+            while (ep < E_int && std::min(T.f1p[ep], T.f2p[ep]) < lo_row) ++ep;
+            while (g < T.E_g && T.f1p[E_int + g] < lo_row) ++g;
+            while (b < (int)T.bcell.size() && T.bcell[b] < lo_row) ++b;
+            T.iedge_ptr[pp] = ep; T.gedge_ptr[pp] = g; T.bcell_ptr[pp] = b;
+        }
+    }
     return "";
 }
 

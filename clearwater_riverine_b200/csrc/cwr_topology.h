@@ -18,6 +18,9 @@
 
 namespace cwr {
 
+constexpr int32_t kLaterBit = (int32_t)0x80000000;
+constexpr int32_t kColMask = 0x7fffffff;
+
 struct Topology {
     int n = 0;        // real cells = matrix order (reference: nreal + 1)
     int F = 0;        // real + ghost cells
@@ -40,10 +43,21 @@ struct Topology {
     std::vector<int32_t> bptr;        // (nb+1) ranges into bedge
     std::vector<int32_t> bedge;       // (E_g)  device edge ids, ascending original id within a cell
     int W = 4;                        // ELL width: max row length rounded up to a multiple of 4
-    std::vector<int32_t> ell_col;     // (n*W) row-major; padding points at the row itself
+    std::vector<int32_t> ell_col;     // (n*W) row-major; padding points at the row itself; bit 31 (kLaterBit): the
+                                      // neighbour's colour is >= the row's (visited later in a Gauss-Seidel sweep)
     std::vector<int32_t> ell_code;    // (n*W) slot_edge code, -1 for padding
-    std::vector<int32_t> color_ptr;   // (n_colors+1) row ranges of the colours ({0, n} when not multicoloured)
+    // Gauss-Seidel colours: rows are ordered (part, colour, level, RCM position)
+    int n_colors = 0;                 // 0: no colouring (rows in RCM order, parts = equal chunks of it)
+    std::vector<int32_t> color_ptr;   // (n_parts, n_colors+1) absolute row ranges of part p's colours
+    std::vector<uint8_t> color_of;    // (n) colour of a row (new numbering)
     int n_levels = 1;                 // downstream levels of the flow hint the colours were cut from (diagnostic)
+    // domain decomposition (n_parts = 1: everything is one part)
+    std::vector<int32_t> part_ptr;    // (n_parts+1) row range owned by part p
+    std::vector<uint8_t> send_mask;   // (n) bit q set: part q (not the owner) reads this row
+    std::vector<int32_t> send_ptr;    // (n_parts+1) ranges into send_rows
+    std::vector<int32_t> send_rows;   // rows with a non-zero send_mask, by owner, ascending
+    std::vector<int32_t> iedge_ptr, gedge_ptr, bcell_ptr;   // (n_parts+1) owned internal edges / ghost edges (index into the
+                                      // ghost block) / boundary cells: an internal edge belongs to the part of its lower cell
     int max_row_len = 0;
     int64_t bandwidth = 0;            // max |row - col| after reordering (diagnostic)
 };
@@ -51,7 +65,8 @@ struct Topology {
 // Returns an empty string on success, else an error message.
 // n_colors > 0: rows are regrouped into that many colours for the multicolour Gauss-Seidel sweeps; hint
 // (may be NULL): one signed flow per edge (reference order, > 0 = out of f1) the colours are aligned with.
+// n_parts: strips of a domain decomposition (1 = none); rows are then ordered part-major.
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
-                           bool rcm, int n_colors, const float* hint, Topology& out);
+                           bool rcm, int n_colors, const float* hint, int n_parts, Topology& out);
 
 }  // namespace cwr

@@ -58,7 +58,11 @@ typedef struct {
                                0 = Jacobi steps, z = (I + N + ... + N^(m-1)) u with N = I - D^-1 A */
     int precond_colors;     /* colours of the Gauss-Seidel sweeps (raised to max row degree + 1 if smaller);
                                0 (default) = chosen from the mesh size so that one colour moves ~20 MB */
-    int reserved[3];
+    int dd_rank, dd_world;  /* domain decomposition: this handle is rank dd_rank of dd_world (<= 8) handles, one per
+                               GPU/process, each given the WHOLE mesh and the same inputs; rows are cut into dd_world
+                               strips and a handle computes its strip, exchanging boundary rows and dot products with
+                               the others over NVLink peer memory (cwr_dd_export / cwr_dd_attach).  0 / 0 or 1: off */
+    int reserved[1];
 } cwr_options;
 
 typedef struct {
@@ -135,6 +139,28 @@ int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_to
  * (E,) f64 each, any may be NULL.  Enabled when options.mass_flux != 0. */
 int cwr_get_flux_sums(cwr_handle* h, int k, double* total_sum, double* in_sum, double* out_sum);
 
+/* --- domain decomposition over NVLink (BASELINE configs[4]) ----------------------------
+ * One process per GPU creates a handle with options.dd_rank / dd_world set, every rank with the SAME mesh,
+ * hydrodynamics and inputs (the mesh is replicated, the rows are not: a rank assembles, solves and stores
+ * only its strip).  cwr_dd_export gives the CUDA IPC handle of the rank's symmetric slab (CWR_IPC_HANDLE_BYTES
+ * bytes); the host exchanges them (torch.distributed / MPI all-gather) and passes all dd_world of them, in
+ * rank order, to cwr_dd_attach.  From then on the kernels store boundary rows straight into the peers that read
+ * them and all-reduce the BiCGSTAB dot products through peer inboxes; every rank must make the same calls in
+ * the same order.  Outputs of a rank are valid for the cells / edges it owns (cwr_dd_layout masks, reference
+ * numbering) plus its halo; mass totals and flux sums are partial sums over the owned part. */
+#define CWR_IPC_HANDLE_BYTES 64
+typedef struct {
+    int rank, world;
+    int rows_owned;         /* cells of this rank's strip */
+    int rows_sent;          /* of those, cells other ranks read (halo volume per exchange) */
+    int neighbour_mask;     /* bit q: rank q exchanges rows with this one */
+    int n_colors, n_levels;
+} cwr_dd_info;
+int cwr_dd_export(cwr_handle* h, void* ipc_handle);
+int cwr_dd_attach(cwr_handle* h, const void* ipc_handles /* dd_world * CWR_IPC_HANDLE_BYTES */);
+int cwr_dd_layout(cwr_handle* h, cwr_dd_info* info, uint8_t* owned_cells /* (n_real,) or NULL */,
+                  uint8_t* owned_edges /* (E,) or NULL */);
+
 /* --- introspection used by the parity tests -------------------------------------------------- */
 /* CSR of A(t) as last assembled, reference numbering, diagonal included, columns sorted:
  * call with NULL arrays to get nnz. */
@@ -143,13 +169,16 @@ int cwr_get_rhs(cwr_handle* h, int k, double* b);           /* (n,) f64, unscale
 int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old); /* (n,) */
 int cwr_get_options(const cwr_handle* h, cwr_options* resolved); /* the options in force (autos resolved) */
 int cwr_stream(cwr_handle* h, void** cuda_stream);           /* the handle's cudaStream_t */
-/* Host only (no device needed): the cell ordering cwr_create / the first cwr_set_hydro* would build --
- * reverse Cuthill-McKee, then (n_colors > 0) the flow-aligned multicolouring of the Gauss-Seidel sweeps.
- * flow_hint: (E,) signed face flow (> 0 leaves f1) or NULL; new_of_old: (n_real,); color_ptr: (65,) row
- * ranges of the colours in the new numbering (n_colors_out + 1 entries used), may be NULL. */
-int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int reorder, int n_colors,
-                    const float* flow_hint, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out, int* n_levels);
 int cwr_counters(cwr_handle* h, int64_t* kernel_launches, int64_t* solver_iterations);
+/* Host only (no device needed): the cell ordering cwr_create / the first cwr_set_hydro* would build --
+ * reverse Cuthill-McKee, then (n_colors > 0) the flow-aligned multicolouring of the Gauss-Seidel sweeps, then
+ * (n_parts > 1) the strips of the domain decomposition; rows end up ordered (part, colour, level, RCM).
+ * flow_hint: (E,) signed face flow (> 0 leaves f1) or NULL; new_of_old: (n_real,); color_ptr: (n_parts, n_colors_out+1)
+ * absolute row ranges of each part's colours (room for 8 * 65 entries), may be NULL; part_ptr: (n_parts+1) rows owned
+ * by each part, may be NULL; n_send: (n_parts) rows of a part that other parts read (halo volume), may be NULL. */
+int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int reorder, int n_colors,
+                    const float* flow_hint, int n_parts, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out,
+                    int* n_levels, int32_t* part_ptr, int32_t* n_send);
 
 /* --- device timing of the dominant kernel (bench.py roofline) -------------------------------- */
 /* Per-kernel-family device time inside cwr_step, measured with CUDA events recorded on the handle's

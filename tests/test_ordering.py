@@ -56,3 +56,38 @@ def test_cyclic_flow_hint_terminates():
     col = colours_of(p, cptr)
     internal = plan.f2 < plan.n_real
     assert np.all(col[plan.f1[internal]] != col[plan.f2[internal]])
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+@pytest.mark.parametrize("n_colors", [0, 12])
+def test_domain_decomposition_strips(n_parts, n_colors):
+    """Rows are ordered (part, colour, ...): parts are equal contiguous row ranges, each part's colours tile
+    its range, colours still separate coupled rows across parts, and only a thin layer of rows is read by
+    other parts (strips across the flow / the RCM band)."""
+    plan = synthetic.make_plan(64, 48, 6, tri_fraction=0.15, dry_fraction=0.02, seed=6)
+    n = plan.n_real
+    hint = plan.face_flow.mean(0)
+    p, cptr, n_levels, part_ptr, n_send = order_cells(plan.f1, plan.f2, plan.n_face, True, n_colors, hint, n_parts)
+    assert np.array_equal(np.sort(p), np.arange(n))
+    assert part_ptr[0] == 0 and part_ptr[-1] == n
+    sizes = np.diff(part_ptr)
+    assert sizes.max() - sizes.min() <= 1
+    part = np.searchsorted(part_ptr, p, side="right") - 1
+    internal = plan.f2 < n
+    a, b = plan.f1[internal], plan.f2[internal]
+    cut = part[a] != part[b]
+    # halo rows per part = rows with a neighbour in another part
+    sent = np.zeros(n, bool); sent[a[cut]] = True; sent[b[cut]] = True
+    assert np.array_equal(n_send, np.bincount(part[sent], minlength=n_parts))
+    assert n_send.sum() < 0.35 * n            # thin strips boundaries (64 x 48 cells, up to 8 strips)
+    if n_colors:
+        assert cptr.shape == (n_parts, cptr.shape[1])
+        for q in range(n_parts):
+            assert cptr[q, 0] == part_ptr[q] and cptr[q, -1] == part_ptr[q + 1] and np.all(np.diff(cptr[q]) >= 0)
+        colour = np.empty(n, np.int64)
+        for q in range(n_parts):
+            rows = np.arange(part_ptr[q], part_ptr[q + 1])
+            colour_of_row = np.searchsorted(cptr[q], rows, side="right") - 1
+            inv = np.empty(n, np.int64)
+            colour[np.isin(p, rows)] = colour_of_row[p[np.isin(p, rows)] - part_ptr[q]]
+        assert np.all(colour[a] != colour[b]), "coupled rows share a colour"
