@@ -192,6 +192,8 @@ def main():
     plan, K = workload_plan(args.workload, T, seed=2, scale=args.scale)
     n, E, F = plan.n_real, plan.n_edge, plan.n_face
     n_units = K * world                      # weak scaling: every rank brings its own K constituents
+    if args.workload == "16m" and world > 1:
+        n_units = K                          # one model cut into strips: total work fixed (strong scaling)
     if args.workload == "ens64":             # 64 scenarios sharded over the ranks (total work fixed)
         n_units = 64
         mine = ensemble.shard_units(n_units, world, rank)
@@ -199,6 +201,9 @@ def main():
         scales = np.exp(np.random.default_rng(100).normal(0.0, 0.5, size=n_units))      # same table on every rank
         base = synthetic.make_inputs(plan, 1, seed=2)[0]
         inputs = np.stack(ensemble.scenario_inputs(base, n, scales[mine.start:mine.stop]))
+    elif args.workload == "16m" and world > 1:   # every rank holds the same inputs, owns a strip of the rows
+        mine = range(K)
+        inputs = synthetic.make_inputs(plan, K, seed=2)
     else:                                    # independent constituents: own ICs / BC series per rank
         mine = range(rank * K, (rank + 1) * K)
         inputs = synthetic.make_inputs(plan, K, seed=2 + 1000 * rank)
@@ -208,12 +213,20 @@ def main():
     for kv in args.opt:
         key, val = kv.split("=", 1)
         opts[key] = float(val) if key == "rtol" else int(val)
-    be = TransportBackend(plan.f1, plan.f2, F, T, K, DIFFUSION, device=local, **opts)
+    # the Gauss-Seidel colours (and the strips of a domain decomposition) follow the time-mean flow
+    hint = plan.face_flow[:: max(1, T // 32)].mean(axis=0, dtype=np.float64).astype(np.float32)
+    dd = args.workload == "16m" and world > 1          # ONE model cut into `world` strips (NVLink halo exchange)
+    if dd:
+        from clearwater_riverine_b200.domain import DomainDecomposedBackend, merge_owned
+        be = DomainDecomposedBackend(plan.f1, plan.f2, F, T, K, DIFFUSION, rank, world, device=local, flow_hint=hint, **opts)
+    else:
+        be = TransportBackend(plan.f1, plan.f2, F, T, K, DIFFUSION, device=local, flow_hint=hint, **opts)
     be.set_geometry(plan.face_x, plan.face_y)
     chunk = max(1, (256 << 20) // (4 * E))
     for t0 in range(0, T, chunk):
         t1 = min(T, t0 + chunk)
         be.set_hydro_raw(t0, plan.face_flow[t0:t1], plan.edge_velocity[t0:t1], plan.volume[t0:t1], dt[t0:t1])
+    dd_info = be.attach() if dd else None
     for k in range(K):
         be.set_inputs(k, inputs[k])
     stream = torch.cuda.ExternalStream(be.stream())
@@ -306,12 +319,16 @@ def main():
         m = be.mass_totals(k, 0, W + K_steps)
         _, f_in, f_out = be.flux_sums(k)
         local_rows[unit] = (m.mass_start, m.mass_end, float(np.nansum(f_in)), float(np.nansum(f_out)))
-    mass_table = ensemble.reduce_mass_balance(local_rows, n_units, device="cuda")
+    if dd:      # every rank holds PARTIAL sums over its strip of the same units: add them up (NCCL all-reduce)
+        part = np.array([local_rows[u] for u in range(n_units)])
+        mass_table = merge_owned(part, np.ones(part.shape[1], bool), axis=1)
+    else:
+        mass_table = ensemble.reduce_mass_balance(local_rows, n_units, device="cuda")
     be.close()
 
     # ---- end to end through the reference-facing API with host buffers -------------------------------------------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not dd:
         model = ClearwaterRiverine.from_arrays(
             plan.f1, plan.f2, plan.face_x, plan.face_y, plan.time_seconds, pinned(plan.face_flow),
             pinned(plan.edge_velocity), pinned(plan.volume), DIFFUSION, {f"c{k}": inputs[k] for k in range(K)},
@@ -344,18 +361,23 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": W,
             "ms_per_step": ms_total / K_steps, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "ens64" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if args.workload == "ens64" or dd else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": {"1m16": "synthetic 1M-cell unstructured mesh, 16 constituents batched (BASELINE configs[2])",
                                     "ohio": "Ohio-River-shaped synthetic mesh (2943 cells), 1 constituent (BASELINE configs[1])",
                                     "ens64": "64 boundary-condition scenarios on the Ohio-shaped mesh (BASELINE configs[3])",
-                                    "16m": "synthetic 16M-cell mesh, 1 constituent, single GPU"}[args.workload],
+                                    "16m": "synthetic 16M-cell mesh, 1 constituent (BASELINE configs[4]): domain-decomposed over the GPUs"
+                                           if dd else "synthetic 16M-cell mesh, 1 constituent, single GPU"}[args.workload],
                        "cells": n, "edges": E, "nnz_offdiag": nnz, "constituents_per_gpu": K, "dt_s": float(dt[0]),
                        "diffusion_coefficient": DIFFUSION, "rtol": be.options.rtol,
                        "precond_steps": be.options.precond_steps, "precond_sweep": be.options.precond_sweep,
                        "precond_precision": be.options.precond_precision, "precond_colors": be.options.precond_colors,
                        "l2": "per-step working set (7 vectors x n x K x 8 B + matrix) >> 126 MB L2; no flush needed"
                              if n * K * 56 > 4 * 126e6 else "working set is L2-resident: launch/latency bound, HBM fraction not meaningful",
-                       "sharding": "independent constituents/scenarios per rank, mesh replicated, no data-path collective",
+                       "sharding": ("domain decomposition: rows cut into strips of the RCM band, halo rows stored into the peers over NVLink "
+                                    "from inside the producer kernels, dot products all-reduced through peer inboxes (no NCCL on the data path)"
+                                    if dd else "independent constituents/scenarios per rank, mesh replicated, no data-path collective"),
+                       "domain_decomposition": None if not dd else {"rows_owned_rank0": dd_info.rows_owned, "halo_rows_sent_rank0": dd_info.rows_sent,
+                                                                      "neighbour_mask_rank0": dd_info.neighbour_mask},
                        "units_per_rank": ensemble.ensemble_plan(n_units, world)},
             "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(l1 - l0),

@@ -77,6 +77,8 @@ def load_library():
         "cwr_default_options": ([C.POINTER(CwrOptions)], C.c_int),
         "cwr_create": ([C.POINTER(H), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_double,
                         C.POINTER(CwrOptions)], C.c_int),
+        "cwr_create_with_hint": ([C.POINTER(H), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, ip, ip, C.c_double,
+                                  C.POINTER(CwrOptions), fp], C.c_int),
         "cwr_destroy": ([H], None),
         "cwr_last_error": ([H], C.c_char_p),
         "cwr_set_hydro": ([H, C.c_int, C.c_int, fp, dp, fp, fp, dp], C.c_int),
@@ -155,7 +157,7 @@ class TransportBackend:
     """One model on one GPU: fixed topology, K constituents, T time slices."""
 
     def __init__(self, f1, f2, n_face: int, n_time: int, n_constituents: int, diffusion_coefficient: float,
-                 device: int = 0, **options):
+                 device: int = 0, flow_hint=None, **options):
         self._lib = load_library()
         self._h = C.c_void_p()
         f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
@@ -170,8 +172,10 @@ class TransportBackend:
                 raise TypeError(f"unknown option {key!r}")
             setattr(opt, key, val)
         self.options = opt
-        rc = self._lib.cwr_create(C.byref(self._h), device, self.n_real, self.n_face, self.n_edge, self.n_time, self.K,
-                                  _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), self.diffusion_coefficient, C.byref(opt))
+        hint = None if flow_hint is None else _arr(flow_hint, np.float32, (self.n_edge,), "flow_hint")
+        rc = self._lib.cwr_create_with_hint(C.byref(self._h), device, self.n_real, self.n_face, self.n_edge, self.n_time,
+                                            self.K, _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), self.diffusion_coefficient,
+                                            C.byref(opt), _ptr(hint, C.c_float))
         if rc != CWR_OK:
             msg = self._lib.cwr_last_error(None).decode()
             self._h = C.c_void_p()

@@ -315,7 +315,7 @@ void cwr_destroy(cwr_handle* h) {
 }
 
 static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
-                       const int32_t* f1, const int32_t* f2, double D, const cwr_options* opt) {
+                       const int32_t* f1, const int32_t* f2, double D, const cwr_options* opt, const float* flow_hint) {
     if (!f1 || !f2) FAIL(CWR_EINVAL, "f1/f2 must not be NULL");
     if (n_time < 2) FAIL(CWR_EINVAL, "n_time must be >= 2");
     if (n_const < 1 || n_const > kMaxK) FAIL(CWR_EINVAL, "n_const must be in [1, 128]");
@@ -338,7 +338,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->opt.precond_colors <= 0) {
         // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
         // bytes per row of one sweep = indices + values + three vectors in the sweep type
-        const double bytes = (double)n_real * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
+        const double bytes = (double)n_real / std::max(1, h->opt.dd_world) * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
         h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / 20e6)));
     }
     h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
@@ -355,8 +355,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
-                                      h->gauss_seidel ? h->opt.precond_colors : 0, nullptr, h->world, h->topo);
+                                      h->gauss_seidel ? h->opt.precond_colors : 0, h->gauss_seidel ? flow_hint : nullptr, h->world, h->topo);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
+    if (flow_hint) h->hint_done = true;
     const Topology& tp = h->topo;
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
@@ -497,10 +498,15 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
 
 int cwr_create(cwr_handle** out, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
                const int32_t* f1, const int32_t* f2, double D, const cwr_options* opt) {
+    return cwr_create_with_hint(out, device, n_real, n_face, n_edge, n_time, n_const, f1, f2, D, opt, nullptr);
+}
+
+int cwr_create_with_hint(cwr_handle** out, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
+                         const int32_t* f1, const int32_t* f2, double D, const cwr_options* opt, const float* flow_hint) {
     if (!out) return CWR_EINVAL;
     *out = nullptr;
     cwr_handle* h = new cwr_handle();
-    int rc = create_impl(h, device, n_real, n_face, n_edge, n_time, n_const, f1, f2, D, opt);
+    int rc = create_impl(h, device, n_real, n_face, n_edge, n_time, n_const, f1, f2, D, opt, flow_hint);
     if (rc != CWR_OK) {
         g_create_error = h->err;
         cwr_destroy(h);

@@ -446,7 +446,11 @@ __device__ __forceinline__ void dd_wait(const DeviceModel& M, bool dots, unsigne
     if (*reinterpret_cast<volatile int*>(&M.dd->timeout)) return;     // a peer already went missing: fail fast
     while (!dd_arrived(M, dots, e, mask))
         if (++spins > (1u << 22)) { M.dd->timeout = 1; break; }       // never hang the device (seconds)
-    __threadfence_system();
+    // The rows / totals the peer announced were performed at system scope before its flag store (its
+    // fence.sys), they live in THIS device's memory and are read through L2 (ld.cg / cp.async.cg / the next
+    // kernel): a device-scope fence orders those reads after the flag read.  (fence.sys costs 1.75 us on
+    // B200, fence.gpu 0.4 us -- tools/microbench/peer_latency.cu.)
+    __threadfence();
 }
 
 // tot[0 .. pairs) (shared memory, this rank's totals, complete) -> sums over all ranks, by the whole CTA
@@ -461,10 +465,10 @@ __device__ __forceinline__ void dd_allreduce(const DeviceModel& M, double* tot, 
         const double v = tot[pair];
         for (int q = 0; q < M.world; ++q) peer_ptr(M, q, M.dd)->dot_inbox[buf][M.rank][pair] = v;
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned all = (1u << M.world) - 1u;
+        __threadfence_system();               // the CTA's inbox stores (ordered before it by the barrier), then the flags
         dd_signal(M, true, e, all);
         dd_wait(M, true, e, all);
     }
@@ -493,11 +497,11 @@ __global__ void __launch_bounds__(kThreads) k_halo_push(DeviceModel M, T* vec, c
             peer_ptr(M, r, vec)[(size_t)row * K + k] = v;
         }
     }
-    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();        // this CTA's peer stores, before its arrival below
     if (!last_block_arrives(&M.ctl->ticket_halo)) return;
     if (threadIdx.x == 0) {
         const unsigned long long e = ++M.dd->bar_epoch;
-        __threadfence_system();
         dd_signal(M, false, e, M.nbr_mask);
         dd_wait(M, false, e, M.nbr_mask);
     }
@@ -642,13 +646,16 @@ __device__ __forceinline__ Pk<T, V> ldk_cg(const T* p) {
 // Grid barrier of the persistent sweep kernel.  With several ranks it is also the halo barrier: the last
 // CTA of this rank to arrive (every CTA's stores, peer stores included, are fenced before its arrival)
 // announces epoch `e` to the neighbour ranks, and every CTA also waits for the neighbours' announcements.
-__device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned target, unsigned long long e) {
+__device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned target, unsigned long long e, bool pushed) {
     SolverCtl* ctl = M.ctl;
-    __syncthreads();
+    // system-scope fence only in the CTAs that stored rows into a peer since the last barrier
+    const int any_pushed = M.world > 1 ? __syncthreads_or(pushed) : (__syncthreads(), 0);
     if (threadIdx.x == 0) {
-        if (M.world > 1) __threadfence_system(); else __threadfence();
+        if (any_pushed) __threadfence_system(); else __threadfence();
         const unsigned t = atomicAdd(&ctl->gs_bar[0], 1u);
-        if (M.world > 1 && t == target - 1) { __threadfence_system(); dd_signal(M, false, e, M.nbr_mask); }
+        // every CTA that stored into a peer fenced at system scope BEFORE its arrival; seeing all arrivals
+        // (device-scope fence) therefore orders all of this rank's peer stores before the announcement
+        if (M.world > 1 && t == target - 1) { __threadfence(); dd_signal(M, false, e, M.nbr_mask); }
         unsigned spins = 0;
         while (*reinterpret_cast<volatile unsigned*>(&ctl->gs_bar[0]) < target)
             if (++spins > (1u << 27)) { ctl->barrier_timeout = 1; break; }      // never hang the device
@@ -695,8 +702,10 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     const bool multi = M.world > 1;
     const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;     // halo epochs continue where the last kernel stopped
     // a finished row also goes to the ranks that read it (NVLink peer stores)
+    bool pushed = false;
     auto push = [&](int i, int cc, const Pk<ST, VEC>& o) {
         unsigned m = M.send_mask[i];
+        pushed |= m != 0;
         while (m) {
             const int q = __ffs(m) - 1;
             m &= m - 1;
@@ -811,10 +820,11 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         if (step + 1 < n_steps) {
             prefetch(step + 1);
             ++epoch;
-            grid_barrier(M, epoch * nvb, e0 + epoch);
+            grid_barrier(M, epoch * nvb, e0 + epoch, pushed);
+            pushed = false;
         } else if (multi) {       // the products that follow gather the neighbours' last colour too
             ++epoch;
-            grid_barrier(M, epoch * nvb, e0 + epoch);
+            grid_barrier(M, epoch * nvb, e0 + epoch, pushed);
         }
     }
     // the last CTA to leave re-arms the barrier for the next launch

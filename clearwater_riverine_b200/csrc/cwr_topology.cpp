@@ -191,25 +191,19 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             }
         }
         // ---- partition into n_parts strips (domain decomposition), then colour-major inside a part ------
-        // Cells are cut into equal chunks of the (level, RCM position) order when the hint gave levels
-        // (strips across the flow), else of the RCM order (strips of the RCM band): compact parts whose
-        // rows only couple to the neighbouring strips.
-        std::vector<int32_t> order(n);
-        std::iota(order.begin(), order.end(), 0);
-        const bool have_levels = max_level + 1 > nc;
-        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-            if (have_levels && level[a] != level[b]) return level[a] < level[b];
-            return rcm_pos[a] < rcm_pos[b];
-        });
+        // Parts are equal chunks of the RCM order (strips of the RCM band: breadth-first wavefronts, so a
+        // part only couples to its two neighbouring strips and the cut is a smooth front).  Final order:
+        // (part, colour, level, RCM position), sorted through one 64-bit key per cell.
+        if (max_level >= (1 << 22)) return "flow hint has more than 4M downstream levels";
         std::vector<int32_t> part(n);
-        for (int i = 0; i < n; ++i) part[order[i]] = (int32_t)(((int64_t)i * n_parts) / n);
-        std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
-            if (part[a] != part[b]) return part[a] < part[b];
-            const int ca = level[a] % nc, cb = level[b] % nc;
-            if (ca != cb) return ca < cb;
-            if (level[a] != level[b]) return level[a] < level[b];
-            return rcm_pos[a] < rcm_pos[b];
-        });
+        for (int i = 0; i < n; ++i) part[i] = (int32_t)(((int64_t)rcm_pos[i] * n_parts) / n);
+        std::vector<uint64_t> key(n);
+        for (int i = 0; i < n; ++i)
+            key[i] = ((uint64_t)part[i] << 60) | ((uint64_t)(level[i] % nc) << 54) | ((uint64_t)level[i] << 32) | (uint32_t)rcm_pos[i];
+        std::sort(key.begin(), key.end());
+        std::vector<int32_t> order(n);
+        for (int i = 0; i < n; ++i) order[i] = T.old_of_new[(uint32_t)key[i]];       // RCM position -> cell
+        std::vector<uint64_t>().swap(key);
         T.n_colors = nc;
         T.color_ptr.assign((size_t)n_parts * (nc + 1), 0);
         T.part_ptr.assign(n_parts + 1, 0);
@@ -242,20 +236,21 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     // internal edges: sort by (min new cell, max new cell, original id); ghost edges: by (new cell, original id)
     std::vector<int32_t> internal, ghost;
     internal.reserve(E_int); ghost.reserve(T.E_g);
-    for (int e = 0; e < E; ++e) (f2[e] < n ? internal : ghost).push_back(e);
-    auto lo = [&](int32_t e) { return std::min(T.new_of_old[f1[e]], T.new_of_old[f2[e]]); };
-    auto hi = [&](int32_t e) { return std::max(T.new_of_old[f1[e]], T.new_of_old[f2[e]]); };
-    std::sort(internal.begin(), internal.end(), [&](int32_t a, int32_t b) {
-        int32_t la = lo(a), lb = lo(b);
-        if (la != lb) return la < lb;
-        int32_t ha = hi(a), hb = hi(b);
-        if (ha != hb) return ha < hb;
-        return a < b;
-    });
-    std::sort(ghost.begin(), ghost.end(), [&](int32_t a, int32_t b) {
-        int32_t ca = T.new_of_old[f1[a]], cb = T.new_of_old[f1[b]];
-        return ca != cb ? ca < cb : a < b;
-    });
+    {
+        std::vector<std::pair<uint64_t, int32_t>> ik; ik.reserve(E_int);
+        std::vector<uint64_t> gk; gk.reserve(T.E_g);
+        for (int e = 0; e < E; ++e) {
+            const int32_t a = T.new_of_old[f1[e]];
+            if (f2[e] < n) {
+                const int32_t b = T.new_of_old[f2[e]];
+                ik.emplace_back(((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b), e);
+            } else gk.push_back(((uint64_t)(uint32_t)a << 32) | (uint32_t)e);
+        }
+        std::sort(ik.begin(), ik.end());
+        std::sort(gk.begin(), gk.end());
+        for (auto& pr : ik) internal.push_back(pr.second);
+        for (uint64_t k : gk) ghost.push_back((int32_t)(uint32_t)k);
+    }
     T.eperm.resize(E); T.f1p.resize(E); T.f2p.resize(E);
     for (int i = 0; i < E_int; ++i) T.eperm[i] = internal[i];
     for (int i = 0; i < T.E_g; ++i) T.eperm[E_int + i] = ghost[i];

@@ -52,10 +52,10 @@ class DomainDecomposedBackend(TransportBackend):
     every rank in the same order with the same arguments.  `attach()` after construction (collective)."""
 
     def __init__(self, f1, f2, n_face, n_time, n_constituents, diffusion_coefficient, rank: int, world: int,
-                 device: int = 0, group=None, **options):
+                 device: int = 0, group=None, flow_hint=None, **options):
         options.setdefault("solver_path", 1)
         super().__init__(f1, f2, n_face, n_time, n_constituents, diffusion_coefficient, device=device,
-                         dd_rank=rank, dd_world=world, **options)
+                         flow_hint=flow_hint, dd_rank=rank, dd_world=world, **options)
         self.rank, self.world, self.group = rank, world, group
         self._owned_cells = self._owned_edges = None
 

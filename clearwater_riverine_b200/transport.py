@@ -162,14 +162,13 @@ class ClearwaterRiverine:
         self.stream_hydro = bool(backend_options.pop("stream_hydro", False))
         if self.stream_hydro:
             backend_options.setdefault("hydro_capacity", 3)
+        q = mesh[FLOW_ACROSS_FACE]      # Gauss-Seidel colours follow the time-mean flow
+        hint = np.nanmean(q[:: max(1, T // 32)], axis=0, dtype=np.float64).astype(np.float32)
         self.backend = TransportBackend(mesh[EDGES_FACE1], mesh[EDGES_FACE2], F, T, len(inputs), D, device=device,
-                                        **backend_options)
+                                        flow_hint=hint, **backend_options)
         # derived coefficients (utilities.py:513-541) are computed on the device from the raw arrays
         self.backend.set_geometry(mesh["face_x"], mesh["face_y"])
         self._resident = set()
-        if self.backend.options.precond_sweep == 1:      # Gauss-Seidel colours follow the time-mean flow
-            q = mesh[FLOW_ACROSS_FACE]
-            self.backend.set_flow_hint(np.nanmean(q[:: max(1, T // 32)], axis=0, dtype=np.float64).astype(np.float32))
         if self.stream_hydro:
             self._upload_slice(0)
         else:

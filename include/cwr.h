@@ -85,6 +85,11 @@ int cwr_default_options(cwr_options* opt);
  * boundary-cell lists once.  n_real = nreal + 1 = max(f1) + 1 (io/hdf.py:268-269). */
 int cwr_create(cwr_handle** h, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
                const int32_t* f1, const int32_t* f2, double diffusion_coefficient, const cwr_options* opt);
+/* The same with the flow hint of cwr_set_flow_hint given up front ((E,) f32 or NULL): the ordering is built once
+ * (it costs seconds on meshes of millions of cells). */
+int cwr_create_with_hint(cwr_handle** h, int device, int n_real, int n_face, int n_edge, int n_time, int n_const,
+                         const int32_t* f1, const int32_t* f2, double diffusion_coefficient, const cwr_options* opt,
+                         const float* flow_hint);
 void cwr_destroy(cwr_handle* h);
 const char* cwr_last_error(const cwr_handle* h);   /* h may be NULL: error of the last failed cwr_create */
 
