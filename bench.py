@@ -261,6 +261,10 @@ def main():
     nnz = 2 * int(np.count_nonzero(plan.f2 < n))
     o = be.options
     Wd = 4 * ((int(np.bincount(np.concatenate([plan.f1[plan.f2 < n], plan.f2[plan.f2 < n]]), minlength=n).max()) + 3) // 4)
+    n_all, nnz_all, E_all = n, nnz, E
+    if dd:      # a rank's kernels run over its strip: algorithmic bytes of the strip (rank 0's, the strips are equal)
+        frac_own = dd_info.rows_owned / n
+        n, nnz, E = int(dd_info.rows_owned), int(nnz * frac_own), int(E * frac_own)
     V = 8.0 * n * K                                     # one fp64 (n, K) vector
     sweeps = max(0, o.precond_steps - 1)
     sb = 4 if o.precond_precision == 32 else 8          # bytes per entry of the sweep type
@@ -313,6 +317,7 @@ def main():
                     "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "ms_per_launch": d["ms_per_launch"],
                     "share_of_step": d["share_of_step"], "kernels": kernels}
 
+    n, nnz, E = n_all, nnz_all, E_all
     # ---- mass-balance scalars: the only collective (NCCL all-reduce over the ranks' units) ------------------------
     local_rows = {}
     for k, unit in enumerate(mine):

@@ -339,7 +339,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
         // bytes per row of one sweep = indices + values + three vectors in the sweep type
         const double bytes = (double)n_real / std::max(1, h->opt.dd_world) * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
-        h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / 20e6)));
+        // (a colour's barrier also waits for the neighbour ranks of a domain decomposition: ~10 us, so 40 MB there)
+        h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / (h->opt.dd_world > 1 ? 40e6 : 20e6))));
     }
     h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
     int ndev = 0;
