@@ -92,6 +92,9 @@ def load_library():
         "cwr_run": ([H, C.c_int, C.c_int, C.POINTER(CwrStepInfo)], C.c_int),
         "cwr_get_state": ([H, C.c_int, C.c_int, dp], C.c_int),
         "cwr_get_state_all": ([H, C.c_int, dp], C.c_int),
+        "cwr_get_state_rows": ([H, C.c_int, C.POINTER(C.c_void_p)], C.c_int),
+        "cwr_host_register": ([C.c_void_p, C.c_size_t], C.c_int),
+        "cwr_host_unregister": ([C.c_void_p], C.c_int),
         "cwr_get_mass_flux": ([H, C.c_int, C.c_int, dp, dp, dp], C.c_int),
         "cwr_mass_totals_at": ([H, C.c_int, C.c_int, C.c_int, C.POINTER(CwrMassTotals)], C.c_int),
         "cwr_get_flux_sums": ([H, C.c_int, dp, dp, dp], C.c_int),
@@ -126,6 +129,21 @@ def _arr(a, dtype, shape=None, name="array") -> np.ndarray:
     if shape is not None and tuple(out.shape) != tuple(shape):
         raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(out.shape)}")
     return out
+
+
+def pin_host_array(a: np.ndarray) -> bool:
+    """Page-lock a numpy array in place (cudaHostRegister); False if that is not possible (no device...)."""
+    try:
+        return load_library().cwr_host_register(a.ctypes.data, a.nbytes) == CWR_OK
+    except Exception:
+        return False
+
+
+def unpin_host_array(a: np.ndarray) -> None:
+    try:
+        load_library().cwr_host_unregister(a.ctypes.data)
+    except Exception:
+        pass
 
 
 def order_cells(f1, f2, n_face: int, reorder: bool = True, n_colors: int = 0, flow_hint=None, n_parts: int = 1):
@@ -268,6 +286,16 @@ class TransportBackend:
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.K, self.n_real)
         self._check(self._lib.cwr_get_state_all(self._h, t, _ptr(out, C.c_double)))
         return out
+
+    def get_state_rows(self, t: int, rows: Sequence[Optional[np.ndarray]]):
+        """c[t] of constituent k (real cells) straight into rows[k][:n] -- e.g. row t of each constituent's (T,F) array."""
+        ptrs = (C.c_void_p * self.K)()
+        for k, r in enumerate(rows):
+            if r is None:
+                continue
+            assert r.dtype == np.float64 and r.flags.c_contiguous and r.shape[0] >= self.n_real
+            ptrs[k] = r.ctypes.data
+        self._check(self._lib.cwr_get_state_rows(self._h, t, ptrs))
 
     def get_mass_flux(self, k: int, t: int, advection=None, diffusion=None, total=None):
         outs = []

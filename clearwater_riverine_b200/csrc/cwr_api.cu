@@ -1048,6 +1048,41 @@ int cwr_get_state_all(cwr_handle* h, int t, double* out) {
     return CWR_OK;
 }
 
+int cwr_get_state_rows(cwr_handle* h, int t, double* const* rows) {
+    if (!h) return CWR_EINVAL;
+    if (!rows) FAIL(CWR_EINVAL, "NULL array");
+    int rc = state_available(h, t);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    const size_t nK = (size_t)h->n * h->K;
+    rc = ensure_stage(h, nK * 8);
+    if (rc) return rc;
+    k_extract_all<<<grid_for((int64_t)nK, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+        (double*)h->d_stage, state_slot(h, t), h->d_new_of_old, h->n, h->K);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    for (int k = 0; k < h->K; ++k) {
+        if (!rows[k]) continue;
+        CK(cudaMemcpyAsync(rows[k], (const double*)h->d_stage + (size_t)k * h->n, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+int cwr_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return CWR_EINVAL;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); cudaGetLastError(); return CWR_ECUDA; }
+    return CWR_OK;
+}
+
+int cwr_host_unregister(void* p) {
+    if (!p) return CWR_EINVAL;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return CWR_ECUDA; }
+    return CWR_OK;
+}
+
 int cwr_get_mass_flux(cwr_handle* h, int k, int t, double* adv, double* diff, double* tot) {
     if (!h) return CWR_EINVAL;
     if (k < 0 || k >= h->K) FAIL(CWR_EINVAL, "constituent index out of range");

@@ -19,7 +19,7 @@ from typing import Any, Dict, Optional, Tuple
 
 import numpy as np
 
-from .backend import CWR_OK, STATUS_NAMES, SolverWarning, TransportBackend
+from .backend import CWR_OK, STATUS_NAMES, SolverWarning, TransportBackend, pin_host_array, unpin_host_array
 
 # reference variables.py names
 ADVECTION_COEFFICIENT = "advection_coeff"
@@ -180,12 +180,9 @@ class ClearwaterRiverine:
         for k, name in enumerate(self.constituents):
             self.backend.set_inputs(k, self.constituent_dict[name].input_array)
         self._index = {name: k for k, name in enumerate(self.constituents)}
-        self._all = np.empty((len(inputs), int(np.max(f1)) + 1))
-        try:                                   # page-locked landing buffer for the per-step device->host copy
-            import torch
-            self._all = torch.from_numpy(self._all).pin_memory().numpy()
-        except Exception:
-            pass
+        # update() copies c[t+1] of every constituent straight into row t+1 of its output array; page-locking
+        # those arrays lets the copies run at the full PCIe rate with no intermediate host buffer
+        self._pinned = [self.mesh[name] for name in self.constituents if pin_host_array(self.mesh[name])]
         self.solver_info = []
 
     def _upload_slice(self, t: int):
@@ -227,10 +224,9 @@ class ClearwaterRiverine:
         """c[t1] of every constituent in one device->host copy; ghost cells get their BC value where
         one is set and stay NaN elsewhere (transport.py:252-264)."""
         n = self.mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
-        self.backend.get_state_all(t1, self._all)
+        self.backend.get_state_rows(t1, [self.mesh[name][t1] for name in self.constituents])
         for name, k in self._index.items():
             row = self.mesh[name][t1]
-            row[:n] = self._all[k]
             c = self.constituent_dict[name]
             bc = c.input_array[t1, n:]
             row[n:] = np.where(bc != 0, bc, np.nan)
@@ -253,4 +249,7 @@ class ClearwaterRiverine:
         return info
 
     def finalize(self):
+        for a in getattr(self, "_pinned", []):
+            unpin_host_array(a)
+        self._pinned = []
         self.backend.close()

@@ -16,6 +16,7 @@
 #ifndef CWR_H
 #define CWR_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -130,6 +131,14 @@ int cwr_run(cwr_handle* h, int t_begin, int t_end, cwr_step_info* worst);
 int cwr_get_state(cwr_handle* h, int k, int t, double* c_out);
 /* All constituents at once, real cells only: (K, n) f64 (what a coupling loop reads each step). */
 int cwr_get_state_all(cwr_handle* h, int t, double* c_out);
+/* The same, every constituent straight into its own destination: rows[k] -> (n,) f64 (e.g. row t of the
+ * caller's (T,F) output array of constituent k; NULL skips k).  One device->host copy per constituent with no
+ * intermediate host buffer; at full PCIe rate when the destinations are page-locked (cwr_host_register). */
+int cwr_get_state_rows(cwr_handle* h, int t, double* const* rows);
+/* Page-lock / release a caller-owned host array (cudaHostRegister) so that the copies above run asynchronously
+ * at full rate.  Optional; no handle needed (a CUDA device must be present). */
+int cwr_host_register(void* p, size_t bytes);
+int cwr_host_unregister(void* p);
 /* All overrides at once: (K, n) f64; mask[k] != 0 selects the constituents to overwrite. */
 int cwr_set_state_all(cwr_handle* h, int t, const double* c, const uint8_t* mask);
 
