@@ -651,7 +651,7 @@ __device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned targ
     // system-scope fence only in the CTAs that stored rows into a peer since the last barrier
     const int any_pushed = M.world > 1 ? __syncthreads_or(pushed) : (__syncthreads(), 0);
     if (threadIdx.x == 0) {
-        if (any_pushed) __threadfence_system(); else __threadfence();
+        if (any_pushed) __threadfence_system(); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
         const unsigned t = atomicAdd(&ctl->gs_bar[0], 1u);
         // every CTA that stored into a peer fenced at system scope BEFORE its arrival; seeing all arrivals
         // (device-scope fence) therefore orders all of this rank's peer stores before the announcement
@@ -659,7 +659,7 @@ __device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned targ
         unsigned spins = 0;
         while (*reinterpret_cast<volatile unsigned*>(&ctl->gs_bar[0]) < target)
             if (++spins > (1u << 27)) { ctl->barrier_timeout = 1; break; }      // never hang the device
-        if (M.world > 1) dd_wait(M, false, e, M.nbr_mask); else __threadfence();
+        if (M.world > 1) dd_wait(M, false, e, M.nbr_mask); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }

@@ -374,3 +374,44 @@ def test_large_mesh_properties():
     assert np.array_equal(Ao.indices, A.indices)
     assert np.abs(Ao.data - A.data).max() <= 1e-13 * np.abs(Ao.data).max()
     be.close()
+
+
+def test_full_size_1m_x16_residual_linearity_and_repeatability():
+    """BASELINE configs[2] at its full size (1M cells x 16 constituents), where the oracle's SuperLU would need
+    ~50 s per constituent-step: size-independent properties instead.  (1) A x = b through an independent host
+    product for every constituent; (2) linearity: the constituent whose inputs are the sum of two others is
+    their sum; (3) the default preconditioner (fp32 flow-aligned Gauss-Seidel) and fp64 Jacobi steps give the
+    same answer; (4) two runs are bitwise identical."""
+    import bench
+    from clearwater_riverine_b200 import TransportBackend, synthetic
+    T = 3
+    plan, K = bench.workload_plan("1m16", T, seed=2)
+    assert plan.n_real == 1_000_000 and K == 16
+    n = plan.n_real
+    inputs = synthetic.make_inputs(plan, K, seed=2)
+    inputs[2] = inputs[0] + inputs[1]
+    dt = np.append(np.diff(plan.time_seconds), np.nan)
+    hint = plan.face_flow.mean(axis=0)
+    outs = {}
+    for name, opts in (("gs", {}), ("gs2", {}), ("jacobi64", dict(precond_sweep=0, precond_precision=64, precond_steps=8))):
+        be = TransportBackend(plan.f1, plan.f2, plan.n_face, T, K, bench.DIFFUSION, flow_hint=hint, **opts)
+        be.set_geometry(plan.face_x, plan.face_y)
+        be.set_hydro_raw(0, plan.face_flow, plan.edge_velocity, plan.volume, dt)
+        for k in range(K):
+            be.set_inputs(k, inputs[k])
+        for t in range(2):
+            info = be.step(t)
+            assert info.status == 0 and info.max_relres <= 1e-13
+        outs[name] = be.get_state_all(2)
+        if name == "gs":
+            A = be.get_lhs()                                # LHS of the last step, reference numbering
+            for k in range(K):
+                b = be.get_rhs(k)
+                r = A @ outs[name][k] - b
+                assert np.linalg.norm(r) <= 1e-11 * np.linalg.norm(b), k
+        be.close()
+    x = outs["gs"]
+    scale = np.abs(x).max()
+    assert np.abs(x[2] - (x[0] + x[1])).max() <= 1e-9 * scale                       # linearity
+    assert np.abs(x - outs["jacobi64"]).max() <= 1e-9 * scale                       # preconditioner-independent
+    assert np.array_equal(x, outs["gs2"])                                           # bitwise repeatable
