@@ -45,6 +45,8 @@ struct cwr_handle {
     std::vector<int32_t> f1_ref, f2_ref;   // the caller's connectivity (kept for the flow-aligned recolouring)
     int last_iters = 0;              // iterations of the previous solve (launch-ahead prediction)
     bool small_path = false;         // one-CTA-per-column in-kernel solve (small meshes)
+    bool tiny = false;               // ... entirely on chip (k_solve_tiny: matrix in shared memory, Gauss-Seidel sweeps)
+    int tiny_rpt = 1;                // rows per thread of k_solve_tiny
     bool in_run = false;             // inside cwr_run: the small path does not synchronise per step
     SmallStats* d_stats = nullptr; SmallStats* h_stats = nullptr;
     int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0, grid_spmm = 0, grid_xrp = 0;
@@ -191,6 +193,17 @@ static int ensure_stage(cwr_handle* h, size_t bytes) {
         if (h->SVEC == 2) { constexpr int SVEC = 2; SWEEP_KC_CASES(__VA_ARGS__) }             \
         else { constexpr int SVEC = 1; SWEEP_KC_CASES(__VA_ARGS__) }                          \
     }
+// binds RPT (rows per thread) and W4 (ELL width 4) for k_solve_tiny
+#define TINY_RPT_CASES(...)                                        \
+    switch (h->tiny_rpt) {                                         \
+        case 1: { constexpr int RPT = 1; __VA_ARGS__; break; }     \
+        case 2: { constexpr int RPT = 2; __VA_ARGS__; break; }     \
+        case 3: { constexpr int RPT = 3; __VA_ARGS__; break; }     \
+        default: { constexpr int RPT = 4; __VA_ARGS__; break; }    \
+    }
+#define TINY_DISPATCH(...)                                                     \
+    if (h->topo.W == 4) { constexpr bool W4 = true; TINY_RPT_CASES(__VA_ARGS__) } \
+    else { constexpr bool W4 = false; TINY_RPT_CASES(__VA_ARGS__) }
 // binds PT: the type of the preconditioned vectors p^ / s^ the products and the update kernel read
 #define PT_DISPATCH(...)                                                                      \
     if (h->m_steps > 1 && h->sweep_f32) { using PT = float; KC_DISPATCH(h->KC, __VA_ARGS__) } \
@@ -239,7 +252,7 @@ static void set_owned_ranges(cwr_handle* h) {
 // direction (time mean of the face flows over the call's slices).  Only possible while nothing that
 // depends on the cell order is on the device yet (no inputs, no hydro slices, no steps).
 static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
-    if (!h->gauss_seidel || h->hint_done) return CWR_OK;
+    if (!(h->gauss_seidel || h->tiny) || h->hint_done) return CWR_OK;
     h->hint_done = true;
     for (uint8_t s : h->inputs_set) if (s) return CWR_OK;
     const int E = h->E;
@@ -324,7 +337,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->opt.max_iter <= 0) h->opt.max_iter = 500;
     if (h->opt.check_every <= 0) h->opt.check_every = 1;
     const bool small = h->opt.solver_path == 2 || (h->opt.solver_path == 0 && n_real <= 32768);
-    if (h->opt.precond_steps <= 0) h->opt.precond_steps = (h->opt.precond_sweep == 1 && !small) ? 5 : 8;   // auto
+    // tiny meshes (<= 4096 cells, the Ohio River model): the whole solve on chip with Gauss-Seidel sweeps
+    const bool tiny = small && h->opt.precond_sweep == 1 && h->opt.precond_steps != 1 && n_real <= kTinyThreads * kTinyMaxRows;
+    if (h->opt.precond_steps <= 0) h->opt.precond_steps = (h->opt.precond_sweep == 1 && (!small || tiny)) ? 5 : 8;   // auto
     h->m_steps = std::min(h->opt.precond_steps, 64);
     if (h->opt.precond_precision != 64) h->opt.precond_precision = 32;
     h->sweep_f32 = h->opt.precond_precision == 32;
@@ -334,6 +349,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->world > kMaxRanks || h->rank < 0 || h->rank >= h->world) FAIL(CWR_EINVAL, "dd_rank / dd_world out of range (at most 8 ranks)");
     if (h->world > 1 && (small || h->m_steps < 2))
         FAIL(CWR_EINVAL, "domain decomposition needs the multi-CTA solver path (solver_path = 1) and precond_steps >= 2");
+    h->tiny = tiny;
     h->gauss_seidel = h->opt.precond_sweep == 1 && !h->small_path && h->m_steps > 1;
     if (h->opt.precond_colors <= 0) {
         // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
@@ -341,6 +357,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         const double bytes = (double)n_real / std::max(1, h->opt.dd_world) * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
         // (a colour's barrier also waits for the neighbour ranks of a domain decomposition: ~10 us, so 40 MB there)
         h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / (h->opt.dd_world > 1 ? 40e6 : 20e6))));
+        if (tiny) h->opt.precond_colors = 12;       // on chip a colour costs a __syncthreads(): measured optimum on the Ohio-shaped mesh
     }
     h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
     int ndev = 0;
@@ -356,7 +373,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
-                                      h->gauss_seidel ? h->opt.precond_colors : 0, h->gauss_seidel ? flow_hint : nullptr, h->world, h->topo);
+                                      (h->gauss_seidel || h->tiny) ? h->opt.precond_colors : 0,
+                                      (h->gauss_seidel || h->tiny) ? flow_hint : nullptr, h->world, h->topo);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (flow_hint) h->hint_done = true;
     const Topology& tp = h->topo;
@@ -394,6 +412,18 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
             // every CTA must be resident (grid barrier): SM count x occupancy, and no more CTAs than the
             // largest colour has row groups
             h->grid_gs = h->num_sms * occ_gs;      // every CTA resident: the kernel synchronises grid-wide
+        }
+    }
+    if (h->tiny) {
+        const size_t need = tiny_smem_bytes(n, tp.W);
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (need + 1024 > (size_t)max_optin) h->tiny = false;      // falls back to k_solve_small (Jacobi steps, any row order)
+        else {
+            h->tiny_rpt = (n + kTinyThreads - 1) / kTinyThreads;
+            cudaError_t e = cudaSuccess;
+            TINY_DISPATCH(e = cudaFuncSetAttribute(k_solve_tiny<RPT, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            CK(e);
         }
     }
     h->grid_rows = grid_for(tp.part_ptr[h->rank + 1] - tp.part_ptr[h->rank], kThreads / kc, h->max_grid);
@@ -856,6 +886,11 @@ static int read_small_stats(cwr_handle* h, cwr_step_info* info) {
 static int solve_small(cwr_handle* h, cwr_step_info* info) {
     if (!h->in_run) CK(cudaMemsetAsync(h->d_stats, 0, sizeof(SmallStats), h->stream));
     mark(h, CWR_FAM_SOLVE_SMALL);
+    if (h->tiny) {
+        const size_t sm = tiny_smem_bytes(h->n, h->topo.W);
+        const int sweeps = h->m_steps - 1;
+        TINY_DISPATCH((k_solve_tiny<RPT, W4><<<h->K, kTinyThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats)));
+    } else
     k_solve_small<<<h->K, kSmallThreads, 0, h->stream>>>(h->M, h->m_steps, h->d_stats);
     h->launches += 1;
     CK(cudaGetLastError());
@@ -1288,8 +1323,9 @@ int cwr_dd_layout(cwr_handle* h, cwr_dd_info* out, uint8_t* owned_cells, uint8_t
 int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     if (!h || !out) return CWR_EINVAL;
     *out = h->opt;
-    out->precond_colors = h->gauss_seidel ? h->topo.n_colors : 0;
-    out->precond_sweep = h->gauss_seidel ? 1 : 0;
+    out->precond_colors = (h->gauss_seidel || h->tiny) ? h->topo.n_colors : 0;
+    out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
+    out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     return CWR_OK;
 }
 

@@ -55,7 +55,8 @@ __device__ __forceinline__ double ell_row_dot(const DeviceModel& M, int i, const
     double s = 0.0;
     const int W = M.W;
     for (int w = 0; w < W; w += 4) {
-        const int4 c4 = __ldg(reinterpret_cast<const int4*>(M.ell_col + (size_t)i * W + w));
+        int4 c4 = __ldg(reinterpret_cast<const int4*>(M.ell_col + (size_t)i * W + w));
+        c4.x &= kColMask; c4.y &= kColMask; c4.z &= kColMask; c4.w &= kColMask;
         const double2 v01 = *reinterpret_cast<const double2*>(M.val + (size_t)i * W + w);
         const double2 v23 = *reinterpret_cast<const double2*>(M.val + (size_t)i * W + w + 2);
         s = fma(v23.y, z[c4.w], fma(v23.x, z[c4.z], fma(v01.y, z[c4.y], fma(v01.x, z[c4.x], s))));
@@ -182,4 +183,206 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M,
     }
 }
 
+
+
+// ---------------------------------------------------------------------------------------------
+// Tiny meshes (the Ohio River model: 2,943 cells): the whole solve of one column ON CHIP.
+// One CTA per constituent / scenario; the matrix (column-major ELL: fp64 values + 16-bit column
+// indices), the gathered vector z, b and rhat live in shared memory (<= 227 KB), the other BiCGSTAB
+// vectors (x, r, p, v, t, p^) in registers -- a thread owns rows tid, tid + 1024, ...  A pass over the
+// matrix then costs shared-memory bandwidth (~80 B per row) instead of L2 latency, and the
+// preconditioner is the same flow-aligned multicolour Gauss-Seidel as on large meshes, with
+// __syncthreads() between colours: a sweep moves the bytes of one Jacobi step and carries information
+// several cells downstream.  Same recurrences, stopping test, restart and NaN / zero-rhs rules as
+// k_solve_small.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTinyThreads = 1024;
+constexpr int kTinyMaxRows = 4;          // rows per thread: n <= 4096
+
+__host__ __device__ inline size_t tiny_smem_bytes(int n, int W) {
+    // val (n*W f64) | z, b, rhat (n f64 each) | idx (n*W u16)
+    return (size_t)n * W * 8 + (size_t)3 * n * 8 + (((size_t)n * W * 2 + 15) & ~(size_t)15);
+}
+
+// W4: ELL width 4 (quad / triangle meshes): a row's four values are two 16-byte shared loads, its four
+// 16-bit column indices one 8-byte load.
+template <int RPT, bool W4>
+__global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, int n_sweeps, SmallStats* stats) {
+    extern __shared__ double tiny_smem[];
+    __shared__ double red[4 * 32];
+    const int k = blockIdx.x, n = M.n, K = M.K, W = M.W, nc = M.n_colors;
+    double* sval = tiny_smem;                       // [W][n]   (W4: double2 [2][n])
+    double* z = sval + (size_t)n * W;               // [n] the gathered vector
+    double* sb = z + n;                             // [n] b
+    double* srh = sb + n;                           // [n] rhat
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(srh + n);   // [W][n] (W4: [n][4]), bit 15 = visited later in a sweep
+    double* __restrict__ xg = M.sp->state_t1 + k;   // stride K
+    const double* __restrict__ bg = M.b + k;
+
+    // ---- matrix -> shared memory (column-major), b ------------------------------------------------
+    for (int q = threadIdx.x; q < n * W; q += kTinyThreads) {
+        const int i = q / W, w = q % W;
+        const int32_t cj = M.ell_col[q];
+        const unsigned short packed = (unsigned short)((cj & 0x7fff) | (cj < 0 ? 0x8000 : 0));
+        if (W4) { sval[((size_t)(w >> 1) * n + i) * 2 + (w & 1)] = M.val[q]; sidx[(size_t)i * 4 + w] = packed; }
+        else { sval[(size_t)w * n + i] = M.val[q]; sidx[(size_t)w * n + i] = packed; }
+    }
+    int row[RPT]; bool on[RPT]; int colr[RPT];
+    double x[RPT], r[RPT], p[RPT], v[RPT], t[RPT], ph[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        row[q] = threadIdx.x + q * kTinyThreads; on[q] = row[q] < n;
+        x[q] = on[q] ? xg[(size_t)row[q] * K] : 0.0;
+        if (on[q]) sb[row[q]] = bg[(size_t)row[q] * K];
+        r[q] = p[q] = v[q] = t[q] = ph[q] = 0.0;
+        colr[q] = 0;
+        if (on[q]) for (int c = 0; c < nc; ++c) if (row[q] >= M.color_ptr[c + 1]) colr[q] = c + 1;
+    }
+    __syncthreads();
+
+    auto row_dot = [&](int i, bool first) {      // (L z)_i ; first: skip neighbours not visited yet (z = 0 there)
+        if (W4) {
+            const uint2 id = reinterpret_cast<const uint2*>(sidx)[i];
+            const double2 a = reinterpret_cast<const double2*>(sval)[i], b2 = reinterpret_cast<const double2*>(sval)[n + i];
+            const unsigned j0 = id.x & 0xffffu, j1 = id.x >> 16, j2 = id.y & 0xffffu, j3 = id.y >> 16;
+            const double z0 = (first && (j0 & 0x8000u)) ? 0.0 : z[j0 & 0x7fffu], z1 = (first && (j1 & 0x8000u)) ? 0.0 : z[j1 & 0x7fffu];
+            const double z2 = (first && (j2 & 0x8000u)) ? 0.0 : z[j2 & 0x7fffu], z3 = (first && (j3 & 0x8000u)) ? 0.0 : z[j3 & 0x7fffu];
+            return fma(b2.y, z3, fma(b2.x, z2, fma(a.y, z1, a.x * z0)));
+        }
+        double s = 0.0;
+        for (int w = 0; w < W; ++w) {
+            const unsigned short cj = sidx[(size_t)w * n + i];
+            if (first && (cj & 0x8000)) continue;
+            s = fma(sval[(size_t)w * n + i], z[cj & 0x7fff], s);
+        }
+        return s;
+    };
+    // z = M^-1 u (u in registers): n_sweeps multicolour Gauss-Seidel sweeps from z = 0; ends synchronised
+    auto precondition = [&](const double (&u)[RPT]) {
+        if (n_sweeps <= 0) {
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) if (on[q]) z[row[q]] = u[q];
+            __syncthreads();
+            return;
+        }
+        for (int s = 0; s < n_sweeps; ++s)
+            for (int c = 0; c < nc; ++c) {
+#pragma unroll
+                for (int q = 0; q < RPT; ++q)
+                    if (on[q] && colr[q] == c) z[row[q]] = u[q] - row_dot(row[q], s == 0);
+                __syncthreads();
+            }
+    };
+    // y = A z for this thread's rows (z complete and synchronised)
+    auto product = [&](double (&y)[RPT]) {
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) y[q] = on[q] ? z[row[q]] + row_dot(row[q], false) : 0.0;
+    };
+
+    int flags = 0, iters = 0, restarts = 0;
+    double bb = 0.0, rr = 0.0;
+    for (;;) {
+        // r = b - A x ; rhat = p = r
+#pragma unroll
+        for (int q = 0; q < RPT; ++q) if (on[q]) z[row[q]] = x[q];
+        __syncthreads();
+        double ax[RPT];
+        product(ax);
+        double d2[2] = {0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < RPT; ++q)
+            if (on[q]) {
+                const double bi = sb[row[q]];
+                r[q] = bi - ax[q]; p[q] = r[q]; srh[row[q]] = r[q];
+                d2[0] = fma(r[q], r[q], d2[0]); d2[1] = fma(bi, bi, d2[1]);
+            }
+        cta_sum<2>(d2, red);
+        rr = d2[0]; bb = d2[1];
+        if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) {
+            flags |= FL_NAN;
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) x[q] = qnan();
+            break;
+        }
+        if (bb == 0.0 && rr != 0.0) {                    // b == 0  =>  x = 0
+            flags |= FL_ZERO_RHS | FL_CONVERGED;
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) x[q] = 0.0;
+            rr = 0.0;
+            break;
+        }
+        if (rr <= M.tol2 * bb) { flags |= FL_CONVERGED; break; }
+        double rho = rr;
+        bool breakdown = false;
+        while (iters < M.max_iter) {
+            precondition(p);
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) ph[q] = on[q] ? z[row[q]] : 0.0;
+            product(v);
+            double d1[1] = {0.0};
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) if (on[q]) d1[0] = fma(srh[row[q]], v[q], d1[0]);
+            cta_sum<1>(d1, red);
+            if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
+            const double alpha = rho / d1[0];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) r[q] = fma(-alpha, v[q], r[q]);      // s
+            precondition(r);
+            double sh[RPT];
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) sh[q] = on[q] ? z[row[q]] : 0.0;
+            product(t);
+            double d4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < RPT; ++q)
+                if (on[q]) {
+                    const double rh = srh[row[q]];
+                    d4[0] = fma(t[q], r[q], d4[0]); d4[1] = fma(t[q], t[q], d4[1]);
+                    d4[2] = fma(rh, t[q], d4[2]); d4[3] = fma(rh, r[q], d4[3]);
+                }
+            cta_sum<4>(d4, red);
+            const double omega = d4[1] > 0.0 ? d4[0] / d4[1] : 0.0;
+            const double rho_new = d4[3] - omega * d4[2];
+            double beta = 0.0;
+            bool stagnated = false;
+            if (omega != 0.0 && rho != 0.0) beta = (rho_new / rho) * (alpha / omega);
+            else if (d4[1] > 0.0) stagnated = true;
+            if (!(beta == beta) || isinf(beta)) { beta = 0.0; stagnated = true; }
+            double dr[1] = {0.0};
+#pragma unroll
+            for (int q = 0; q < RPT; ++q)
+                if (on[q]) {
+                    x[q] = fma(omega, sh[q], fma(alpha, ph[q], x[q]));
+                    const double rn = fma(-omega, t[q], r[q]);
+                    r[q] = rn;
+                    p[q] = fma(beta, fma(-omega, v[q], p[q]), rn);
+                    dr[0] = fma(rn, rn, dr[0]);
+                }
+            cta_sum<1>(dr, red);
+            rr = dr[0];
+            ++iters;
+            rho = rho_new;
+            if (!(rr == rr) || isinf(rr)) { flags |= FL_NAN; break; }
+            if (rr <= M.tol2 * bb) { flags |= FL_CONVERGED; break; }
+            if (stagnated) { breakdown = true; break; }
+        }
+        if ((flags & (FL_CONVERGED | FL_NAN)) || iters >= M.max_iter) break;
+        if (breakdown && restarts < 3) { ++restarts; continue; }     // new shadow residual from the current iterate
+        if (breakdown) flags |= FL_BREAKDOWN;
+        break;
+    }
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) if (on[q]) xg[(size_t)row[q] * K] = x[q];
+    if (threadIdx.x == 0) {
+        M.colflags[k] = flags; M.coliters[k] = iters;
+        M.sc[SC_BNORM2 * K + k] = bb; M.sc[SC_RNORM2 * K + k] = rr;
+        atomicMax(&stats->max_iterations, iters);
+        atomicAdd(&stats->sum_iterations, (unsigned long long)iters);
+        atomicOr(&stats->flags_or, flags & (FL_BREAKDOWN | FL_NAN));
+        atomicMax(&stats->restarts, restarts);
+        if (!(flags & FL_CONVERGED)) atomicAdd(&stats->not_converged, 1);
+        const double rel2 = bb > 0.0 ? rr / bb : (rr > 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : 0.0);
+        if (rel2 == rel2) atomicMax(&stats->max_relres2_bits, (unsigned long long)__double_as_longlong(rel2));
+    }
+}
 }  // namespace cwr

@@ -44,7 +44,8 @@ typedef struct {
     int hydro_capacity;     /* time slices resident on the device; 0 = all n_time (default) */
     int mass_flux;          /* 1 = compute the three per-edge mass-flux arrays every step (default, as the
                                reference does, transport.py:267-273), 0 = skip */
-    int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = single-CTA persistent solve (small meshes) */
+    int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = one CTA per constituent runs the whole solve (small meshes;
+                               <= 4096 cells with Gauss-Seidel sweeps: entirely on chip -- cwr_get_options reports 3) */
     int use_graph;          /* 1 = device-side iteration loop in a CUDA graph (default), 0 = host-polled loop */
     int check_every;        /* host-polled loop: iterations launched per convergence poll; default 1 */
     int precond_steps;      /* m: the preconditioner applies m - 1 sweeps; 1 = diagonal (Jacobi) scaling only;

@@ -191,6 +191,16 @@ def test_preconditioner_variants(K, opts):
     run_against_oracle(mesh, inputs, 5, solver_path=1, **opts)
 
 
+@pytest.mark.parametrize("opts", [dict(precond_sweep=0), dict(precond_sweep=0, precond_steps=3), dict(precond_steps=2),
+                                  dict(precond_steps=6, precond_colors=16), dict(precond_colors=5)])
+@pytest.mark.parametrize("shape", [(40, 25), (70, 50)])
+def test_small_mesh_paths(shape, opts):
+    """One CTA per constituent: k_solve_tiny (on chip, Gauss-Seidel; 1 and 4 rows per thread) and k_solve_small
+    (Jacobi steps through L2)."""
+    _, mesh, inputs = synthetic_case(shape[0], shape[1], 6, 3, seed=31, dry_fraction=0.02)
+    run_against_oracle(mesh, inputs, 5, solver_path=2, **opts)
+
+
 def test_gauss_seidel_is_deterministic_and_hint_independent():
     """Same inputs, with and without the flow hint (different row orders): both within rtol of the oracle;
     two runs with the same order are bitwise identical."""
