@@ -58,33 +58,88 @@ def workload_plan(name: str, n_time: int, seed: int, scale: float = 1.0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every
+    10 ms from a thread (no process start-up latency, so even a 100 ms region is covered); `nvidia-smi -lms` as
+    the fallback.  Samples are tagged inside / outside the timed window; the summary uses the ones inside."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device: int):
         self.device, self.proc, self.lines = device, None, []
+        self.samples = []            # (time, sm_mhz, reasons bitmask)
+        self.t0 = self.t1 = None
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_mhz = None
+        self.source = None
+
+    def _poll_nvml(self, nv, h):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        i, reasons = 0, 0
+        while not self._stop.is_set():
+            try:
+                if i % 4 == 0:                       # the reasons query is the slow one
+                    reasons = int(get_reasons(h))
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), reasons))
+            except Exception:
+                pass
+            i += 1
+            self._stop.wait(0.005)
 
     def start(self):
+        """Begin sampling (call before the warm-up: the device is under load from then on)."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nv = nv
+            self._thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self._thread.start()
+            self.source = "nvml, 10 ms"
+            return
+        except Exception:
+            self._thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.device)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.source = "nvidia-smi -lms 50"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def window_begin(self):
+        self.t0 = time.perf_counter()
+
+    def window_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        if self._thread is not None:
+            time.sleep(0.03)
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            nv = self._nv
+            bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= (self.t1 or 1e300)]
+            used = inside if inside else self.samples        # all samples are under load (warm-up + timed steps)
+            reasons = sorted(nm for nm, bit in bits.items() if any(s[2] & bit for s in used))
+            return {"sm_mhz": float(np.median([s[1] for s in used])) if used else None, "sm_max_mhz": self.max_mhz,
+                    "samples": len(used), "samples_in_timed_region": len(inside), "reasons": reasons, "source": self.source}
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml and nvidia-smi unavailable"]}
+        time.sleep(0.1)
+        self.proc.terminate()
+        sm, mx, reasons, n_in = [], [], set(), 0
+        for ts, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -92,11 +147,12 @@ class ClockSampler:
                 sm.append(float(f[1])); mx.append(float(f[2]))
             except ValueError:
                 continue
+            n_in += int(self.t0 is not None and self.t0 <= ts <= (self.t1 or 1e300))
             for nm, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "samples_in_timed_region": n_in, "reasons": sorted(reasons), "source": self.source}
 
 
 def measured_peak():
@@ -232,13 +288,14 @@ def main():
     stream = torch.cuda.ExternalStream(be.stream())
 
     iters = []
+    sampler = ClockSampler(local)
+    sampler.start()
     for t in range(W):
         iters.append(be.step(t).iterations)
-    sampler = ClockSampler(local)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    sampler.window_begin()
     l0, i0 = be.counters()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -246,6 +303,7 @@ def main():
     worst_status, worst_relres = info.status, info.max_relres
     e1.record(stream)
     torch.cuda.synchronize()
+    sampler.window_end()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()

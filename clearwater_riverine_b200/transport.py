@@ -183,6 +183,8 @@ class ClearwaterRiverine:
         # update() copies c[t+1] of every constituent straight into row t+1 of its output array; page-locking
         # those arrays lets the copies run at the full PCIe rate with no intermediate host buffer
         self._pinned = [self.mesh[name] for name in self.constituents if pin_host_array(self.mesh[name])]
+        self._row_cache = None
+        self._store_flux = bool(store_mass_flux)
         self.solver_info = []
 
     def _upload_slice(self, t: int):
@@ -224,13 +226,19 @@ class ClearwaterRiverine:
         """c[t1] of every constituent in one device->host copy; ghost cells get their BC value where
         one is set and stay NaN elsewhere (transport.py:252-264)."""
         n = self.mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
-        self.backend.get_state_rows(t1, [self.mesh[name][t1] for name in self.constituents])
+        if self._row_cache is None:       # per constituent: its (T,F) array, ghost-column BC values (NaN where unset)
+            self._row_cache = []
+            for name in self.constituents:
+                bc = self.constituent_dict[name].input_array[:, n:]
+                self._row_cache.append((self.mesh[name], np.where(bc != 0, bc, np.nan)))
+        self.backend.get_state_rows(t1, [out[t1] for out, _ in self._row_cache])
+        for out, ghost in self._row_cache:
+            out[t1, n:] = ghost[t1]
+        if not (self._store_flux and self.backend.options.mass_flux):
+            return
         for name, k in self._index.items():
-            row = self.mesh[name][t1]
             c = self.constituent_dict[name]
-            bc = c.input_array[t1, n:]
-            row[n:] = np.where(bc != 0, bc, np.nan)
-            if c.total_mass_flux is not None and self.backend.options.mass_flux:
+            if c.total_mass_flux is not None:
                 self.backend.get_mass_flux(k, t1 - 1, c.advection_mass_flux[t1 - 1], c.diffusion_mass_flux[t1 - 1],
                                            c.total_mass_flux[t1 - 1])
 
