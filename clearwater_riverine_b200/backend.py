@@ -26,7 +26,7 @@ class CwrOptions(C.Structure):
                 ("hydro_capacity", C.c_int), ("mass_flux", C.c_int), ("solver_path", C.c_int),
                 ("use_graph", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int),
                 ("precond_precision", C.c_int), ("precond_sweep", C.c_int), ("precond_colors", C.c_int),
-                ("dd_rank", C.c_int), ("dd_world", C.c_int), ("reserved", C.c_int * 1)]
+                ("dd_rank", C.c_int), ("dd_world", C.c_int), ("dd_halo_per_colour", C.c_int)]
 
 
 class CwrStepInfo(C.Structure):

@@ -246,6 +246,9 @@ static void set_owned_ranges(cwr_handle* h) {
     unsigned nbr = 0;
     for (int32_t j = tp.send_ptr[r]; j < tp.send_ptr[r + 1]; ++j) nbr |= tp.send_mask[tp.send_rows[j]];
     M.nbr_mask = nbr;        // symmetric: whoever reads my rows owns rows I read
+    M.send_rows = h->d_send_rows + tp.send_ptr[r];
+    M.n_send = tp.send_ptr[r + 1] - tp.send_ptr[r];
+    M.halo_per_sweep = h->opt.dd_halo_per_colour ? 0 : 1;
 }
 
 // Gauss-Seidel colours follow the flow: the first hydrodynamic slices the caller uploads give the
@@ -804,7 +807,6 @@ static int launch_iteration(cwr_handle* h) {
 
 static int solve(cwr_handle* h, cwr_step_info* info) {
     DeviceModel& M = h->M;
-    const int g = h->grid_rows;
     int restarts = 0;
     int total_iter = 0;
     for (;;) {

@@ -74,6 +74,8 @@ struct DeviceModel {
     int rank, world;
     unsigned nbr_mask;            // ranks this one exchanges halo rows with
     const uint8_t* send_mask;     // (n) bit q: rank q reads this row (0 for interior rows)
+    const int32_t* send_rows; int n_send;   // this rank's rows with a non-zero send_mask
+    int halo_per_sweep;           // Gauss-Seidel kernel: halo rows cross once per sweep (1) or after every colour (0)
     char* peer_base[kMaxRanks];   // every rank's symmetric slab (own included): DdCtl, p^, s^, tmp, state slots
     char* sym_base;               // == peer_base[rank]
     DdCtl* dd;
@@ -646,20 +648,21 @@ __device__ __forceinline__ Pk<T, V> ldk_cg(const T* p) {
 // Grid barrier of the persistent sweep kernel.  With several ranks it is also the halo barrier: the last
 // CTA of this rank to arrive (every CTA's stores, peer stores included, are fenced before its arrival)
 // announces epoch `e` to the neighbour ranks, and every CTA also waits for the neighbours' announcements.
-__device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned target, unsigned long long e, bool pushed) {
+// cross: this barrier is also a halo barrier (epoch e) -- else it only synchronises this device's CTAs.
+__device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned target, unsigned long long e, bool pushed, bool cross) {
     SolverCtl* ctl = M.ctl;
     // system-scope fence only in the CTAs that stored rows into a peer since the last barrier
-    const int any_pushed = M.world > 1 ? __syncthreads_or(pushed) : (__syncthreads(), 0);
+    const int any_pushed = cross ? __syncthreads_or(pushed) : (__syncthreads(), 0);
     if (threadIdx.x == 0) {
         if (any_pushed) __threadfence_system(); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
         const unsigned t = atomicAdd(&ctl->gs_bar[0], 1u);
         // every CTA that stored into a peer fenced at system scope BEFORE its arrival; seeing all arrivals
         // (device-scope fence) therefore orders all of this rank's peer stores before the announcement
-        if (M.world > 1 && t == target - 1) { __threadfence(); dd_signal(M, false, e, M.nbr_mask); }
+        if (cross && t == target - 1) { __threadfence(); dd_signal(M, false, e, M.nbr_mask); }
         unsigned spins = 0;
         while (*reinterpret_cast<volatile unsigned*>(&ctl->gs_bar[0]) < target)
             if (++spins > (1u << 27)) { ctl->barrier_timeout = 1; break; }      // never hang the device
-        if (M.world > 1) dd_wait(M, false, e, M.nbr_mask); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (cross) dd_wait(M, false, e, M.nbr_mask); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -700,10 +703,18 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     const int n_steps = n_sweeps * nc;
     unsigned epoch = 0;
     const bool multi = M.world > 1;
+    // Several ranks: either every finished boundary row goes to its readers at once and every colour's barrier is
+    // a halo barrier (exact multi-rank Gauss-Seidel), or (halo_per_sweep, default) the boundary rows cross once at
+    // the end of each sweep: within a sweep the neighbours' rows are one sweep old (zero in the first sweep) --
+    // Gauss-Seidel inside a strip, Jacobi across strips -- and only one barrier per sweep waits for NVLink.
+    const bool per_sweep = multi && M.halo_per_sweep, per_colour = multi && !M.halo_per_sweep;
+    const int row_lo = M.row_lo, row_hi = M.row_hi;
     const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;     // halo epochs continue where the last kernel stopped
+    unsigned long long xe = 0;                                         // halo barriers of this launch
     // a finished row also goes to the ranks that read it (NVLink peer stores)
     bool pushed = false;
     auto push = [&](int i, int cc, const Pk<ST, VEC>& o) {
+        if (!per_colour) return;
         unsigned m = M.send_mask[i];
         pushed |= m != 0;
         while (m) {
@@ -744,7 +755,8 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             Pk<ST, VEC> y[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (first_sweep && ds[u] < 0) {              // bit 31: visited later in the sweep, still 0
+                const int dj = ds[u] & kColMask;
+                if (first_sweep && (ds[u] < 0 || (per_sweep && (dj < row_lo || dj >= row_hi)))) {   // not visited yet: still 0
 #pragma unroll
                     for (int q = 0; q < VEC; ++q) y[u].a[q] = (ST)0;
                 } else y[u] = ldk_cg<ST, VEC>(z + (size_t)(ds[u] & kColMask) * K + cc);
@@ -758,7 +770,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
         stk<ST, VEC>(z + (size_t)i * K + cc, acc);
         if (first_sweep) stk<ST, VEC>(us + (size_t)i * K + cc, own);
-        if (multi) push(i, cc, acc);
+        push(i, cc, acc);
     };
     Pk<ST, VEC> zero;
 #pragma unroll
@@ -780,7 +792,8 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const bool skip = first_sweep && cs[u] < 0;          // bit 31: visited later in the sweep from z = 0
+                const int cj = cs[u] & kColMask;                     // bit 31: visited later in the sweep from z = 0
+                const bool skip = first_sweep && (cs[u] < 0 || (per_sweep && (cj < row_lo || cj >= row_hi)));
                 if constexpr (SMEM) {
                     int4* slot = gs_land + (r * 4 + u) * kGsThreads + threadIdx.x;
                     if (skip) *slot = make_int4(0, 0, 0, 0);
@@ -817,14 +830,38 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         for (int i = rb + gid + NR * TG; i < re; i += TG)
             for (int cc = c; cc < c_end; cc += KC * VEC)
                 relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), first_sweep);
-        if (step + 1 < n_steps) {
+        const bool last_step = step + 1 == n_steps;
+        if (per_sweep && col == nc - 1) {
+            // end of a sweep: once the last colour is complete on this device, the strip's boundary rows go to
+            // the ranks that read them, and the next barrier also waits for theirs
+            ++epoch;
+            grid_barrier(M, epoch * nvb, 0, false, false);
+            const int packs = (K + VEC - 1) / VEC;
+            for (int q = blockIdx.x * kGsThreads + threadIdx.x; q < M.n_send * packs; q += gridDim.x * kGsThreads) {
+                const int i = M.send_rows[q / packs], cc = (q % packs) * VEC;
+                if (cc + VEC > K) continue;
+                const Pk<ST, VEC> o = ldk_cg<ST, VEC>(z + (size_t)i * K + cc);
+                unsigned m = M.send_mask[i];
+                pushed |= m != 0;
+                while (m) {
+                    const int r = __ffs(m) - 1;
+                    m &= m - 1;
+                    stk<ST, VEC>(peer_ptr(M, r, z) + (size_t)i * K + cc, o);
+                }
+            }
+            if (!last_step) prefetch(step + 1);
+            ++epoch; ++xe;
+            grid_barrier(M, epoch * nvb, e0 + xe, pushed, true);
+            pushed = false;
+        } else if (!last_step) {
             prefetch(step + 1);
             ++epoch;
-            grid_barrier(M, epoch * nvb, e0 + epoch, pushed);
+            if (per_colour) ++xe;
+            grid_barrier(M, epoch * nvb, e0 + xe, pushed, per_colour);
             pushed = false;
-        } else if (multi) {       // the products that follow gather the neighbours' last colour too
-            ++epoch;
-            grid_barrier(M, epoch * nvb, e0 + epoch, pushed);
+        } else if (per_colour) {       // the products that follow gather the neighbours' last colour too
+            ++epoch; ++xe;
+            grid_barrier(M, epoch * nvb, e0 + xe, pushed, true);
         }
     }
     // the last CTA to leave re-arms the barrier for the next launch
@@ -833,7 +870,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
         if (t == (unsigned)nvb - 1) {
             M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
-            if (multi) M.dd->bar_epoch = e0 + epoch;
+            if (multi) M.dd->bar_epoch = e0 + xe;
             __threadfence();
         }
     }

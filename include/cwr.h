@@ -46,8 +46,10 @@ typedef struct {
                                reference does, transport.py:267-273), 0 = skip */
     int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = one CTA per constituent runs the whole solve (small meshes;
                                <= 4096 cells with Gauss-Seidel sweeps: entirely on chip -- cwr_get_options reports 3) */
-    int use_graph;          /* 1 = device-side iteration loop in a CUDA graph (default), 0 = host-polled loop */
-    int check_every;        /* host-polled loop: iterations launched per convergence poll; default 1 */
+    int use_graph;          /* reserved (a CUDA-graph form of the large-mesh iteration loop); ignored: the loop is launched ahead
+                               from the previous solve's iteration count and stops itself through a device-side flag */
+    int check_every;        /* large meshes: iterations launched per convergence poll once the launch-ahead burst is used up;
+                               default 1 */
     int precond_steps;      /* m: the preconditioner applies m - 1 sweeps; 1 = diagonal (Jacobi) scaling only;
                                0 (default) = 5 with Gauss-Seidel sweeps, 8 with Jacobi steps / the small-mesh path */
     int precond_precision;  /* 32 (default): the sweeps and the preconditioned vectors are fp32 (half the bytes;
@@ -64,7 +66,9 @@ typedef struct {
                                GPU/process, each given the WHOLE mesh and the same inputs; rows are cut into dd_world
                                strips and a handle computes its strip, exchanging boundary rows and dot products with
                                the others over NVLink peer memory (cwr_dd_export / cwr_dd_attach).  0 / 0 or 1: off */
-    int reserved[1];
+    int dd_halo_per_colour; /* domain decomposition, Gauss-Seidel sweeps: 0 (default) = boundary rows cross NVLink once per sweep
+                               (Gauss-Seidel inside a strip, one sweep of lag across strips; one halo barrier per sweep),
+                               1 = after every colour (exact multi-rank Gauss-Seidel; a halo barrier per colour) */
 } cwr_options;
 
 typedef struct {

@@ -42,7 +42,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D = 0.1
     ok_all = True
-    cases = [dict(), dict(precond_sweep=0, precond_steps=4), dict(precond_precision=64, precond_steps=3, precond_colors=9)]
+    cases = [dict(), dict(dd_halo_per_colour=1), dict(precond_sweep=0, precond_steps=4),
+             dict(precond_precision=64, precond_steps=3, precond_colors=9)]
     for ci, opts in enumerate(cases):
         K, T = args.K, args.steps + 1
         plan = synthetic.make_plan(args.side, args.side * 3 // 4, T, dt=30.0, tri_fraction=0.1, dry_fraction=0.02,
@@ -58,7 +59,8 @@ def main():
             be.set_inputs(k, inputs[k])
         single = oracle = None
         if rank == 0:
-            single = TransportBackend(plan.f1, plan.f2, plan.n_face, T, K, D, device=local, solver_path=1, **opts)
+            single = TransportBackend(plan.f1, plan.f2, plan.n_face, T, K, D, device=local, solver_path=1,
+                                      **{k: v for k, v in opts.items() if not k.startswith("dd_")})
             single.set_hydro(0, adv, cdiff, plan.edge_velocity, plan.volume, dt)
             for k in range(K):
                 single.set_inputs(k, inputs[k])
