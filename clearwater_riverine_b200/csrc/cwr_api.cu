@@ -49,7 +49,7 @@ struct cwr_handle {
     int tiny_rpt = 1;                // rows per thread of k_solve_tiny
     bool in_run = false;             // inside cwr_run: the small path does not synchronise per step
     SmallStats* d_stats = nullptr; SmallStats* h_stats = nullptr;
-    int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0, grid_spmm = 0, grid_xrp = 0;
+    int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0, grid_spmm = 0, grid_at = 0, grid_xrp = 0;
     DeviceModel M{};
     // device buffers
     int32_t *d_ell_col = nullptr, *d_ell_code = nullptr, *d_f1p = nullptr, *d_f2p = nullptr;
@@ -403,7 +403,10 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmm, k_spmm<KC, VEC, MODE_AT, double>, kThreads, 0));
         KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_xrp, k_update_xrp<KC, VEC, double>, kThreads, 0));
         const int n_own = tp.part_ptr[h->rank + 1] - tp.part_ptr[h->rank];
-        h->grid_spmm = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_spmm));
+        int occ_av = occ_spmm;
+        KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_av, k_spmm<KC, VEC, MODE_AV, double>, kThreads, 0));
+        h->grid_at = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_spmm));
+        h->grid_spmm = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_av));
         h->grid_xrp = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_xrp));
         h->grid_sweep = grid_for(n_own, kThreads / h->SKC, h->num_sms * CWR_SPMM_MIN_BLOCKS);
         if (h->gauss_seidel) {
@@ -798,7 +801,7 @@ static int launch_iteration(cwr_handle* h) {
     KC_DISPATCH(h->KC, (k_update_s<KC, VEC><<<g, kThreads, 0, h->stream>>>(M)));
     const void* sh = precondition(h, M.r, M.sh, M.tmp);
     mark(h, CWR_FAM_SPMM_T);
-    PT_DISPATCH((k_spmm<KC, VEC, MODE_AT, PT><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, (const PT*)sh, nullptr)));
+    PT_DISPATCH((k_spmm<KC, VEC, MODE_AT, PT><<<h->grid_at, kThreads, 0, h->stream>>>(M, (const PT*)sh, nullptr)));
     mark(h, CWR_FAM_UPDATE_XRP);
     PT_DISPATCH((k_update_xrp<KC, VEC, PT><<<h->grid_xrp, kThreads, 0, h->stream>>>(M, (const PT*)ph, (const PT*)sh)));
     h->launches += 4;
