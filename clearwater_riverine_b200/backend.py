@@ -85,6 +85,7 @@ def load_library():
         "cwr_set_geometry": ([H, dp, dp], C.c_int),
         "cwr_set_flow_hint": ([H, fp], C.c_int),
         "cwr_set_hydro_raw": ([H, C.c_int, C.c_int, fp, fp, fp, dp], C.c_int),
+        "cwr_prefetch_hydro_raw": ([H, C.c_int, C.c_int, fp, fp, fp, dp], C.c_int),
         "cwr_set_inputs": ([H, C.c_int, dp], C.c_int),
         "cwr_set_state": ([H, C.c_int, C.c_int, dp], C.c_int),
         "cwr_set_state_all": ([H, C.c_int, dp, C.POINTER(C.c_uint8)], C.c_int),
@@ -247,6 +248,16 @@ class TransportBackend:
         dt = _arr(dt, np.float64).reshape(nt)
         self._check(self._lib.cwr_set_hydro_raw(self._h, t0, nt, _ptr(q, C.c_float), _ptr(u, C.c_float),
                                                 _ptr(v, C.c_float), _ptr(dt, C.c_double)))
+
+    def prefetch_hydro_raw(self, t0: int, face_flow, edge_velocity, volume, dt):
+        """set_hydro_raw on the upload stream (overlaps the next device->host copy); the arrays must be float32 /
+        float64 contiguous already (no conversion copy is kept alive here) and stay valid until the next step."""
+        q, u, v, d = face_flow, edge_velocity, volume, dt
+        for a, ty in ((q, np.float32), (u, np.float32), (v, np.float32), (d, np.float64)):
+            assert a.dtype == ty and a.flags.c_contiguous
+        nt = q.shape[0] if q.ndim == 2 else 1
+        self._check(self._lib.cwr_prefetch_hydro_raw(self._h, t0, nt, _ptr(q, C.c_float), _ptr(u, C.c_float),
+                                                     _ptr(v, C.c_float), _ptr(d, C.c_double)))
 
     def set_inputs(self, k: int, input_array):
         a = _arr(input_array, np.float64, (self.n_time, self.n_face), "input_array")

@@ -61,6 +61,9 @@ struct cwr_handle {
     double* d_state = nullptr;                                    // (S,n,K)
     double* d_dist = nullptr;                                     // (E) reference order
     void* d_stage = nullptr; size_t stage_bytes = 0;
+    // second stream for uploads that overlap the device->host copies of the previous step (cwr_prefetch_hydro_raw)
+    cudaStream_t up_stream = nullptr; cudaEvent_t up_done = nullptr, compute_mark = nullptr;
+    void* d_stage_up = nullptr; size_t stage_up_bytes = 0; bool up_pending = false;
     StepParams* d_sp = nullptr;
     SolverCtl* h_ctl = nullptr;                                   // pinned
     double* h_sc = nullptr; int* h_flags = nullptr; int* h_iters = nullptr;   // pinned
@@ -317,6 +320,10 @@ void cwr_destroy(cwr_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamDestroy(h->up_stream); }
+    if (h->up_done) cudaEventDestroy(h->up_done);
+    if (h->compute_mark) cudaEventDestroy(h->compute_mark);
+    if (h->d_stage_up) cudaFree(h->d_stage_up);
     for (void* p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
@@ -562,6 +569,8 @@ static int check_slices(cwr_handle* h, int t0, int nt) {
     return CWR_OK;
 }
 
+static int join_prefetch(cwr_handle* h);
+
 int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double* cdiff, const float* vel,
                   const float* vol, const double* dt) {
     if (!h) return CWR_EINVAL;
@@ -570,6 +579,8 @@ int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double*
     if (rc) return rc;
     CK(cudaSetDevice(h->device));
     rc = align_colours_with_flow(h, adv, nt);
+    if (rc) return rc;
+    rc = join_prefetch(h);
     if (rc) return rc;
     const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
     // staging: adv f32 (E) | vel f32 (E) | vol f32 (F) | cdiff f64 (E)
@@ -625,6 +636,37 @@ int cwr_set_geometry(cwr_handle* h, const double* face_x, const double* face_y) 
     return CWR_OK;
 }
 
+// slices [t0, t0+nt) of the raw arrays -> device order + derived coefficients, on `stream` through staging buffer `st`
+static int upload_raw(cwr_handle* h, cudaStream_t stream, char* st, int t0, int nt, const float* face_flow,
+                      const float* edge_velocity, const float* volume, const double* dt) {
+    const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
+    const size_t off_vel = (size_t)E * 4, off_vol = off_vel + (size_t)E * 4;
+    for (int s = 0; s < nt; ++s) {
+        const int t = t0 + s, slot = t % h->C;
+        CK(cudaMemcpyAsync(st, face_flow + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(st + off_vel, edge_velocity + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, stream));
+        CK(cudaMemcpyAsync(st + off_vol, volume + (size_t)s * F, (size_t)F * 4, cudaMemcpyHostToDevice, stream));
+        k_derive<<<grid_for(E, kThreads, h->max_grid), kThreads, 0, stream>>>(
+            h->d_adv + (size_t)slot * E, h->d_cdiff + (size_t)slot * E, h->d_velg + (size_t)slot * std::max(1, Eg),
+            (const float*)st, (const float*)(st + off_vel), h->d_dist, h->d_eperm, E, Ei, (float)h->M.diffusion_coefficient);
+        k_gather<float><<<grid_for(n, kThreads, h->max_grid), kThreads, 0, stream>>>(
+            h->d_vol + (size_t)slot * n, (const float*)(st + off_vol), h->d_old_of_new, n);
+        h->launches += 2;
+        h->dt[t] = dt[s];
+        h->slot_time[slot] = t;
+    }
+    CK(cudaGetLastError());
+    return CWR_OK;
+}
+
+// the compute stream must see a prefetched slice before it reads the hydro window again
+static int join_prefetch(cwr_handle* h) {
+    if (!h->up_pending) return CWR_OK;
+    CK(cudaStreamWaitEvent(h->stream, h->up_done, 0));
+    h->up_pending = false;
+    return CWR_OK;
+}
+
 int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
                       const float* volume, const double* dt) {
     if (!h) return CWR_EINVAL;
@@ -635,26 +677,39 @@ int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, con
     CK(cudaSetDevice(h->device));
     rc = align_colours_with_flow(h, face_flow, nt);
     if (rc) return rc;
-    const int n = h->n, E = h->E, F = h->F, Eg = h->topo.E_g, Ei = h->topo.E_int;
-    const size_t off_vel = (size_t)E * 4, off_vol = off_vel + (size_t)E * 4;
-    rc = ensure_stage(h, off_vol + (size_t)F * 4);
+    rc = join_prefetch(h);
     if (rc) return rc;
-    char* st = (char*)h->d_stage;
-    for (int s = 0; s < nt; ++s) {
-        const int t = t0 + s, slot = t % h->C;
-        CK(cudaMemcpyAsync(st, face_flow + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(st + off_vel, edge_velocity + (size_t)s * E, (size_t)E * 4, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaMemcpyAsync(st + off_vol, volume + (size_t)s * F, (size_t)F * 4, cudaMemcpyHostToDevice, h->stream));
-        k_derive<<<grid_for(E, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
-            h->d_adv + (size_t)slot * E, h->d_cdiff + (size_t)slot * E, h->d_velg + (size_t)slot * std::max(1, Eg),
-            (const float*)st, (const float*)(st + off_vel), h->d_dist, h->d_eperm, E, Ei, (float)h->M.diffusion_coefficient);
-        k_gather<float><<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
-            h->d_vol + (size_t)slot * n, (const float*)(st + off_vol), h->d_old_of_new, n);
-        h->launches += 2;
-        h->dt[t] = dt[s];
-        h->slot_time[slot] = t;
+    rc = ensure_stage(h, (size_t)h->E * 8 + (size_t)h->F * 4);
+    if (rc) return rc;
+    return upload_raw(h, h->stream, (char*)h->d_stage, t0, nt, face_flow, edge_velocity, volume, dt);
+}
+
+int cwr_prefetch_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
+                           const float* volume, const double* dt) {
+    if (!h) return CWR_EINVAL;
+    if (!face_flow || !edge_velocity || !volume || !dt) FAIL(CWR_EINVAL, "NULL array");
+    if (!h->have_geometry) FAIL(CWR_EINVAL, "cwr_set_geometry must be called before cwr_prefetch_hydro_raw");
+    int rc = check_slices(h, t0, nt);
+    if (rc) return rc;
+    CK(cudaSetDevice(h->device));
+    if (!h->up_stream) {
+        CK(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&h->up_done, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->compute_mark, cudaEventDisableTiming));
     }
-    CK(cudaGetLastError());
+    const size_t need = (size_t)h->E * 8 + (size_t)h->F * 4;
+    if (need > h->stage_up_bytes) {
+        if (h->d_stage_up) { CK(cudaStreamSynchronize(h->up_stream)); CK(cudaFree(h->d_stage_up)); h->d_stage_up = nullptr; }
+        CK(cudaMalloc(&h->d_stage_up, need));
+        h->stage_up_bytes = need;
+    }
+    // the slots being overwritten may still be read by work already queued on the compute stream
+    CK(cudaEventRecord(h->compute_mark, h->stream));
+    CK(cudaStreamWaitEvent(h->up_stream, h->compute_mark, 0));
+    rc = upload_raw(h, h->up_stream, (char*)h->d_stage_up, t0, nt, face_flow, edge_velocity, volume, dt);
+    if (rc) return rc;
+    CK(cudaEventRecord(h->up_done, h->up_stream));
+    h->up_pending = true;
     return CWR_OK;
 }
 
@@ -923,6 +978,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     const int s0 = find_slot(h, t), s1 = find_slot(h, t + 1);
     if (s0 < 0 || s1 < 0) FAIL(CWR_EINVAL, "hydrodynamic slices t and t+1 are not resident; call cwr_set_hydro");
     CK(cudaSetDevice(h->device));
+    { int rcj = join_prefetch(h); if (rcj) return rcj; }
     const int64_t launches0 = h->launches;
     const int n = h->n, E = h->E, K = h->K, Eg = std::max(1, h->topo.E_g), G = std::max(1, h->G);
     StepParams p;

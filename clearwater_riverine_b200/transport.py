@@ -187,12 +187,12 @@ class ClearwaterRiverine:
         self._store_flux = bool(store_mass_flux)
         self.solver_info = []
 
-    def _upload_slice(self, t: int):
+    def _upload_slice(self, t: int, overlap: bool = False):
         if t in self._resident or t >= len(self.mesh["time"]):
             return
         m = self.mesh
-        self.backend.set_hydro_raw(t, m[FLOW_ACROSS_FACE][t:t + 1], m[EDGE_VELOCITY][t:t + 1], m[VOLUME][t:t + 1],
-                                   m[CHANGE_IN_TIME][t:t + 1])
+        send = self.backend.prefetch_hydro_raw if overlap else self.backend.set_hydro_raw
+        send(t, m[FLOW_ACROSS_FACE][t:t + 1], m[EDGE_VELOCITY][t:t + 1], m[VOLUME][t:t + 1], m[CHANGE_IN_TIME][t:t + 1])
         cap = self.backend.options.hydro_capacity
         self._resident = {s for s in self._resident if s % cap != t % cap} | {t}
 
@@ -218,6 +218,8 @@ class ClearwaterRiverine:
         if info.status != CWR_OK:
             warnings.warn(f"step {t}: {STATUS_NAMES.get(info.status, info.status)} "
                           f"({info.iterations} iterations, relres {info.max_relres:.3e})", SolverWarning)
+        if self.stream_hydro:                                 # slice t+2 goes up while c[t+1] comes down (full duplex)
+            self._upload_slice(t + 2, overlap=True)
         if self.output == "eager":
             self._fetch(t + 1)
         self.time_step += 1                                   # transport.py:276

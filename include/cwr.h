@@ -112,6 +112,13 @@ int cwr_set_geometry(cwr_handle* h, const double* face_x, const double* face_y);
 int cwr_set_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
                       const float* volume, const double* dt);
 
+/* cwr_set_hydro_raw on a second stream: the copy and the derivation overlap whatever the handle's stream and the
+ * caller do next (typically the device->host copy of the step just taken); the next call that reads the hydro
+ * window waits for it on the device.  The host arrays must stay valid until then (page-locked for a truly
+ * asynchronous copy). */
+int cwr_prefetch_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow, const float* edge_velocity,
+                           const float* volume, const double* dt);
+
 /* Optional, before any other set_* call: one representative signed face flow per edge ((E,) f32, e.g. the
  * time mean of `Face Flow`) for the flow-aligned colouring of the Gauss-Seidel sweeps (precond_sweep = 1).
  * Without it the first cwr_set_hydro* call's slices are used.  Affects speed only, never results beyond rtol. */

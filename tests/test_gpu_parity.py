@@ -317,13 +317,15 @@ def test_uniform_concentration_is_preserved_on_steady_flow():
     be.close()
 
 
-def test_host_mirror_update_loop_matches_oracle():
+@pytest.mark.parametrize("opts", [dict(), dict(stream_hydro=True), dict(stream_hydro=True, solver_path=1, keep_history=0)])
+def test_host_mirror_update_loop_matches_oracle(opts):
     """ClearwaterRiverine.update() with update_concentration, as a coupling loop drives it
-    (examples/03_01_coupling_riverine_modules_nsm.ipynb cell 47)."""
+    (examples/03_01_coupling_riverine_modules_nsm.ipynb cell 47); also with the hydrodynamics streamed slice by
+    slice (slice t+2 prefetched on the upload stream while c[t+1] is copied back)."""
     from clearwater_riverine_b200 import ClearwaterRiverine
     plan, mesh, inputs = synthetic_case(20, 14, 7, 2, seed=4)
     model = ClearwaterRiverine.from_arrays(plan.f1, plan.f2, plan.face_x, plan.face_y, plan.time_seconds, plan.face_flow,
-                                           plan.edge_velocity, plan.volume, 0.1, {"a": inputs[0], "b": inputs[1]})
+                                           plan.edge_velocity, plan.volume, 0.1, {"a": inputs[0], "b": inputs[1]}, **opts)
     oracle = ref.OracleRiverine(mesh, {"a": inputs[0], "b": inputs[1]})
     n = mesh.n
     rng = np.random.default_rng(1)
