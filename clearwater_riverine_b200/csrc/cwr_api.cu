@@ -496,6 +496,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     M.ic = ic;
     CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
     CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
+    // t is multiplied by omega = 0 when a solve ends at a half step before t = A s^ was ever formed: keep it finite
+    CK(cudaMemsetAsync(M.tt, 0, nK * sizeof(double), h->stream)); CK(cudaMemsetAsync(M.v, 0, nK * sizeof(double), h->stream));
     if (need_precond_vectors) {
         double* us;
         CK(dalloc(h, &us, nK));

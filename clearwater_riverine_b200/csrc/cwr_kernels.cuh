@@ -41,7 +41,7 @@ struct StepParams {
 };
 
 enum ScalarRow { SC_RHO = 0, SC_ALPHA, SC_OMEGA, SC_BETA, SC_BNORM2, SC_RNORM2, SC_RHATV, SC_ROWS };
-enum ColFlag { FL_CONVERGED = 1, FL_BREAKDOWN = 2, FL_NAN = 4, FL_ZERO_RHS = 8, FL_PENDING = 16 };
+enum ColFlag { FL_CONVERGED = 1, FL_BREAKDOWN = 2, FL_NAN = 4, FL_ZERO_RHS = 8, FL_PENDING = 16, FL_HALF = 32 };
 
 struct SolverCtl {
     int all_done;       // every column converged / failed / fixed
@@ -53,6 +53,8 @@ struct SolverCtl {
     int pad[2];
     unsigned ticket[4]; // last-block tickets (one per kernel family)
     unsigned ticket_halo; // k_halo_push
+    unsigned ticket_s;    // k_update_s
+    int finish_half;      // every active column converged at the half step: skip the sweeps on s and t = A s^
     unsigned gs_bar[2]; // k_precond_gs: grid barrier arrivals, exits
 };
 
@@ -113,7 +115,7 @@ struct DeviceModel {
 
 __global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl) {
     *dst = p;
-    ctl->all_done = 0; ctl->iter = 0; ctl->flags_or = 0; ctl->hit_max_iter = 0;
+    ctl->all_done = 0; ctl->iter = 0; ctl->flags_or = 0; ctl->hit_max_iter = 0; ctl->finish_half = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -584,7 +586,7 @@ __device__ __forceinline__ Vd<VEC> ldz(const ZT* p) {
 template <typename ST, int KC, int VEC, bool FIRST>
 __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_sweep(DeviceModel M, const double* __restrict__ u64,
                                                                          const ST* z, ST* out, int row_begin, int row_end) {
-    if (M.ctl->all_done) return;
+    if (M.ctl->all_done || M.ctl->finish_half) return;
     const int K = M.K, W = M.W;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
@@ -720,7 +722,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     constexpr bool SMEM = sizeof(ST) * VEC == 16;
     constexpr int NR = kGsRows;
     extern __shared__ int4 gs_land[];          // [NR rows][4 neighbours][kGsThreads] landing slots (SMEM path)
-    if (M.ctl->all_done) return;
+    if (M.ctl->all_done || M.ctl->finish_half) return;
     const int K = M.K, W = M.W, nc = M.n_colors;
     const int vb = blockIdx.x, nvb = gridDim.x, c_end = K;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kGsThreads / KC;
@@ -924,6 +926,7 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
     __shared__ double smem[HAS_DOTS ? (kThreads / 32) * kMaxDots * 2 * 32 : 1];
     __shared__ double tot[HAS_DOTS ? kMaxDots * kMaxK : 1];
     if (MODE == MODE_AV || MODE == MODE_AT) { if (M.ctl->all_done) return; }
+    if (MODE == MODE_AT) { if (M.ctl->finish_half) return; }
     const int K = M.K, n = M.row_hi, W = M.W;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
@@ -1032,7 +1035,7 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
             const double rr = tot[0 * K + k], bb = tot[1 * K + k];
             sc[SC_RHO * K + k] = rr; sc[SC_BNORM2 * K + k] = bb; sc[SC_RNORM2 * K + k] = rr;
             sc[SC_ALPHA * K + k] = 0.0; sc[SC_OMEGA * K + k] = 0.0; sc[SC_BETA * K + k] = 0.0;
-            f &= ~(FL_CONVERGED | FL_BREAKDOWN | FL_PENDING | FL_ZERO_RHS | FL_NAN);
+            f &= ~(FL_CONVERGED | FL_BREAKDOWN | FL_PENDING | FL_ZERO_RHS | FL_NAN | FL_HALF);
             if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) f |= FL_NAN | FL_PENDING;
             else if (bb == 0.0 && rr != 0.0) f |= FL_ZERO_RHS | FL_PENDING;     // b == 0  =>  x = 0
             else if (rr <= M.tol2 * bb) { f |= FL_CONVERGED; M.coliters[k] = M.ctl->iter; }
@@ -1048,7 +1051,7 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
         } else {
             const double ts = tot[0 * K + k], t2 = tot[1 * K + k], rt = tot[2 * K + k], rs = tot[3 * K + k];
             double omega = 0.0, beta = 0.0;
-            if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING))) {
+            if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING | FL_HALF))) {
                 const double rho = sc[SC_RHO * K + k], alpha = sc[SC_ALPHA * K + k];
                 omega = t2 > 0.0 ? ts / t2 : 0.0;
                 const double rho_new = rs - omega * rt;          // (rhat, s - omega t)
@@ -1065,26 +1068,57 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
     if (MODE == MODE_INIT && threadIdx.x == 0) publish_done(M, K);
 }
 
-// s = r - alpha v  (in place on r)
+// s = r - alpha v  (in place on r), fused with (s,s): a column whose ||s|| already meets the tolerance stops at
+// the half step (FL_HALF: omega = 0, so k_update_xrp reduces to x += alpha p^ and finds it converged); when every
+// column has, the second half of the iteration (the sweeps on s and t = A s^) is skipped (ctl->finish_half).
 template <int KC, int VEC>
 __global__ void __launch_bounds__(kThreads) k_update_s(DeviceModel M) {
+    __shared__ double smem[(kThreads / 32) * kMaxDots * 2 * 32];
+    __shared__ double tot[kMaxDots * kMaxK];
     if (M.ctl->all_done) return;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
-    for (int c = lane * VEC; c < K; c += KC * VEC) {
-        double alpha[VEC];
-        bool any = false;
+    const int nchunk = (K + KC * VEC - 1) / (KC * VEC);
+    for (int chunk = 0; chunk < nchunk; ++chunk) {
+        const int c = (chunk * KC + lane) * VEC;
+        double acc[VEC];
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) { alpha[q] = M.sc[SC_ALPHA * K + c + q]; any |= alpha[q] != 0.0; }
-        if (!any) continue;        // frozen columns: s = r
-        for (int i = M.row_lo + blockIdx.x * GPB + group; i < M.row_hi; i += gridDim.x * GPB) {
-            const size_t idx = (size_t)i * K + c;
-            Vd<VEC> r = ldv<VEC>(M.r + idx);
-            const Vd<VEC> v = ldv<VEC>(M.v + idx);
+        for (int q = 0; q < VEC; ++q) acc[q] = 0.0;
+        if (c < K) {
+            double alpha[VEC];
+            bool any = false;
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) r.a[q] = fma(-alpha[q], v.a[q], r.a[q]);
-            stv<VEC>(M.r + idx, r);
+            for (int q = 0; q < VEC; ++q) { alpha[q] = M.sc[SC_ALPHA * K + c + q]; any |= alpha[q] != 0.0; }
+            if (any)       // frozen columns (alpha = 0): s = r, nothing to do
+                for (int i = M.row_lo + blockIdx.x * GPB + group; i < M.row_hi; i += gridDim.x * GPB) {
+                    const size_t idx = (size_t)i * K + c;
+                    Vd<VEC> r = ldv<VEC>(M.r + idx);
+                    const Vd<VEC> v = ldv<VEC>(M.v + idx);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) { r.a[q] = fma(-alpha[q], v.a[q], r.a[q]); acc[q] = fma(r.a[q], r.a[q], acc[q]); }
+                    stv<VEC>(M.r + idx, r);
+                }
         }
+        block_dots<1, KC, VEC>(acc, smem, M.partials, K, chunk);
     }
+    if (!last_block_arrives(&M.ctl->ticket_s)) return;
+    grid_totals<1>(M.partials, tot, K);
+    dd_allreduce(M, tot, K);
+    __shared__ int not_half;
+    if (threadIdx.x == 0) not_half = 0;
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        int f = M.colflags[k];
+        if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN | FL_PENDING))) {
+            const double ss = tot[k];
+            if (M.sc[SC_ALPHA * K + k] != 0.0 && ss == ss && ss <= M.tol2 * M.sc[SC_BNORM2 * K + k]) {
+                f |= FL_HALF;
+                M.sc[SC_OMEGA * K + k] = 0.0; M.sc[SC_BETA * K + k] = 0.0;
+                M.colflags[k] = f;
+            } else atomicOr(&not_half, 1);
+        } else if (f & FL_PENDING) atomicOr(&not_half, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) M.ctl->finish_half = not_half ? 0 : 1;
 }
 
 // x += alpha ph + omega sh ; r = s - omega t ; p = r + beta (p - omega v) ; dot (r,r); convergence
@@ -1146,6 +1180,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const PT
             f &= ~FL_PENDING;
             if (f & FL_ZERO_RHS) { f |= FL_CONVERGED; M.sc[SC_RNORM2 * K + k] = 0.0; M.coliters[k] = M.ctl->iter; }
         } else if (!(f & (FL_CONVERGED | FL_BREAKDOWN | FL_NAN))) {
+            f &= ~FL_HALF;
             const double rr = tot[k];
             M.sc[SC_RNORM2 * K + k] = rr;
             if (!(rr == rr) || isinf(rr)) f |= FL_NAN;
@@ -1154,7 +1189,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const PT
         M.colflags[k] = f;
     }
     __syncthreads();
-    if (threadIdx.x == 0) publish_done(M, K);
+    if (threadIdx.x == 0) { M.ctl->finish_half = 0; publish_done(M, K); }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -128,8 +128,14 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M,
             cta_sum<1>(d1, red);
             if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
             const double alpha = rho / d1[0];
-            for (int i = threadIdx.x; i < n; i += blockDim.x) r[i] = fma(-alpha, v[i], r[i]);     // s
-            __syncthreads();
+            double dh[1] = {0.0};
+            for (int i = threadIdx.x; i < n; i += blockDim.x) { r[i] = fma(-alpha, v[i], r[i]); dh[0] = fma(r[i], r[i], dh[0]); }     // s
+            cta_sum<1>(dh, red);
+            if (dh[0] <= M.tol2 * bb) {                      // converged at the half step: x += alpha p^
+                for (int i = threadIdx.x; i < n; i += blockDim.x) xc[i] = fma(alpha, ph[i], xc[i]);
+                rr = dh[0]; ++iters; flags |= FL_CONVERGED;
+                break;
+            }
             const double* sh = small_precondition(M, n, m_steps, r, shb, tmp);
             double d4[4] = {0.0, 0.0, 0.0, 0.0};
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -325,8 +331,16 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
             cta_sum<1>(d1, red);
             if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
             const double alpha = rho / d1[0];
+            double dh[1] = {0.0};
 #pragma unroll
-            for (int q = 0; q < RPT; ++q) r[q] = fma(-alpha, v[q], r[q]);      // s
+            for (int q = 0; q < RPT; ++q) { r[q] = fma(-alpha, v[q], r[q]); if (on[q]) dh[0] = fma(r[q], r[q], dh[0]); }      // s
+            cta_sum<1>(dh, red);
+            if (dh[0] <= M.tol2 * bb) {                      // converged at the half step: x += alpha p^
+#pragma unroll
+                for (int q = 0; q < RPT; ++q) x[q] = fma(alpha, ph[q], x[q]);
+                rr = dh[0]; ++iters; flags |= FL_CONVERGED;
+                break;
+            }
             precondition(r);
             double sh[RPT];
 #pragma unroll
