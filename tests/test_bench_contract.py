@@ -1,0 +1,34 @@
+"""bench.py's reference arm runs on the host cores only (oracle = reference arithmetic incl. SuperLU) and must
+print the contract's JSON line; checked here on CPU.  (The GPU arm needs a B200 and is exercised by the driver.)"""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.mark.timeout(300)
+def test_reference_arm_json_line():
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=280, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "cell_timesteps_per_sec" and line["unit"] == "cell-timesteps/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1
+    assert line["value"] > 0 and line["ms_per_step"] > 0
+    cb = line["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == line["value"] and "sample" in cb
+    e2e = line["e2e"]
+    assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_gpu_arm_refuses_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True,
+                         timeout=120, cwd=ROOT)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
