@@ -1,10 +1,12 @@
-// sm_100a kernels of the transport step.  fp64 throughout; HBM-bound gather/stream work, so the
+// sm_100a kernels of the transport step.  Results, BiCGSTAB recurrences, products and dot products are fp64; only
+// the preconditioner sweeps and the preconditioned vectors are fp32.  HBM-bound gather/stream work, so the
 // design rules are: coalescing (constituents interleaved, x[row*K + k]: one 128 B line per row at
-// K = 16, moved as 128-bit double2 per lane), a fixed-width row-major ELL matrix (one int4 + two
+// K = 16, moved as 128-bit packs per lane), a fixed-width row-major ELL matrix (one int4 + two
 // double2 broadcast loads per row, no rowptr dependency in front of the gathers), persistent grids
 // sized from the SM count, fused dot products with a deterministic two-level reduction (no
-// floating-point atomics anywhere), and per-step parameters read from a device-resident struct so
-// that a step is the same launch sequence every time.
+// floating-point atomics anywhere), per-step parameters read from a device-resident struct so
+// that a step is the same launch sequence every time, and -- across GPUs -- boundary rows and dot products
+// exchanged through peer-mapped memory from inside the kernels (see the domain-decomposition section).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -215,12 +215,13 @@ enum {
     CWR_FAM_RHS,            /* k_rhs + k_boundary_rhs */
     CWR_FAM_SPMM_INIT,      /* r = b - A x0 */
     CWR_FAM_SPMM_V,         /* v = A p  with (rhat, v) */
-    CWR_FAM_UPDATE_S,       /* s = r - alpha v */
+    CWR_FAM_UPDATE_S,       /* s = r - alpha v with (s, s): the half-step convergence test */
     CWR_FAM_SPMM_T,         /* t = A s  with the four dots */
     CWR_FAM_UPDATE_XRP,     /* x, r, p updates with (r, r) */
     CWR_FAM_MASS_FLUX,
-    CWR_FAM_PRECOND,        /* Jacobi steps of the polynomial preconditioner: out = u + N z */
-    CWR_FAM_SOLVE_SMALL,    /* small meshes: the whole solve of every column, one CTA each (k_solve_small) */
+    CWR_FAM_PRECOND,        /* the preconditioner: one k_precond_gs launch = all Gauss-Seidel sweeps of one application
+                               (precond_sweep = 1), or one Jacobi step out = u + N z per launch (precond_sweep = 0) */
+    CWR_FAM_SOLVE_SMALL,    /* small meshes: the whole solve of every column, one CTA each (k_solve_tiny / k_solve_small) */
     CWR_PROFILE_FAMILIES
 };
 int cwr_profile(cwr_handle* h, int enable, double* ms, int64_t* counts);
