@@ -375,19 +375,25 @@ def main():
     total_ms = sum(v[0] for v in prof.values())
     kernels = {}
     for fam, (ms, cnt) in prof.items():
-        if cnt and fam in fam_bytes:
-            per = ms / cnt
+        if not cnt:
+            continue
+        per = ms / cnt
+        entry = {"ms_per_launch": per, "launches_per_step": cnt / P, "ms_per_step": ms / P,
+                 "share_of_step": ms / total_ms if total_ms else None}
+        if fam in fam_bytes:
             gbs = fam_bytes[fam] / (per * 1e-3) / 1e9
-            kernels[fam] = {"ms_per_launch": per, "launches_per_step": cnt / P, "ms_per_step": ms / P,
-                            "share_of_step": ms / total_ms if total_ms else None,
-                            "algorithmic_bytes_per_launch": fam_bytes[fam], "achieved_gbs": gbs, "frac": gbs / peak}
+            entry.update({"algorithmic_bytes_per_launch": fam_bytes[fam], "achieved_gbs": gbs, "frac": gbs / peak})
+        else:       # the one-CTA-per-constituent solve of small meshes works out of shared memory / L2: no HBM roofline
+            entry.update({"algorithmic_bytes_per_launch": None, "achieved_gbs": None, "frac": None})
+        kernels[fam] = entry
     roofline = None
     if kernels:
         dom = max(kernels, key=lambda f: kernels[f]["ms_per_step"])
         names = {"precond": ("k_precond_gs (multicolour Gauss-Seidel preconditioner: all sweeps of one application, persistent, "
                              "one grid barrier per colour)" if o.precond_sweep == 1 else "k_sweep (one Jacobi step of the polynomial preconditioner)"),
                  "spmm_t": "k_spmm<AT> (t = A s^ fused with four dot products)", "spmm_v": "k_spmm<AV> (v = A p^ fused with (rhat, v))",
-                 "update_xrp": "k_update_xrp", "solve_small": "k_solve_small"}
+                 "update_xrp": "k_update_xrp",
+                 "solve_small": "k_solve_tiny / k_solve_small (whole solve of a constituent in one CTA, on chip up to 4096 cells)"}
         traffic = None
         tp = ROOT / "profiles" / "dominant_kernel_traffic.json"
         if tp.is_file():
@@ -398,7 +404,8 @@ def main():
             except Exception:
                 pass
         d = kernels[dom]
-        roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "family": dom, "achieved": d["achieved_gbs"], "peak": peak,
+        roofline = {"bound": "hbm" if d["frac"] is not None else "latency (shared-memory / L2 resident: HBM roofline not applicable)",
+                    "kernel": names.get(dom, dom), "family": dom, "achieved": d["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": d["frac"], "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": d["algorithmic_bytes_per_launch"], "ms_per_launch": d["ms_per_launch"],
                     "share_of_step": d["share_of_step"], "kernels": kernels}
