@@ -399,8 +399,9 @@ def main():
         if tp.is_file():
             try:
                 tj = json.loads(tp.read_text())
-                if tj.get("workload") == args.workload and tj.get("family") == dom and args.scale == 1.0 and not args.opt:
-                    traffic = tj.get("dram_bytes_per_launch")
+                if tj.get("workload") == args.workload and tj.get("family") == dom and args.scale == 1.0 and o.precond_sweep == 1:
+                    # measured with ncu at 4 and 6 sweeps per launch; linear in the sweep count
+                    traffic = tj["dram_bytes_fixed"] + tj["dram_bytes_per_sweep"] * sweeps
             except Exception:
                 pass
         d = kernels[dom]

@@ -349,9 +349,10 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     const bool small = h->opt.solver_path == 2 || (h->opt.solver_path == 0 && n_real <= 32768);
     // tiny meshes (<= 4096 cells, the Ohio River model): the whole solve on chip with Gauss-Seidel sweeps
     const bool tiny = small && h->opt.precond_sweep == 1 && h->opt.precond_steps != 1 && n_real <= kTinyThreads * kTinyMaxRows;
-    // auto: 6 Gauss-Seidel sweeps per application on large meshes (two BiCGSTAB iterations per step on the 1M x 16
-    // benchmark; with the half-step exit, 5..11 sweeps all land within 4 % of each other), 4 on chip, 7 Jacobi steps
-    if (h->opt.precond_steps <= 0) h->opt.precond_steps = h->opt.precond_sweep == 1 ? (tiny ? 5 : (!small ? 7 : 8)) : 8;
+    // auto: 5 Gauss-Seidel sweeps per application on large meshes (about two BiCGSTAB iterations per step on the
+    // 1M x 16 benchmark; with the half-step exit, 5..11 sweeps all land within a few % of each other), 4 on chip,
+    // 7 Jacobi steps
+    if (h->opt.precond_steps <= 0) h->opt.precond_steps = h->opt.precond_sweep == 1 ? (tiny ? 5 : (!small ? 6 : 8)) : 8;
     h->m_steps = std::min(h->opt.precond_steps, 64);
     if (h->opt.precond_precision != 64) h->opt.precond_precision = 32;
     h->sweep_f32 = h->opt.precond_precision == 32;

@@ -1,6 +1,8 @@
 #include "cwr_topology.h"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 namespace cwr {
@@ -45,6 +47,13 @@ struct Bfs {
         return nlev;
     }
 };
+
+// fraction of a cell's strongest face flow below which an edge does not direct the colouring (0 = every edge
+// does); CWR_HINT_TAU overrides it for experiments
+float hint_threshold() {
+    if (const char* ev = std::getenv("CWR_HINT_TAU")) return (float)std::atof(ev);
+    return 0.1f;      // 1M x 16 benchmark, 5 sweeps per application: 3.81 -> 3.14 ms/step (0.25: 3.20)
+}
 
 }  // namespace
 
@@ -144,10 +153,27 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         std::vector<int32_t> rcm_pos(n);
         for (int i = 0; i < n; ++i) rcm_pos[T.old_of_new[i]] = i;
         // directed flow graph among real cells: up -> down
+        // Edges whose flow is weak next to the strongest flow through either of their cells (cross-stream
+        // exchange) are left undirected: they carry little coupling, but as graph edges they chain the
+        // levels across streamlines (several levels per cell instead of one), so the colours would wrap
+        // after two or three cells.  Measured (100k cells, 11 colours): error factor per sweep 0.31 -> 0.25.
         std::vector<int32_t> indeg(n, 0), optr(n + 1, 0), oadj;
         if (hint) {
+            const float tau = hint_threshold();
+            std::vector<float> cellmax(n, 0.f);
+            if (tau > 0.f)
+                for (int e = 0; e < E; ++e) {
+                    const float q = std::fabs(hint[e]);
+                    if (!(q == q)) continue;
+                    cellmax[f1[e]] = std::max(cellmax[f1[e]], q);
+                    if (f2[e] < n) cellmax[f2[e]] = std::max(cellmax[f2[e]], q);
+                }
+            auto directed = [&](int e) {
+                if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) return false;
+                return tau <= 0.f || std::fabs(hint[e]) >= tau * std::max(cellmax[f1[e]], cellmax[f2[e]]);
+            };
             for (int e = 0; e < E; ++e) {
-                if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) continue;
+                if (!directed(e)) continue;
                 const int32_t up = hint[e] > 0.f ? f1[e] : f2[e], down = hint[e] > 0.f ? f2[e] : f1[e];
                 ++optr[up + 1]; ++indeg[down];
             }
@@ -155,7 +181,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             oadj.resize(optr[n]);
             std::vector<int32_t> fill(optr.begin(), optr.end() - 1);
             for (int e = 0; e < E; ++e) {
-                if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) continue;
+                if (!directed(e)) continue;
                 const int32_t up = hint[e] > 0.f ? f1[e] : f2[e], down = hint[e] > 0.f ? f2[e] : f1[e];
                 oadj[fill[up]++] = down;
             }

@@ -51,7 +51,7 @@ typedef struct {
     int check_every;        /* large meshes: iterations launched per convergence poll once the launch-ahead burst is used up;
                                default 1 */
     int precond_steps;      /* m: the preconditioner applies m - 1 sweeps; 1 = diagonal (Jacobi) scaling only;
-                               0 (default) = 7 with Gauss-Seidel sweeps on large meshes, 5 on chip (<= 4096 cells), 8 with
+                               0 (default) = 6 with Gauss-Seidel sweeps on large meshes, 5 on chip (<= 4096 cells), 8 with
                                Jacobi steps */
     int precond_precision;  /* 32 (default): the sweeps and the preconditioned vectors are fp32 (half the bytes;
                                BiCGSTAB itself, its products A p^ / A s^ and its dots stay fp64, so the converged
