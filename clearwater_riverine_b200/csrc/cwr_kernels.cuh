@@ -694,8 +694,10 @@ __device__ __forceinline__ void grid_barrier(const DeviceModel& M, unsigned targ
         // (device-scope fence) therefore orders all of this rank's peer stores before the announcement
         if (cross && t == target - 1) { __threadfence(); dd_signal(M, false, e, M.nbr_mask); }
         unsigned spins = 0;
+        // never hang the device: a barrier that gave up once (never expected) makes the later ones fall through
+        const unsigned limit = *reinterpret_cast<volatile int*>(&ctl->barrier_timeout) ? 0u : (1u << 27);
         while (*reinterpret_cast<volatile unsigned*>(&ctl->gs_bar[0]) < target)
-            if (++spins > (1u << 27)) { ctl->barrier_timeout = 1; break; }      // never hang the device
+            if (++spins > limit) { ctl->barrier_timeout = 1; break; }
         if (cross) dd_wait(M, false, e, M.nbr_mask); else asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
