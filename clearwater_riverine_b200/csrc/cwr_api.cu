@@ -1386,6 +1386,28 @@ int cwr_dd_layout(cwr_handle* h, cwr_dd_info* out, uint8_t* owned_cells, uint8_t
     return CWR_OK;
 }
 
+int cwr_tile_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
+                    int tile_rows, int tile_cap, int tile_halo, int* n_tiles, int* ext_total, int* ell_width, int* n_colors_out,
+                    int32_t* new_of_old, int32_t* tile_ptr, int32_t* ext_ptr, int32_t* ext_rows, int32_t* lcolor_ptr,
+                    uint16_t* tile_ell, int32_t* ell_col) {
+    if (!f1 || !f2) return CWR_EINVAL;
+    Topology t;
+    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, 1, t, tile_rows, tile_cap, tile_halo);
+    if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
+    if (n_tiles) *n_tiles = (int)t.tile_ptr.size() - 1;
+    if (ext_total) *ext_total = (int)t.ext_rows.size();
+    if (ell_width) *ell_width = t.W;
+    if (n_colors_out) *n_colors_out = t.n_colors;
+    if (new_of_old) std::copy(t.new_of_old.begin(), t.new_of_old.end(), new_of_old);
+    if (tile_ptr) std::copy(t.tile_ptr.begin(), t.tile_ptr.end(), tile_ptr);
+    if (ext_ptr) std::copy(t.ext_ptr.begin(), t.ext_ptr.end(), ext_ptr);
+    if (ext_rows) std::copy(t.ext_rows.begin(), t.ext_rows.end(), ext_rows);
+    if (lcolor_ptr) std::copy(t.lcolor_ptr.begin(), t.lcolor_ptr.end(), lcolor_ptr);
+    if (tile_ell) std::copy(t.tile_ell.begin(), t.tile_ell.end(), tile_ell);
+    if (ell_col) std::copy(t.ell_col.begin(), t.ell_col.end(), ell_col);
+    return CWR_OK;
+}
+
 int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     if (!h || !out) return CWR_EINVAL;
     *out = h->opt;

@@ -207,6 +207,18 @@ int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const
                     const float* flow_hint, int n_parts, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out,
                     int* n_levels, int32_t* part_ptr, int32_t* n_send);
 
+/* Host only, EXPERIMENTAL (precond_sweep = 2, tile-local sweeps): the tiling build_topology
+ * makes -- compact tiles of about tile_rows cells, each extended by up to tile_halo layers of neighbours while it stays
+ * within tile_cap rows; rows ordered (tile, colour, RCM position).  Call once with the array pointers NULL for the sizes
+ * (n_tiles, ext_total, ell_width, n_colors_out), then with arrays: new_of_old (n_real), tile_ptr (n_tiles+1), ext_ptr
+ * (n_tiles+1), ext_rows (ext_total; bit 31 = halo row), lcolor_ptr (n_tiles, n_colors+1), tile_ell (ext_total, W: local
+ * neighbour index, bit 15 = visited later in a sweep, bit 14 = outside the tile), ell_col (n_real, W: global neighbour
+ * rows, bit 31 = visited later). */
+int cwr_tile_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
+                    int tile_rows, int tile_cap, int tile_halo, int* n_tiles, int* ext_total, int* ell_width, int* n_colors_out,
+                    int32_t* new_of_old, int32_t* tile_ptr, int32_t* ext_ptr, int32_t* ext_rows, int32_t* lcolor_ptr,
+                    uint16_t* tile_ell, int32_t* ell_col);
+
 /* --- device timing of the dominant kernel (bench.py roofline) -------------------------------- */
 /* Per-kernel-family device time inside cwr_step, measured with CUDA events recorded on the handle's
  * stream between the launches.  cwr_profile(h, 1, NULL, NULL) switches it on (and zeroes the sums),
