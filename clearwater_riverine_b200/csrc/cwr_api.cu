@@ -33,6 +33,9 @@ struct cwr_handle {
     int m_steps = 1;                 // sweeps of the preconditioner + 1 (1 = diagonal scaling only)
     bool sweep_f32 = true;           // preconditioner sweeps (and p^, s^) in fp32
     bool gauss_seidel = false;       // multicolour Gauss-Seidel sweeps instead of Jacobi steps
+    bool tiled = false;              // EXPERIMENTAL: tile-local sweeps (precond_sweep = 2, k_precond_tile)
+    int32_t *d_ext_ptr = nullptr, *d_ext_rows = nullptr, *d_lcolor_ptr = nullptr; uint16_t* d_tile_ell = nullptr;
+    size_t tile_smem = 0;
     bool hint_done = false;          // the colours have been aligned with the flow (or it is too late to)
     int grid_sweep = 0, grid_gs = 0;
     int32_t* d_color_ptr = nullptr;
@@ -231,6 +234,10 @@ static int upload_topology(cwr_handle* h) {
     CK(put(h, h->d_new_of_old, tp.new_of_old)); CK(put(h, h->d_old_of_new, tp.old_of_new));
     CK(put(h, h->d_color_ptr, tp.color_ptr));
     CK(put(h, h->d_send_mask, tp.send_mask)); CK(put(h, h->d_send_rows, tp.send_rows));
+    if (h->tiled) {
+        CK(put(h, h->d_ext_ptr, tp.ext_ptr)); CK(put(h, h->d_ext_rows, tp.ext_rows));
+        CK(put(h, h->d_lcolor_ptr, tp.lcolor_ptr)); CK(put(h, h->d_tile_ell, tp.tile_ell));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return CWR_OK;
 }
@@ -246,6 +253,8 @@ static void set_owned_ranges(cwr_handle* h) {
     M.b_lo = tp.bcell_ptr[r]; M.b_hi = tp.bcell_ptr[r + 1];
     M.n_colors = tp.n_colors;
     M.color_ptr = h->d_color_ptr + (size_t)r * (tp.n_colors + 1);
+    M.ext_ptr = h->d_ext_ptr; M.ext_rows = h->d_ext_rows; M.lcolor_ptr = h->d_lcolor_ptr; M.tile_ell = h->d_tile_ell;
+    M.n_tiles = h->tiled ? (int)tp.tile_ptr.size() - 1 : 0; M.max_ext = tp.max_ext;
     unsigned nbr = 0;
     for (int32_t j = tp.send_ptr[r]; j < tp.send_ptr[r + 1]; ++j) nbr |= tp.send_mask[tp.send_rows[j]];
     M.nbr_mask = nbr;        // symmetric: whoever reads my rows owns rows I read
@@ -364,6 +373,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         FAIL(CWR_EINVAL, "domain decomposition needs the multi-CTA solver path (solver_path = 1) and precond_steps >= 2");
     h->tiny = tiny;
     h->gauss_seidel = h->opt.precond_sweep == 1 && !h->small_path && h->m_steps > 1;
+    h->tiled = h->opt.precond_sweep == 2 && !h->small_path && h->m_steps > 1;
+    if (h->opt.precond_sweep == 2 && !h->tiled) FAIL(CWR_EINVAL, "precond_sweep = 2 (experimental tile-local sweeps) needs solver_path = 1 and precond_steps >= 2");
+    if (h->tiled && h->world > 1) FAIL(CWR_EINVAL, "precond_sweep = 2 (experimental) is single-GPU only");
     if (h->opt.precond_colors <= 0) {
         // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
         // bytes per row of one sweep = indices + values + three vectors in the sweep type
@@ -385,11 +397,19 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->num_sms = prop.multiProcessorCount;
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
+    int tile_rows = 0, tile_cap = 0;
+    if (h->tiled) {      // rows (core + 4 halo layers) that fit in one CTA's shared memory: z, u (K each), values, indices (W = 4 assumed)
+        const int stb = h->sweep_f32 ? 4 : 8;
+        tile_cap = (int)std::min<size_t>(8191, (size_t)(226 * 1024) / ((size_t)2 * n_const * stb + 4 * stb + 8));
+        tile_rows = std::max(16, (int)(tile_cap * 0.55));
+        if (h->opt.precond_colors < 8) h->opt.precond_colors = 11;
+    }
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
-                                      (h->gauss_seidel || h->tiny) ? h->opt.precond_colors : 0,
-                                      (h->gauss_seidel || h->tiny) ? flow_hint : nullptr, h->world, h->topo);
+                                      (h->gauss_seidel || h->tiny || h->tiled) ? h->opt.precond_colors : 0,
+                                      (h->gauss_seidel || h->tiny || h->tiled) ? flow_hint : nullptr, h->world, h->topo,
+                                      tile_rows, tile_cap, 4);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
-    if (flow_hint) h->hint_done = true;
+    if (flow_hint || h->tiled) h->hint_done = true;     // (the tile arrays' sizes depend on the order: no re-ordering later)
     const Topology& tp = h->topo;
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
@@ -454,6 +474,17 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     CK(dalloc(h, &h->d_new_of_old, (size_t)n)); CK(dalloc(h, &h->d_old_of_new, (size_t)n));
     CK(dalloc(h, &h->d_color_ptr, tp.color_ptr.size()));
     CK(dalloc(h, &h->d_send_mask, (size_t)n)); CK(dalloc(h, &h->d_send_rows, (size_t)n));
+    if (h->tiled) {
+        CK(dalloc(h, &h->d_ext_ptr, tp.ext_ptr.size())); CK(dalloc(h, &h->d_ext_rows, tp.ext_rows.size()));
+        CK(dalloc(h, &h->d_lcolor_ptr, tp.lcolor_ptr.size())); CK(dalloc(h, &h->d_tile_ell, tp.tile_ell.size()));
+        h->tile_smem = tile_smem_bytes(tp.max_ext, K, tp.W, h->sweep_f32 ? 4 : 8);
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+        if (h->tile_smem > (size_t)max_optin) FAIL(CWR_EINVAL, "precond_sweep = 2: a tile does not fit in shared memory (rows wider than 4?)");
+        cudaError_t e = cudaSuccess;
+        SWEEP_DISPATCH(e = cudaFuncSetAttribute(k_precond_tile<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
+        CK(e);
+    }
     {
         int rc = upload_topology(h);
         if (rc) return rc;
@@ -828,6 +859,12 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
     const int J = h->m_steps - 1;
     if (J <= 0) return u;
     DeviceModel& M = h->M;
+    if (h->tiled) {          // EXPERIMENTAL: all sweeps of the application inside one CTA per tile
+        mark(h, CWR_FAM_PRECOND);
+        SWEEP_DISPATCH((k_precond_tile<ST, SKC, SVEC><<<M.n_tiles, kTileThreads, h->tile_smem, h->stream>>>(M, u, (ST*)dst, J)));
+        h->launches += 1;
+        return dst;
+    }
     if (h->gauss_seidel) {
         mark(h, CWR_FAM_PRECOND);
         int sweeps = J;
@@ -1412,7 +1449,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     if (!h || !out) return CWR_EINVAL;
     *out = h->opt;
     out->precond_colors = (h->gauss_seidel || h->tiny) ? h->topo.n_colors : 0;
-    out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
+    out->precond_sweep = h->tiled ? 2 : ((h->gauss_seidel || h->tiny) ? 1 : 0);
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     return CWR_OK;
 }

@@ -91,6 +91,9 @@ struct DeviceModel {
     const int32_t* f1p; const int32_t* f2p;
     const int32_t* bcell; const int32_t* bptr; const int32_t* bedge;
     const int32_t* color_ptr; int n_colors;   // (n_colors+1) row ranges of the Gauss-Seidel colours
+    // tile-local sweeps (EXPERIMENTAL, precond_sweep = 2; cwr_topology.h)
+    const int32_t* ext_ptr; const int32_t* ext_rows; const int32_t* lcolor_ptr; const uint16_t* tile_ell;
+    int n_tiles, max_ext;
     double* val;        // (n,W) off-diagonals of D^-1 A
     float* valf;        // (n,W) the same in fp32 (fp32 preconditioner sweeps), or nullptr
     double* diag;       // (n)   D
@@ -909,6 +912,87 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             if (multi) M.dd->bar_epoch = e0 + xe;
             __threadfence();
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EXPERIMENTAL -- written at the end of round 1, compiled, its host data structures and its arithmetic
+// emulated and tested on the CPU (tests/test_tile_layout.py), NOT YET RUN ON A GPU; off unless
+// precond_sweep = 2.  Tile-local multicolour Gauss-Seidel (restricted additive Schwarz with overlap):
+// one CTA per tile loads the tile's core + halo rows (u as the sweep type, matrix values, 16-bit local
+// column indices) into shared memory, does ALL sweeps of the application there with __syncthreads()
+// between colours -- rows outside the tile count as 0 -- and writes its core rows.  No grid barrier;
+// the matrix and u cross HBM once per application (~1.6x redundancy from the halos) instead of once
+// per sweep.  A scipy emulation needs 3 BiCGSTAB iterations with it against 2 with the global sweeps
+// (tools/experiments/emulate_tiled_gauss_seidel.py).
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileThreads = 512;
+
+__host__ __device__ inline size_t tile_smem_bytes(int max_ext, int K, int W, int st_bytes) {
+    // z, u: (max_ext, K) ST | val: (max_ext, W) ST | idx: (max_ext, W) u16
+    return (size_t)2 * max_ext * K * st_bytes + (size_t)max_ext * W * st_bytes + ((((size_t)max_ext * W * 2) + 15) & ~(size_t)15);
+}
+
+template <typename ST, int KC, int VEC>
+__global__ void __launch_bounds__(kTileThreads, 1) k_precond_tile(DeviceModel M, const double* __restrict__ u64, ST* __restrict__ dst,
+                                                                  int n_sweeps) {
+    extern __shared__ int4 tile_smem[];
+    if (M.ctl->all_done || M.ctl->finish_half) return;
+    const int K = M.K, W = M.W, nc = M.n_colors, t = blockIdx.x;
+    const int base = M.ext_ptr[t], m = M.ext_ptr[t + 1] - base;
+    ST* z = reinterpret_cast<ST*>(tile_smem);
+    ST* u = z + (size_t)M.max_ext * K;
+    ST* val = u + (size_t)M.max_ext * K;
+    unsigned short* idx = reinterpret_cast<unsigned short*>(val + (size_t)M.max_ext * W);
+    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
+    const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kTileThreads / KC;
+    // ---- the tile's rows -> shared memory -------------------------------------------------------------
+    for (int l = group; l < m; l += GPB) {
+        const int gi = M.ext_rows[base + l] & kColMask;
+        for (int c = lane * VEC; c < K; c += KC * VEC) {
+            const Pk<double, VEC> d = ldk<double, VEC>(u64 + (size_t)gi * K + c);
+            Pk<ST, VEC> us;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) us.a[q] = (ST)d.a[q];
+            stk<ST, VEC>(u + (size_t)l * K + c, us);
+        }
+        if (lane == 0)
+            for (int w = 0; w < W; ++w) {
+                val[(size_t)l * W + w] = eval[(size_t)gi * W + w];
+                idx[(size_t)l * W + w] = M.tile_ell[(size_t)(base + l) * W + w];
+            }
+    }
+    __syncthreads();
+    // ---- sweeps from z = 0: rows outside the tile, and in the first sweep rows visited later, count as 0 --------
+    const int32_t* __restrict__ lcp = M.lcolor_ptr + (size_t)t * (nc + 1);
+    for (int s = 0; s < n_sweeps; ++s)
+        for (int c = 0; c < nc; ++c) {
+            const int lo = lcp[c], hi = lcp[c + 1];
+            for (int l = lo + group; l < hi; l += GPB)
+                for (int cc = lane * VEC; cc < K; cc += KC * VEC) {
+                    Pk<ST, VEC> acc;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc.a[q] = (ST)0;
+                    for (int w = 0; w < W; ++w) {
+                        const unsigned short code = idx[(size_t)l * W + w];
+                        if ((code & kTileOutside) || (s == 0 && (code & kTileLater))) continue;
+                        const Pk<ST, VEC> x = ldk<ST, VEC>(z + (size_t)(code & kTileIndexMask) * K + cc);
+                        const ST a = val[(size_t)l * W + w];
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) acc.a[q] += a * x.a[q];
+                    }
+                    const Pk<ST, VEC> own = ldk<ST, VEC>(u + (size_t)l * K + cc);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
+                    stk<ST, VEC>(z + (size_t)l * K + cc, acc);
+                }
+            __syncthreads();
+        }
+    // ---- core rows -> the preconditioned vector ---------------------------------------------------------------
+    for (int l = group; l < m; l += GPB) {
+        const int r = M.ext_rows[base + l];
+        if (r < 0) continue;                    // halo row: another tile owns it
+        for (int cc = lane * VEC; cc < K; cc += KC * VEC) stk<ST, VEC>(dst + (size_t)r * K + cc, ldk<ST, VEC>(z + (size_t)l * K + cc));
     }
 }
 

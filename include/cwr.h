@@ -60,7 +60,9 @@ typedef struct {
                                application in one persistent kernel with a grid barrier per colour; the rows are
                                regrouped colour-major and the colours follow the flow (cwr_set_flow_hint, or the
                                first hydrodynamic slices uploaded -- upload hydro before inputs);
-                               0 = Jacobi steps, z = (I + N + ... + N^(m-1)) u with N = I - D^-1 A */
+                               0 = Jacobi steps, z = (I + N + ... + N^(m-1)) u with N = I - D^-1 A;
+                               2 = EXPERIMENTAL, not yet validated on a GPU: tile-local sweeps in shared memory, one CTA
+                               per tile, no grid barrier */
     int precond_colors;     /* colours of the Gauss-Seidel sweeps (raised to max row degree + 1 if smaller);
                                0 (default) = chosen from the mesh size so that one colour moves ~20 MB */
     int dd_rank, dd_world;  /* domain decomposition: this handle is rank dd_rank of dd_world (<= 8) handles, one per
