@@ -24,14 +24,14 @@ STATUS_NAMES = {0: "CWR_OK", -1: "CWR_EINVAL", -2: "CWR_ECUDA", -3: "CWR_ENOTCON
 class CwrOptions(C.Structure):
     _fields_ = [("rtol", C.c_double), ("max_iter", C.c_int), ("reorder", C.c_int), ("keep_history", C.c_int),
                 ("hydro_capacity", C.c_int), ("mass_flux", C.c_int), ("solver_path", C.c_int),
-                ("use_graph", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int),
+                ("solver", C.c_int), ("check_every", C.c_int), ("precond_steps", C.c_int),
                 ("precond_precision", C.c_int), ("precond_sweep", C.c_int), ("precond_colors", C.c_int),
-                ("dd_rank", C.c_int), ("dd_world", C.c_int), ("dd_halo_per_colour", C.c_int)]
+                ("dd_rank", C.c_int), ("dd_world", C.c_int), ("dd_halo_per_colour", C.c_int), ("precond_sync", C.c_int)]
 
 
 class CwrStepInfo(C.Structure):
     _fields_ = [("iterations", C.c_int), ("restarts", C.c_int), ("status", C.c_int),
-                ("max_relres", C.c_double), ("n_launches", C.c_int)]
+                ("max_relres", C.c_double), ("n_launches", C.c_int), ("sweeps", C.c_int)]
 
 
 class CwrDdInfo(C.Structure):
@@ -105,6 +105,8 @@ def load_library():
         "cwr_tile_layout": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                              C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), ip, ip, ip, ip, ip,
                              C.POINTER(C.c_uint16), ip], C.c_int),
+        "cwr_strip_layout": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                              ip, ip, ip, ip, C.POINTER(C.c_uint8)], C.c_int),
         "cwr_get_options": ([H, C.POINTER(CwrOptions)], C.c_int),
         "cwr_dd_export": ([H, C.c_void_p], C.c_int),
         "cwr_dd_attach": ([H, C.c_void_p], C.c_int),
@@ -113,6 +115,7 @@ def load_library():
         "cwr_order_cells": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, C.c_int, fp, C.c_int, ip, ip, C.POINTER(C.c_int),
                              C.POINTER(C.c_int), ip, ip], C.c_int),
         "cwr_counters": ([H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
+        "cwr_solver_stats": ([H, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
         "cwr_time_spmm": ([H, C.c_int, dp, dp], C.c_int),
         "cwr_profile": ([H, C.c_int, dp, C.POINTER(C.c_int64)], C.c_int),
     }
@@ -196,6 +199,30 @@ def tile_layout(f1, f2, n_face: int, n_colors: int, flow_hint, tile_rows: int, t
     if rc != CWR_OK:
         raise CwrError(rc, lib.cwr_last_error(None).decode())
     out.update(n_tiles=nt.value, n_colors=nc.value, W=W.value)
+    return out
+
+
+def strip_layout(f1, f2, n_face: int, n_colors: int, flow_hint, n_strips: int, n_parts: int = 1):
+    """Host-only: the strips of the neighbour-synchronised sweep kernel (cwr_strip_layout) as a dict of numpy arrays."""
+    lib = load_library()
+    f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
+    n = int(f1.max()) + 1
+    hint = None if flow_hint is None else _arr(flow_hint, np.float32, f1.shape, "flow_hint")
+    nc, nb = C.c_int(), C.c_int()
+    args = (n, int(n_face), len(f1), _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), int(n_colors), _ptr(hint, C.c_float),
+            int(n_parts), int(n_strips), C.byref(nc), C.byref(nb))
+    rc = lib.cwr_strip_layout(*args, None, None, None, None, None)
+    if rc != CWR_OK:
+        raise CwrError(rc, lib.cwr_last_error(None).decode())
+    NS = n_parts * n_strips
+    out = {"new_of_old": np.empty(n, np.int32), "strip_cptr": np.empty((NS, nc.value + 1), np.int32),
+           "strip_nptr": np.empty(NS + 1, np.int32), "strip_nbr": np.empty(max(1, nb.value), np.int32), "color_of": np.empty(n, np.uint8)}
+    rc = lib.cwr_strip_layout(*args, _ptr(out["new_of_old"], C.c_int32), _ptr(out["strip_cptr"], C.c_int32),
+                              _ptr(out["strip_nptr"], C.c_int32), _ptr(out["strip_nbr"], C.c_int32), _ptr(out["color_of"], C.c_uint8))
+    if rc != CWR_OK:
+        raise CwrError(rc, lib.cwr_last_error(None).decode())
+    out["strip_nbr"] = out["strip_nbr"][: nb.value]
+    out.update(n_colors=nc.value, n_strips=n_strips, n_parts=n_parts)
     return out
 
 
@@ -397,12 +424,18 @@ class TransportBackend:
         self._check(self._lib.cwr_counters(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def solver_stats(self):
+        """(Gauss-Seidel sweeps so far, solves that fell back to BiCGSTAB, strips of the sweep kernel, max strip neighbours)."""
+        a, b, c, d = C.c_int64(), C.c_int64(), C.c_int(), C.c_int()
+        self._check(self._lib.cwr_solver_stats(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
     def stream(self) -> int:
         s = C.c_void_p()
         self._check(self._lib.cwr_stream(self._h, C.byref(s)))
         return s.value or 0
 
-    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux", "precond", "solve_small")
+    PROFILE_FAMILIES = ("assemble", "rhs", "spmm_init", "spmm_v", "update_s", "spmm_t", "update_xrp", "mass_flux", "precond", "solve_small", "dc_update")
 
     def profile(self, enable: int = -1):
         """enable = 1/0 switches per-kernel-family event timing on/off; returns {family: (ms, launches)}."""

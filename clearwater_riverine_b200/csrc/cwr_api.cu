@@ -39,6 +39,18 @@ struct cwr_handle {
     bool hint_done = false;          // the colours have been aligned with the flow (or it is too late to)
     int grid_sweep = 0, grid_gs = 0;
     int32_t* d_color_ptr = nullptr;
+    bool dc = false;                 // defect-correction solver (options.solver = 2) instead of BiCGSTAB
+    bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2)
+    int n_strips = 0;
+    int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
+    unsigned long long* d_strip_flag = nullptr;
+    unsigned long long gs_seq = 0;   // launches of the sweep kernel so far (epoch of the strip flags)
+    int last_cycles = 0;             // cycles of the previous defect-correction solve (launch-ahead prediction)
+    double* cur_x = nullptr;         // c[t+1] slot of the step being solved (the iterate)
+    int64_t sweeps_total = 0, fallbacks = 0;
+    // sparse real-cell overrides of one step, flattened for k_patch_rows
+    std::vector<long long> ov_idx; std::vector<double> ov_val;
+    long long* d_ov_idx = nullptr; double* d_ov_val = nullptr; size_t ov_cap = 0;
     // domain decomposition (world == 1: plain single-GPU handle)
     int rank = 0, world = 1;
     bool attached = false;           // peers' slabs are mapped (cwr_dd_attach)
@@ -238,6 +250,17 @@ static int upload_topology(cwr_handle* h) {
         CK(put(h, h->d_ext_ptr, tp.ext_ptr)); CK(put(h, h->d_ext_rows, tp.ext_rows));
         CK(put(h, h->d_lcolor_ptr, tp.lcolor_ptr)); CK(put(h, h->d_tile_ell, tp.tile_ell));
     }
+    if (h->strips) {
+        CK(put(h, h->d_strip_cptr, tp.strip_cptr)); CK(put(h, h->d_strip_nptr, tp.strip_nptr));
+        if (tp.strip_nbr.size() > h->strip_nbr_cap) {          // the neighbour lists depend on the ordering
+            CK(cudaStreamSynchronize(h->stream));
+            if (h->d_strip_nbr) CK(cudaFree(h->d_strip_nbr));
+            h->d_strip_nbr = nullptr;
+            h->strip_nbr_cap = tp.strip_nbr.size() + tp.strip_nbr.size() / 4 + 16;
+            CK(cudaMalloc((void**)&h->d_strip_nbr, h->strip_nbr_cap * sizeof(int32_t)));
+        }
+        CK(put(h, h->d_strip_nbr, tp.strip_nbr));
+    }
     CK(cudaStreamSynchronize(h->stream));
     return CWR_OK;
 }
@@ -255,6 +278,8 @@ static void set_owned_ranges(cwr_handle* h) {
     M.color_ptr = h->d_color_ptr + (size_t)r * (tp.n_colors + 1);
     M.ext_ptr = h->d_ext_ptr; M.ext_rows = h->d_ext_rows; M.lcolor_ptr = h->d_lcolor_ptr; M.tile_ell = h->d_tile_ell;
     M.n_tiles = h->tiled ? (int)tp.tile_ptr.size() - 1 : 0; M.max_ext = tp.max_ext;
+    M.strip_cptr = h->d_strip_cptr; M.strip_nptr = h->d_strip_nptr; M.strip_nbr = h->d_strip_nbr; M.strip_flag = h->d_strip_flag;
+    M.n_strips = h->strips ? h->n_strips : 0; M.strip0 = r * M.n_strips;
     unsigned nbr = 0;
     for (int32_t j = tp.send_ptr[r]; j < tp.send_ptr[r + 1]; ++j) nbr |= tp.send_mask[tp.send_rows[j]];
     M.nbr_mask = nbr;        // symmetric: whoever reads my rows owns rows I read
@@ -279,13 +304,14 @@ static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
     for (int e = 0; e < E; ++e) hint[e] = (float)mean[e];
     Topology t2;
     std::string terr = build_topology(h->n, h->F, E, h->f1_ref.data(), h->f2_ref.data(), h->opt.reorder != 0,
-                                      h->opt.precond_colors, hint.data(), h->world, t2);
+                                      h->opt.precond_colors, hint.data(), h->world, t2, 0, 0, 0, h->strips ? h->n_strips : 0);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
     if (h->attached) return CWR_OK;                 // peers already rely on the current ownership
     h->topo = std::move(t2);
+    int rc = upload_topology(h);                    // (may move the strip neighbour list)
     set_owned_ranges(h);
-    return upload_topology(h);
+    return rc;
 }
 
 // domain decomposition: this rank's boundary rows of a slab vector -> the ranks that read them, followed
@@ -314,12 +340,13 @@ int cwr_default_options(cwr_options* o) {
     o->hydro_capacity = 0;
     o->mass_flux = 1;
     o->solver_path = 0;
-    o->use_graph = 1;
+    o->solver = 0;
     o->check_every = 1;
     o->precond_steps = 0;
     o->precond_precision = 32;
     o->precond_sweep = 1;
     o->precond_colors = 0;
+    o->precond_sync = 0;
     return CWR_OK;
 }
 
@@ -333,6 +360,9 @@ void cwr_destroy(cwr_handle* h) {
     if (h->up_done) cudaEventDestroy(h->up_done);
     if (h->compute_mark) cudaEventDestroy(h->compute_mark);
     if (h->d_stage_up) cudaFree(h->d_stage_up);
+    if (h->d_strip_nbr) cudaFree(h->d_strip_nbr);
+    if (h->d_ov_idx) cudaFree(h->d_ov_idx);
+    if (h->d_ov_val) cudaFree(h->d_ov_val);
     for (void* p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
@@ -376,15 +406,6 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->tiled = h->opt.precond_sweep == 2 && !h->small_path && h->m_steps > 1;
     if (h->opt.precond_sweep == 2 && !h->tiled) FAIL(CWR_EINVAL, "precond_sweep = 2 (experimental tile-local sweeps) needs solver_path = 1 and precond_steps >= 2");
     if (h->tiled && h->world > 1) FAIL(CWR_EINVAL, "precond_sweep = 2 (experimental) is single-GPU only");
-    if (h->opt.precond_colors <= 0) {
-        // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
-        // bytes per row of one sweep = indices + values + three vectors in the sweep type
-        const double bytes = (double)n_real / std::max(1, h->opt.dd_world) * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
-        // (a colour's barrier also waits for the neighbour ranks of a domain decomposition: ~10 us, so 40 MB there)
-        h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / (h->opt.dd_world > 1 ? 40e6 : 20e6))));
-        if (tiny) h->opt.precond_colors = 12;       // on chip a colour costs a __syncthreads(): measured optimum on the Ohio-shaped mesh
-    }
-    h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) FAIL(CWR_ECUDA, "no CUDA device: this library has no CPU fallback");
@@ -395,6 +416,60 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     h->num_sms = prop.multiProcessorCount;
+    {   // lanes per row / columns per lane (128-bit packs), for the fp64 vectors and for the sweep type
+        const int K = n_const;
+        h->VEC = (K % 2 == 0) ? 2 : 1;
+        int kc = 1;
+        while (kc * h->VEC < K && kc < 32) kc <<= 1;
+        h->KC = kc;
+        const int vmax = h->sweep_f32 ? 4 : 2;
+        int sv = vmax;
+        while (sv > 1 && K % sv != 0) sv >>= 1;
+        int skc = 1;
+        while (skc * sv < K && skc < 32) skc <<= 1;
+        h->SVEC = sv; h->SKC = skc;
+    }
+    // solver: defect correction with the sweeps themselves where they are Gauss-Seidel sweeps, else BiCGSTAB
+    if (h->opt.solver != 1 && h->opt.solver != 2) h->opt.solver = h->gauss_seidel ? 2 : 1;
+    h->dc = h->opt.solver == 2 && !h->small_path && h->m_steps > 1;
+    if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
+    // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
+    if (h->opt.precond_sync != 1 && h->opt.precond_sync != 2) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 2;
+    if (h->opt.precond_sync == 2 && h->opt.dd_halo_per_colour)
+        FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
+    h->strips = h->gauss_seidel && h->opt.precond_sync == 2;
+    if (h->gauss_seidel) {
+        int occ_gs = 0, coop = 0;
+        if (h->strips) {
+            SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
+            SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC, true>, kGsThreads, kGsSmemBytes));
+        } else {
+            SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
+            SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC, false>, kGsThreads, kGsSmemBytes));
+        }
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        if (!coop || occ_gs < 1) FAIL(CWR_ECUDA, "cooperative launch not available: use precond_sweep = 0");
+        h->grid_gs = h->num_sms * occ_gs;      // every CTA resident: the kernel synchronises between CTAs
+        // a strip needs rows of every colour for every lane group to be worth a CTA: small meshes get fewer strips
+        const int rows_rank = n_real / std::max(1, h->opt.dd_world);
+        h->n_strips = std::max(1, std::min(h->grid_gs, rows_rank / 512));
+        if (h->strips) h->grid_gs = h->n_strips;
+    }
+    if (h->opt.precond_colors <= 0 && h->strips) {
+        // one colour of a strip = one pass of the CTA: kGsRows rows per lane group (the pipelined rows of k_precond_gs)
+        const double rows_strip = (double)n_real / std::max(1, h->opt.dd_world) / h->n_strips;
+        const int per_pass = kGsRows * (kGsThreads / h->SKC);
+        h->opt.precond_colors = (int)std::min(48.0, std::max(8.0, std::ceil(rows_strip * 1.15 / per_pass)));
+    }
+    if (h->opt.precond_colors <= 0) {
+        // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
+        // bytes per row of one sweep = indices + values + three vectors in the sweep type
+        const double bytes = (double)n_real / std::max(1, h->opt.dd_world) * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
+        // (a colour's barrier also waits for the neighbour ranks of a domain decomposition: ~10 us, so 40 MB there)
+        h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / (h->opt.dd_world > 1 ? 40e6 : 20e6))));
+        if (tiny) h->opt.precond_colors = 12;       // on chip a colour costs a __syncthreads(): measured optimum on the Ohio-shaped mesh
+    }
+    h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
     int tile_rows = 0, tile_cap = 0;
@@ -407,29 +482,18 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
                                       (h->gauss_seidel || h->tiny || h->tiled) ? h->opt.precond_colors : 0,
                                       (h->gauss_seidel || h->tiny || h->tiled) ? flow_hint : nullptr, h->world, h->topo,
-                                      tile_rows, tile_cap, 4);
+                                      tile_rows, tile_cap, 4, h->strips ? h->n_strips : 0);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (flow_hint || h->tiled) h->hint_done = true;     // (the tile arrays' sizes depend on the order: no re-ordering later)
     const Topology& tp = h->topo;
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
     h->C = (h->opt.hydro_capacity <= 0 || h->opt.hydro_capacity > T) ? T : std::max(2, h->opt.hydro_capacity);
-    h->VEC = (K % 2 == 0) ? 2 : 1;
-    int kc = 1;
-    while (kc * h->VEC < K && kc < 32) kc <<= 1;
-    h->KC = kc;
-    {   // sweep lanes: 128-bit packs of the sweep type
-        const int vmax = h->sweep_f32 ? 4 : 2;
-        int sv = vmax;
-        while (sv > 1 && K % sv != 0) sv >>= 1;
-        int skc = 1;
-        while (skc * sv < K && skc < 32) skc <<= 1;
-        h->SVEC = sv; h->SKC = skc;
-    }
+    const int kc = h->KC;
     h->max_grid = h->num_sms * 8;
     // persistent single-wave grids: SM count x resident CTAs per SM of the kernel that owns the grid
     {
-        int occ_spmm = 4, occ_xrp = 3, occ_gs = 0;
+        int occ_spmm = 4, occ_xrp = 3;
         KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_spmm, k_spmm<KC, VEC, MODE_AT, double>, kThreads, 0));
         KC_DISPATCH(h->KC, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_xrp, k_update_xrp<KC, VEC, double>, kThreads, 0));
         const int n_own = tp.part_ptr[h->rank + 1] - tp.part_ptr[h->rank];
@@ -439,16 +503,6 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         h->grid_spmm = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_av));
         h->grid_xrp = grid_for(n_own, kThreads / kc, h->num_sms * std::max(1, occ_xrp));
         h->grid_sweep = grid_for(n_own, kThreads / h->SKC, h->num_sms * CWR_SPMM_MIN_BLOCKS);
-        if (h->gauss_seidel) {
-            SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
-            SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC>, kGsThreads, kGsSmemBytes));
-            int coop = 0;
-            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
-            if (!coop || occ_gs < 1) FAIL(CWR_ECUDA, "cooperative launch not available: use precond_sweep = 0");
-            // every CTA must be resident (grid barrier): SM count x occupancy, and no more CTAs than the
-            // largest colour has row groups
-            h->grid_gs = h->num_sms * occ_gs;      // every CTA resident: the kernel synchronises grid-wide
-        }
     }
     if (h->tiny) {
         const size_t need = tiny_smem_bytes(n, tp.W);
@@ -474,6 +528,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     CK(dalloc(h, &h->d_new_of_old, (size_t)n)); CK(dalloc(h, &h->d_old_of_new, (size_t)n));
     CK(dalloc(h, &h->d_color_ptr, tp.color_ptr.size()));
     CK(dalloc(h, &h->d_send_mask, (size_t)n)); CK(dalloc(h, &h->d_send_rows, (size_t)n));
+    if (h->strips) {
+        CK(dalloc(h, &h->d_strip_cptr, tp.strip_cptr.size())); CK(dalloc(h, &h->d_strip_nptr, tp.strip_nptr.size()));
+        CK(dalloc(h, &h->d_strip_flag, (size_t)h->n_strips));
+        CK(cudaMemsetAsync(h->d_strip_flag, 0, (size_t)h->n_strips * sizeof(unsigned long long), h->stream));
+    }
     if (h->tiled) {
         CK(dalloc(h, &h->d_ext_ptr, tp.ext_ptr.size())); CK(dalloc(h, &h->d_ext_rows, tp.ext_rows.size()));
         CK(dalloc(h, &h->d_lcolor_ptr, tp.lcolor_ptr.size())); CK(dalloc(h, &h->d_tile_ell, tp.tile_ell.size()));
@@ -528,13 +587,18 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     double* ic = nullptr;
     CK(dalloc(h, &ic, nK)); CK(cudaMemsetAsync(ic, 0, nK * sizeof(double), h->stream));
     M.ic = ic;
-    CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK)); CK(dalloc(h, &M.rhat, nK));
-    CK(dalloc(h, &M.p, nK)); CK(dalloc(h, &M.v, nK)); CK(dalloc(h, &M.tt, nK));
-    // t is multiplied by omega = 0 when a solve ends at a half step before t = A s^ was ever formed: keep it finite
-    CK(cudaMemsetAsync(M.tt, 0, nK * sizeof(double), h->stream)); CK(cudaMemsetAsync(M.v, 0, nK * sizeof(double), h->stream));
+    CK(dalloc(h, &M.b, nK)); CK(dalloc(h, &M.r, nK));
+    CK(cudaMemsetAsync(M.b, 0, nK * sizeof(double), h->stream)); CK(cudaMemsetAsync(M.r, 0, nK * sizeof(double), h->stream));
+    {   // the Krylov vectors (the defect-correction solver only needs them if it ever falls back: allocated either way,
+        // 4 x 128 MB at 1M x 16 of 180 GB); all zeroed: t is multiplied by omega = 0 when a solve ends at a half step
+        // before t = A s^ was ever formed, and no kernel may ever gather uninitialised rows
+        double** vs[] = {&M.rhat, &M.p, &M.v, &M.tt};
+        for (double** v : vs) { CK(dalloc(h, v, nK)); CK(cudaMemsetAsync(*v, 0, nK * sizeof(double), h->stream)); }
+    }
     if (need_precond_vectors) {
         double* us;
         CK(dalloc(h, &us, nK));
+        CK(cudaMemsetAsync(us, 0, nK * sizeof(double), h->stream));
         M.ph = h->d_slab + kDdCtlBytes; M.sh = h->d_slab + kDdCtlBytes + vec_bytes; M.tmp = h->d_slab + kDdCtlBytes + 2 * vec_bytes;
         M.us = us;
         if (h->sweep_f32 && !h->small_path) CK(dalloc(h, &M.valf, (size_t)n * tp.W));
@@ -559,6 +623,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(dalloc(h, &M.bsum, (size_t)3 * std::max(1, tp.E_g) * K));
         CK(cudaMemsetAsync(M.bsum, 0, (size_t)3 * std::max(1, tp.E_g) * K * sizeof(double), h->stream));
     }
+    M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
     M.tol2 = h->opt.rtol * h->opt.rtol;
     M.diffusion_coefficient = D;
     M.max_iter = h->opt.max_iter;
@@ -855,7 +920,7 @@ static int poll(cwr_handle* h) {
 // z = M^-1 u with m - 1 sweeps, result in `dst` (sweep type); returns u itself when m == 1.
 //   Jacobi:        z_1 = u + N u, z_{j+1} = u + N z_j  (N = I - D^-1 A)  =>  z = (I + N + ... + N^(m-1)) u
 //   Gauss-Seidel:  the same first step, then m - 2 in-place multicolour sweeps (one launch per colour)
-static const void* precondition(cwr_handle* h, const double* u, void* dst, void* other) {
+static const void* precondition(cwr_handle* h, const double* u, void* dst, void* other, bool planned = false) {
     const int J = h->m_steps - 1;
     if (J <= 0) return u;
     DeviceModel& M = h->M;
@@ -867,10 +932,12 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
     }
     if (h->gauss_seidel) {
         mark(h, CWR_FAM_PRECOND);
-        int sweeps = J;
-        void* args[] = {(void*)&M, (void*)&u, (void*)&dst, (void*)&sweeps};
+        int sweeps = planned ? 0 : J;                 // 0: the count the defect-correction solver planned on the device
+        unsigned long long seq = ++h->gs_seq;
+        void* args[] = {(void*)&M, (void*)&u, (void*)&dst, (void*)&sweeps, (void*)&seq};
         cudaError_t e = cudaSuccess;
-        SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream));
+        if (h->strips) { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, true>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
+        else { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, false>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
         if (e != cudaSuccess) h->err = std::string("k_precond_gs: ") + cudaGetErrorString(e);
         h->launches += 1;
         return dst;
@@ -935,6 +1002,8 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
             // restart from the current iterate: new shadow residual (standard cure for rho ~ 0)
             ++restarts;
             CK(cudaMemsetAsync(&M.ctl->all_done, 0, 2 * sizeof(int), h->stream));   // all_done, iter
+            // domain decomposition: the new residual gathers the neighbours' rows of the CURRENT iterate
+            { int rch = halo_push(h, h->cur_x); if (rch) return rch; }
             continue;
         }
         break;
@@ -964,6 +1033,77 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
         if (dd_timeout) { h->err = "a peer rank did not answer (halo barrier / dot-product exchange timed out)"; return CWR_ECUDA; }
     }
     if (info) { info->iterations = total_iter; info->restarts = restarts; info->status = status; info->max_relres = worst; }
+    return status;
+}
+
+// Defect correction with the preconditioner sweeps as the solver (options.solver = 2):
+//   r = b - A x0;  repeat { z = M^-1 r (fp32 Gauss-Seidel sweeps from 0);  x += z;  r -= A z }  until ||r|| <= rtol ||b||
+// Gauss-Seidel sweeps on A z = r from z = 0 followed by x += z ARE Gauss-Seidel sweeps on A x = b: the cycle only
+// exists to carry the residual and the iterate in fp64 around sweeps that run in fp32.  On the upwind M-matrices of
+// this problem the flow-aligned sweeps contract the error by ~0.2 each, Krylov acceleration adds nothing, and the
+// solve needs neither the Krylov vectors' traffic nor their dot products: one reduction per cycle, for the
+// convergence test.  The sweeps per cycle are planned on the device (dc_plan); the cycles of the previous solve are
+// queued before the first poll, every kernel of a cycle returns at once when all_done is set.
+// Returns 1 when the sweeps stagnate or diverge (the matrix is not what the sweeps assume): the caller restores
+// x0 and solves with BiCGSTAB.
+static int solve_dc(cwr_handle* h, cwr_step_info* info, bool* fell_back) {
+    DeviceModel& M = h->M;
+    *fell_back = false;
+    mark(h, CWR_FAM_SPMM_INIT);
+    KC_DISPATCH(h->KC, (k_spmm<KC, VEC, MODE_INIT_DC, double><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, nullptr, nullptr)));
+    h->launches += 1;
+    mark(h, -1);
+    int ahead = std::max(1, h->last_cycles);
+    h->h_ctl->all_done = 0;
+    int rc = CWR_OK;
+    int launched = 0;
+    while (!h->h_ctl->all_done) {
+        const int burst = ahead > 0 ? ahead : h->opt.check_every;
+        ahead = 0;
+        for (int i = 0; i < burst; ++i) {
+            const void* z = precondition(h, M.r, M.ph, M.tmp, true);
+            mark(h, CWR_FAM_DC_UPDATE);
+            PT_DISPATCH((k_spmm<KC, VEC, MODE_DC, PT><<<h->grid_spmm, kThreads, 0, h->stream>>>(M, (const PT*)z, nullptr)));
+            h->launches += 1;
+            ++launched;
+        }
+        mark(h, -1);
+        rc = poll(h);
+        if (rc) return rc;
+        if (launched > h->opt.max_iter + 8) break;       // (the device sets hit_max_iter long before)
+    }
+    CK(cudaGetLastError());
+    h->last_cycles = h->h_ctl->iter;
+    h->sweeps_total += h->h_ctl->sweeps_done;
+    if (h->h_ctl->barrier_timeout) { h->err = "a sweep-kernel barrier timed out"; return CWR_ECUDA; }
+    if (h->h_ctl->dc_fail) { *fell_back = true; return CWR_OK; }
+    if (h->h_ctl->flags_or & FL_PENDING) {          // NaN right-hand sides / b == 0: fill those columns
+        k_fix_columns<<<grid_for((int64_t)(M.row_hi - M.row_lo) * h->K, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+        k_fix_flags<<<1, 128, 0, h->stream>>>(M);
+        h->launches += 2;
+    }
+    CK(cudaMemcpyAsync(h->h_sc, M.sc, (size_t)SC_ROWS * h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_flags, M.colflags, h->K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->iterations += h->h_ctl->iter;
+    int status = CWR_OK;
+    double worst = 0.0;
+    for (int k = 0; k < h->K; ++k) {
+        const double bb = h->h_sc[SC_BNORM2 * h->K + k], rr = h->h_sc[SC_RNORM2 * h->K + k];
+        const double rel = bb > 0 ? std::sqrt(rr / bb) : (rr > 0 ? INFINITY : 0.0);
+        if (rel == rel) worst = std::max(worst, rel);
+        const int f = h->h_flags[k];
+        if (f & FL_NAN) status = CWR_ENAN;
+        else if (!(f & FL_CONVERGED) && status == CWR_OK) status = CWR_ENOTCONVERGED;
+    }
+    if (h->h_ctl->singular) status = CWR_ESINGULAR;
+    if (h->world > 1) {
+        int dd_timeout = 0;
+        CK(cudaMemcpyAsync(&dd_timeout, &h->M.dd->timeout, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (dd_timeout) { h->err = "a peer rank did not answer (halo barrier / dot-product exchange timed out)"; return CWR_ECUDA; }
+    }
+    if (info) { info->iterations = h->h_ctl->iter; info->restarts = 0; info->status = status; info->max_relres = worst; info->sweeps = h->h_ctl->sweeps_done; }
     return status;
 }
 
@@ -1010,6 +1150,54 @@ static int find_slot(cwr_handle* h, int t) {
     return h->slot_time[s] == t ? s : -1;
 }
 
+// sparse real-cell entries of input_array[t] (rare): one upload + one kernel for all constituents
+static int patch_real_cells(cwr_handle* h, int t, int before_solve) {
+    DeviceModel& M = h->M;
+    h->ov_idx.clear(); h->ov_val.clear();
+    for (int k = 0; k < h->K; ++k) {
+        auto it = h->real_overrides[k].find(t);
+        if (it == h->real_overrides[k].end()) continue;
+        for (auto& cv : it->second)
+            if (cv.first >= M.row_lo && cv.first < M.row_hi) {      // (another rank's rows are that rank's business)
+                h->ov_idx.push_back((long long)cv.first * h->K + k);
+                h->ov_val.push_back(cv.second);
+            }
+    }
+    const size_t cnt = h->ov_idx.size();
+    if (cnt == 0) return CWR_OK;
+    if (cnt > h->ov_cap) {
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->d_ov_idx) CK(cudaFree(h->d_ov_idx));
+        if (h->d_ov_val) CK(cudaFree(h->d_ov_val));
+        h->d_ov_idx = nullptr; h->d_ov_val = nullptr;
+        h->ov_cap = cnt + cnt / 2 + 64;
+        CK(cudaMalloc((void**)&h->d_ov_idx, h->ov_cap * sizeof(long long)));
+        CK(cudaMalloc((void**)&h->d_ov_val, h->ov_cap * sizeof(double)));
+    }
+    // pageable sources: the copies have left the host vectors when the calls return
+    CK(cudaMemcpyAsync(h->d_ov_idx, h->ov_idx.data(), cnt * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_ov_val, h->ov_val.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    k_patch_rows<<<grid_for((int64_t)cnt, kThreads, 64), kThreads, 0, h->stream>>>(M, h->d_ov_idx, h->d_ov_val, (int)cnt, before_solve);
+    h->launches += 1;
+    return CWR_OK;
+}
+
+// b and the warm start x0 = c~ of step t (after the LHS: b is row-scaled by the diagonal), then x0's boundary rows to
+// the ranks that gather them
+static int build_rhs(cwr_handle* h, int t) {
+    DeviceModel& M = h->M;
+    mark(h, CWR_FAM_RHS);
+    KC_DISPATCH(h->KC, (k_rhs<KC, VEC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
+    h->launches += 1;
+    int rc = patch_real_cells(h, t, 1);
+    if (rc) return rc;
+    if (M.b_hi - M.b_lo > 0) {
+        k_boundary_rhs<<<h->grid_b, kThreads, 0, h->stream>>>(M);
+        h->launches += 1;
+    }
+    return halo_push(h, h->cur_x);      // x0 = c~: the first residual gathers the neighbours' rows
+}
+
 int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     if (!h) return CWR_EINVAL;
     if (t < 0 || t + 1 >= h->T) FAIL(CWR_EINVAL, "cwr_step: t must satisfy 0 <= t < n_time - 1 (dt[n_time-1] is NaN)");
@@ -1033,54 +1221,37 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
     DeviceModel& M = h->M;
     k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl);
+    h->cur_x = p.state_t1;
     mark(h, CWR_FAM_ASSEMBLE);
     if (h->world > 1 && !h->attached) FAIL(CWR_EINVAL, "domain-decomposed handle: call cwr_dd_attach before stepping");
     const int nb_own = M.b_hi - M.b_lo;
     if (nb_own > 0) k_boundary_diag<<<grid_for(nb_own, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
     k_assemble<<<grid_for(M.row_hi - M.row_lo, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
-    mark(h, CWR_FAM_RHS);
-    KC_DISPATCH(h->KC, (k_rhs<KC, VEC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
-    h->launches += 3 + (nb_own > 0);
-    // sparse real-cell overrides of c~ (input_array[t][real cell] != 0 at t >= 1): recompute those rows
-    for (int k = 0; k < K; ++k) {
-        auto it = h->real_overrides[k].find(t);
-        if (it == h->real_overrides[k].end()) continue;
-        // applied through the state + a second k_rhs pass restricted by value: simplest faithful form is to
-        // patch c~ in place on a scratch copy of c[t]; since c[t] itself must stay untouched (the reference
-        // only patches its temporary `solver` array), patch state_t1 and b directly on the host side values.
-        std::vector<double> conc(1), dummy;
-        for (auto& cv : it->second) {
-            if (cv.first < M.row_lo || cv.first >= M.row_hi) continue;      // another rank's row
-            const size_t idx = (size_t)cv.first * K + k;
-            float vol; double diag;
-            CK(cudaMemcpyAsync(&vol, p.vol_t + cv.first, 4, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaMemcpyAsync(&diag, M.diag + cv.first, 8, cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-            const double b = ((double)vol * cv.second / p.dt) / diag;
-            CK(cudaMemcpyAsync(M.b + idx, &b, 8, cudaMemcpyHostToDevice, h->stream));
-            CK(cudaMemcpyAsync(p.state_t1 + idx, &cv.second, 8, cudaMemcpyHostToDevice, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-        }
-    }
-    if (nb_own > 0) {
-        k_boundary_rhs<<<h->grid_b, kThreads, 0, h->stream>>>(M);
-        h->launches += 1;
-    }
+    h->launches += 2 + (nb_own > 0);
     h->lhs_step = t;
-    { int rc = halo_push(h, p.state_t1); if (rc) return rc; }      // x0 = c~: the first residual gathers the neighbours' rows
-    cwr_step_info local;
-    int status = h->small_path ? solve_small(h, &local) : solve(h, &local);
+    { int rc = build_rhs(h, t); if (rc) return rc; }
+    cwr_step_info local{};
+    int status;
+    if (h->small_path) status = solve_small(h, &local);
+    else if (h->dc) {
+        bool fell_back = false;
+        status = solve_dc(h, &local, &fell_back);
+        if (fell_back) {
+            // the sweeps did not contract (not the M-matrix they assume): start again from c~ with BiCGSTAB
+            ++h->fallbacks;
+            const int cycles = h->h_ctl->iter, sweeps = h->h_ctl->sweeps_done;
+            CK(cudaMemsetAsync(&M.ctl->all_done, 0, 2 * sizeof(int), h->stream));   // all_done, iter
+            h->last_iters = 0;
+            { int rc = build_rhs(h, t); if (rc) return rc; }
+            status = solve(h, &local);
+            local.restarts += 1 + cycles;
+            local.sweeps = sweeps;
+        }
+    } else status = solve(h, &local);
     if (status == CWR_ECUDA) return status;
     // transport.py:258-264: non-zero input_array[t+1] entries are re-imposed on the stored row -- ghost cells
     // are handled where they are read (k_mass_flux, k_extract_state); real cells (rare) are patched here.
-    for (int k = 0; k < K; ++k) {
-        auto it = h->real_overrides[k].find(t + 1);
-        if (it == h->real_overrides[k].end()) continue;
-        for (auto& cv : it->second)
-            if (cv.first >= M.row_lo && cv.first < M.row_hi)
-                CK(cudaMemcpyAsync(p.state_t1 + (size_t)cv.first * K + k, &cv.second, 8, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-    }
+    { int rc = patch_real_cells(h, t + 1, 0); if (rc) return rc; }
     // c[t+1] of the neighbours' boundary rows: the mass flux of a cut edge and the next cwr_get_state read them
     { int rc = halo_push(h, p.state_t1); if (rc) return rc; }
     if (M.want_flux) {
@@ -1445,12 +1616,31 @@ int cwr_tile_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const
     return CWR_OK;
 }
 
+int cwr_strip_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
+                     int n_parts, int n_strips, int* n_colors_out, int* nbr_total, int32_t* new_of_old, int32_t* strip_cptr,
+                     int32_t* strip_nptr, int32_t* strip_nbr, uint8_t* color_of) {
+    if (!f1 || !f2) return CWR_EINVAL;
+    Topology t;
+    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, std::max(1, n_parts), t, 0, 0, 0, n_strips);
+    if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
+    if (n_colors_out) *n_colors_out = t.n_colors;
+    if (nbr_total) *nbr_total = (int)t.strip_nbr.size();
+    if (new_of_old) std::copy(t.new_of_old.begin(), t.new_of_old.end(), new_of_old);
+    if (strip_cptr) std::copy(t.strip_cptr.begin(), t.strip_cptr.end(), strip_cptr);
+    if (strip_nptr) std::copy(t.strip_nptr.begin(), t.strip_nptr.end(), strip_nptr);
+    if (strip_nbr) std::copy(t.strip_nbr.begin(), t.strip_nbr.end(), strip_nbr);
+    if (color_of) std::copy(t.color_of.begin(), t.color_of.end(), color_of);
+    return CWR_OK;
+}
+
 int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     if (!h || !out) return CWR_EINVAL;
     *out = h->opt;
     out->precond_colors = (h->gauss_seidel || h->tiny) ? h->topo.n_colors : 0;
     out->precond_sweep = h->tiled ? 2 : ((h->gauss_seidel || h->tiny) ? 1 : 0);
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
+    out->solver = h->dc ? 2 : 1;
+    out->precond_sync = h->gauss_seidel ? (h->strips ? 2 : 1) : 0;
     return CWR_OK;
 }
 
@@ -1464,6 +1654,15 @@ int cwr_counters(cwr_handle* h, int64_t* launches, int64_t* iterations) {
     if (!h) return CWR_EINVAL;
     if (launches) *launches = h->launches;
     if (iterations) *iterations = h->iterations;
+    return CWR_OK;
+}
+
+int cwr_solver_stats(cwr_handle* h, int64_t* sweeps, int64_t* fallbacks, int* n_strips, int* max_strip_neighbours) {
+    if (!h) return CWR_EINVAL;
+    if (sweeps) *sweeps = h->sweeps_total;
+    if (fallbacks) *fallbacks = h->fallbacks;
+    if (n_strips) *n_strips = h->strips ? h->n_strips : 0;
+    if (max_strip_neighbours) *max_strip_neighbours = h->strips ? h->topo.max_strip_nbr : 0;
     return CWR_OK;
 }
 

@@ -58,6 +58,13 @@ struct SolverCtl {
     unsigned ticket_s;    // k_update_s
     int finish_half;      // every active column converged at the half step: skip the sweeps on s and t = A s^
     unsigned gs_bar[2]; // k_precond_gs: grid barrier arrivals, exits
+    // defect-correction solver (solver = 2): x += GS^S(r), r -= A z, with S planned on the device after every cycle
+    int dc_sweeps;        // sweeps of the next cycle
+    int dc_fail;          // the sweeps stagnate or diverge (not an M-matrix?): the host falls back to BiCGSTAB
+    int dc_slow;          // consecutive cycles that reduced the residual by less than 0.7
+    int sweeps_done;      // Gauss-Seidel sweeps of this solve
+    double dc_rate;       // error factor per sweep measured over the last cycle (kept across steps)
+    double dc_worst;      // max over columns of (||r|| / ||b||) / rtol after the last cycle
 };
 
 constexpr int kMaxRanks = 8;
@@ -94,6 +101,12 @@ struct DeviceModel {
     // tile-local sweeps (EXPERIMENTAL, precond_sweep = 2; cwr_topology.h)
     const int32_t* ext_ptr; const int32_t* ext_rows; const int32_t* lcolor_ptr; const uint16_t* tile_ell;
     int n_tiles, max_ext;
+    // strips of the neighbour-synchronised Gauss-Seidel kernel (cwr_topology.h): CTA b owns strip strip0 + b
+    const int32_t* strip_cptr; const int32_t* strip_nptr; const int32_t* strip_nbr;
+    unsigned long long* strip_flag;   // (n_strips) last step a strip has finished: (launch sequence << 20) | (step + 1)
+    int n_strips, strip0;
+    int dc_smin, dc_smax;             // sweeps per defect-correction cycle: bounds of the device-side plan
+    double dc_floor;                  // largest residual reduction one cycle can deliver in the sweep precision
     double* val;        // (n,W) off-diagonals of D^-1 A
     float* valf;        // (n,W) the same in fp32 (fp32 preconditioner sweeps), or nullptr
     double* diag;       // (n)   D
@@ -121,6 +134,7 @@ struct DeviceModel {
 __global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl) {
     *dst = p;
     ctl->all_done = 0; ctl->iter = 0; ctl->flags_or = 0; ctl->hit_max_iter = 0; ctl->finish_half = 0;
+    ctl->singular = 0; ctl->dc_fail = 0; ctl->dc_slow = 0; ctl->sweeps_done = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -349,6 +363,19 @@ __global__ void __launch_bounds__(kThreads) k_rhs(DeviceModel M) {
             stv<VEC>(M.b + idx, bb);
             stv<VEC>(sp.state_t1 + idx, conc);
         }
+}
+
+// Sparse real-cell entries of input_array at t >= 1 (rare): before the solve they replace c~ where non-zero
+// (linalg.py:199-200: state and load term recomputed; k_boundary_rhs, which runs afterwards, adds the ghost terms),
+// after it they are re-imposed on the stored row (transport.py:258-264).  idx = row * K + column, device order.
+__global__ void k_patch_rows(DeviceModel M, const long long* __restrict__ idx, const double* __restrict__ val, int count, int before_solve) {
+    const StepParams& sp = *M.sp;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
+        const long long i = idx[q];
+        const int row = (int)(i / M.K);
+        sp.state_t1[i] = val[q];
+        if (before_solve) M.b[i] = ((double)sp.vol_t[row] * val[q] / sp.dt) / M.diag[row];
+    }
 }
 
 // Boundary cells: b_i = load + ghost_in + ghost_out with the reference's selection and
@@ -613,8 +640,15 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_sweep(DeviceM
             const Pk<ST, 4> v = vn;
             Pk<ST, VEC> x0, x1, x2, x3, own;
             if (FIRST) {
-                const Pk<double, VEC> d0 = ldk<double, VEC>(u64 + (size_t)c4.x * K + c), d1 = ldk<double, VEC>(u64 + (size_t)c4.y * K + c);
-                const Pk<double, VEC> d2 = ldk<double, VEC>(u64 + (size_t)c4.z * K + c), d3 = ldk<double, VEC>(u64 + (size_t)c4.w * K + c);
+                // u is one of the solver's own vectors: under domain decomposition only this rank's rows of it exist,
+                // the other ranks' rows count as 0 in this first step (their z arrives with the halo push that follows)
+                const bool dd = M.world > 1;
+                const int lo = M.row_lo, hi = M.row_hi;
+                const Pk<double, VEC> dz = {};
+                const Pk<double, VEC> d0 = dd && (c4.x < lo || c4.x >= hi) ? dz : ldk<double, VEC>(u64 + (size_t)c4.x * K + c);
+                const Pk<double, VEC> d1 = dd && (c4.y < lo || c4.y >= hi) ? dz : ldk<double, VEC>(u64 + (size_t)c4.y * K + c);
+                const Pk<double, VEC> d2 = dd && (c4.z < lo || c4.z >= hi) ? dz : ldk<double, VEC>(u64 + (size_t)c4.z * K + c);
+                const Pk<double, VEC> d3 = dd && (c4.w < lo || c4.w >= hi) ? dz : ldk<double, VEC>(u64 + (size_t)c4.w * K + c);
                 const Pk<double, VEC> dn = ldk<double, VEC>(u64 + idx);
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {
@@ -642,7 +676,8 @@ __global__ void __launch_bounds__(kThreads, CWR_SPMM_MIN_BLOCKS) k_sweep(DeviceM
                 for (int u = 0; u < 4; ++u) {
                     Pk<ST, VEC> y;
                     if (FIRST) {
-                        const Pk<double, VEC> d = ldk<double, VEC>(u64 + (size_t)cs[u] * K + c);
+                        Pk<double, VEC> d = {};
+                        if (!(M.world > 1 && (cs[u] < M.row_lo || cs[u] >= M.row_hi))) d = ldk<double, VEC>(u64 + (size_t)cs[u] * K + c);
 #pragma unroll
                         for (int q = 0; q < VEC; ++q) y.a[q] = (ST)d.a[q];
                     } else y = ldk<ST, VEC>(z + (size_t)cs[u] * K + c);
@@ -724,29 +759,57 @@ __device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) 
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-template <typename ST, int KC, int VEC>
-__global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, const double* __restrict__ u64, ST* z, int n_sweeps) {
+// STRIP = false: rows colour-major (color_ptr), lane groups dealt grid-wide, a GRID barrier between colours.
+// STRIP = true (precond_sync = 2): rows strip-major -- CTA b owns the contiguous strip strip0 + b, colour-major
+// inside (strip_cptr) -- and a colour only waits for the strips this strip's rows are coupled to (strip_nbr; two
+// or three of them when the strips are cut from the RCM order): every CTA publishes (launch sequence, step)
+// in strip_flag after a step and polls its neighbours' flags before the next one.  A CTA is then never more
+// than one step ahead of a strip it exchanges values with, which orders exactly the reads and writes the grid
+// barrier ordered -- the results are bit-identical to the grid-barrier sweep over the same colours -- but a
+// step costs one release/acquire between neighbours instead of a device-wide rendezvous, and slow CTAs only
+// hold up their neighbours.  n_sweeps <= 0: the count is read from ctl->dc_sweeps (planned on the device by the
+// defect-correction solver).
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr int kMaxColors = 64;
+
+template <typename ST, int KC, int VEC, bool STRIP>
+__global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, const double* __restrict__ u64, ST* z, int n_sweeps_arg,
+                                                              unsigned long long seq) {
     constexpr bool SMEM = sizeof(ST) * VEC == 16;
     constexpr int NR = kGsRows;
     extern __shared__ int4 gs_land[];          // [NR rows][4 neighbours][kGsThreads] landing slots (SMEM path)
+    __shared__ int s_cp[kMaxColors + 1];       // row ranges of the colours this CTA sweeps
     if (M.ctl->all_done || M.ctl->finish_half) return;
+    const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
     const int K = M.K, W = M.W, nc = M.n_colors;
     const int vb = blockIdx.x, nvb = gridDim.x, c_end = K;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kGsThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
     const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
     ST* us = reinterpret_cast<ST*>(M.us);
-    const int TG = nvb * GPB, gid = vb * GPB + group;
+    // lane groups that share a colour's rows, and this group's position among them
+    const int TG = STRIP ? GPB : nvb * GPB, gid = STRIP ? group : vb * GPB + group;
+    const int sid = M.strip0 + vb;                                          // STRIP: the strip this CTA owns
+    const int32_t* __restrict__ cp_src = STRIP ? M.strip_cptr + (size_t)sid * (nc + 1) : M.color_ptr;
+    for (int q = threadIdx.x; q <= nc; q += kGsThreads) s_cp[q] = cp_src[q];
+    const int nb0 = STRIP ? M.strip_nptr[sid] : 0, n_nbr = STRIP ? M.strip_nptr[sid + 1] - nb0 : 0;
+    __syncthreads();
     const int c = lane * VEC;
     const bool lane_on = c < c_end;
     const int n_steps = n_sweeps * nc;
     unsigned epoch = 0;
     const bool multi = M.world > 1;
     // Several ranks: either every finished boundary row goes to its readers at once and every colour's barrier is
-    // a halo barrier (exact multi-rank Gauss-Seidel), or (halo_per_sweep, default) the boundary rows cross once at
-    // the end of each sweep: within a sweep the neighbours' rows are one sweep old (zero in the first sweep) --
-    // Gauss-Seidel inside a strip, Jacobi across strips -- and only one barrier per sweep waits for NVLink.
-    const bool per_sweep = multi && M.halo_per_sweep, per_colour = multi && !M.halo_per_sweep;
+    // a halo barrier (exact multi-rank Gauss-Seidel; grid-barrier kernel only), or (halo_per_sweep, default) the
+    // boundary rows cross once at the end of each sweep: within a sweep the neighbours' rows are one sweep old (zero
+    // in the first sweep) -- Gauss-Seidel inside a rank's rows, Jacobi across ranks -- and only one barrier per sweep
+    // waits for NVLink.
+    const bool per_sweep = multi && (STRIP || M.halo_per_sweep), per_colour = multi && !per_sweep;
     const int row_lo = M.row_lo, row_hi = M.row_hi;
     const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;     // halo epochs continue where the last kernel stopped
     unsigned long long xe = 0;                                         // halo barriers of this launch
@@ -775,7 +838,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     int4 pc[NR]; Pk<ST, 4> pv[NR];
     auto prefetch = [&](int step) {
         const int col = step % nc;
-        const int rb = __ldg(M.color_ptr + col), re = __ldg(M.color_ptr + col + 1);
+        const int rb = s_cp[col], re = s_cp[col + 1];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const int i = rb + gid + r * TG;
@@ -784,6 +847,26 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
                 pv[r] = ldk<ST, 4>(eval + (size_t)i * W);
             }
         }
+    };
+    // STRIP: this strip has finished `step` (all of the CTA's stores, then the flag) / wait until the
+    // neighbouring strips have
+    auto publish = [&](int step) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_flag(M.strip_flag + vb, (seq << 20) | (unsigned long long)(step + 1));
+        }
+    };
+    auto wait_nbrs = [&](int step) {
+        const unsigned long long target = (seq << 20) | (unsigned long long)(step + 1);
+        for (int j = threadIdx.x; j < n_nbr; j += kGsThreads) {
+            const unsigned long long* f = M.strip_flag + (M.strip_nbr[nb0 + j] - M.strip0);
+            unsigned spins = 0;
+            const unsigned limit = *reinterpret_cast<volatile int*>(&M.ctl->barrier_timeout) ? 0u : (1u << 26);
+            while (ld_acquire_u64(f) < target)
+                if (++spins > limit) { M.ctl->barrier_timeout = 1; break; }      // never hang the device
+        }
+        __syncthreads();
     };
     // one row, columns [cc, cc + VEC): remaining ELL blocks through registers, then the update and the store
     auto relax_tail = [&](int i, int cc, int w0, Pk<ST, VEC> acc, const Pk<ST, VEC>& own, bool first_sweep) {
@@ -819,7 +902,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     for (int step = 0; step < n_steps; ++step) {
         const int col = step % nc;
         const bool first_sweep = step < nc;
-        const int rb = __ldg(M.color_ptr + col), re = __ldg(M.color_ptr + col + 1);
+        const int rb = s_cp[col], re = s_cp[col + 1];
         bool on[NR]; int row[NR];
 #pragma unroll
         for (int r = 0; r < NR; ++r) { row[r] = rb + gid + r * TG; on[r] = row[r] < re && lane_on; }
@@ -870,8 +953,9 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             for (int cc = c; cc < c_end; cc += KC * VEC)
                 relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), first_sweep);
         const bool last_step = step + 1 == n_steps;
+        if (STRIP && !last_step) publish(step);
         if (per_sweep && col == nc - 1) {
-            // end of a sweep: once the last colour is complete on this device, the strip's boundary rows go to
+            // end of a sweep: once the last colour is complete on this device, the rank's boundary rows go to
             // the ranks that read them, and the next barrier also waits for theirs
             ++epoch;
             grid_barrier(M, epoch * nvb, 0, false, false);
@@ -892,6 +976,8 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             ++epoch; ++xe;
             grid_barrier(M, epoch * nvb, e0 + xe, pushed, true);
             pushed = false;
+        } else if (STRIP) {
+            if (!last_step) { prefetch(step + 1); wait_nbrs(step); }
         } else if (!last_step) {
             prefetch(step + 1);
             ++epoch;
@@ -903,6 +989,8 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             grid_barrier(M, epoch * nvb, e0 + xe, pushed, true);
         }
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
+    if (STRIP && !multi) return;           // no grid barrier was used: nothing to re-arm
     // the last CTA to leave re-arms the barrier for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1003,23 +1091,45 @@ __global__ void __launch_bounds__(kTileThreads, 1) k_precond_tile(DeviceModel M,
 //   AV   : v = z + L z                ; dot (rhat, v)                      -> alpha
 //   AT   : t = z + L z                ; dots (t,s),(t,t),(rhat,t),(rhat,s) -> omega, rho', beta
 //   PLAIN: y = z + L z                (timing / tests)
+// Defect-correction solver (solver = 2; no Krylov vectors at all):
+//   INIT_DC: r = b - (x + L x)        ; dots (r,r), (b,b); plans the first cycle's sweeps
+//   DC     : r -= z + L z ; x += z    ; dot (r,r); convergence, stagnation test, plan of the next cycle
 // ---------------------------------------------------------------------------------------------
-enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_PLAIN = 4 };
+enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_PLAIN = 4, MODE_INIT_DC = 5, MODE_DC = 6 };
+
+// Sweeps of the next defect-correction cycle: `worst` = how far the worst column is from the tolerance
+// ((||r||/||b||)/rtol > 1), `rate` = measured error factor per sweep.  A cycle in the sweep precision cannot
+// reduce the residual by more than ~1/floor_gain (fp32: a few 1e-6), so longer cycles would be wasted; the last
+// cycle gets one sweep of margin (another cycle costs about four sweeps of memory traffic).
+__device__ __forceinline__ int dc_plan(double worst, double rate, int smin, int smax, double floor_gain) {
+    rate = fmin(fmax(rate, 0.02), 0.97);
+    const double l = -log(rate);
+    int cap = (int)floor(log(floor_gain) / l);
+    cap = max(smin, min(cap, smax));
+    int s = (int)ceil(log(fmax(worst, 1.0)) / l + 1.0);
+    if (s > cap) {
+        const int cycles = (s + cap - 1) / cap;
+        s = (s + cycles - 1) / cycles;
+    }
+    return max(smin, min(s, cap));
+}
 
 template <int KC, int VEC, int MODE, typename ZT>
 __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_SPMM_MIN_BLOCKS) k_spmm(DeviceModel M, const ZT* __restrict__ zin,
                                                                         double* __restrict__ out) {
-    constexpr int ND = MODE == MODE_INIT ? 2 : MODE == MODE_AV ? 1 : MODE == MODE_AT ? 4 : 1;
-    constexpr bool HAS_DOTS = MODE == MODE_INIT || MODE == MODE_AV || MODE == MODE_AT;
+    constexpr bool IS_INIT = MODE == MODE_INIT || MODE == MODE_INIT_DC;
+    constexpr int ND = IS_INIT ? 2 : MODE == MODE_AV ? 1 : MODE == MODE_AT ? 4 : 1;
+    constexpr bool HAS_DOTS = IS_INIT || MODE == MODE_AV || MODE == MODE_AT || MODE == MODE_DC;
     __shared__ double smem[HAS_DOTS ? (kThreads / 32) * kMaxDots * 2 * 32 : 1];
     __shared__ double tot[HAS_DOTS ? kMaxDots * kMaxK : 1];
-    if (MODE == MODE_AV || MODE == MODE_AT) { if (M.ctl->all_done) return; }
+    if (MODE == MODE_AV || MODE == MODE_AT || MODE == MODE_DC) { if (M.ctl->all_done) return; }
     if (MODE == MODE_AT) { if (M.ctl->finish_half) return; }
     const int K = M.K, n = M.row_hi, W = M.W;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const int32_t* __restrict__ ecol = M.ell_col;
     const double* __restrict__ eval = M.val;
-    if (MODE == MODE_INIT) zin = reinterpret_cast<const ZT*>(M.sp->state_t1);     // ZT = double
+    if (IS_INIT) zin = reinterpret_cast<const ZT*>(M.sp->state_t1);     // ZT = double
+    double* __restrict__ xs = M.sp->state_t1;
     const int nchunk = (K + KC * VEC - 1) / (KC * VEC);
     for (int chunk = 0; chunk < nchunk; ++chunk) {
         const int c = (chunk * KC + lane) * VEC;
@@ -1051,8 +1161,9 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
                 // the row's own operands are issued now as well, so nothing waits behind the gathers
                 const Vd<VEC> own = ldz<ZT, VEC>(zin + idx);
                 Vd<VEC> aux1 = own, aux2 = own;
-                if (MODE == MODE_INIT) aux1 = ldv<VEC>(M.b + idx);
+                if (IS_INIT) aux1 = ldv<VEC>(M.b + idx);
                 if (MODE == MODE_AV || MODE == MODE_AT) aux1 = ldv<VEC>(M.rhat + idx);
+                if (MODE == MODE_DC) { aux1 = ldv<VEC>(M.r + idx); aux2 = ldv<VEC>(xs + idx); }
                 if (MODE == MODE_AT) aux2 = ldv<VEC>(M.r + idx);          // s lives in the r buffer
                 const int inext = i + stride;
                 if (inext < n) {
@@ -1080,7 +1191,7 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
                 Vd<VEC> y;
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) y.a[q] = own.a[q] + s.a[q];
-                if (MODE == MODE_INIT) {
+                if (IS_INIT) {
                     const Vd<VEC> bi = aux1;
                     Vd<VEC> r;
 #pragma unroll
@@ -1089,7 +1200,17 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
                         acc[0 * VEC + q] = fma(r.a[q], r.a[q], acc[0 * VEC + q]);
                         acc[1 * VEC + q] = fma(bi.a[q], bi.a[q], acc[1 * VEC + q]);
                     }
-                    stv<VEC>(M.r + idx, r); stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r);
+                    stv<VEC>(M.r + idx, r);
+                    if (MODE == MODE_INIT) { stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r); }
+                } else if (MODE == MODE_DC) {
+                    Vd<VEC> r = aux1, xv = aux2;
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) {
+                        r.a[q] -= y.a[q];
+                        xv.a[q] += own.a[q];
+                        acc[q] = fma(r.a[q], r.a[q], acc[q]);
+                    }
+                    stv<VEC>(M.r + idx, r); stv<VEC>(xs + idx, xv);
                 } else if (MODE == MODE_AV) {
                     const Vd<VEC> rh = aux1;
                     stv<VEC>(M.v + idx, y);
@@ -1113,10 +1234,66 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
         if (HAS_DOTS) block_dots<ND, KC, VEC>(acc, smem, M.partials, K, chunk);
     }
     if (!HAS_DOTS) return;
-    if (!last_block_arrives(&M.ctl->ticket[MODE])) return;
+    if (!last_block_arrives(&M.ctl->ticket[MODE == MODE_INIT_DC ? 0 : MODE == MODE_DC ? 1 : MODE])) return;
     grid_totals<ND>(M.partials, tot, K);
     dd_allreduce(M, tot, ND * K);
     double* sc = M.sc;
+    if constexpr (MODE == MODE_INIT_DC || MODE == MODE_DC) {
+        // defect correction: convergence per column, the worst distance from the tolerance, the plan of the next cycle
+        __shared__ unsigned long long worst_bits;
+        __shared__ int not_done, failed, any_flags;
+        if (threadIdx.x == 0) { worst_bits = 0ull; not_done = 0; failed = 0; any_flags = 0; }
+        __syncthreads();
+        const int iter_now = M.ctl->iter + (MODE == MODE_DC ? 1 : 0);
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            int f = M.colflags[k];
+            if (MODE == MODE_INIT_DC) {
+                const double rr = tot[0 * K + k], bb = tot[1 * K + k];
+                sc[SC_BNORM2 * K + k] = bb; sc[SC_RNORM2 * K + k] = rr;
+                f &= ~(FL_CONVERGED | FL_BREAKDOWN | FL_PENDING | FL_ZERO_RHS | FL_NAN | FL_HALF);
+                if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) f |= FL_NAN | FL_PENDING;
+                else if (bb == 0.0 && rr != 0.0) f |= FL_ZERO_RHS | FL_PENDING;     // b == 0  =>  x = 0
+            }
+            if (!(f & FL_PENDING)) {
+                const double rr = tot[k], bb = sc[SC_BNORM2 * K + k];
+                if (MODE == MODE_DC) sc[SC_RNORM2 * K + k] = rr;
+                if (!(rr == rr) || isinf(rr)) atomicOr(&failed, 1);                 // finite at the start, not any more
+                else if (rr <= M.tol2 * bb) { if (!(f & FL_CONVERGED)) { f |= FL_CONVERGED; M.coliters[k] = iter_now; } }
+                else {
+                    f &= ~FL_CONVERGED;
+                    atomicOr(&not_done, 1);
+                    atomicMax(&worst_bits, (unsigned long long)__double_as_longlong(rr / (M.tol2 * bb)));
+                }
+            }
+            atomicOr(&any_flags, f);
+            M.colflags[k] = f;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            SolverCtl* ctl = M.ctl;
+            ctl->iter = iter_now;
+            ctl->flags_or = any_flags;
+            int done = !not_done, fail = failed;
+            if (!done && !fail) {
+                const double worst = sqrt(__longlong_as_double((long long)worst_bits));
+                double rate = ctl->dc_rate;
+                if (!(rate > 0.0)) rate = 0.3;
+                if (MODE == MODE_DC) {
+                    const double prev = ctl->dc_worst;
+                    const int S = max(1, ctl->dc_sweeps);
+                    if (prev > 0.0 && worst < prev) rate = pow(worst / prev, 1.0 / S); else rate = 0.97;
+                    if (worst > 0.7 * prev) ctl->dc_slow += 1; else ctl->dc_slow = 0;
+                    if (ctl->dc_slow >= 2) fail = 1;
+                } else ctl->dc_slow = 0;
+                ctl->dc_rate = rate;
+                ctl->dc_worst = worst;
+                ctl->dc_sweeps = dc_plan(worst, rate, M.dc_smin, M.dc_smax, M.dc_floor);
+            }
+            if (!done && !fail && iter_now >= M.max_iter) { ctl->hit_max_iter = 1; done = 1; }
+            if (fail) { ctl->dc_fail = 1; done = 1; }
+            ctl->all_done = done;
+        }
+    } else {
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         int f = M.colflags[k];
         if (MODE == MODE_INIT) {
@@ -1154,6 +1331,30 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
     }
     __syncthreads();
     if (MODE == MODE_INIT && threadIdx.x == 0) publish_done(M, K);
+    }
+}
+
+// Defect-correction solver, after the last cycle: columns that cannot be iterated -- a non-finite right-hand side
+// fills the column with NaN as spsolve does, b == 0 gives x = 0 (the BiCGSTAB path does this in k_update_xrp).
+__global__ void __launch_bounds__(kThreads) k_fix_columns(DeviceModel M) {
+    const int K = M.K;
+    double* __restrict__ x = M.sp->state_t1;
+    const size_t total = (size_t)(M.row_hi - M.row_lo) * K;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(q % K);
+        const int f = M.colflags[k];
+        if (f & FL_PENDING) x[(size_t)M.row_lo * K + q] = (f & FL_NAN) ? qnan() : 0.0;
+    }
+}
+__global__ void k_fix_flags(DeviceModel M) {
+    for (int k = threadIdx.x; k < M.K; k += blockDim.x) {
+        int f = M.colflags[k];
+        if (f & FL_PENDING) {
+            f &= ~FL_PENDING;
+            if (f & FL_ZERO_RHS) { f |= FL_CONVERGED; M.sc[SC_RNORM2 * M.K + k] = 0.0; M.coliters[k] = M.ctl->iter; }
+            M.colflags[k] = f;
+        }
+    }
 }
 
 // s = r - alpha v  (in place on r), fused with (s,s): a column whose ||s|| already meets the tolerance stops at

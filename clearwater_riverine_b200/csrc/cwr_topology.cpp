@@ -59,8 +59,10 @@ float hint_threshold() {
 
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
                            bool rcm, int n_colors, const float* hint, int n_parts, Topology& T,
-                           int tile_rows, int tile_cap, int tile_halo) {
+                           int tile_rows, int tile_cap, int tile_halo, int n_strips) {
     if (n_parts < 1 || n_parts > 8) return "n_parts must be in [1, 8]";
+    if (n_strips < 0 || n_strips > 4096) return "n_strips must be in [0, 4096]";
+    if (n_strips > 0 && (n_colors <= 0 || tile_rows > 0)) return "strips need colours and exclude tiles";
     if (tile_rows > 0 && (n_colors <= 0 || n_parts != 1)) return "tile-local sweeps need colours and a single part";
     if (tile_rows > 0 && (tile_cap < tile_rows || tile_cap > (int)kTileIndexMask)) return "tile_cap must be in [tile_rows, 8191]";
     if (n_real <= 0 || n_face < n_real || n_edge <= 0) return "n_real, n_face, n_edge must be positive and n_face >= n_real";
@@ -226,6 +228,12 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         if (max_level >= (1 << 22)) return "flow hint has more than 4M downstream levels";
         std::vector<int32_t> part(n);
         for (int i = 0; i < n; ++i) part[i] = (int32_t)(((int64_t)rcm_pos[i] * n_parts) / n);
+        // strips: equal chunks of the RCM order nested in the parts (global strip id = part * n_strips + strip)
+        std::vector<int32_t> strip;
+        if (n_strips > 0) {
+            strip.resize(n);
+            for (int i = 0; i < n; ++i) strip[i] = (int32_t)(((int64_t)rcm_pos[i] * n_parts * n_strips) / n);
+        }
         // tiles (tile-local sweeps): compact blobs grown breadth-first from the first free cell in RCM order
         std::vector<int32_t> tile_of;
         int n_tiles = 0;
@@ -252,6 +260,8 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         for (int i = 0; i < n; ++i)
             key[i] = tile_rows > 0
                 ? ((uint64_t)tile_of[i] << 38) | ((uint64_t)(level[i] % nc) << 32) | (uint32_t)rcm_pos[i]
+                : n_strips > 0
+                ? ((uint64_t)strip[i] << 44) | ((uint64_t)(level[i] % nc) << 38) | (uint32_t)rcm_pos[i]
                 : ((uint64_t)part[i] << 60) | ((uint64_t)(level[i] % nc) << 54) | ((uint64_t)level[i] << 32) | (uint32_t)rcm_pos[i];
         std::sort(key.begin(), key.end());
         std::vector<int32_t> order(n);
@@ -270,6 +280,22 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 T.color_ptr[(size_t)p * (nc + 1) + nc] = pos;
             }
             T.part_ptr[n_parts] = pos;
+        }
+        T.n_strips = n_strips;
+        T.strip_cptr.clear();
+        if (n_strips > 0) {        // rows are (strip, colour)-major: the ranges of every strip's colours
+            const int NS = n_parts * n_strips;
+            std::vector<int32_t> cnt((size_t)NS * nc, 0);
+            for (int i = 0; i < n; ++i) ++cnt[(size_t)strip[i] * nc + level[i] % nc];
+            T.strip_cptr.assign((size_t)NS * (nc + 1), 0);
+            int32_t pos = 0;
+            for (int s = 0; s < NS; ++s) {
+                for (int c = 0; c < nc; ++c) { T.strip_cptr[(size_t)s * (nc + 1) + c] = pos; pos += cnt[(size_t)s * nc + c]; }
+                T.strip_cptr[(size_t)s * (nc + 1) + nc] = pos;
+            }
+            // color_ptr keeps its shape; a part's colours are not contiguous in this mode
+            for (int p = 0; p < n_parts; ++p)
+                for (int c = 0; c <= nc; ++c) T.color_ptr[(size_t)p * (nc + 1) + c] = c == 0 ? T.part_ptr[p] : T.part_ptr[p + 1];
         }
         T.old_of_new.swap(order);
         T.n_levels = max_level + 1;
@@ -435,6 +461,32 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             for (int32_t i : members) local_of[i] = -1;
         }
         T.ext_ptr[nt] = (int32_t)T.ext_rows.size();
+    }
+
+    // ---- strips: which strips of the same part a strip's rows are coupled to ---------------------------------
+    T.strip_nptr.clear(); T.strip_nbr.clear(); T.max_strip_nbr = 0;
+    if (T.n_strips > 0) {
+        const int NS = n_parts * T.n_strips, nc = T.n_colors;
+        std::vector<int32_t> srow(n);
+        for (int s = 0; s < NS; ++s)
+            for (int32_t i = T.strip_cptr[(size_t)s * (nc + 1)]; i < T.strip_cptr[(size_t)s * (nc + 1) + nc]; ++i) srow[i] = s;
+        std::vector<uint64_t> pairs;
+        for (int ep = 0; ep < E_int; ++ep) {
+            const int32_t sa = srow[T.f1p[ep]], sb = srow[T.f2p[ep]];
+            if (sa == sb || sa / T.n_strips != sb / T.n_strips) continue;      // other parts: the halo exchange's business
+            pairs.push_back(((uint64_t)(uint32_t)sa << 32) | (uint32_t)sb);
+            pairs.push_back(((uint64_t)(uint32_t)sb << 32) | (uint32_t)sa);
+        }
+        std::sort(pairs.begin(), pairs.end());
+        pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+        T.strip_nptr.assign(NS + 1, 0);
+        for (uint64_t pr : pairs) ++T.strip_nptr[(pr >> 32) + 1];
+        for (int s = 0; s < NS; ++s) {
+            T.max_strip_nbr = std::max(T.max_strip_nbr, T.strip_nptr[s + 1]);
+            T.strip_nptr[s + 1] += T.strip_nptr[s];
+        }
+        T.strip_nbr.reserve(pairs.size());
+        for (uint64_t pr : pairs) T.strip_nbr.push_back((int32_t)(uint32_t)pr);
     }
 
     // ---- domain decomposition: who reads whose rows, which edges / boundary cells a part owns ----------

@@ -67,6 +67,15 @@ struct Topology {
     std::vector<uint16_t> tile_ell;   // (ext_total, W) local index of each neighbour (bits 0-12); bit 15 = neighbour
                                       // visited later in a sweep, bit 14 = neighbour outside the tile (counts as 0)
     int max_ext = 0;                  // largest core + halo row count of a tile
+    // strips (neighbour-synchronised Gauss-Seidel sweeps, n_strips > 0): every part is cut into n_strips equal chunks
+    // of the RCM order and the rows are ordered (part, strip, colour, RCM position) -- a strip is a contiguous row
+    // range owned by ONE CTA of the sweep kernel, which then only waits for the strips its rows are coupled to
+    // (color_ptr is not meaningful in this mode)
+    int n_strips = 0;                      // strips per part
+    std::vector<int32_t> strip_cptr;       // (n_parts * n_strips, n_colors+1) absolute row ranges of a strip's colours
+    std::vector<int32_t> strip_nptr;       // (n_parts * n_strips + 1) ranges into strip_nbr
+    std::vector<int32_t> strip_nbr;        // strips OF THE SAME PART (global strip ids) a strip shares an edge with
+    int max_strip_nbr = 0;
     std::vector<int32_t> iedge_ptr, gedge_ptr, bcell_ptr;   // (n_parts+1) owned internal edges / ghost edges (index into the
                                       // ghost block) / boundary cells: an internal edge belongs to the part of its lower cell
     int max_row_len = 0;
@@ -79,8 +88,9 @@ struct Topology {
 // n_parts: strips of a domain decomposition (1 = none); rows are then ordered part-major.
 // tile_rows > 0 (needs n_colors > 0, n_parts == 1): rows are grouped into tiles of about that many cells grown
 // breadth-first, each extended by up to tile_halo layers of neighbours while it stays within tile_cap rows.
+// n_strips > 0 (needs n_colors > 0, tile_rows == 0): rows ordered (part, strip, colour, RCM position), see Topology.
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
                            bool rcm, int n_colors, const float* hint, int n_parts, Topology& out,
-                           int tile_rows = 0, int tile_cap = 0, int tile_halo = 0);
+                           int tile_rows = 0, int tile_cap = 0, int tile_halo = 0, int n_strips = 0);
 
 }  // namespace cwr

@@ -29,7 +29,7 @@ typedef enum {
     CWR_OK = 0,
     CWR_EINVAL = -1,        /* bad argument / state not available */
     CWR_ECUDA = -2,         /* CUDA runtime error */
-    CWR_ENOTCONVERGED = -3, /* BiCGSTAB hit max_iter (results are still stored) */
+    CWR_ENOTCONVERGED = -3, /* the solver hit max_iter (results are still stored) */
     CWR_EBREAKDOWN = -4,    /* BiCGSTAB breakdown that restarts could not cure */
     CWR_ENAN = -5,          /* non-finite residual (NaN/Inf in the inputs, e.g. a NaN boundary value) */
     CWR_ESINGULAR = -6,     /* zero diagonal: the reference's spsolve would warn MatrixRankWarning */
@@ -38,7 +38,7 @@ typedef enum {
 
 typedef struct {
     double rtol;            /* stop when ||r||_2 <= rtol * ||b||_2 (row-scaled system); default 1e-13 */
-    int max_iter;           /* BiCGSTAB iterations per solve; default 500 */
+    int max_iter;           /* BiCGSTAB iterations / defect-correction cycles per solve; default 500 */
     int reorder;            /* 0 = keep cell order, 1 = reverse Cuthill-McKee (default) */
     int keep_history;       /* 1 = keep every c[t] on the device (default), 0 = only c[t], c[t+1] */
     int hydro_capacity;     /* time slices resident on the device; 0 = all n_time (default) */
@@ -46,8 +46,12 @@ typedef struct {
                                reference does, transport.py:267-273), 0 = skip */
     int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = one CTA per constituent runs the whole solve (small meshes;
                                <= 4096 cells with Gauss-Seidel sweeps: entirely on chip -- cwr_get_options reports 3) */
-    int use_graph;          /* reserved (a CUDA-graph form of the large-mesh iteration loop); ignored: the loop is launched ahead
-                               from the previous solve's iteration count and stops itself through a device-side flag */
+    int solver;             /* large meshes (solver_path 1): 1 = right-preconditioned BiCGSTAB; 2 = defect correction with the
+                               preconditioner sweeps themselves: x += M^-1 r, r -= A (M^-1 r) in fp64, no Krylov vectors -- with
+                               flow-aligned Gauss-Seidel sweeps the sweeps ARE the solver (18-19 of them reach 1e-13 where
+                               BiCGSTAB spends 25 plus its own vector traffic); the number of sweeps per cycle is planned on the
+                               device from the measured error factor, and a solve whose sweeps stagnate or diverge (not an
+                               M-matrix) falls back to BiCGSTAB by itself; 0 (default) = 2 with Gauss-Seidel sweeps, else 1 */
     int check_every;        /* large meshes: iterations launched per convergence poll once the launch-ahead burst is used up;
                                default 1 */
     int precond_steps;      /* m: the preconditioner applies m - 1 sweeps; 1 = diagonal (Jacobi) scaling only;
@@ -71,15 +75,20 @@ typedef struct {
                                the others over NVLink peer memory (cwr_dd_export / cwr_dd_attach).  0 / 0 or 1: off */
     int dd_halo_per_colour; /* domain decomposition, Gauss-Seidel sweeps: 0 (default) = boundary rows cross NVLink once per sweep
                                (Gauss-Seidel inside a strip, one sweep of lag across strips; one halo barrier per sweep),
-                               1 = after every colour (exact multi-rank Gauss-Seidel; a halo barrier per colour) */
+                               1 = after every colour (exact multi-rank Gauss-Seidel; a halo barrier per colour; precond_sync 1) */
+    int precond_sync;       /* Gauss-Seidel sweep kernel: 1 = rows colour-major, a grid barrier between colours; 2 = rows cut into
+                               one strip per CTA (colour-major inside), a CTA only waits for the strips its rows are coupled
+                               to (per-strip flags: release/acquire between neighbours instead of a device-wide rendezvous);
+                               same arithmetic, bit-identical results; 0 (default) = 2 unless dd_halo_per_colour */
 } cwr_options;
 
 typedef struct {
-    int iterations;         /* max over constituents */
+    int iterations;         /* BiCGSTAB iterations (max over constituents) / defect-correction cycles */
     int restarts;
     int status;             /* cwr_status of the solve */
     double max_relres;      /* max over constituents of ||r|| / ||b|| at exit */
     int n_launches;         /* kernels this step launched */
+    int sweeps;             /* Gauss-Seidel sweeps of the solve (defect-correction solver; 0 otherwise) */
 } cwr_step_info;
 
 typedef struct {
@@ -199,6 +208,9 @@ int cwr_get_permutation(cwr_handle* h, int32_t* new_of_old); /* (n,) */
 int cwr_get_options(const cwr_handle* h, cwr_options* resolved); /* the options in force (autos resolved) */
 int cwr_stream(cwr_handle* h, void** cuda_stream);           /* the handle's cudaStream_t */
 int cwr_counters(cwr_handle* h, int64_t* kernel_launches, int64_t* solver_iterations);
+/* Defect-correction solver: Gauss-Seidel sweeps done so far, solves that fell back to BiCGSTAB; the strips of the
+ * neighbour-synchronised sweep kernel (0 when it is not in use) and the most strips any strip waits for.  Any may be NULL. */
+int cwr_solver_stats(cwr_handle* h, int64_t* sweeps, int64_t* fallbacks, int* n_strips, int* max_strip_neighbours);
 /* Host only (no device needed): the cell ordering cwr_create / the first cwr_set_hydro* would build --
  * reverse Cuthill-McKee, then (n_colors > 0) the flow-aligned multicolouring of the Gauss-Seidel sweeps, then
  * (n_parts > 1) the strips of the domain decomposition; rows end up ordered (part, colour, level, RCM).
@@ -221,6 +233,15 @@ int cwr_tile_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const
                     int32_t* new_of_old, int32_t* tile_ptr, int32_t* ext_ptr, int32_t* ext_rows, int32_t* lcolor_ptr,
                     uint16_t* tile_ell, int32_t* ell_col);
 
+/* Host only: the strips of the neighbour-synchronised sweep kernel (precond_sync = 2) build_topology makes -- every part
+ * cut into n_strips equal chunks of the RCM order, rows ordered (part, strip, colour, RCM position).  Call once with the
+ * array pointers NULL for the sizes (n_colors_out, nbr_total), then with arrays: new_of_old (n_real), strip_cptr
+ * (n_parts * n_strips, n_colors + 1: absolute row ranges of a strip's colours), strip_nptr (n_parts * n_strips + 1) and
+ * strip_nbr (nbr_total): the strips of the same part a strip shares an edge with, color_of (n_real, new numbering). */
+int cwr_strip_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
+                     int n_parts, int n_strips, int* n_colors_out, int* nbr_total, int32_t* new_of_old, int32_t* strip_cptr,
+                     int32_t* strip_nptr, int32_t* strip_nbr, uint8_t* color_of);
+
 /* --- device timing of the dominant kernel (bench.py roofline) -------------------------------- */
 /* Per-kernel-family device time inside cwr_step, measured with CUDA events recorded on the handle's
  * stream between the launches.  cwr_profile(h, 1, NULL, NULL) switches it on (and zeroes the sums),
@@ -237,6 +258,7 @@ enum {
     CWR_FAM_PRECOND,        /* the preconditioner: one k_precond_gs launch = all Gauss-Seidel sweeps of one application
                                (precond_sweep = 1), or one Jacobi step out = u + N z per launch (precond_sweep = 0) */
     CWR_FAM_SOLVE_SMALL,    /* small meshes: the whole solve of every column, one CTA each (k_solve_tiny / k_solve_small) */
+    CWR_FAM_DC_UPDATE,      /* defect-correction solver: r -= A z, x += z with (r, r) and the plan of the next cycle */
     CWR_PROFILE_FAMILIES
 };
 int cwr_profile(cwr_handle* h, int enable, double* ms, int64_t* counts);

@@ -191,6 +191,100 @@ def test_preconditioner_variants(K, opts):
     run_against_oracle(mesh, inputs, 5, solver_path=1, **opts)
 
 
+SOLVER_VARIANTS = [dict(solver=1, precond_sync=1), dict(solver=1, precond_sync=2), dict(solver=2, precond_sync=1),
+                   dict(solver=2, precond_sync=2), dict(solver=2, precond_sync=2, precond_precision=64),
+                   dict(solver=2, precond_sync=2, precond_colors=5), dict(solver=2, precond_sweep=0, precond_steps=6),
+                   dict(solver=1, precond_sweep=2), dict(solver=2, precond_sweep=2)]
+
+
+@pytest.mark.parametrize("K", [1, 3, 16])
+@pytest.mark.parametrize("opts", SOLVER_VARIANTS, ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()))
+def test_solver_and_sweep_kernel_variants(K, opts):
+    """Large-mesh path on a 12k-cell mesh (23 strips): BiCGSTAB / defect correction with the sweeps as the solver,
+    grid-barrier / neighbour-synchronised Gauss-Seidel kernel, Jacobi steps, the tile-local sweeps in shared memory --
+    the solver and the sweep kernel change the work, never the converged answer."""
+    _, mesh, inputs = synthetic_case(120, 90, 6, K, seed=200 + K, dry_fraction=0.02)
+    be = make_backend(mesh, list(inputs), solver_path=1, **opts)
+    assert be.options.solver == opts["solver"]
+    if opts.get("precond_sweep", 1) == 1:
+        assert be.options.precond_sync == opts["precond_sync"]
+        assert be.solver_stats()[2] == (23 if opts["precond_sync"] == 2 else 0)
+    be.close()
+    run_against_oracle(mesh, inputs, 5, solver_path=1, **opts)
+
+
+def test_strip_kernel_with_every_cta_and_sync_variants_agree():
+    """170k cells: one strip per resident CTA (2 x 148).  The grid-barrier and the neighbour-synchronised kernels do
+    the same arithmetic on differently ordered rows: answers agree far inside rtol, the sweep counts are equal."""
+    _, mesh, inputs = synthetic_case(410, 380, 4, 2, seed=77, dry_fraction=0.02)
+    outs, sweeps = [], []
+    for sync in (1, 2):
+        be = make_backend(mesh, list(inputs), solver_path=1, solver=2, precond_sync=sync)
+        for t in range(3):
+            info = be.step(t)
+            assert info.status == 0 and info.max_relres <= 1e-13 and info.sweeps > 0
+        outs.append(be.get_state_all(3))
+        sweeps.append(be.solver_stats()[0])
+        if sync == 2:
+            assert be.solver_stats()[2] >= 148 and be.solver_stats()[1] == 0
+        be.close()
+    close(outs[1], outs[0], 1e-11, "neighbour-synchronised vs grid-barrier sweeps")
+    assert sweeps[0] == sweeps[1], sweeps
+    oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(2)})
+    for _ in range(3):
+        oracle.update()
+    for k in range(2):
+        close(outs[1][k], oracle.constituent_dict[f"c{k}"].concentration[3][:mesh.n], RTOL, f"170k cells k{k}")
+
+
+def test_defect_correction_falls_back_to_bicgstab_when_the_sweeps_diverge():
+    """Velocity / flow sign disagreement on 5 % of the faces makes `area = flow / velocity` negative there: with D = 2
+    the matrix has negative diagonal entries and Gauss-Seidel sweeps diverge (spectral radius ~3.4) while spsolve --
+    and BiCGSTAB -- still solve it.  The defect-correction solver must notice and hand over."""
+    from clearwater_riverine_b200 import synthetic
+    plan = synthetic.make_plan(60, 50, 6, seed=41, dry_fraction=0.02)
+    vel = plan.edge_velocity.copy()
+    vel[:, np.random.default_rng(1).random(plan.n_edge) < 0.05] *= -1
+    D = 2.0
+    adv, _, _, cdiff, dt = ref.derive_coefficients(plan.face_flow, vel, plan.face_x, plan.face_y, plan.f1, plan.f2, D, plan.time_seconds)
+    mesh = ref.HydroMesh(plan.f1, plan.f2, plan.n_face, adv, cdiff, vel, plan.volume, dt, D)
+    inputs = synthetic.make_inputs(plan, 2, seed=41)
+    be = make_backend(mesh, list(inputs), solver_path=1, solver=2)
+    oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(2)})
+    for t in range(3):
+        info = be.step(t)
+        assert info.status == 0, (t, info.status, info.iterations, info.max_relres)
+        oracle.update()
+        for k in range(2):
+            close(be.get_state(k, t + 1), oracle.constituent_dict[f"c{k}"].concentration[t + 1], 1e-8, f"fallback k{k} t{t}")
+    assert be.solver_stats()[1] >= 1, "the sweeps diverge on this matrix: the solver should have fallen back"
+    be.close()
+
+
+def test_nan_boundary_and_zero_rhs_on_the_large_path():
+    """NaN boundary value -> the column is NaN like spsolve's result (CWR_ENAN); a constituent with nothing set -> 0."""
+    plan, mesh, inputs = synthetic_case(60, 40, 6, 3, seed=21)
+    n = mesh.n
+    ghost = np.nonzero(mesh.f2 >= n)[0]
+    inputs[1][:] = 0.0
+    inputs[2][3:, mesh.f2[ghost[1]]] = np.nan
+    for solver in (1, 2):
+        be = make_backend(mesh, list(inputs), solver_path=1, solver=solver)
+        oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(3)})
+        for t in range(5):
+            info = be.step(t)
+            oracle.update()
+            for k in range(2):
+                close(be.get_state(k, t + 1), oracle.constituent_dict[f"c{k}"].concentration[t + 1], RTOL, f"k{k} t{t}")
+            want = oracle.constituent_dict["c2"].concentration[t + 1]
+            got = be.get_state(2, t + 1)
+            if np.isnan(want[:n]).any():
+                assert info.status == -5 and np.isnan(got[:n]).all()
+            else:
+                close(got, want, RTOL, f"k2 t{t}")
+        be.close()
+
+
 @pytest.mark.parametrize("opts", [dict(precond_sweep=0), dict(precond_sweep=0, precond_steps=3), dict(precond_steps=2),
                                   dict(precond_steps=6, precond_colors=16), dict(precond_colors=5)])
 @pytest.mark.parametrize("shape", [(40, 25), (70, 50)])

@@ -1,0 +1,82 @@
+"""Host-side layout of the neighbour-synchronised Gauss-Seidel sweep kernel (precond_sync = 2; no device needed):
+rows ordered (part, strip, colour, RCM position), one strip per CTA, and a numpy emulation of the kernel's
+synchronisation rule -- "a strip starts step k once every strip it is coupled to has finished step k - 1" -- under
+random legal interleavings, which must reproduce the sequential colour-by-colour sweep exactly."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from clearwater_riverine_b200 import synthetic
+from clearwater_riverine_b200.backend import strip_layout
+
+
+def _plan(seed=3):
+    return synthetic.make_plan(37, 29, 6, tri_fraction=0.2, dry_fraction=0.02, seed=seed)
+
+
+@pytest.mark.parametrize("n_parts,n_strips,n_colors", [(1, 1, 8), (1, 7, 8), (1, 24, 12), (2, 5, 9), (4, 3, 8)])
+def test_strips_partition_the_rows_and_list_their_neighbours(n_parts, n_strips, n_colors):
+    plan = _plan()
+    n = plan.n_real
+    L = strip_layout(plan.f1, plan.f2, plan.n_face, n_colors, plan.face_flow.mean(0), n_strips, n_parts)
+    p, cptr, nc = L["new_of_old"], L["strip_cptr"], L["n_colors"]
+    NS = n_parts * n_strips
+    assert np.array_equal(np.sort(p), np.arange(n))
+    # strips tile [0, n) contiguously, colours tile every strip, strips have equal sizes (+-1 per part)
+    assert cptr[0, 0] == 0 and cptr[-1, -1] == n
+    assert np.all(cptr[1:, 0] == cptr[:-1, -1]) and np.all(np.diff(cptr, axis=1) >= 0)
+    sizes = cptr[:, -1] - cptr[:, 0]
+    assert sizes.max() - sizes.min() <= 2
+    # the colour of a row, from its position, equals color_of and separates coupled rows
+    strip_of = np.searchsorted(cptr[:, 0], np.arange(n), side="right") - 1
+    col_pos = np.array([np.searchsorted(cptr[strip_of[i]], i, side="right") - 1 for i in range(n)])
+    assert np.array_equal(col_pos, L["color_of"])
+    internal = plan.f2 < n
+    a, b = p[plan.f1[internal]], p[plan.f2[internal]]
+    assert np.all(col_pos[a] != col_pos[b])
+    # neighbour lists: symmetric, same part only, and complete for every internal edge inside a part
+    nptr, nbr = L["strip_nptr"], L["strip_nbr"]
+    pairs = {(s, int(q)) for s in range(NS) for q in nbr[nptr[s]:nptr[s + 1]]}
+    assert all((q, s) in pairs for (s, q) in pairs)
+    assert all(s // n_strips == q // n_strips and s != q for (s, q) in pairs)
+    sa, sb = strip_of[a], strip_of[b]
+    cross = (sa != sb) & (sa // n_strips == sb // n_strips)
+    assert {(int(x), int(y)) for x, y in zip(sa[cross], sb[cross])} <= pairs
+    assert len(pairs) == 2 * len({(min(x, y), max(x, y)) for x, y in zip(sa[cross].tolist(), sb[cross].tolist())})
+
+
+def test_neighbour_synchronised_schedule_equals_the_sequential_sweep():
+    plan = _plan(seed=5)
+    n = plan.n_real
+    n_strips, n_sweeps = 9, 3
+    L = strip_layout(plan.f1, plan.f2, plan.n_face, 8, plan.face_flow.mean(0), n_strips)
+    p, cptr, nc, nptr, nbr = L["new_of_old"], L["strip_cptr"], L["n_colors"], L["strip_nptr"], L["strip_nbr"]
+    rng = np.random.default_rng(0)
+    internal = plan.f2 < n
+    a, b = p[plan.f1[internal]], p[plan.f2[internal]]
+    w = -rng.random(2 * len(a)) * 0.2
+    Lo = sp.csr_matrix((w, (np.concatenate([a, b]), np.concatenate([b, a]))), shape=(n, n))     # off-diagonals of I + L
+    u = rng.random(n)
+    color_of = L["color_of"].astype(int)
+
+    def relax(z, rows):
+        z[rows] = u[rows] - Lo[rows] @ z
+
+    # sequential reference: colour by colour over all strips
+    zs = np.zeros(n)
+    for s in range(n_sweeps):
+        for c in range(nc):
+            relax(zs, np.nonzero(color_of == c)[0])
+    # random legal interleavings of the strips
+    for trial in range(3):
+        z = np.zeros(n)
+        done = np.zeros(n_strips, int)               # steps finished per strip
+        total = n_sweeps * nc
+        while done.min() < total:
+            ready = [s for s in range(n_strips) if done[s] < total and all(done[q] >= done[s] for q in nbr[nptr[s]:nptr[s + 1]])]
+            assert ready, "deadlock"
+            s = ready[rng.integers(len(ready))]
+            c = done[s] % nc
+            relax(z, np.arange(cptr[s, c], cptr[s, c + 1]))
+            done[s] += 1
+        assert np.array_equal(z, zs)

@@ -49,10 +49,12 @@ def main():
         for t in range(args.warmup):
             be.step(t)
         _, i0 = be.counters()
+        sw0 = be.solver_stats()[0]
         t0 = time.perf_counter()
         info = be.run(args.warmup, args.warmup + args.steps)
         wall = (time.perf_counter() - t0) / args.steps * 1e3
         _, i1 = be.counters()
+        sw1, fb, nstrips, maxnbr = be.solver_stats()
         be.profile(1)
         for t in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
             be.step(t)
@@ -63,7 +65,9 @@ def main():
         if ref_state is None:
             ref_state = state
         dev = float(np.nanmax(np.abs(state - ref_state)) / np.nanmax(np.abs(ref_state)))
-        print(f"[{spec}] {wall:.3f} ms/step  iters/step {(i1 - i0) / args.steps:.2f}  status {info.status} relres {info.max_relres:.2e} "
+        o = be.options
+        print(f"[{spec}] {wall:.3f} ms/step  iters/step {(i1 - i0) / args.steps:.2f} sweeps/step {(sw1 - sw0) / args.steps:.2f} fallbacks {fb} "
+              f"solver {o.solver} sync {o.precond_sync} colours {o.precond_colors} strips {nstrips} (max nbrs {maxnbr})  status {info.status} relres {info.max_relres:.2e} "
               f"dev_vs_first {dev:.2e} create {t_c:.2f}s\n    ms/step by family: {fam}\n    us/launch: {per}", flush=True)
         be.close()
 
