@@ -40,7 +40,8 @@ struct cwr_handle {
     int grid_sweep = 0, grid_gs = 0;
     int32_t* d_color_ptr = nullptr;
     bool dc = false;                 // defect-correction solver (options.solver = 2) instead of BiCGSTAB
-    bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2)
+    bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
+    bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
     int n_strips = 0;
     int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
     unsigned long long* d_strip_flag = nullptr;
@@ -226,6 +227,22 @@ static int ensure_stage(cwr_handle* h, size_t bytes) {
 #define PT_DISPATCH(...)                                                                      \
     if (h->m_steps > 1 && h->sweep_f32) { using PT = float; KC_DISPATCH(h->KC, __VA_ARGS__) } \
     else { using PT = double; KC_DISPATCH(h->KC, __VA_ARGS__) }
+
+// k_gs_strip exists for 16-byte packs of the sweep type only
+template <typename ST, int SKC, int SVEC>
+static cudaError_t gs3_prepare(int* occ) {
+    if constexpr (sizeof(ST) * SVEC == 16) {
+        cudaError_t e = cudaFuncSetAttribute(k_gs_strip<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs3_smem_bytes<ST>());
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gs_strip<ST, SKC, SVEC>, kGsThreads, gs3_smem_bytes<ST>());
+    } else { *occ = 0; return cudaSuccess; }
+}
+template <typename ST, int SKC, int SVEC>
+static cudaError_t gs3_launch(int grid, void** args, cudaStream_t stream) {
+    if constexpr (sizeof(ST) * SVEC == 16)
+        return cudaLaunchCooperativeKernel((const void*)k_gs_strip<ST, SKC, SVEC>, dim3(grid), dim3(kGsThreads), args, gs3_smem_bytes<ST>(), stream);
+    else return cudaErrorInvalidValue;
+}
 
 // copy the (re)built topology into the device arrays allocated by create_impl (sizes do not depend on
 // the ordering)
@@ -434,13 +451,19 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->dc = h->opt.solver == 2 && !h->small_path && h->m_steps > 1;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
-    if (h->opt.precond_sync != 1 && h->opt.precond_sync != 2) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 2;
-    if (h->opt.precond_sync == 2 && h->opt.dd_halo_per_colour)
+    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 3) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 3;
+    if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
-    h->strips = h->gauss_seidel && h->opt.precond_sync == 2;
+    h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
+    h->pipelined = h->gauss_seidel && h->opt.precond_sync == 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16;
+    if (h->gauss_seidel && h->opt.precond_sync == 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
     if (h->gauss_seidel) {
         int occ_gs = 0, coop = 0;
-        if (h->strips) {
+        if (h->pipelined) {
+            cudaError_t e = cudaSuccess;
+            SWEEP_DISPATCH(e = gs3_prepare<ST, SKC, SVEC>(&occ_gs));
+            CK(e);
+        } else if (h->strips) {
             SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
             SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC, true>, kGsThreads, kGsSmemBytes));
         } else {
@@ -624,6 +647,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(cudaMemsetAsync(M.bsum, 0, (size_t)3 * std::max(1, tp.E_g) * K * sizeof(double), h->stream));
     }
     M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
+    M.sweep_f32 = h->sweep_f32 ? 1 : 0;
+    M.us_from_producer = (h->dc && h->pipelined) ? 1 : 0;
     M.tol2 = h->opt.rtol * h->opt.rtol;
     M.diffusion_coefficient = D;
     M.max_iter = h->opt.max_iter;
@@ -936,6 +961,15 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
         unsigned long long seq = ++h->gs_seq;
         void* args[] = {(void*)&M, (void*)&u, (void*)&dst, (void*)&sweeps, (void*)&seq};
         cudaError_t e = cudaSuccess;
+        if (h->pipelined) {
+            if (!M.us_from_producer) {        // BiCGSTAB: u is one of its fp64 vectors
+                if (h->sweep_f32) k_to_sweep_type<float><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (float*)M.us);
+                else k_to_sweep_type<double><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (double*)M.us);
+                h->launches += 1;
+            }
+            void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
+            SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream)));
+        } else
         if (h->strips) { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, true>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
         else { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, false>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
         if (e != cudaSuccess) h->err = std::string("k_precond_gs: ") + cudaGetErrorString(e);
@@ -1640,7 +1674,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     out->precond_sweep = h->tiled ? 2 : ((h->gauss_seidel || h->tiny) ? 1 : 0);
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
-    out->precond_sync = h->gauss_seidel ? (h->strips ? 2 : 1) : 0;
+    out->precond_sync = h->gauss_seidel ? (h->pipelined ? 3 : (h->strips ? 2 : 1)) : 0;
     return CWR_OK;
 }
 

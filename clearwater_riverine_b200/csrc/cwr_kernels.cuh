@@ -105,6 +105,8 @@ struct DeviceModel {
     const int32_t* strip_cptr; const int32_t* strip_nptr; const int32_t* strip_nbr;
     unsigned long long* strip_flag;   // (n_strips) last step a strip has finished: (launch sequence << 20) | (step + 1)
     int n_strips, strip0;
+    int us_from_producer;             // the kernels that produce the residual also write it in the sweep type to M.us (k_gs_strip)
+    int sweep_f32;                    // sweep type is float
     int dc_smin, dc_smax;             // sweeps per defect-correction cycle: bounds of the device-side plan
     double dc_floor;                  // largest residual reduction one cycle can deliver in the sweep precision
     double* val;        // (n,W) off-diagonals of D^-1 A
@@ -1004,6 +1006,245 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Strip sweep kernel, software-pipelined across the synchronisation (precond_sync = 3; 16-byte packs only).
+// Same rows, colours, flags and arithmetic as k_precond_gs<STRIP = true>; what changes is WHEN the loads go out.
+// Measured on the 1M x 16 benchmark, a colour step of that kernel costs ~3.5 us of dependent latency (fence,
+// flag, poll, gathers: three round trips through a saturated memory system) on top of its ~2.5 us of bandwidth,
+// with or without the grid barrier.  But of everything step k reads, only the neighbours of the colour swept
+// in step k - 1 (kPrevBit) can still be missing when step k - 1 has finished here: a strip is never more than
+// one step ahead of the strips it is coupled to, so every other neighbour already holds exactly the version step
+// k must see, and cannot be overwritten before this strip has published step k.  So after its own step k - 1 a
+// CTA issues, as cp.async copies into per-thread shared-memory slots, the matrix values, the right-hand side u
+// and all EARLY gathers of step k, publishes step k - 1, waits for its neighbours, issues the few LATE gathers
+// (L2 hits: written a moment ago), and computes: the dependent chain overlaps the streaming instead of
+// alternating with it.  u arrives in the sweep type (M.us, written by the kernel that produced the residual), so
+// a row is 16 B indices (registers, prefetched one step ahead) + 6 slots of 16 B.
+// ---------------------------------------------------------------------------------------------
+template <typename ST> struct GsSlots { static constexpr int val = sizeof(ST) * 4 / 16, total = 5 + val; };
+template <typename ST> constexpr int gs3_smem_bytes() { return kGsRows * GsSlots<ST>::total * 16 * kGsThreads; }
+
+template <typename ST, int KC, int VEC>
+__global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z, int n_sweeps_arg, unsigned long long seq) {
+    static_assert(sizeof(ST) * VEC == 16, "k_gs_strip moves 16-byte packs");
+    constexpr int NR = kGsRows, VS = GsSlots<ST>::val, NS = GsSlots<ST>::total;
+    extern __shared__ int4 gs_land[];          // [NR rows][4 gathers | u | values][kGsThreads]
+    __shared__ int s_cp[kMaxColors + 1];
+    if (M.ctl->all_done || M.ctl->finish_half) return;
+    const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
+    const int K = M.K, W = M.W, nc = M.n_colors;
+    const int vb = blockIdx.x, nvb = gridDim.x;
+    const int lane = threadIdx.x % KC, group = threadIdx.x / KC;
+    constexpr int GPB = kGsThreads / KC;
+    const int32_t* __restrict__ ecol = M.ell_col;
+    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
+    const ST* __restrict__ us = reinterpret_cast<const ST*>(M.us);
+    const int sid = M.strip0 + vb;
+    const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)sid * (nc + 1);
+    for (int q = threadIdx.x; q <= nc; q += kGsThreads) s_cp[q] = cp_src[q];
+    const int nb0 = M.strip_nptr[sid], n_nbr = M.strip_nptr[sid + 1] - nb0;
+    __syncthreads();
+    const int c = lane * VEC;
+    const bool lane_on = c < K;
+    const int n_steps = n_sweeps * nc;
+    const bool multi = M.world > 1;           // several ranks: boundary rows cross NVLink once per sweep (see k_precond_gs)
+    const int row_lo = M.row_lo, row_hi = M.row_hi;
+    const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;
+    unsigned long long xe = 0;
+    unsigned epoch = 0;
+    auto slot = [&](int r, int s) { return gs_land + (r * NS + s) * kGsThreads + threadIdx.x; };
+    auto skipped = [&](int cj, bool first_sweep) {     // first sweep from z = 0: not visited yet / another rank's row
+        const int j = cj & kColMask;
+        return first_sweep && (cj < 0 || (multi && (j < row_lo || j >= row_hi)));
+    };
+    int4 pc[NR], pcn[NR];
+    auto load_idx = [&](int4 (&dst)[NR], int step) {
+        const int col = step % nc;
+        const int rb = s_cp[col], re = s_cp[col + 1];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int i = rb + group + r * GPB;
+            if (i < re) dst[r] = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
+        }
+    };
+    // everything of `step` that does not depend on the step before it
+    auto issue_early = [&](int step) {
+        const int col = step % nc;
+        const bool first_sweep = step < nc;
+        const int rb = s_cp[col], re = s_cp[col + 1];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int i = rb + group + r * GPB;
+            if (i >= re || !lane_on) continue;
+            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (skipped(cs[u], first_sweep)) *slot(r, u) = make_int4(0, 0, 0, 0);
+                else if (!(cs[u] & kPrevBit)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
+            }
+            cp_async_cg16(slot(r, 4), us + (size_t)i * K + c);
+#pragma unroll
+            for (int v = 0; v < VS; ++v) cp_async_cg16(slot(r, 5 + v), reinterpret_cast<const char*>(eval + (size_t)i * W) + 16 * v);
+        }
+    };
+    auto issue_late = [&](int step) {
+        const int col = step % nc;
+        const bool first_sweep = step < nc;
+        const int rb = s_cp[col], re = s_cp[col + 1];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int i = rb + group + r * GPB;
+            if (i >= re || !lane_on) continue;
+            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((cs[u] & kPrevBit) && !skipped(cs[u], first_sweep)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
+        }
+    };
+    auto publish = [&](int step) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            st_flag(M.strip_flag + vb, (seq << 20) | (unsigned long long)(step + 1));
+        }
+    };
+    auto wait_nbrs = [&](int step) {
+        const unsigned long long target = (seq << 20) | (unsigned long long)(step + 1);
+        for (int j = threadIdx.x; j < n_nbr; j += kGsThreads) {
+            const unsigned long long* f = M.strip_flag + (M.strip_nbr[nb0 + j] - M.strip0);
+            unsigned spins = 0;
+            const unsigned limit = *reinterpret_cast<volatile int*>(&M.ctl->barrier_timeout) ? 0u : (1u << 26);
+            while (ld_acquire_u64(f) < target)
+                if (++spins > limit) { M.ctl->barrier_timeout = 1; break; }
+        }
+        __syncthreads();
+    };
+    // a row through registers (rows beyond the pipelined ones, ELL blocks beyond the first, further column chunks)
+    auto relax_slow = [&](int i, int cc, int w0, Pk<ST, VEC> acc, bool first_sweep) {
+        for (int w = w0; w < W; w += 4) {
+            const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+            const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
+            const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (skipped(ds[u], first_sweep)) continue;
+                const Pk<ST, VEC> y = ldk_cg<ST, VEC>(z + (size_t)(ds[u] & kColMask) * K + cc);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) acc.a[q] += wv.a[u] * y.a[q];
+            }
+        }
+        const Pk<ST, VEC> own = ldk_cg<ST, VEC>(us + (size_t)i * K + cc);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
+        stk<ST, VEC>(z + (size_t)i * K + cc, acc);
+    };
+    Pk<ST, VEC> zero;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) zero.a[q] = (ST)0;
+
+    load_idx(pc, 0);
+    issue_early(0);
+    for (int step = 0; step < n_steps; ++step) {
+        const int col = step % nc;
+        const bool first_sweep = step < nc, last_step = step + 1 == n_steps;
+        const int rb = s_cp[col], re = s_cp[col + 1];
+        if (!last_step) load_idx(pcn, step + 1);                 // indices of the next step, in flight across this one
+        if (step > 0) wait_nbrs(step - 1);
+        issue_late(step);
+        cp_async_wait_all();
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int i = rb + group + r * GPB;
+            if (i >= re || !lane_on) continue;
+            ST vals[4];
+#pragma unroll
+            for (int v = 0; v < VS; ++v) *reinterpret_cast<int4*>(reinterpret_cast<char*>(vals) + 16 * v) = *slot(r, 5 + v);
+            Pk<ST, VEC> o = zero;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const Pk<ST, VEC> x = *reinterpret_cast<const Pk<ST, VEC>*>(slot(r, u));
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) o.a[q] += vals[u] * x.a[q];
+            }
+            if (W > 4) {
+                // wider rows: the remaining ELL blocks through registers, then the update from the accumulated sum
+                for (int w = 4; w < W; w += 4) {
+                    const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+                    const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
+                    const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (skipped(ds[u], first_sweep)) continue;
+                        const Pk<ST, VEC> y = ldk_cg<ST, VEC>(z + (size_t)(ds[u] & kColMask) * K + c);
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) o.a[q] += wv.a[u] * y.a[q];
+                    }
+                }
+            }
+            const Pk<ST, VEC> own = *reinterpret_cast<const Pk<ST, VEC>*>(slot(r, 4));
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - o.a[q];
+            stk<ST, VEC>(z + (size_t)i * K + c, o);
+        }
+        // further column chunks of those rows (more columns than lanes x VEC), colours with more rows per lane group
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r) {
+            const int i = rb + group + r * GPB;
+            if (i < re)
+                for (int cc = c + KC * VEC; cc < K; cc += KC * VEC) relax_slow(i, cc, 0, zero, first_sweep);
+        }
+#pragma unroll 1
+        for (int i = rb + group + NR * GPB; i < re; i += GPB)
+            for (int cc = c; cc < K; cc += KC * VEC) relax_slow(i, cc, 0, zero, first_sweep);
+        if (last_step && !(multi && col == nc - 1)) break;
+        if (!last_step) publish(step);
+        if (multi && col == nc - 1) {
+            // end of a sweep: this rank's boundary rows go to the ranks that read them (see k_precond_gs)
+            bool pushed = false;
+            ++epoch;
+            grid_barrier(M, epoch * nvb, 0, false, false);
+            const int packs = (K + VEC - 1) / VEC;
+            for (int q = blockIdx.x * kGsThreads + threadIdx.x; q < M.n_send * packs; q += gridDim.x * kGsThreads) {
+                const int i = M.send_rows[q / packs], cc = (q % packs) * VEC;
+                if (cc + VEC > K) continue;
+                const Pk<ST, VEC> o = ldk_cg<ST, VEC>(z + (size_t)i * K + cc);
+                unsigned m = M.send_mask[i];
+                pushed |= m != 0;
+                while (m) {
+                    const int r = __ffs(m) - 1;
+                    m &= m - 1;
+                    stk<ST, VEC>(peer_ptr(M, r, z) + (size_t)i * K + cc, o);
+                }
+            }
+            ++epoch; ++xe;
+            grid_barrier(M, epoch * nvb, e0 + xe, pushed, true);
+            if (last_step) break;
+        }
+#pragma unroll
+        for (int r = 0; r < NR; ++r) pc[r] = pcn[r];
+        issue_early(step + 1);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
+    if (!multi) return;
+    __syncthreads();
+    if (threadIdx.x == 0) {        // the last CTA to leave re-arms the grid barrier for the next launch
+        const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
+        if (t == (unsigned)nvb - 1) {
+            M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
+            M.dd->bar_epoch = e0 + xe;
+            __threadfence();
+        }
+    }
+}
+
+// u (fp64) -> the sweep type, own rows (the BiCGSTAB path in front of k_gs_strip: its vectors are fp64)
+template <typename ST>
+__global__ void __launch_bounds__(kThreads) k_to_sweep_type(DeviceModel M, const double* __restrict__ u, ST* __restrict__ out) {
+    const size_t lo = (size_t)M.row_lo * M.K, hi = (size_t)M.row_hi * M.K;
+    if (M.ctl->all_done || M.ctl->finish_half) return;
+    for (size_t q = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < hi; q += (size_t)gridDim.x * blockDim.x) out[q] = (ST)u[q];
+}
+
+// ---------------------------------------------------------------------------------------------
 // EXPERIMENTAL -- written at the end of round 1, compiled, its host data structures and its arithmetic
 // emulated and tested on the CPU (tests/test_tile_layout.py), NOT YET RUN ON A GPU; off unless
 // precond_sweep = 2.  Tile-local multicolour Gauss-Seidel (restricted additive Schwarz with overlap):
@@ -1202,6 +1443,14 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
                     }
                     stv<VEC>(M.r + idx, r);
                     if (MODE == MODE_INIT) { stv<VEC>(M.rhat + idx, r); stv<VEC>(M.p + idx, r); }
+                    if (MODE == MODE_INIT_DC && M.us_from_producer) {
+                        if (M.sweep_f32) {
+                            Pk<float, VEC> rs;
+#pragma unroll
+                            for (int q = 0; q < VEC; ++q) rs.a[q] = (float)r.a[q];
+                            stk<float, VEC>(reinterpret_cast<float*>(M.us) + idx, rs);
+                        } else stv<VEC>(reinterpret_cast<double*>(M.us) + idx, r);
+                    }
                 } else if (MODE == MODE_DC) {
                     Vd<VEC> r = aux1, xv = aux2;
 #pragma unroll
@@ -1211,6 +1460,12 @@ __global__ void __launch_bounds__(kThreads, MODE == 2 ? CWR_AT_MIN_BLOCKS : CWR_
                         acc[q] = fma(r.a[q], r.a[q], acc[q]);
                     }
                     stv<VEC>(M.r + idx, r); stv<VEC>(xs + idx, xv);
+                    if (M.us_from_producer) {
+                        Pk<ZT, VEC> rs;
+#pragma unroll
+                        for (int q = 0; q < VEC; ++q) rs.a[q] = (ZT)r.a[q];
+                        stk<ZT, VEC>(reinterpret_cast<ZT*>(M.us) + idx, rs);
+                    }
                 } else if (MODE == MODE_AV) {
                     const Vd<VEC> rh = aux1;
                     stv<VEC>(M.v + idx, y);

@@ -81,6 +81,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     T.nnz = 2 * (int64_t)E_int;
     if (T.nnz > 0x7fffffffLL) return "too many non-zeros for 32-bit indices";
     if ((int64_t)E > 0x3fffffffLL) return "too many edges";
+    if ((int64_t)n > 0x3fffffffLL) return "too many cells (row indices carry two flag bits)";
 
     // ---- adjacency of real cells (both directions of every internal edge) --------------------
     std::vector<int32_t> aptr(n + 1, 0), adj(T.nnz);
@@ -401,7 +402,9 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         for (int i = 0; i < n; ++i)
             for (int w = 0; w < T.W; ++w) {
                 int32_t& cj = T.ell_col[(size_t)i * T.W + w];
-                if (T.color_of[cj] >= T.color_of[i]) cj |= kLaterBit;
+                const int ci = T.color_of[i], cn = T.color_of[cj];
+                if (cn >= ci) cj |= kLaterBit;
+                if (cn == (ci + T.n_colors - 1) % T.n_colors && cn != ci) cj |= kPrevBit;
             }
 
     // ---- tile-local sweeps: halo layers, local numbering, local ELL ------------------------------------------

@@ -19,7 +19,8 @@
 namespace cwr {
 
 constexpr int32_t kLaterBit = (int32_t)0x80000000;
-constexpr int32_t kColMask = 0x7fffffff;
+constexpr int32_t kPrevBit = 0x40000000;      // the neighbour has the colour swept immediately before the row's
+constexpr int32_t kColMask = 0x3fffffff;
 constexpr uint16_t kTileLater = 0x8000, kTileOutside = 0x4000, kTileIndexMask = 0x1fff;
 
 struct Topology {
@@ -45,7 +46,9 @@ struct Topology {
     std::vector<int32_t> bedge;       // (E_g)  device edge ids, ascending original id within a cell
     int W = 4;                        // ELL width: max row length rounded up to a multiple of 4
     std::vector<int32_t> ell_col;     // (n*W) row-major; padding points at the row itself; bit 31 (kLaterBit): the
-                                      // neighbour's colour is >= the row's (visited later in a Gauss-Seidel sweep)
+                                      // neighbour's colour is >= the row's (visited later in a Gauss-Seidel sweep);
+                                      // bit 30 (kPrevBit): the neighbour's colour is the one swept just before the row's
+                                      // (the only values a sweep step has to wait for: cwr_kernels.cuh, k_gs_strip)
     std::vector<int32_t> ell_code;    // (n*W) slot_edge code, -1 for padding
     // Gauss-Seidel colours: rows are ordered (part, colour, level, RCM position)
     int n_colors = 0;                 // 0: no colouring (rows in RCM order, parts = equal chunks of it)

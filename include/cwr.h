@@ -79,7 +79,11 @@ typedef struct {
     int precond_sync;       /* Gauss-Seidel sweep kernel: 1 = rows colour-major, a grid barrier between colours; 2 = rows cut into
                                one strip per CTA (colour-major inside), a CTA only waits for the strips its rows are coupled
                                to (per-strip flags: release/acquire between neighbours instead of a device-wide rendezvous);
-                               same arithmetic, bit-identical results; 0 (default) = 2 unless dd_halo_per_colour */
+                               3 = the same strips, software-pipelined across that wait: everything a colour reads except the
+                               values of the colour swept just before it is fetched (cp.async into shared memory) BEFORE the
+                               wait, so the dependent latency overlaps the streaming (16-byte packs: K a multiple of 4 with
+                               fp32 sweeps; otherwise 2 is used).  Same arithmetic in all three; 0 (default) = 3 unless
+                               dd_halo_per_colour */
 } cwr_options;
 
 typedef struct {

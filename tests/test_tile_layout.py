@@ -10,7 +10,7 @@ from clearwater_riverine_b200 import synthetic
 from clearwater_riverine_b200.backend import tile_layout
 from oracle import reference_step as ref
 
-MASK31 = 0x7FFFFFFF
+MASK31 = 0x3FFFFFFF
 LATER, OUTSIDE, IDX = 0x8000, 0x4000, 0x1FFF
 
 
