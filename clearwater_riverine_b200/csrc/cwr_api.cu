@@ -42,6 +42,8 @@ struct cwr_handle {
     bool dc = false;                 // defect-correction solver (options.solver = 2) instead of BiCGSTAB
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
+    bool flow = false;               // ... or no synchronisation at all: versioned packs, dataflow (k_gs_flow, precond_sync = 4)
+    std::map<void*, unsigned> flow_launches;   // launches of k_gs_flow per destination buffer (its launch parity)
     int n_strips = 0;
     int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
     unsigned long long* d_strip_flag = nullptr;
@@ -236,6 +238,17 @@ static cudaError_t gs3_prepare(int* occ) {
         if (e != cudaSuccess) return e;
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gs_strip<ST, SKC, SVEC>, kGsThreads, gs3_smem_bytes<ST>());
     } else { *occ = 0; return cudaSuccess; }
+}
+template <typename ST, int SKC, int SVEC>
+static cudaError_t flow_prepare(int* occ) {
+    if constexpr (sizeof(ST) * SVEC == 16) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gs_flow<ST, SKC, SVEC>, kFlowThreads, 0);
+    else { *occ = 0; return cudaSuccess; }
+}
+template <typename ST, int SKC, int SVEC>
+static cudaError_t flow_launch(int grid, void** args, cudaStream_t stream) {
+    if constexpr (sizeof(ST) * SVEC == 16)
+        return cudaLaunchCooperativeKernel((const void*)k_gs_flow<ST, SKC, SVEC>, dim3(grid), dim3(kFlowThreads), args, 0, stream);
+    else return cudaErrorInvalidValue;
 }
 template <typename ST, int SKC, int SVEC>
 static cudaError_t gs3_launch(int grid, void** args, cudaStream_t stream) {
@@ -451,7 +464,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->dc = h->opt.solver == 2 && !h->small_path && h->m_steps > 1;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
-    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 3) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 3;
+    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 4) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : (h->world > 1 ? 3 : 4);
+    if (h->opt.precond_sync == 4 && h->world > 1) FAIL(CWR_EINVAL, "precond_sync = 4 (dataflow sweeps) is single-GPU; use 3 with domain decomposition");
+    if (h->gauss_seidel && h->opt.precond_sync == 4) {
+        if ((h->sweep_f32 ? 4 : 8) * h->SVEC == 16) h->flow = true; else h->opt.precond_sync = 2;      // packs narrower than 16 bytes
+    }
     if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
     h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
@@ -459,7 +476,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->gauss_seidel && h->opt.precond_sync == 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
     if (h->gauss_seidel) {
         int occ_gs = 0, coop = 0;
-        if (h->pipelined) {
+        if (h->flow) {
+            cudaError_t e = cudaSuccess;
+            SWEEP_DISPATCH(e = flow_prepare<ST, SKC, SVEC>(&occ_gs));
+            CK(e);
+        } else if (h->pipelined) {
             cudaError_t e = cudaSuccess;
             SWEEP_DISPATCH(e = gs3_prepare<ST, SKC, SVEC>(&occ_gs));
             CK(e);
@@ -648,7 +669,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     }
     M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
     M.sweep_f32 = h->sweep_f32 ? 1 : 0;
-    M.us_from_producer = (h->dc && h->pipelined) ? 1 : 0;
+    M.us_from_producer = (h->dc && (h->pipelined || h->flow)) ? 1 : 0;
+    if (h->flow) M.dc_floor = h->sweep_f32 ? 1e5 : 1e12;        // two mantissa bits of every z element carry its version
     M.tol2 = h->opt.rtol * h->opt.rtol;
     M.diffusion_coefficient = D;
     M.max_iter = h->opt.max_iter;
@@ -961,14 +983,17 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
         unsigned long long seq = ++h->gs_seq;
         void* args[] = {(void*)&M, (void*)&u, (void*)&dst, (void*)&sweeps, (void*)&seq};
         cudaError_t e = cudaSuccess;
-        if (h->pipelined) {
+        if (h->pipelined || h->flow) {
             if (!M.us_from_producer) {        // BiCGSTAB: u is one of its fp64 vectors
                 if (h->sweep_f32) k_to_sweep_type<float><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (float*)M.us);
                 else k_to_sweep_type<double><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (double*)M.us);
                 h->launches += 1;
             }
+            int parity = (int)(++h->flow_launches[dst] & 1u);        // (zero-filled buffer = parity 0: the first launch is 1)
             void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
-            SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream)));
+            void* args4[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&parity};
+            if (h->flow) { SWEEP_DISPATCH(e = (flow_launch<ST, SKC, SVEC>(h->grid_gs, args4, h->stream))); }
+            else { SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream))); }
         } else
         if (h->strips) { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, true>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
         else { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, false>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
@@ -1674,7 +1699,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     out->precond_sweep = h->tiled ? 2 : ((h->gauss_seidel || h->tiny) ? 1 : 0);
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
-    out->precond_sync = h->gauss_seidel ? (h->pipelined ? 3 : (h->strips ? 2 : 1)) : 0;
+    out->precond_sync = h->gauss_seidel ? (h->flow ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
     return CWR_OK;
 }
 

@@ -1236,6 +1236,201 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Dataflow sweep kernel (precond_sync = 4; single rank, 16-byte packs): no barrier and no flag at all.
+// ncu on k_gs_strip (profiles/r02_notes.md): 39 % of the warp samples still sit at the two __syncthreads() around the
+// neighbour wait -- a step's dependent chain (stores, fence, flag, poll, late gathers) is ~3.5 us, every CTA runs
+// it in lock-step with its neighbours, and the memory system idles meanwhile.  Here the DATA is the flag: every
+// 16-byte pack of z carries, in the two low mantissa bits of each of its elements, the version that wrote it
+// (launch parity of this buffer, sweep parity), and a gather simply re-reads a pack until all its elements show the
+// version the sweep order says it must see.  That is enough:
+//   * a row of colour c in sweep s must see neighbours of earlier colours at version s and the others at s - 1;
+//     a neighbour can only ever be one version behind that (the row itself was needed, at its previous version,
+//     to produce the neighbour's previous version), so one parity bit tells the two apart, and the buffer's launch
+//     parity tells this launch's packs from whatever an earlier launch left;
+//   * nothing can be overwritten too early: every reader of a row's version s is a neighbour whose own new value
+//     the row needs before it can produce version s + 1 (the coupling is symmetric), so the true dependencies
+//     already order every write after the reads of the value it replaces;
+//   * a torn 16-byte access would show elements of two versions and is re-read like a stale pack.
+// Warps therefore run free: each takes its rows of (sweep, colour) in order and stalls only on the packs that are
+// really missing -- usually none: they were written a whole step ago -- so the dependent chain of a step shrinks
+// to store -> L2 -> load, and the CTAs drift apart instead of marching in lock-step.  Two mantissa bits: z carries
+// 21 bits per element, far below what the sweeps resolve anyway (error factor ~0.2 per sweep).  Needs every CTA
+// resident (cooperative launch) and a fair scheduler among them, as the other sweep kernels do.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFlowThreads = 512;
+
+__device__ __forceinline__ int4 ld_relaxed_v4(const void* p) {
+    int4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// all elements of a pack carry `tag` (fp32: four low words; fp64: the low words of its two elements)
+template <typename ST>
+__device__ __forceinline__ bool pack_has_tag(const int4& v, int tag) {
+    if constexpr (sizeof(ST) == 4) return (((v.x ^ tag) | (v.y ^ tag) | (v.z ^ tag) | (v.w ^ tag)) & 3) == 0;
+    else return (((v.x ^ tag) | (v.z ^ tag)) & 3) == 0;
+}
+template <typename ST>
+__device__ __forceinline__ int4 pack_set_tag(int4 v, int tag) {
+    if constexpr (sizeof(ST) == 4) { v.x = (v.x & ~3) | tag; v.y = (v.y & ~3) | tag; v.z = (v.z & ~3) | tag; v.w = (v.w & ~3) | tag; }
+    else { v.x = (v.x & ~3) | tag; v.z = (v.z & ~3) | tag; }
+    return v;
+}
+
+template <typename ST, int KC, int VEC>
+__global__ void __launch_bounds__(kFlowThreads, 2) k_gs_flow(DeviceModel M, ST* z, int n_sweeps_arg, int launch_parity) {
+    static_assert(sizeof(ST) * VEC == 16, "k_gs_flow moves 16-byte packs");
+    __shared__ int s_cp[kMaxColors + 1];
+    if (M.ctl->all_done || M.ctl->finish_half) return;
+    const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
+    const int K = M.K, W = M.W, nc = M.n_colors;
+    const int lane = threadIdx.x % KC, group = threadIdx.x / KC;
+    constexpr int GPB = kFlowThreads / KC;
+    const int32_t* __restrict__ ecol = M.ell_col;
+    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
+    const ST* __restrict__ us = reinterpret_cast<const ST*>(M.us);
+    const int sid = M.strip0 + blockIdx.x;
+    const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)sid * (nc + 1);
+    for (int q = threadIdx.x; q <= nc; q += kFlowThreads) s_cp[q] = cp_src[q];
+    __syncthreads();                              // the only CTA-wide synchronisation of the kernel
+    const int c = lane * VEC;
+    if (c >= K) return;                           // (lanes beyond the last column have nothing to do and nobody waits for them)
+    const unsigned spin_limit = 1u << 22;
+    bool gave_up = false;
+    // The lanes of a warp stay on the SAME colour (a lane that spun on a value another lane of its warp is about to
+    // store would never see it: the compiler reconverges the warp behind the spin loop).  So the walk over
+    // (sweep, colour, pass) is warp-uniform -- pass p takes row  first-of-colour + group + p * GPB  -- and lane groups
+    // whose colour has fewer rows idle through the warp's last pass of it.  idx / values / u of the next row are
+    // fetched while the current one gathers.
+    const int g0 = (int)(threadIdx.x & ~31u) / KC;            // this warp's first lane group: it has the most rows
+    int sw = 0, col = 0, pass = 0;
+    auto settle = [&]() {                                      // move (sw, col, pass) to the warp's next existing pass
+        while (sw < n_sweeps && s_cp[col] + g0 + pass * GPB >= s_cp[col + 1]) {
+            pass = 0;
+            if (++col == nc) { col = 0; ++sw; }
+        }
+    };
+    settle();
+    int4 nidx = make_int4(0, 0, 0, 0); Pk<ST, 4> nval = {}; Pk<ST, VEC> nown = {};
+    int nrow = 0; bool nact = false;
+    auto fetch = [&]() {
+        nrow = s_cp[col] + group + pass * GPB;
+        nact = nrow < s_cp[col + 1];
+        if (nact) {
+            nidx = *reinterpret_cast<const int4*>(ecol + (size_t)nrow * W);
+            nval = ldk<ST, 4>(eval + (size_t)nrow * W);
+            nown = ldk_cg<ST, VEC>(us + (size_t)nrow * K + c);
+        }
+    };
+    if (sw < n_sweeps) fetch();
+    while (sw < n_sweeps) {
+        const int row = nrow, rsw = sw;
+        const bool active = nact;
+        const int4 idx = nidx; const Pk<ST, 4> val = nval; const Pk<ST, VEC> own = nown;
+        // versions: this sweep's for neighbours of an earlier colour, the previous sweep's for the others
+        const int tag_new = (launch_parity << 1) | (rsw & 1), tag_old = (launch_parity << 1) | ((rsw + 1) & 1);
+        const bool first_sweep = rsw == 0;
+        const int cs[4] = {idx.x, idx.y, idx.z, idx.w};
+        int4 x[4]; int want[4]; bool need[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = cs[u] & kColMask;
+            need[u] = active && !(first_sweep && cs[u] < 0) && j != row;      // not visited yet in the sweep from z = 0; padding
+            want[u] = cs[u] < 0 ? tag_old : tag_new;
+            x[u] = need[u] ? ld_relaxed_v4(z + (size_t)j * K + c) : make_int4(0, 0, 0, 0);
+        }
+        // the next row's operands go out under the gathers
+        ++pass;
+        settle();
+        if (sw < n_sweeps) fetch();
+        // re-read the packs that do not show the version they must (rare: they were written a step ago)
+        unsigned spins = 0;
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (need[u] && !pack_has_tag<ST>(x[u], want[u])) {
+                    ok = false;
+                    x[u] = ld_relaxed_v4(z + (size_t)(cs[u] & kColMask) * K + c);
+                }
+            if (ok || gave_up) break;
+            if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }     // never hang the device
+            if (spins > 4) __nanosleep(40);
+        }
+        Pk<ST, VEC> o;
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) o.a[q] = (ST)0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int4 clean = pack_set_tag<ST>(x[u], 0);
+            const Pk<ST, VEC> xv = *reinterpret_cast<const Pk<ST, VEC>*>(&clean);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o.a[q] += val.a[u] * xv.a[q];
+        }
+        if (!active) continue;
+        for (int w = 4; w < W; w += 4) {              // rows wider than 4: the remaining ELL blocks, same protocol
+            const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)row * W + w);
+            const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)row * W + w);
+            const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = ds[u] & kColMask;
+                if ((first_sweep && ds[u] < 0) || j == row) continue;
+                const int wt = ds[u] < 0 ? tag_old : tag_new;
+                int4 y = ld_relaxed_v4(z + (size_t)j * K + c);
+                unsigned sp2 = 0;
+                while (!pack_has_tag<ST>(y, wt) && !gave_up) {
+                    if (++sp2 > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }
+                    __nanosleep(40);
+                    y = ld_relaxed_v4(z + (size_t)j * K + c);
+                }
+                y = pack_set_tag<ST>(y, 0);
+                const Pk<ST, VEC> yv = *reinterpret_cast<const Pk<ST, VEC>*>(&y);
+#pragma unroll
+                for (int q = 0; q < VEC; ++q) o.a[q] += wv.a[u] * yv.a[q];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - o.a[q];
+        const int4 tagged = pack_set_tag<ST>(*reinterpret_cast<const int4*>(&o), tag_new);
+        *reinterpret_cast<int4*>(z + (size_t)row * K + c) = tagged;
+        // further column chunks of the row (more columns than lanes x VEC): same protocol, one pack at a time
+        for (int cc = c + KC * VEC; cc < K; cc += KC * VEC) {
+            Pk<ST, VEC> o2;
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o2.a[q] = (ST)0;
+            for (int w = 0; w < W; w += 4) {
+                const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)row * W + w);
+                const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)row * W + w);
+                const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = ds[u] & kColMask;
+                    if ((first_sweep && ds[u] < 0) || j == row) continue;
+                    const int wt = ds[u] < 0 ? tag_old : tag_new;
+                    int4 y = ld_relaxed_v4(z + (size_t)j * K + cc);
+                    unsigned sp2 = 0;
+                    while (!pack_has_tag<ST>(y, wt) && !gave_up) {
+                        if (++sp2 > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }
+                        __nanosleep(40);
+                        y = ld_relaxed_v4(z + (size_t)j * K + cc);
+                    }
+                    y = pack_set_tag<ST>(y, 0);
+                    const Pk<ST, VEC> yv = *reinterpret_cast<const Pk<ST, VEC>*>(&y);
+#pragma unroll
+                    for (int q = 0; q < VEC; ++q) o2.a[q] += wv.a[u] * yv.a[q];
+                }
+            }
+            const Pk<ST, VEC> own2 = ldk_cg<ST, VEC>(us + (size_t)row * K + cc);
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) o2.a[q] = own2.a[q] - o2.a[q];
+            *reinterpret_cast<int4*>(z + (size_t)row * K + cc) = pack_set_tag<ST>(*reinterpret_cast<const int4*>(&o2), tag_new);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
+}
+
 // u (fp64) -> the sweep type, own rows (the BiCGSTAB path in front of k_gs_strip: its vectors are fp64)
 template <typename ST>
 __global__ void __launch_bounds__(kThreads) k_to_sweep_type(DeviceModel M, const double* __restrict__ u, ST* __restrict__ out) {
