@@ -43,7 +43,6 @@ struct cwr_handle {
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
     bool flow = false;               // ... or no synchronisation at all: versioned packs, dataflow (k_gs_flow, precond_sync = 4)
-    std::map<void*, unsigned> flow_launches;   // launches of k_gs_flow per destination buffer (its launch parity)
     int n_strips = 0;
     int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
     unsigned long long* d_strip_flag = nullptr;
@@ -241,13 +240,16 @@ static cudaError_t gs3_prepare(int* occ) {
 }
 template <typename ST, int SKC, int SVEC>
 static cudaError_t flow_prepare(int* occ) {
-    if constexpr (sizeof(ST) * SVEC == 16) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gs_flow<ST, SKC, SVEC>, kFlowThreads, 0);
-    else { *occ = 0; return cudaSuccess; }
+    if constexpr (sizeof(ST) * SVEC == 16) {
+        cudaError_t e = cudaFuncSetAttribute(k_gs_flow<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs3_smem_bytes<ST>());
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gs_flow<ST, SKC, SVEC>, kFlowThreads, gs3_smem_bytes<ST>());
+    } else { *occ = 0; return cudaSuccess; }
 }
 template <typename ST, int SKC, int SVEC>
 static cudaError_t flow_launch(int grid, void** args, cudaStream_t stream) {
     if constexpr (sizeof(ST) * SVEC == 16)
-        return cudaLaunchCooperativeKernel((const void*)k_gs_flow<ST, SKC, SVEC>, dim3(grid), dim3(kFlowThreads), args, 0, stream);
+        return cudaLaunchCooperativeKernel((const void*)k_gs_flow<ST, SKC, SVEC>, dim3(grid), dim3(kFlowThreads), args, gs3_smem_bytes<ST>(), stream);
     else return cudaErrorInvalidValue;
 }
 template <typename ST, int SKC, int SVEC>
@@ -989,7 +991,7 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
                 else k_to_sweep_type<double><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (double*)M.us);
                 h->launches += 1;
             }
-            int parity = (int)(++h->flow_launches[dst] & 1u);        // (zero-filled buffer = parity 0: the first launch is 1)
+            int parity = dst == M.sh ? 1 : 0;                         // which z buffer: its launch parity lives on the device
             void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
             void* args4[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&parity};
             if (h->flow) { SWEEP_DISPATCH(e = (flow_launch<ST, SKC, SVEC>(h->grid_gs, args4, h->stream))); }

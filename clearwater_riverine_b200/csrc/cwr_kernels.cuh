@@ -63,6 +63,7 @@ struct SolverCtl {
     int dc_fail;          // the sweeps stagnate or diverge (not an M-matrix?): the host falls back to BiCGSTAB
     int dc_slow;          // consecutive cycles that reduced the residual by less than 0.7
     int sweeps_done;      // Gauss-Seidel sweeps of this solve
+    int flow_parity[2];   // k_gs_flow: launch parity last written into the two z buffers (p^, s^)
     double dc_rate;       // error factor per sweep measured over the last cycle (kept across steps)
     double dc_worst;      // max over columns of (||r|| / ||b||) / rtol after the last cycle
 };
@@ -1278,12 +1279,24 @@ __device__ __forceinline__ int4 pack_set_tag(int4 v, int tag) {
     return v;
 }
 
+// Structure of a step (one colour of one sweep), per thread, no CTA-wide synchronisation anywhere: the indices of
+// the step's rows are in registers (prefetched one step ahead); all copies -- matrix values, u, the gathers, those
+// of the colour swept just before (kPrevBit: the ones that may not have landed yet) last -- go out as cp.async into
+// the thread's own shared-memory slots; after they have arrived every needed pack is checked and the stale ones
+// are fetched again until they show their version; then the rows are updated and stored with this sweep's version.
+// All lanes of a warp work on the same colour at any time (a lane spinning on a value that another lane of its own
+// warp is about to store would never see it: the warp reconverges behind the spin loop).
+// The buffer's launch parity lives on the device (ctl->flow_parity[buf]; flipped by the last CTA to leave), because
+// launches queued ahead of a converged solve return at once and must not count.
 template <typename ST, int KC, int VEC>
-__global__ void __launch_bounds__(kFlowThreads, 2) k_gs_flow(DeviceModel M, ST* z, int n_sweeps_arg, int launch_parity) {
+__global__ void __launch_bounds__(kFlowThreads, 2) k_gs_flow(DeviceModel M, ST* z, int n_sweeps_arg, int buf) {
     static_assert(sizeof(ST) * VEC == 16, "k_gs_flow moves 16-byte packs");
+    constexpr int NR = kGsRows, VS = GsSlots<ST>::val, NS = GsSlots<ST>::total;
+    extern __shared__ int4 gs_land[];          // [NR rows][4 gathers | u | values][kFlowThreads]
     __shared__ int s_cp[kMaxColors + 1];
     if (M.ctl->all_done || M.ctl->finish_half) return;
     const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
+    const int launch_parity = M.ctl->flow_parity[buf] ^ 1;
     const int K = M.K, W = M.W, nc = M.n_colors;
     const int lane = threadIdx.x % KC, group = threadIdx.x / KC;
     constexpr int GPB = kFlowThreads / KC;
@@ -1293,142 +1306,148 @@ __global__ void __launch_bounds__(kFlowThreads, 2) k_gs_flow(DeviceModel M, ST* 
     const int sid = M.strip0 + blockIdx.x;
     const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)sid * (nc + 1);
     for (int q = threadIdx.x; q <= nc; q += kFlowThreads) s_cp[q] = cp_src[q];
-    __syncthreads();                              // the only CTA-wide synchronisation of the kernel
+    __syncthreads();                              // (colour ranges; the sweeps themselves never synchronise the CTA)
     const int c = lane * VEC;
-    if (c >= K) return;                           // (lanes beyond the last column have nothing to do and nobody waits for them)
+    const bool lane_on = c < K;
+    const int n_steps = n_sweeps * nc;
     const unsigned spin_limit = 1u << 22;
     bool gave_up = false;
-    // The lanes of a warp stay on the SAME colour (a lane that spun on a value another lane of its warp is about to
-    // store would never see it: the compiler reconverges the warp behind the spin loop).  So the walk over
-    // (sweep, colour, pass) is warp-uniform -- pass p takes row  first-of-colour + group + p * GPB  -- and lane groups
-    // whose colour has fewer rows idle through the warp's last pass of it.  idx / values / u of the next row are
-    // fetched while the current one gathers.
-    const int g0 = (int)(threadIdx.x & ~31u) / KC;            // this warp's first lane group: it has the most rows
-    int sw = 0, col = 0, pass = 0;
-    auto settle = [&]() {                                      // move (sw, col, pass) to the warp's next existing pass
-        while (sw < n_sweeps && s_cp[col] + g0 + pass * GPB >= s_cp[col + 1]) {
-            pass = 0;
-            if (++col == nc) { col = 0; ++sw; }
-        }
-    };
-    settle();
-    int4 nidx = make_int4(0, 0, 0, 0); Pk<ST, 4> nval = {}; Pk<ST, VEC> nown = {};
-    int nrow = 0; bool nact = false;
-    auto fetch = [&]() {
-        nrow = s_cp[col] + group + pass * GPB;
-        nact = nrow < s_cp[col + 1];
-        if (nact) {
-            nidx = *reinterpret_cast<const int4*>(ecol + (size_t)nrow * W);
-            nval = ldk<ST, 4>(eval + (size_t)nrow * W);
-            nown = ldk_cg<ST, VEC>(us + (size_t)nrow * K + c);
-        }
-    };
-    if (sw < n_sweeps) fetch();
-    while (sw < n_sweeps) {
-        const int row = nrow, rsw = sw;
-        const bool active = nact;
-        const int4 idx = nidx; const Pk<ST, 4> val = nval; const Pk<ST, VEC> own = nown;
-        // versions: this sweep's for neighbours of an earlier colour, the previous sweep's for the others
-        const int tag_new = (launch_parity << 1) | (rsw & 1), tag_old = (launch_parity << 1) | ((rsw + 1) & 1);
-        const bool first_sweep = rsw == 0;
-        const int cs[4] = {idx.x, idx.y, idx.z, idx.w};
-        int4 x[4]; int want[4]; bool need[4];
+    auto slot = [&](int r, int s) { return gs_land + (r * NS + s) * kFlowThreads + threadIdx.x; };
+    int4 pc[NR], pcn[NR];
+    auto load_idx = [&](int4 (&dst)[NR], int step) {
+        const int col = step % nc;
+        const int rb = s_cp[col], re = s_cp[col + 1];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = cs[u] & kColMask;
-            need[u] = active && !(first_sweep && cs[u] < 0) && j != row;      // not visited yet in the sweep from z = 0; padding
-            want[u] = cs[u] < 0 ? tag_old : tag_new;
-            x[u] = need[u] ? ld_relaxed_v4(z + (size_t)j * K + c) : make_int4(0, 0, 0, 0);
+        for (int r = 0; r < NR; ++r) {
+            const int i = rb + group + r * GPB;
+            if (i < re) dst[r] = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
         }
-        // the next row's operands go out under the gathers
-        ++pass;
-        settle();
-        if (sw < n_sweeps) fetch();
-        // re-read the packs that do not show the version they must (rare: they were written a step ago)
+    };
+    // a pack of z that shows version `want` (re-read until it does), version bits cleared
+    auto gather_checked = [&](const ST* src, int want) {
+        int4 y = ld_relaxed_v4(src);
         unsigned spins = 0;
-        for (;;) {
-            bool ok = true;
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (need[u] && !pack_has_tag<ST>(x[u], want[u])) {
-                    ok = false;
-                    x[u] = ld_relaxed_v4(z + (size_t)(cs[u] & kColMask) * K + c);
-                }
-            if (ok || gave_up) break;
+        while (!pack_has_tag<ST>(y, want) && !gave_up) {
             if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }     // never hang the device
-            if (spins > 4) __nanosleep(40);
+            if (spins > 2) __nanosleep(64);
+            y = ld_relaxed_v4(src);
         }
-        Pk<ST, VEC> o;
+        y = pack_set_tag<ST>(y, 0);
+        return *reinterpret_cast<const Pk<ST, VEC>*>(&y);
+    };
+    Pk<ST, VEC> zero;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) o.a[q] = (ST)0;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int4 clean = pack_set_tag<ST>(x[u], 0);
-            const Pk<ST, VEC> xv = *reinterpret_cast<const Pk<ST, VEC>*>(&clean);
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) o.a[q] += val.a[u] * xv.a[q];
-        }
-        if (!active) continue;
-        for (int w = 4; w < W; w += 4) {              // rows wider than 4: the remaining ELL blocks, same protocol
-            const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)row * W + w);
-            const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)row * W + w);
+    for (int q = 0; q < VEC; ++q) zero.a[q] = (ST)0;
+    // a row through registers (rows beyond the pipelined ones, ELL blocks beyond the first, further column chunks)
+    auto relax_slow = [&](int i, int cc, int w0, Pk<ST, VEC> acc, bool first_sweep, int tag_new, int tag_old) {
+        for (int w = w0; w < W; w += 4) {
+            const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
+            const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
             const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = ds[u] & kColMask;
-                if ((first_sweep && ds[u] < 0) || j == row) continue;
-                const int wt = ds[u] < 0 ? tag_old : tag_new;
-                int4 y = ld_relaxed_v4(z + (size_t)j * K + c);
-                unsigned sp2 = 0;
-                while (!pack_has_tag<ST>(y, wt) && !gave_up) {
-                    if (++sp2 > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }
-                    __nanosleep(40);
-                    y = ld_relaxed_v4(z + (size_t)j * K + c);
-                }
-                y = pack_set_tag<ST>(y, 0);
-                const Pk<ST, VEC> yv = *reinterpret_cast<const Pk<ST, VEC>*>(&y);
+                if ((first_sweep && ds[u] < 0) || j == i) continue;          // not visited yet in the sweep from z = 0; padding
+                const Pk<ST, VEC> y = gather_checked(z + (size_t)j * K + cc, ds[u] < 0 ? tag_old : tag_new);
 #pragma unroll
-                for (int q = 0; q < VEC; ++q) o.a[q] += wv.a[u] * yv.a[q];
+                for (int q = 0; q < VEC; ++q) acc.a[q] += wv.a[u] * y.a[q];
             }
         }
+        return acc;
+    };
+    auto store_row = [&](int i, int cc, const Pk<ST, VEC>& own, const Pk<ST, VEC>& acc, int tag_new) {
+        Pk<ST, VEC> o;
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - o.a[q];
-        const int4 tagged = pack_set_tag<ST>(*reinterpret_cast<const int4*>(&o), tag_new);
-        *reinterpret_cast<int4*>(z + (size_t)row * K + c) = tagged;
-        // further column chunks of the row (more columns than lanes x VEC): same protocol, one pack at a time
-        for (int cc = c + KC * VEC; cc < K; cc += KC * VEC) {
-            Pk<ST, VEC> o2;
+        for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - acc.a[q];
+        *reinterpret_cast<int4*>(z + (size_t)i * K + cc) = pack_set_tag<ST>(*reinterpret_cast<const int4*>(&o), tag_new);
+    };
+
+    load_idx(pc, 0);
+    for (int step = 0; step < n_steps; ++step) {
+        const int col = step % nc, sw = step / nc;
+        const bool first_sweep = sw == 0, last_step = step + 1 == n_steps;
+        // versions: this sweep's for neighbours of an earlier colour, the previous sweep's for the others
+        const int tag_new = (launch_parity << 1) | (sw & 1), tag_old = (launch_parity << 1) | ((sw + 1) & 1);
+        const int rb = s_cp[col], re = s_cp[col + 1];
+        bool on[NR]; int row[NR];
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) o2.a[q] = (ST)0;
-            for (int w = 0; w < W; w += 4) {
-                const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)row * W + w);
-                const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)row * W + w);
-                const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+        for (int r = 0; r < NR; ++r) { row[r] = rb + group + r * GPB; on[r] = row[r] < re && lane_on; }
+        // ---- copies: values, u, gathers; the colour swept just before this one last -------------------------------
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = ds[u] & kColMask;
-                    if ((first_sweep && ds[u] < 0) || j == row) continue;
-                    const int wt = ds[u] < 0 ? tag_old : tag_new;
-                    int4 y = ld_relaxed_v4(z + (size_t)j * K + cc);
-                    unsigned sp2 = 0;
-                    while (!pack_has_tag<ST>(y, wt) && !gave_up) {
-                        if (++sp2 > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }
-                        __nanosleep(40);
-                        y = ld_relaxed_v4(z + (size_t)j * K + cc);
+        for (int r = 0; r < NR; ++r) {
+            if (!on[r]) continue;
+            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
+            cp_async_cg16(slot(r, 4), us + (size_t)row[r] * K + c);
+#pragma unroll
+            for (int v = 0; v < VS; ++v) cp_async_cg16(slot(r, 5 + v), reinterpret_cast<const char*>(eval + (size_t)row[r] * W) + 16 * v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = cs[u] & kColMask;
+                if ((first_sweep && cs[u] < 0) || j == row[r]) *slot(r, u) = make_int4(0, 0, 0, 0);
+                else if (!(cs[u] & kPrevBit)) cp_async_cg16(slot(r, u), z + (size_t)j * K + c);
+            }
+        }
+        if (!last_step) load_idx(pcn, step + 1);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (!on[r]) continue;
+            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((cs[u] & kPrevBit) && !(first_sweep && cs[u] < 0)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
+        }
+        cp_async_wait_all();
+        // ---- check the versions, update, store ------------------------------------------------------------------
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (!on[r]) continue;
+            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
+            ST vals[4];
+#pragma unroll
+            for (int v = 0; v < VS; ++v) *reinterpret_cast<int4*>(reinterpret_cast<char*>(vals) + 16 * v) = *slot(r, 5 + v);
+            Pk<ST, VEC> o = zero;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = cs[u] & kColMask;
+                int4 x = *slot(r, u);
+                if (!((first_sweep && cs[u] < 0) || j == row[r])) {
+                    const int want = cs[u] < 0 ? tag_old : tag_new;
+                    unsigned spins = 0;
+                    while (!pack_has_tag<ST>(x, want) && !gave_up) {
+                        if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }
+                        if (spins > 2) __nanosleep(64);
+                        x = ld_relaxed_v4(z + (size_t)j * K + c);
                     }
-                    y = pack_set_tag<ST>(y, 0);
-                    const Pk<ST, VEC> yv = *reinterpret_cast<const Pk<ST, VEC>*>(&y);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) o2.a[q] += wv.a[u] * yv.a[q];
+                    x = pack_set_tag<ST>(x, 0);
                 }
-            }
-            const Pk<ST, VEC> own2 = ldk_cg<ST, VEC>(us + (size_t)row * K + cc);
+                const Pk<ST, VEC> xv = *reinterpret_cast<const Pk<ST, VEC>*>(&x);
 #pragma unroll
-            for (int q = 0; q < VEC; ++q) o2.a[q] = own2.a[q] - o2.a[q];
-            *reinterpret_cast<int4*>(z + (size_t)row * K + cc) = pack_set_tag<ST>(*reinterpret_cast<const int4*>(&o2), tag_new);
+                for (int q = 0; q < VEC; ++q) o.a[q] += vals[u] * xv.a[q];
+            }
+            if (W > 4) o = relax_slow(row[r], c, 4, o, first_sweep, tag_new, tag_old);
+            store_row(row[r], c, *reinterpret_cast<const Pk<ST, VEC>*>(slot(r, 4)), o, tag_new);
         }
+        // further column chunks of those rows (more columns than lanes x VEC), colours with more rows per lane group
+#pragma unroll 1
+        for (int r = 0; r < NR; ++r)
+            if (row[r] < re)
+                for (int cc = c + KC * VEC; cc < K; cc += KC * VEC)
+                    store_row(row[r], cc, ldk_cg<ST, VEC>(us + (size_t)row[r] * K + cc), relax_slow(row[r], cc, 0, zero, first_sweep, tag_new, tag_old), tag_new);
+#pragma unroll 1
+        for (int i = rb + group + NR * GPB; i < re; i += GPB)
+            for (int cc = c; cc < K; cc += KC * VEC)
+                store_row(i, cc, ldk_cg<ST, VEC>(us + (size_t)i * K + cc), relax_slow(i, cc, 0, zero, first_sweep, tag_new, tag_old), tag_new);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) pc[r] = pcn[r];
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
+    // the last CTA to leave records the parity this launch wrote into the buffer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
+        __threadfence();
+        const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
+        if (t == gridDim.x - 1) { M.ctl->gs_bar[1] = 0; M.ctl->flow_parity[buf] = launch_parity; __threadfence(); }
+    }
 }
 
 // u (fp64) -> the sweep type, own rows (the BiCGSTAB path in front of k_gs_strip: its vectors are fp64)
