@@ -102,9 +102,6 @@ def load_library():
         "cwr_get_lhs": ([H, C.POINTER(C.c_int64), ip, ip, dp], C.c_int),
         "cwr_get_rhs": ([H, C.c_int, dp], C.c_int),
         "cwr_get_permutation": ([H, ip], C.c_int),
-        "cwr_tile_layout": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
-                             C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), ip, ip, ip, ip, ip,
-                             C.POINTER(C.c_uint16), ip], C.c_int),
         "cwr_strip_layout": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                               ip, ip, ip, ip, C.POINTER(C.c_uint8)], C.c_int),
         "cwr_get_options": ([H, C.POINTER(CwrOptions)], C.c_int),
@@ -176,30 +173,6 @@ def order_cells(f1, f2, n_face: int, reorder: bool = True, n_colors: int = 0, fl
     if n_parts == 1:
         return new_of_old, (colours[0] if nc.value else colours), nl.value
     return new_of_old, colours, nl.value, part_ptr[: n_parts + 1].copy(), n_send[:n_parts].copy()
-
-
-def tile_layout(f1, f2, n_face: int, n_colors: int, flow_hint, tile_rows: int, tile_cap: int, tile_halo: int):
-    """Host-only, experimental: the tiling of the tile-local sweeps (cwr_tile_layout) as a dict of numpy arrays."""
-    lib = load_library()
-    f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
-    n = int(f1.max()) + 1
-    hint = None if flow_hint is None else _arr(flow_hint, np.float32, f1.shape, "flow_hint")
-    nt, ne, W, nc = C.c_int(), C.c_int(), C.c_int(), C.c_int()
-    args = (n, int(n_face), len(f1), _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), int(n_colors), _ptr(hint, C.c_float),
-            int(tile_rows), int(tile_cap), int(tile_halo), C.byref(nt), C.byref(ne), C.byref(W), C.byref(nc))
-    rc = lib.cwr_tile_layout(*args, None, None, None, None, None, None, None)
-    if rc != CWR_OK:
-        raise CwrError(rc, lib.cwr_last_error(None).decode())
-    out = {"new_of_old": np.empty(n, np.int32), "tile_ptr": np.empty(nt.value + 1, np.int32), "ext_ptr": np.empty(nt.value + 1, np.int32),
-           "ext_rows": np.empty(ne.value, np.int32), "lcolor_ptr": np.empty((nt.value, nc.value + 1), np.int32),
-           "tile_ell": np.empty((ne.value, W.value), np.uint16), "ell_col": np.empty((n, W.value), np.int32)}
-    rc = lib.cwr_tile_layout(*args, _ptr(out["new_of_old"], C.c_int32), _ptr(out["tile_ptr"], C.c_int32), _ptr(out["ext_ptr"], C.c_int32),
-                             _ptr(out["ext_rows"], C.c_int32), _ptr(out["lcolor_ptr"], C.c_int32), _ptr(out["tile_ell"], C.c_uint16),
-                             _ptr(out["ell_col"], C.c_int32))
-    if rc != CWR_OK:
-        raise CwrError(rc, lib.cwr_last_error(None).decode())
-    out.update(n_tiles=nt.value, n_colors=nc.value, W=W.value)
-    return out
 
 
 def strip_layout(f1, f2, n_face: int, n_colors: int, flow_hint, n_strips: int, n_parts: int = 1):

@@ -33,16 +33,12 @@ struct cwr_handle {
     int m_steps = 1;                 // sweeps of the preconditioner + 1 (1 = diagonal scaling only)
     bool sweep_f32 = true;           // preconditioner sweeps (and p^, s^) in fp32
     bool gauss_seidel = false;       // multicolour Gauss-Seidel sweeps instead of Jacobi steps
-    bool tiled = false;              // EXPERIMENTAL: tile-local sweeps (precond_sweep = 2, k_precond_tile)
-    int32_t *d_ext_ptr = nullptr, *d_ext_rows = nullptr, *d_lcolor_ptr = nullptr; uint16_t* d_tile_ell = nullptr;
-    size_t tile_smem = 0;
     bool hint_done = false;          // the colours have been aligned with the flow (or it is too late to)
     int grid_sweep = 0, grid_gs = 0;
     int32_t* d_color_ptr = nullptr;
     bool dc = false;                 // defect-correction solver (options.solver = 2) instead of BiCGSTAB
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
-    bool flow = false;               // ... or no synchronisation at all: versioned packs, dataflow (k_gs_flow, precond_sync = 4)
     int n_strips = 0;
     int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
     unsigned long long* d_strip_flag = nullptr;
@@ -239,20 +235,6 @@ static cudaError_t gs3_prepare(int* occ) {
     } else { *occ = 0; return cudaSuccess; }
 }
 template <typename ST, int SKC, int SVEC>
-static cudaError_t flow_prepare(int* occ) {
-    if constexpr (sizeof(ST) * SVEC == 16) {
-        cudaError_t e = cudaFuncSetAttribute(k_gs_flow<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, gs3_smem_bytes<ST>());
-        if (e != cudaSuccess) return e;
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k_gs_flow<ST, SKC, SVEC>, kFlowThreads, gs3_smem_bytes<ST>());
-    } else { *occ = 0; return cudaSuccess; }
-}
-template <typename ST, int SKC, int SVEC>
-static cudaError_t flow_launch(int grid, void** args, cudaStream_t stream) {
-    if constexpr (sizeof(ST) * SVEC == 16)
-        return cudaLaunchCooperativeKernel((const void*)k_gs_flow<ST, SKC, SVEC>, dim3(grid), dim3(kFlowThreads), args, gs3_smem_bytes<ST>(), stream);
-    else return cudaErrorInvalidValue;
-}
-template <typename ST, int SKC, int SVEC>
 static cudaError_t gs3_launch(int grid, void** args, cudaStream_t stream) {
     if constexpr (sizeof(ST) * SVEC == 16)
         return cudaLaunchCooperativeKernel((const void*)k_gs_strip<ST, SKC, SVEC>, dim3(grid), dim3(kGsThreads), args, gs3_smem_bytes<ST>(), stream);
@@ -278,10 +260,6 @@ static int upload_topology(cwr_handle* h) {
     CK(put(h, h->d_new_of_old, tp.new_of_old)); CK(put(h, h->d_old_of_new, tp.old_of_new));
     CK(put(h, h->d_color_ptr, tp.color_ptr));
     CK(put(h, h->d_send_mask, tp.send_mask)); CK(put(h, h->d_send_rows, tp.send_rows));
-    if (h->tiled) {
-        CK(put(h, h->d_ext_ptr, tp.ext_ptr)); CK(put(h, h->d_ext_rows, tp.ext_rows));
-        CK(put(h, h->d_lcolor_ptr, tp.lcolor_ptr)); CK(put(h, h->d_tile_ell, tp.tile_ell));
-    }
     if (h->strips) {
         CK(put(h, h->d_strip_cptr, tp.strip_cptr)); CK(put(h, h->d_strip_nptr, tp.strip_nptr));
         if (tp.strip_nbr.size() > h->strip_nbr_cap) {          // the neighbour lists depend on the ordering
@@ -308,8 +286,6 @@ static void set_owned_ranges(cwr_handle* h) {
     M.b_lo = tp.bcell_ptr[r]; M.b_hi = tp.bcell_ptr[r + 1];
     M.n_colors = tp.n_colors;
     M.color_ptr = h->d_color_ptr + (size_t)r * (tp.n_colors + 1);
-    M.ext_ptr = h->d_ext_ptr; M.ext_rows = h->d_ext_rows; M.lcolor_ptr = h->d_lcolor_ptr; M.tile_ell = h->d_tile_ell;
-    M.n_tiles = h->tiled ? (int)tp.tile_ptr.size() - 1 : 0; M.max_ext = tp.max_ext;
     M.strip_cptr = h->d_strip_cptr; M.strip_nptr = h->d_strip_nptr; M.strip_nbr = h->d_strip_nbr; M.strip_flag = h->d_strip_flag;
     M.n_strips = h->strips ? h->n_strips : 0; M.strip0 = r * M.n_strips;
     unsigned nbr = 0;
@@ -336,7 +312,7 @@ static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
     for (int e = 0; e < E; ++e) hint[e] = (float)mean[e];
     Topology t2;
     std::string terr = build_topology(h->n, h->F, E, h->f1_ref.data(), h->f2_ref.data(), h->opt.reorder != 0,
-                                      h->opt.precond_colors, hint.data(), h->world, t2, 0, 0, 0, h->strips ? h->n_strips : 0);
+                                      h->opt.precond_colors, hint.data(), h->world, t2, h->strips ? h->n_strips : 0);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
     if (h->attached) return CWR_OK;                 // peers already rely on the current ownership
@@ -435,9 +411,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         FAIL(CWR_EINVAL, "domain decomposition needs the multi-CTA solver path (solver_path = 1) and precond_steps >= 2");
     h->tiny = tiny;
     h->gauss_seidel = h->opt.precond_sweep == 1 && !h->small_path && h->m_steps > 1;
-    h->tiled = h->opt.precond_sweep == 2 && !h->small_path && h->m_steps > 1;
-    if (h->opt.precond_sweep == 2 && !h->tiled) FAIL(CWR_EINVAL, "precond_sweep = 2 (experimental tile-local sweeps) needs solver_path = 1 and precond_steps >= 2");
-    if (h->tiled && h->world > 1) FAIL(CWR_EINVAL, "precond_sweep = 2 (experimental) is single-GPU only");
+    if (h->opt.precond_sweep != 0 && h->opt.precond_sweep != 1) FAIL(CWR_EINVAL, "precond_sweep must be 0 (Jacobi steps) or 1 (Gauss-Seidel sweeps)");
     int ndev = 0;
     CK(cudaGetDeviceCount(&ndev));
     if (ndev == 0) FAIL(CWR_ECUDA, "no CUDA device: this library has no CPU fallback");
@@ -466,11 +440,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->dc = h->opt.solver == 2 && !h->small_path && h->m_steps > 1;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
-    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 4) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : (h->world > 1 ? 3 : 4);
-    if (h->opt.precond_sync == 4 && h->world > 1) FAIL(CWR_EINVAL, "precond_sync = 4 (dataflow sweeps) is single-GPU; use 3 with domain decomposition");
-    if (h->gauss_seidel && h->opt.precond_sync == 4) {
-        if ((h->sweep_f32 ? 4 : 8) * h->SVEC == 16) h->flow = true; else h->opt.precond_sync = 2;      // packs narrower than 16 bytes
-    }
+    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 3) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 3;
     if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
     h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
@@ -478,11 +448,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->gauss_seidel && h->opt.precond_sync == 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
     if (h->gauss_seidel) {
         int occ_gs = 0, coop = 0;
-        if (h->flow) {
-            cudaError_t e = cudaSuccess;
-            SWEEP_DISPATCH(e = flow_prepare<ST, SKC, SVEC>(&occ_gs));
-            CK(e);
-        } else if (h->pipelined) {
+        if (h->pipelined) {
             cudaError_t e = cudaSuccess;
             SWEEP_DISPATCH(e = gs3_prepare<ST, SKC, SVEC>(&occ_gs));
             CK(e);
@@ -518,19 +484,12 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
-    int tile_rows = 0, tile_cap = 0;
-    if (h->tiled) {      // rows (core + 4 halo layers) that fit in one CTA's shared memory: z, u (K each), values, indices (W = 4 assumed)
-        const int stb = h->sweep_f32 ? 4 : 8;
-        tile_cap = (int)std::min<size_t>(8191, (size_t)(226 * 1024) / ((size_t)2 * n_const * stb + 4 * stb + 8));
-        tile_rows = std::max(16, (int)(tile_cap * 0.55));
-        if (h->opt.precond_colors < 8) h->opt.precond_colors = 11;
-    }
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
-                                      (h->gauss_seidel || h->tiny || h->tiled) ? h->opt.precond_colors : 0,
-                                      (h->gauss_seidel || h->tiny || h->tiled) ? flow_hint : nullptr, h->world, h->topo,
-                                      tile_rows, tile_cap, 4, h->strips ? h->n_strips : 0);
+                                      (h->gauss_seidel || h->tiny) ? h->opt.precond_colors : 0,
+                                      (h->gauss_seidel || h->tiny) ? flow_hint : nullptr, h->world, h->topo,
+                                      h->strips ? h->n_strips : 0);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
-    if (flow_hint || h->tiled) h->hint_done = true;     // (the tile arrays' sizes depend on the order: no re-ordering later)
+    if (flow_hint) h->hint_done = true;
     const Topology& tp = h->topo;
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
@@ -578,17 +537,6 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(dalloc(h, &h->d_strip_cptr, tp.strip_cptr.size())); CK(dalloc(h, &h->d_strip_nptr, tp.strip_nptr.size()));
         CK(dalloc(h, &h->d_strip_flag, (size_t)h->n_strips));
         CK(cudaMemsetAsync(h->d_strip_flag, 0, (size_t)h->n_strips * sizeof(unsigned long long), h->stream));
-    }
-    if (h->tiled) {
-        CK(dalloc(h, &h->d_ext_ptr, tp.ext_ptr.size())); CK(dalloc(h, &h->d_ext_rows, tp.ext_rows.size()));
-        CK(dalloc(h, &h->d_lcolor_ptr, tp.lcolor_ptr.size())); CK(dalloc(h, &h->d_tile_ell, tp.tile_ell.size()));
-        h->tile_smem = tile_smem_bytes(tp.max_ext, K, tp.W, h->sweep_f32 ? 4 : 8);
-        int max_optin = 0;
-        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-        if (h->tile_smem > (size_t)max_optin) FAIL(CWR_EINVAL, "precond_sweep = 2: a tile does not fit in shared memory (rows wider than 4?)");
-        cudaError_t e = cudaSuccess;
-        SWEEP_DISPATCH(e = cudaFuncSetAttribute(k_precond_tile<ST, SKC, SVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->tile_smem));
-        CK(e);
     }
     {
         int rc = upload_topology(h);
@@ -671,8 +619,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     }
     M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
     M.sweep_f32 = h->sweep_f32 ? 1 : 0;
-    M.us_from_producer = (h->dc && (h->pipelined || h->flow)) ? 1 : 0;
-    if (h->flow) M.dc_floor = h->sweep_f32 ? 1e5 : 1e12;        // two mantissa bits of every z element carry its version
+    M.us_from_producer = (h->dc && h->pipelined) ? 1 : 0;
     M.tol2 = h->opt.rtol * h->opt.rtol;
     M.diffusion_coefficient = D;
     M.max_iter = h->opt.max_iter;
@@ -973,29 +920,20 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
     const int J = h->m_steps - 1;
     if (J <= 0) return u;
     DeviceModel& M = h->M;
-    if (h->tiled) {          // EXPERIMENTAL: all sweeps of the application inside one CTA per tile
-        mark(h, CWR_FAM_PRECOND);
-        SWEEP_DISPATCH((k_precond_tile<ST, SKC, SVEC><<<M.n_tiles, kTileThreads, h->tile_smem, h->stream>>>(M, u, (ST*)dst, J)));
-        h->launches += 1;
-        return dst;
-    }
     if (h->gauss_seidel) {
         mark(h, CWR_FAM_PRECOND);
         int sweeps = planned ? 0 : J;                 // 0: the count the defect-correction solver planned on the device
         unsigned long long seq = ++h->gs_seq;
         void* args[] = {(void*)&M, (void*)&u, (void*)&dst, (void*)&sweeps, (void*)&seq};
         cudaError_t e = cudaSuccess;
-        if (h->pipelined || h->flow) {
+        if (h->pipelined) {
             if (!M.us_from_producer) {        // BiCGSTAB: u is one of its fp64 vectors
                 if (h->sweep_f32) k_to_sweep_type<float><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (float*)M.us);
                 else k_to_sweep_type<double><<<h->grid_rows, kThreads, 0, h->stream>>>(M, u, (double*)M.us);
                 h->launches += 1;
             }
-            int parity = dst == M.sh ? 1 : 0;                         // which z buffer: its launch parity lives on the device
             void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
-            void* args4[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&parity};
-            if (h->flow) { SWEEP_DISPATCH(e = (flow_launch<ST, SKC, SVEC>(h->grid_gs, args4, h->stream))); }
-            else { SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream))); }
+            SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream)));
         } else
         if (h->strips) { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, true>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
         else { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, false>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
@@ -1655,34 +1593,12 @@ int cwr_dd_layout(cwr_handle* h, cwr_dd_info* out, uint8_t* owned_cells, uint8_t
     return CWR_OK;
 }
 
-int cwr_tile_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
-                    int tile_rows, int tile_cap, int tile_halo, int* n_tiles, int* ext_total, int* ell_width, int* n_colors_out,
-                    int32_t* new_of_old, int32_t* tile_ptr, int32_t* ext_ptr, int32_t* ext_rows, int32_t* lcolor_ptr,
-                    uint16_t* tile_ell, int32_t* ell_col) {
-    if (!f1 || !f2) return CWR_EINVAL;
-    Topology t;
-    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, 1, t, tile_rows, tile_cap, tile_halo);
-    if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
-    if (n_tiles) *n_tiles = (int)t.tile_ptr.size() - 1;
-    if (ext_total) *ext_total = (int)t.ext_rows.size();
-    if (ell_width) *ell_width = t.W;
-    if (n_colors_out) *n_colors_out = t.n_colors;
-    if (new_of_old) std::copy(t.new_of_old.begin(), t.new_of_old.end(), new_of_old);
-    if (tile_ptr) std::copy(t.tile_ptr.begin(), t.tile_ptr.end(), tile_ptr);
-    if (ext_ptr) std::copy(t.ext_ptr.begin(), t.ext_ptr.end(), ext_ptr);
-    if (ext_rows) std::copy(t.ext_rows.begin(), t.ext_rows.end(), ext_rows);
-    if (lcolor_ptr) std::copy(t.lcolor_ptr.begin(), t.lcolor_ptr.end(), lcolor_ptr);
-    if (tile_ell) std::copy(t.tile_ell.begin(), t.tile_ell.end(), tile_ell);
-    if (ell_col) std::copy(t.ell_col.begin(), t.ell_col.end(), ell_col);
-    return CWR_OK;
-}
-
 int cwr_strip_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
                      int n_parts, int n_strips, int* n_colors_out, int* nbr_total, int32_t* new_of_old, int32_t* strip_cptr,
                      int32_t* strip_nptr, int32_t* strip_nbr, uint8_t* color_of) {
     if (!f1 || !f2) return CWR_EINVAL;
     Topology t;
-    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, std::max(1, n_parts), t, 0, 0, 0, n_strips);
+    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, std::max(1, n_parts), t, n_strips);
     if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
     if (n_colors_out) *n_colors_out = t.n_colors;
     if (nbr_total) *nbr_total = (int)t.strip_nbr.size();
@@ -1698,10 +1614,10 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     if (!h || !out) return CWR_EINVAL;
     *out = h->opt;
     out->precond_colors = (h->gauss_seidel || h->tiny) ? h->topo.n_colors : 0;
-    out->precond_sweep = h->tiled ? 2 : ((h->gauss_seidel || h->tiny) ? 1 : 0);
+    out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
-    out->precond_sync = h->gauss_seidel ? (h->flow ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
+    out->precond_sync = h->gauss_seidel ? (h->pipelined ? 3 : (h->strips ? 2 : 1)) : 0;
     return CWR_OK;
 }
 

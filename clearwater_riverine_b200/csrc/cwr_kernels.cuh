@@ -63,7 +63,6 @@ struct SolverCtl {
     int dc_fail;          // the sweeps stagnate or diverge (not an M-matrix?): the host falls back to BiCGSTAB
     int dc_slow;          // consecutive cycles that reduced the residual by less than 0.7
     int sweeps_done;      // Gauss-Seidel sweeps of this solve
-    int flow_parity[2];   // k_gs_flow: launch parity last written into the two z buffers (p^, s^)
     double dc_rate;       // error factor per sweep measured over the last cycle (kept across steps)
     double dc_worst;      // max over columns of (||r|| / ||b||) / rtol after the last cycle
 };
@@ -99,9 +98,6 @@ struct DeviceModel {
     const int32_t* f1p; const int32_t* f2p;
     const int32_t* bcell; const int32_t* bptr; const int32_t* bedge;
     const int32_t* color_ptr; int n_colors;   // (n_colors+1) row ranges of the Gauss-Seidel colours
-    // tile-local sweeps (EXPERIMENTAL, precond_sweep = 2; cwr_topology.h)
-    const int32_t* ext_ptr; const int32_t* ext_rows; const int32_t* lcolor_ptr; const uint16_t* tile_ell;
-    int n_tiles, max_ext;
     // strips of the neighbour-synchronised Gauss-Seidel kernel (cwr_topology.h): CTA b owns strip strip0 + b
     const int32_t* strip_cptr; const int32_t* strip_nptr; const int32_t* strip_nbr;
     unsigned long long* strip_flag;   // (n_strips) last step a strip has finished: (launch sequence << 20) | (step + 1)
@@ -1237,306 +1233,12 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Dataflow sweep kernel (precond_sync = 4; single rank, 16-byte packs): no barrier and no flag at all.
-// ncu on k_gs_strip (profiles/r02_notes.md): 39 % of the warp samples still sit at the two __syncthreads() around the
-// neighbour wait -- a step's dependent chain (stores, fence, flag, poll, late gathers) is ~3.5 us, every CTA runs
-// it in lock-step with its neighbours, and the memory system idles meanwhile.  Here the DATA is the flag: every
-// 16-byte pack of z carries, in the two low mantissa bits of each of its elements, the version that wrote it
-// (launch parity of this buffer, sweep parity), and a gather simply re-reads a pack until all its elements show the
-// version the sweep order says it must see.  That is enough:
-//   * a row of colour c in sweep s must see neighbours of earlier colours at version s and the others at s - 1;
-//     a neighbour can only ever be one version behind that (the row itself was needed, at its previous version,
-//     to produce the neighbour's previous version), so one parity bit tells the two apart, and the buffer's launch
-//     parity tells this launch's packs from whatever an earlier launch left;
-//   * nothing can be overwritten too early: every reader of a row's version s is a neighbour whose own new value
-//     the row needs before it can produce version s + 1 (the coupling is symmetric), so the true dependencies
-//     already order every write after the reads of the value it replaces;
-//   * a torn 16-byte access would show elements of two versions and is re-read like a stale pack.
-// Warps therefore run free: each takes its rows of (sweep, colour) in order and stalls only on the packs that are
-// really missing -- usually none: they were written a whole step ago -- so the dependent chain of a step shrinks
-// to store -> L2 -> load, and the CTAs drift apart instead of marching in lock-step.  Two mantissa bits: z carries
-// 21 bits per element, far below what the sweeps resolve anyway (error factor ~0.2 per sweep).  Needs every CTA
-// resident (cooperative launch) and a fair scheduler among them, as the other sweep kernels do.
-// ---------------------------------------------------------------------------------------------
-constexpr int kFlowThreads = 512;
-
-__device__ __forceinline__ int4 ld_relaxed_v4(const void* p) {
-    int4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
-}
-// all elements of a pack carry `tag` (fp32: four low words; fp64: the low words of its two elements)
-template <typename ST>
-__device__ __forceinline__ bool pack_has_tag(const int4& v, int tag) {
-    if constexpr (sizeof(ST) == 4) return (((v.x ^ tag) | (v.y ^ tag) | (v.z ^ tag) | (v.w ^ tag)) & 3) == 0;
-    else return (((v.x ^ tag) | (v.z ^ tag)) & 3) == 0;
-}
-template <typename ST>
-__device__ __forceinline__ int4 pack_set_tag(int4 v, int tag) {
-    if constexpr (sizeof(ST) == 4) { v.x = (v.x & ~3) | tag; v.y = (v.y & ~3) | tag; v.z = (v.z & ~3) | tag; v.w = (v.w & ~3) | tag; }
-    else { v.x = (v.x & ~3) | tag; v.z = (v.z & ~3) | tag; }
-    return v;
-}
-
-// Structure of a step (one colour of one sweep), per thread, no CTA-wide synchronisation anywhere: the indices of
-// the step's rows are in registers (prefetched one step ahead); all copies -- matrix values, u, the gathers, those
-// of the colour swept just before (kPrevBit: the ones that may not have landed yet) last -- go out as cp.async into
-// the thread's own shared-memory slots; after they have arrived every needed pack is checked and the stale ones
-// are fetched again until they show their version; then the rows are updated and stored with this sweep's version.
-// All lanes of a warp work on the same colour at any time (a lane spinning on a value that another lane of its own
-// warp is about to store would never see it: the warp reconverges behind the spin loop).
-// The buffer's launch parity lives on the device (ctl->flow_parity[buf]; flipped by the last CTA to leave), because
-// launches queued ahead of a converged solve return at once and must not count.
-template <typename ST, int KC, int VEC>
-__global__ void __launch_bounds__(kFlowThreads, 2) k_gs_flow(DeviceModel M, ST* z, int n_sweeps_arg, int buf) {
-    static_assert(sizeof(ST) * VEC == 16, "k_gs_flow moves 16-byte packs");
-    constexpr int NR = kGsRows, VS = GsSlots<ST>::val, NS = GsSlots<ST>::total;
-    extern __shared__ int4 gs_land[];          // [NR rows][4 gathers | u | values][kFlowThreads]
-    __shared__ int s_cp[kMaxColors + 1];
-    if (M.ctl->all_done || M.ctl->finish_half) return;
-    const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
-    const int launch_parity = M.ctl->flow_parity[buf] ^ 1;
-    const int K = M.K, W = M.W, nc = M.n_colors;
-    const int lane = threadIdx.x % KC, group = threadIdx.x / KC;
-    constexpr int GPB = kFlowThreads / KC;
-    const int32_t* __restrict__ ecol = M.ell_col;
-    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
-    const ST* __restrict__ us = reinterpret_cast<const ST*>(M.us);
-    const int sid = M.strip0 + blockIdx.x;
-    const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)sid * (nc + 1);
-    for (int q = threadIdx.x; q <= nc; q += kFlowThreads) s_cp[q] = cp_src[q];
-    __syncthreads();                              // (colour ranges; the sweeps themselves never synchronise the CTA)
-    const int c = lane * VEC;
-    const bool lane_on = c < K;
-    const int n_steps = n_sweeps * nc;
-    const unsigned spin_limit = 1u << 22;
-    bool gave_up = false;
-    auto slot = [&](int r, int s) { return gs_land + (r * NS + s) * kFlowThreads + threadIdx.x; };
-    int4 pc[NR], pcn[NR];
-    auto load_idx = [&](int4 (&dst)[NR], int step) {
-        const int col = step % nc;
-        const int rb = s_cp[col], re = s_cp[col + 1];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int i = rb + group + r * GPB;
-            if (i < re) dst[r] = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
-        }
-    };
-    // a pack of z that shows version `want` (re-read until it does), version bits cleared
-    auto gather_checked = [&](const ST* src, int want) {
-        int4 y = ld_relaxed_v4(src);
-        unsigned spins = 0;
-        while (!pack_has_tag<ST>(y, want) && !gave_up) {
-            if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }     // never hang the device
-            if (spins > 2) __nanosleep(64);
-            y = ld_relaxed_v4(src);
-        }
-        y = pack_set_tag<ST>(y, 0);
-        return *reinterpret_cast<const Pk<ST, VEC>*>(&y);
-    };
-    Pk<ST, VEC> zero;
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) zero.a[q] = (ST)0;
-    // a row through registers (rows beyond the pipelined ones, ELL blocks beyond the first, further column chunks)
-    auto relax_slow = [&](int i, int cc, int w0, Pk<ST, VEC> acc, bool first_sweep, int tag_new, int tag_old) {
-        for (int w = w0; w < W; w += 4) {
-            const int4 d4 = *reinterpret_cast<const int4*>(ecol + (size_t)i * W + w);
-            const Pk<ST, 4> wv = ldk<ST, 4>(eval + (size_t)i * W + w);
-            const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = ds[u] & kColMask;
-                if ((first_sweep && ds[u] < 0) || j == i) continue;          // not visited yet in the sweep from z = 0; padding
-                const Pk<ST, VEC> y = gather_checked(z + (size_t)j * K + cc, ds[u] < 0 ? tag_old : tag_new);
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) acc.a[q] += wv.a[u] * y.a[q];
-            }
-        }
-        return acc;
-    };
-    auto store_row = [&](int i, int cc, const Pk<ST, VEC>& own, const Pk<ST, VEC>& acc, int tag_new) {
-        Pk<ST, VEC> o;
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) o.a[q] = own.a[q] - acc.a[q];
-        *reinterpret_cast<int4*>(z + (size_t)i * K + cc) = pack_set_tag<ST>(*reinterpret_cast<const int4*>(&o), tag_new);
-    };
-
-    load_idx(pc, 0);
-    for (int step = 0; step < n_steps; ++step) {
-        const int col = step % nc, sw = step / nc;
-        const bool first_sweep = sw == 0, last_step = step + 1 == n_steps;
-        // versions: this sweep's for neighbours of an earlier colour, the previous sweep's for the others
-        const int tag_new = (launch_parity << 1) | (sw & 1), tag_old = (launch_parity << 1) | ((sw + 1) & 1);
-        const int rb = s_cp[col], re = s_cp[col + 1];
-        bool on[NR]; int row[NR];
-#pragma unroll
-        for (int r = 0; r < NR; ++r) { row[r] = rb + group + r * GPB; on[r] = row[r] < re && lane_on; }
-        // ---- copies: values, u, gathers; the colour swept just before this one last -------------------------------
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            if (!on[r]) continue;
-            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
-            cp_async_cg16(slot(r, 4), us + (size_t)row[r] * K + c);
-#pragma unroll
-            for (int v = 0; v < VS; ++v) cp_async_cg16(slot(r, 5 + v), reinterpret_cast<const char*>(eval + (size_t)row[r] * W) + 16 * v);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = cs[u] & kColMask;
-                if ((first_sweep && cs[u] < 0) || j == row[r]) *slot(r, u) = make_int4(0, 0, 0, 0);
-                else if (!(cs[u] & kPrevBit)) cp_async_cg16(slot(r, u), z + (size_t)j * K + c);
-            }
-        }
-        if (!last_step) load_idx(pcn, step + 1);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            if (!on[r]) continue;
-            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if ((cs[u] & kPrevBit) && !(first_sweep && cs[u] < 0)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
-        }
-        cp_async_wait_all();
-        // ---- check the versions, update, store ------------------------------------------------------------------
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            if (!on[r]) continue;
-            const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
-            ST vals[4];
-#pragma unroll
-            for (int v = 0; v < VS; ++v) *reinterpret_cast<int4*>(reinterpret_cast<char*>(vals) + 16 * v) = *slot(r, 5 + v);
-            Pk<ST, VEC> o = zero;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int j = cs[u] & kColMask;
-                int4 x = *slot(r, u);
-                if (!((first_sweep && cs[u] < 0) || j == row[r])) {
-                    const int want = cs[u] < 0 ? tag_old : tag_new;
-                    unsigned spins = 0;
-                    while (!pack_has_tag<ST>(x, want) && !gave_up) {
-                        if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; gave_up = true; break; }
-                        if (spins > 2) __nanosleep(64);
-                        x = ld_relaxed_v4(z + (size_t)j * K + c);
-                    }
-                    x = pack_set_tag<ST>(x, 0);
-                }
-                const Pk<ST, VEC> xv = *reinterpret_cast<const Pk<ST, VEC>*>(&x);
-#pragma unroll
-                for (int q = 0; q < VEC; ++q) o.a[q] += vals[u] * xv.a[q];
-            }
-            if (W > 4) o = relax_slow(row[r], c, 4, o, first_sweep, tag_new, tag_old);
-            store_row(row[r], c, *reinterpret_cast<const Pk<ST, VEC>*>(slot(r, 4)), o, tag_new);
-        }
-        // further column chunks of those rows (more columns than lanes x VEC), colours with more rows per lane group
-#pragma unroll 1
-        for (int r = 0; r < NR; ++r)
-            if (row[r] < re)
-                for (int cc = c + KC * VEC; cc < K; cc += KC * VEC)
-                    store_row(row[r], cc, ldk_cg<ST, VEC>(us + (size_t)row[r] * K + cc), relax_slow(row[r], cc, 0, zero, first_sweep, tag_new, tag_old), tag_new);
-#pragma unroll 1
-        for (int i = rb + group + NR * GPB; i < re; i += GPB)
-            for (int cc = c; cc < K; cc += KC * VEC)
-                store_row(i, cc, ldk_cg<ST, VEC>(us + (size_t)i * K + cc), relax_slow(i, cc, 0, zero, first_sweep, tag_new, tag_old), tag_new);
-#pragma unroll
-        for (int r = 0; r < NR; ++r) pc[r] = pcn[r];
-    }
-    // the last CTA to leave records the parity this launch wrote into the buffer
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (blockIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
-        __threadfence();
-        const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
-        if (t == gridDim.x - 1) { M.ctl->gs_bar[1] = 0; M.ctl->flow_parity[buf] = launch_parity; __threadfence(); }
-    }
-}
-
 // u (fp64) -> the sweep type, own rows (the BiCGSTAB path in front of k_gs_strip: its vectors are fp64)
 template <typename ST>
 __global__ void __launch_bounds__(kThreads) k_to_sweep_type(DeviceModel M, const double* __restrict__ u, ST* __restrict__ out) {
     const size_t lo = (size_t)M.row_lo * M.K, hi = (size_t)M.row_hi * M.K;
     if (M.ctl->all_done || M.ctl->finish_half) return;
     for (size_t q = lo + blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < hi; q += (size_t)gridDim.x * blockDim.x) out[q] = (ST)u[q];
-}
-
-// ---------------------------------------------------------------------------------------------
-// EXPERIMENTAL -- written at the end of round 1, compiled, its host data structures and its arithmetic
-// emulated and tested on the CPU (tests/test_tile_layout.py), NOT YET RUN ON A GPU; off unless
-// precond_sweep = 2.  Tile-local multicolour Gauss-Seidel (restricted additive Schwarz with overlap):
-// one CTA per tile loads the tile's core + halo rows (u as the sweep type, matrix values, 16-bit local
-// column indices) into shared memory, does ALL sweeps of the application there with __syncthreads()
-// between colours -- rows outside the tile count as 0 -- and writes its core rows.  No grid barrier;
-// the matrix and u cross HBM once per application (~1.6x redundancy from the halos) instead of once
-// per sweep.  A scipy emulation needs 3 BiCGSTAB iterations with it against 2 with the global sweeps
-// (tools/experiments/emulate_tiled_gauss_seidel.py).
-// ---------------------------------------------------------------------------------------------
-constexpr int kTileThreads = 512;
-
-__host__ __device__ inline size_t tile_smem_bytes(int max_ext, int K, int W, int st_bytes) {
-    // z, u: (max_ext, K) ST | val: (max_ext, W) ST | idx: (max_ext, W) u16
-    return (size_t)2 * max_ext * K * st_bytes + (size_t)max_ext * W * st_bytes + ((((size_t)max_ext * W * 2) + 15) & ~(size_t)15);
-}
-
-template <typename ST, int KC, int VEC>
-__global__ void __launch_bounds__(kTileThreads, 1) k_precond_tile(DeviceModel M, const double* __restrict__ u64, ST* __restrict__ dst,
-                                                                  int n_sweeps) {
-    extern __shared__ int4 tile_smem[];
-    if (M.ctl->all_done || M.ctl->finish_half) return;
-    const int K = M.K, W = M.W, nc = M.n_colors, t = blockIdx.x;
-    const int base = M.ext_ptr[t], m = M.ext_ptr[t + 1] - base;
-    ST* z = reinterpret_cast<ST*>(tile_smem);
-    ST* u = z + (size_t)M.max_ext * K;
-    ST* val = u + (size_t)M.max_ext * K;
-    unsigned short* idx = reinterpret_cast<unsigned short*>(val + (size_t)M.max_ext * W);
-    const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
-    const int lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kTileThreads / KC;
-    // ---- the tile's rows -> shared memory -------------------------------------------------------------
-    for (int l = group; l < m; l += GPB) {
-        const int gi = M.ext_rows[base + l] & kColMask;
-        for (int c = lane * VEC; c < K; c += KC * VEC) {
-            const Pk<double, VEC> d = ldk<double, VEC>(u64 + (size_t)gi * K + c);
-            Pk<ST, VEC> us;
-#pragma unroll
-            for (int q = 0; q < VEC; ++q) us.a[q] = (ST)d.a[q];
-            stk<ST, VEC>(u + (size_t)l * K + c, us);
-        }
-        if (lane == 0)
-            for (int w = 0; w < W; ++w) {
-                val[(size_t)l * W + w] = eval[(size_t)gi * W + w];
-                idx[(size_t)l * W + w] = M.tile_ell[(size_t)(base + l) * W + w];
-            }
-    }
-    __syncthreads();
-    // ---- sweeps from z = 0: rows outside the tile, and in the first sweep rows visited later, count as 0 --------
-    const int32_t* __restrict__ lcp = M.lcolor_ptr + (size_t)t * (nc + 1);
-    for (int s = 0; s < n_sweeps; ++s)
-        for (int c = 0; c < nc; ++c) {
-            const int lo = lcp[c], hi = lcp[c + 1];
-            for (int l = lo + group; l < hi; l += GPB)
-                for (int cc = lane * VEC; cc < K; cc += KC * VEC) {
-                    Pk<ST, VEC> acc;
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) acc.a[q] = (ST)0;
-                    for (int w = 0; w < W; ++w) {
-                        const unsigned short code = idx[(size_t)l * W + w];
-                        if ((code & kTileOutside) || (s == 0 && (code & kTileLater))) continue;
-                        const Pk<ST, VEC> x = ldk<ST, VEC>(z + (size_t)(code & kTileIndexMask) * K + cc);
-                        const ST a = val[(size_t)l * W + w];
-#pragma unroll
-                        for (int q = 0; q < VEC; ++q) acc.a[q] += a * x.a[q];
-                    }
-                    const Pk<ST, VEC> own = ldk<ST, VEC>(u + (size_t)l * K + cc);
-#pragma unroll
-                    for (int q = 0; q < VEC; ++q) acc.a[q] = own.a[q] - acc.a[q];
-                    stk<ST, VEC>(z + (size_t)l * K + cc, acc);
-                }
-            __syncthreads();
-        }
-    // ---- core rows -> the preconditioned vector ---------------------------------------------------------------
-    for (int l = group; l < m; l += GPB) {
-        const int r = M.ext_rows[base + l];
-        if (r < 0) continue;                    // halo row: another tile owns it
-        for (int cc = lane * VEC; cc < K; cc += KC * VEC) stk<ST, VEC>(dst + (size_t)r * K + cc, ldk<ST, VEC>(z + (size_t)l * K + cc));
-    }
 }
 
 // ---------------------------------------------------------------------------------------------

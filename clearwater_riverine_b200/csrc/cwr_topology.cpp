@@ -59,12 +59,10 @@ float hint_threshold() {
 
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
                            bool rcm, int n_colors, const float* hint, int n_parts, Topology& T,
-                           int tile_rows, int tile_cap, int tile_halo, int n_strips) {
+                           int n_strips) {
     if (n_parts < 1 || n_parts > 8) return "n_parts must be in [1, 8]";
     if (n_strips < 0 || n_strips > 4096) return "n_strips must be in [0, 4096]";
-    if (n_strips > 0 && (n_colors <= 0 || tile_rows > 0)) return "strips need colours and exclude tiles";
-    if (tile_rows > 0 && (n_colors <= 0 || n_parts != 1)) return "tile-local sweeps need colours and a single part";
-    if (tile_rows > 0 && (tile_cap < tile_rows || tile_cap > (int)kTileIndexMask)) return "tile_cap must be in [tile_rows, 8191]";
+    if (n_strips > 0 && n_colors <= 0) return "strips need colours";
     if (n_real <= 0 || n_face < n_real || n_edge <= 0) return "n_real, n_face, n_edge must be positive and n_face >= n_real";
     const int n = n_real, F = n_face, E = n_edge;
     int32_t max_f1 = -1;
@@ -235,33 +233,9 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             strip.resize(n);
             for (int i = 0; i < n; ++i) strip[i] = (int32_t)(((int64_t)rcm_pos[i] * n_parts * n_strips) / n);
         }
-        // tiles (tile-local sweeps): compact blobs grown breadth-first from the first free cell in RCM order
-        std::vector<int32_t> tile_of;
-        int n_tiles = 0;
-        if (tile_rows > 0) {
-            tile_of.assign(n, -1);
-            std::vector<int32_t> bfs;
-            bfs.reserve(tile_rows);
-            for (int i = 0; i < n; ++i) {
-                const int32_t seed = T.old_of_new[i];
-                if (tile_of[seed] >= 0) continue;
-                bfs.clear(); bfs.push_back(seed); tile_of[seed] = n_tiles;
-                for (size_t hd = 0; hd < bfs.size() && (int)bfs.size() < tile_rows; ++hd) {
-                    const int32_t u = bfs[hd];
-                    for (int32_t j = aptr[u]; j < aptr[u + 1] && (int)bfs.size() < tile_rows; ++j) {
-                        const int32_t v = adj[j];
-                        if (tile_of[v] < 0) { tile_of[v] = n_tiles; bfs.push_back(v); }
-                    }
-                }
-                ++n_tiles;
-            }
-            if (n_tiles >= (1 << 22)) return "too many tiles";
-        }
         std::vector<uint64_t> key(n);
         for (int i = 0; i < n; ++i)
-            key[i] = tile_rows > 0
-                ? ((uint64_t)tile_of[i] << 38) | ((uint64_t)(level[i] % nc) << 32) | (uint32_t)rcm_pos[i]
-                : n_strips > 0
+            key[i] = n_strips > 0
                 ? ((uint64_t)strip[i] << 44) | ((uint64_t)(level[i] % nc) << 38) | (uint32_t)rcm_pos[i]
                 : ((uint64_t)part[i] << 60) | ((uint64_t)(level[i] % nc) << 54) | ((uint64_t)level[i] << 32) | (uint32_t)rcm_pos[i];
         std::sort(key.begin(), key.end());
@@ -302,11 +276,6 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         T.n_levels = max_level + 1;
         T.color_of.resize(n);
         for (int i = 0; i < n; ++i) T.color_of[i] = (uint8_t)(level[T.old_of_new[i]] % nc);       // by new id
-        if (tile_rows > 0) {       // core row ranges of the tiles (rows are tile-major now; color_ptr is not meaningful)
-            T.tile_ptr.assign(n_tiles + 1, 0);
-            for (int i = 0; i < n; ++i) ++T.tile_ptr[tile_of[T.old_of_new[i]] + 1];
-            for (int t = 0; t < n_tiles; ++t) T.tile_ptr[t + 1] += T.tile_ptr[t];
-        }
     } else {
         // no colours: parts are equal chunks of the RCM order
         T.n_colors = 0;
@@ -406,65 +375,6 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 if (cn >= ci) cj |= kLaterBit;
                 if (cn == (ci + T.n_colors - 1) % T.n_colors && cn != ci) cj |= kPrevBit;
             }
-
-    // ---- tile-local sweeps: halo layers, local numbering, local ELL ------------------------------------------
-    T.ext_ptr.clear(); T.ext_rows.clear(); T.lcolor_ptr.clear(); T.tile_ell.clear(); T.max_ext = 0;
-    if (tile_rows > 0) {
-        const int nt = (int)T.tile_ptr.size() - 1, nc = T.n_colors, W = T.W;
-        T.ext_ptr.assign(nt + 1, 0);
-        T.lcolor_ptr.assign((size_t)nt * (nc + 1), 0);
-        std::vector<int32_t> local_of(n, -1), members, frontier, next;
-        std::vector<std::pair<int32_t, int32_t>> keyed;      // (colour << 1 | halo?, row) -> sort by colour then row
-        for (int t = 0; t < nt; ++t) {
-            members.clear();
-            for (int32_t i = T.tile_ptr[t]; i < T.tile_ptr[t + 1]; ++i) { members.push_back(i); local_of[i] = 0; }
-            const size_t n_core = members.size();
-            frontier.assign(members.begin(), members.end());
-            for (int layer = 0; layer < tile_halo && !frontier.empty(); ++layer) {
-                next.clear();
-                for (int32_t u : frontier)
-                    for (int32_t j = T.rowptr[u]; j < T.rowptr[u + 1]; ++j) {
-                        const int32_t v = T.col[j];
-                        if (local_of[v] < 0) { local_of[v] = 0; next.push_back(v); }
-                    }
-                if ((int)(members.size() + next.size()) > tile_cap) {          // this layer does not fit: stop here
-                    for (int32_t v : next) local_of[v] = -1;
-                    break;
-                }
-                members.insert(members.end(), next.begin(), next.end());
-                frontier.swap(next);
-            }
-            if ((int)members.size() > tile_cap) return "a tile's core exceeds tile_cap";
-            // local order: by colour, then global row (core rows of a colour are contiguous in memory)
-            keyed.clear();
-            for (size_t m = 0; m < members.size(); ++m) keyed.emplace_back((int32_t)T.color_of[members[m]], members[m]);
-            std::sort(keyed.begin(), keyed.end());
-            const int32_t base = (int32_t)T.ext_rows.size();
-            T.ext_ptr[t] = base;
-            for (size_t l = 0; l < keyed.size(); ++l) local_of[keyed[l].second] = (int32_t)l;
-            int32_t* lcp = &T.lcolor_ptr[(size_t)t * (nc + 1)];
-            for (size_t l = 0; l < keyed.size(); ++l) ++lcp[keyed[l].first + 1];
-            for (int c = 0; c < nc; ++c) lcp[c + 1] += lcp[c];
-            for (size_t l = 0; l < keyed.size(); ++l) {
-                const int32_t i = keyed[l].second;
-                const bool core = i >= T.tile_ptr[t] && i < T.tile_ptr[t + 1];
-                T.ext_rows.push_back(core ? i : (i | kLaterBit));
-                for (int w = 0; w < W; ++w) {
-                    const int32_t cj = T.ell_col[(size_t)i * W + w];
-                    const int32_t j = cj & kColMask;
-                    uint16_t code = 0;
-                    if (local_of[j] < 0) code = kTileOutside;
-                    else code = (uint16_t)local_of[j];
-                    if (cj < 0) code |= kTileLater;
-                    T.tile_ell.push_back(code);
-                }
-            }
-            (void)n_core;
-            T.max_ext = std::max(T.max_ext, (int)keyed.size());
-            for (int32_t i : members) local_of[i] = -1;
-        }
-        T.ext_ptr[nt] = (int32_t)T.ext_rows.size();
-    }
 
     // ---- strips: which strips of the same part a strip's rows are coupled to ---------------------------------
     T.strip_nptr.clear(); T.strip_nbr.clear(); T.max_strip_nbr = 0;

@@ -21,7 +21,6 @@ namespace cwr {
 constexpr int32_t kLaterBit = (int32_t)0x80000000;
 constexpr int32_t kPrevBit = 0x40000000;      // the neighbour has the colour swept immediately before the row's
 constexpr int32_t kColMask = 0x3fffffff;
-constexpr uint16_t kTileLater = 0x8000, kTileOutside = 0x4000, kTileIndexMask = 0x1fff;
 
 struct Topology {
     int n = 0;        // real cells = matrix order (reference: nreal + 1)
@@ -60,16 +59,6 @@ struct Topology {
     std::vector<uint8_t> send_mask;   // (n) bit q set: part q (not the owner) reads this row
     std::vector<int32_t> send_ptr;    // (n_parts+1) ranges into send_rows
     std::vector<int32_t> send_rows;   // rows with a non-zero send_mask, by owner, ascending
-    // tile-local sweeps (experimental, precond_sweep = 2): rows ordered (tile, colour, RCM position); a tile = a
-    // compact blob of cells (its CORE, a contiguous row range) plus a few layers of neighbours (its HALO)
-    std::vector<int32_t> tile_ptr;    // (n_tiles+1) core row range of tile t
-    std::vector<int32_t> ext_ptr;     // (n_tiles+1) ranges into ext_rows / tile_ell: core + halo rows of tile t,
-                                      // sorted by (colour, row)
-    std::vector<int32_t> ext_rows;    // global row of each local row; bit 31 set = halo row (not written back)
-    std::vector<int32_t> lcolor_ptr;  // (n_tiles, n_colors+1) local row ranges of the colours, relative to ext_ptr[t]
-    std::vector<uint16_t> tile_ell;   // (ext_total, W) local index of each neighbour (bits 0-12); bit 15 = neighbour
-                                      // visited later in a sweep, bit 14 = neighbour outside the tile (counts as 0)
-    int max_ext = 0;                  // largest core + halo row count of a tile
     // strips (neighbour-synchronised Gauss-Seidel sweeps, n_strips > 0): every part is cut into n_strips equal chunks
     // of the RCM order and the rows are ordered (part, strip, colour, RCM position) -- a strip is a contiguous row
     // range owned by ONE CTA of the sweep kernel, which then only waits for the strips its rows are coupled to
@@ -89,11 +78,9 @@ struct Topology {
 // n_colors > 0: rows are regrouped into that many colours for the multicolour Gauss-Seidel sweeps; hint
 // (may be NULL): one signed flow per edge (reference order, > 0 = out of f1) the colours are aligned with.
 // n_parts: strips of a domain decomposition (1 = none); rows are then ordered part-major.
-// tile_rows > 0 (needs n_colors > 0, n_parts == 1): rows are grouped into tiles of about that many cells grown
-// breadth-first, each extended by up to tile_halo layers of neighbours while it stays within tile_cap rows.
-// n_strips > 0 (needs n_colors > 0, tile_rows == 0): rows ordered (part, strip, colour, RCM position), see Topology.
+// n_strips > 0 (needs n_colors > 0): rows ordered (part, strip, colour, RCM position), see Topology.
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
                            bool rcm, int n_colors, const float* hint, int n_parts, Topology& out,
-                           int tile_rows = 0, int tile_cap = 0, int tile_halo = 0, int n_strips = 0);
+                           int n_strips = 0);
 
 }  // namespace cwr

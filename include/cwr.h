@@ -60,13 +60,11 @@ typedef struct {
     int precond_precision;  /* 32 (default): the sweeps and the preconditioned vectors are fp32 (half the bytes;
                                BiCGSTAB itself, its products A p^ / A s^ and its dots stay fp64, so the converged
                                answer is the fp64 one); 64: fp64 sweeps */
-    int precond_sweep;      /* 1 (default) = multicolour Gauss-Seidel sweeps from z = 0, all m - 1 sweeps of one
-                               application in one persistent kernel with a grid barrier per colour; the rows are
-                               regrouped colour-major and the colours follow the flow (cwr_set_flow_hint, or the
+    int precond_sweep;      /* 1 (default) = multicolour Gauss-Seidel sweeps from z = 0, all sweeps of one application (or of
+                               one defect-correction cycle) in one persistent kernel (see precond_sync); the rows are
+                               regrouped by colour and the colours follow the flow (cwr_set_flow_hint, or the
                                first hydrodynamic slices uploaded -- upload hydro before inputs);
-                               0 = Jacobi steps, z = (I + N + ... + N^(m-1)) u with N = I - D^-1 A;
-                               2 = EXPERIMENTAL, not yet validated on a GPU: tile-local sweeps in shared memory, one CTA
-                               per tile, no grid barrier */
+                               0 = Jacobi steps, z = (I + N + ... + N^(m-1)) u with N = I - D^-1 A */
     int precond_colors;     /* colours of the Gauss-Seidel sweeps (raised to max row degree + 1 if smaller);
                                0 (default) = chosen from the mesh size so that one colour moves ~20 MB */
     int dd_rank, dd_world;  /* domain decomposition: this handle is rank dd_rank of dd_world (<= 8) handles, one per
@@ -224,18 +222,6 @@ int cwr_solver_stats(cwr_handle* h, int64_t* sweeps, int64_t* fallbacks, int* n_
 int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int reorder, int n_colors,
                     const float* flow_hint, int n_parts, int32_t* new_of_old, int32_t* color_ptr, int* n_colors_out,
                     int* n_levels, int32_t* part_ptr, int32_t* n_send);
-
-/* Host only, EXPERIMENTAL (precond_sweep = 2, tile-local sweeps): the tiling build_topology
- * makes -- compact tiles of about tile_rows cells, each extended by up to tile_halo layers of neighbours while it stays
- * within tile_cap rows; rows ordered (tile, colour, RCM position).  Call once with the array pointers NULL for the sizes
- * (n_tiles, ext_total, ell_width, n_colors_out), then with arrays: new_of_old (n_real), tile_ptr (n_tiles+1), ext_ptr
- * (n_tiles+1), ext_rows (ext_total; bit 31 = halo row), lcolor_ptr (n_tiles, n_colors+1), tile_ell (ext_total, W: local
- * neighbour index, bit 15 = visited later in a sweep, bit 14 = outside the tile), ell_col (n_real, W: global neighbour
- * rows, bit 31 = visited later). */
-int cwr_tile_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
-                    int tile_rows, int tile_cap, int tile_halo, int* n_tiles, int* ext_total, int* ell_width, int* n_colors_out,
-                    int32_t* new_of_old, int32_t* tile_ptr, int32_t* ext_ptr, int32_t* ext_rows, int32_t* lcolor_ptr,
-                    uint16_t* tile_ell, int32_t* ell_col);
 
 /* Host only: the strips of the neighbour-synchronised sweep kernel (precond_sync = 2) build_topology makes -- every part
  * cut into n_strips equal chunks of the RCM order, rows ordered (part, strip, colour, RCM position).  Call once with the
