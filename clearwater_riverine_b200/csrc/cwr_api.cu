@@ -37,6 +37,7 @@ struct cwr_handle {
     int grid_sweep = 0, grid_gs = 0;
     int32_t* d_color_ptr = nullptr;
     bool dc = false;                 // defect-correction solver (options.solver = 2) instead of BiCGSTAB
+    bool dc_fixed = false;           // ... with a fixed number of sweeps per cycle (precond_steps given) instead of the device-side plan
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
     int n_strips = 0;
@@ -77,6 +78,10 @@ struct cwr_handle {
     // second stream for uploads that overlap the device->host copies of the previous step (cwr_prefetch_hydro_raw)
     cudaStream_t up_stream = nullptr; cudaEvent_t up_done = nullptr, compute_mark = nullptr;
     void* d_stage_up = nullptr; size_t stage_up_bytes = 0; bool up_pending = false;
+    // asynchronous outputs (cwr_fetch_async): c[t+1] and the mass fluxes of a step are gathered into one of two staging
+    // slots on the compute stream and copied to the host on a third stream while the next step runs
+    cudaStream_t out_stream = nullptr; cudaEvent_t ev_extract[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    double* d_out[2] = {nullptr, nullptr}; size_t out_bytes[2] = {0, 0}; int out_next = 0; bool out_pending[2] = {false, false};
     StepParams* d_sp = nullptr;
     SolverCtl* h_ctl = nullptr;                                   // pinned
     double* h_sc = nullptr; int* h_flags = nullptr; int* h_iters = nullptr;   // pinned
@@ -163,6 +168,13 @@ static void flush_profile(cwr_handle* h) {
 static inline int grid_for(int64_t items, int per_block, int max_grid) {
     int64_t g = (items + per_block - 1) / per_block;
     return (int)std::max<int64_t>(1, std::min<int64_t>(g, max_grid));
+}
+
+// (rows, K) interleaved device array -> (K, n) in reference order (k_extract_all: gather + transpose)
+static inline void launch_extract(cwr_handle* h, double* out, const double* src, const int32_t* perm, int n, size_t stride_k) {
+    const size_t smem = (size_t)kXposeRows * (h->K + 1) * sizeof(double);
+    k_extract_all<<<grid_for(n, kXposeRows, h->max_grid), kThreads, smem, h->stream>>>(out, src, perm, n, h->K, stride_k);
+    h->launches += 1;
 }
 
 static int ensure_stage(cwr_handle* h, size_t bytes) {
@@ -368,6 +380,12 @@ void cwr_destroy(cwr_handle* h) {
     if (h->up_done) cudaEventDestroy(h->up_done);
     if (h->compute_mark) cudaEventDestroy(h->compute_mark);
     if (h->d_stage_up) cudaFree(h->d_stage_up);
+    if (h->out_stream) { cudaStreamSynchronize(h->out_stream); cudaStreamDestroy(h->out_stream); }
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_extract[i]) cudaEventDestroy(h->ev_extract[i]);
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+        if (h->d_out[i]) cudaFree(h->d_out[i]);
+    }
     if (h->d_strip_nbr) cudaFree(h->d_strip_nbr);
     if (h->d_ov_idx) cudaFree(h->d_ov_idx);
     if (h->d_ov_val) cudaFree(h->d_ov_val);
@@ -399,6 +417,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     // auto: 5 Gauss-Seidel sweeps per application on large meshes (about two BiCGSTAB iterations per step on the
     // 1M x 16 benchmark; with the half-step exit, 5..11 sweeps all land within a few % of each other), 4 on chip,
     // 7 Jacobi steps
+    const bool steps_given = h->opt.precond_steps > 0;
     if (h->opt.precond_steps <= 0) h->opt.precond_steps = h->opt.precond_sweep == 1 ? (tiny ? 5 : (!small ? 6 : 8)) : 8;
     h->m_steps = std::min(h->opt.precond_steps, 64);
     if (h->opt.precond_precision != 64) h->opt.precond_precision = 32;
@@ -438,6 +457,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     // solver: defect correction with the sweeps themselves where they are Gauss-Seidel sweeps, else BiCGSTAB
     if (h->opt.solver != 1 && h->opt.solver != 2) h->opt.solver = h->gauss_seidel ? 2 : 1;
     h->dc = h->opt.solver == 2 && !h->small_path && h->m_steps > 1;
+    h->dc_fixed = h->dc && steps_given;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
     if (h->opt.precond_sync < 1 || h->opt.precond_sync > 3) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 3;
@@ -618,6 +638,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(cudaMemsetAsync(M.bsum, 0, (size_t)3 * std::max(1, tp.E_g) * K * sizeof(double), h->stream));
     }
     M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
+    if (h->dc_fixed) M.dc_smin = M.dc_smax = std::max(1, h->m_steps - 1);   // precond_steps given: every cycle does m - 1 sweeps
     M.sweep_f32 = h->sweep_f32 ? 1 : 0;
     M.us_from_producer = (h->dc && h->pipelined) ? 1 : 0;
     M.tol2 = h->opt.rtol * h->opt.rtol;
@@ -1347,9 +1368,7 @@ int cwr_get_state_all(cwr_handle* h, int t, double* out) {
     const size_t nK = (size_t)h->n * h->K;
     rc = ensure_stage(h, nK * 8);
     if (rc) return rc;
-    k_extract_all<<<grid_for((int64_t)nK, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
-        (double*)h->d_stage, state_slot(h, t), h->d_new_of_old, h->n, h->K);
-    h->launches += 1;
+    launch_extract(h, (double*)h->d_stage, state_slot(h, t), h->d_new_of_old, h->n, (size_t)h->n);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, h->d_stage, nK * 8, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -1365,15 +1384,69 @@ int cwr_get_state_rows(cwr_handle* h, int t, double* const* rows) {
     const size_t nK = (size_t)h->n * h->K;
     rc = ensure_stage(h, nK * 8);
     if (rc) return rc;
-    k_extract_all<<<grid_for((int64_t)nK, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
-        (double*)h->d_stage, state_slot(h, t), h->d_new_of_old, h->n, h->K);
-    h->launches += 1;
+    launch_extract(h, (double*)h->d_stage, state_slot(h, t), h->d_new_of_old, h->n, (size_t)h->n);
     CK(cudaGetLastError());
     for (int k = 0; k < h->K; ++k) {
         if (!rows[k]) continue;
         CK(cudaMemcpyAsync(rows[k], (const double*)h->d_stage + (size_t)k * h->n, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaStreamSynchronize(h->stream));
+    return CWR_OK;
+}
+
+int cwr_fetch_async(cwr_handle* h, int t, double* const* state_rows, double* const* adv_rows, double* const* diff_rows,
+                    double* const* tot_rows) {
+    if (!h) return CWR_EINVAL;
+    int rc = state_available(h, t);
+    if (rc) return rc;
+    const bool want_flux = adv_rows || diff_rows || tot_rows;
+    if (want_flux && !h->M.want_flux) FAIL(CWR_EINVAL, "mass flux disabled (options.mass_flux = 0)");
+    if (want_flux && t - 1 != h->flux_step) FAIL(CWR_EINVAL, "only the most recent step's mass fluxes are on the device");
+    CK(cudaSetDevice(h->device));
+    if (!h->out_stream) {
+        CK(cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&h->ev_extract[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    const int slot = h->out_next;
+    h->out_next ^= 1;
+    const size_t nK = (size_t)h->n * h->K, EK = (size_t)h->E * h->K;
+    const size_t need = (nK + (want_flux ? 3 * EK : 0)) * sizeof(double);
+    // the slot's previous copies (two fetches ago) must have left it
+    if (h->out_pending[slot]) { CK(cudaEventSynchronize(h->ev_copied[slot])); h->out_pending[slot] = false; }
+    if (need > h->out_bytes[slot]) {
+        if (h->d_out[slot]) { CK(cudaFree(h->d_out[slot])); h->d_out[slot] = nullptr; h->out_bytes[slot] = 0; }
+        if (cudaMalloc((void**)&h->d_out[slot], need) != cudaSuccess) { cudaGetLastError(); FAIL(CWR_ENOMEM, "no device memory for the output staging slot"); }
+        h->out_bytes[slot] = need;
+    }
+    double* st = h->d_out[slot];
+    if (state_rows) launch_extract(h, st, state_slot(h, t), h->d_new_of_old, h->n, (size_t)h->n);
+    if (want_flux)
+        for (int w = 0; w < 3; ++w)
+            launch_extract(h, st + nK + (size_t)w * EK, h->M.flux + (size_t)w * EK, h->d_einv, h->E, (size_t)h->E);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_extract[slot], h->stream));
+    CK(cudaStreamWaitEvent(h->out_stream, h->ev_extract[slot], 0));
+    for (int k = 0; k < h->K; ++k) {
+        if (state_rows && state_rows[k])
+            CK(cudaMemcpyAsync(state_rows[k], st + (size_t)k * h->n, (size_t)h->n * 8, cudaMemcpyDeviceToHost, h->out_stream));
+        double* const* fr[3] = {adv_rows, diff_rows, tot_rows};
+        for (int w = 0; w < 3; ++w)
+            if (fr[w] && fr[w][k])
+                CK(cudaMemcpyAsync(fr[w][k], st + nK + (size_t)w * EK + (size_t)k * h->E, (size_t)h->E * 8, cudaMemcpyDeviceToHost, h->out_stream));
+    }
+    CK(cudaEventRecord(h->ev_copied[slot], h->out_stream));
+    h->out_pending[slot] = true;
+    return CWR_OK;
+}
+
+int cwr_fetch_wait(cwr_handle* h) {
+    if (!h) return CWR_EINVAL;
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < 2; ++i)
+        if (h->out_pending[i]) { CK(cudaEventSynchronize(h->ev_copied[i])); h->out_pending[i] = false; }
     return CWR_OK;
 }
 

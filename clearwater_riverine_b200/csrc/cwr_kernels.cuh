@@ -175,13 +175,27 @@ __global__ void k_extract_state(double* __restrict__ out, const double* __restri
     }
 }
 
-// out[(k, j)] for all constituents, real cells only, reference order
-__global__ void k_extract_all(double* __restrict__ out, const double* __restrict__ state,
-                              const int32_t* __restrict__ new_of_old, int n, int K) {
-    size_t total = (size_t)n * K;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        int k = (int)(i / n), j = (int)(i % n);
-        out[i] = state[(size_t)new_of_old[j] * K + k];
+// out[(k, j)] for all constituents, reference order: rows of the interleaved (rows, K) array `src` gathered through
+// `perm` (reference index j -> device row) and transposed through shared memory, so that both the reads (K values of
+// one row: one 8K-byte segment) and the writes (32 consecutive j of one column) are coalesced.  Used for c[t+1]
+// (perm = new_of_old over the n real cells) and for the three mass-flux arrays (perm = einv over the E edges).
+constexpr int kXposeRows = 32;
+__global__ void __launch_bounds__(kThreads) k_extract_all(double* __restrict__ out, const double* __restrict__ src,
+                                                          const int32_t* __restrict__ perm, int n, int K, size_t out_stride_k) {
+    extern __shared__ double xt[];                     // [kXposeRows][K + 1]
+    const int ld = K + 1;
+    for (int j0 = blockIdx.x * kXposeRows; j0 < n; j0 += gridDim.x * kXposeRows) {
+        const int rows = min(kXposeRows, n - j0);
+        for (int q = threadIdx.x; q < rows * K; q += blockDim.x) {
+            const int r = q / K, k = q % K;
+            xt[r * ld + k] = src[(size_t)perm[j0 + r] * K + k];
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < rows * K; q += blockDim.x) {
+            const int k = q / rows, r = q % rows;
+            out[(size_t)k * out_stride_k + j0 + r] = xt[r * ld + k];
+        }
+        __syncthreads();
     }
 }
 

@@ -138,7 +138,11 @@ class ClearwaterRiverine:
     def _setup(self, f1, f2, face_x, face_y, time_seconds, face_flow, edge_velocity, volume, D, inputs, units, time,
                backend_options):
         store_mass_flux = backend_options.pop("store_mass_flux", True)
-        self.output = backend_options.pop("output", "eager")      # 'eager': copy results to host every update()
+        # 'eager': update() returns with the results in the host arrays; 'pipelined': the copies overlap the next
+        # update() (sync() before reading); 'none': results stay on the device (read them through self.backend)
+        self.output = backend_options.pop("output", "eager")
+        if self.output not in ("eager", "pipelined", "none"):
+            raise ValueError("output must be 'eager', 'pipelined' or 'none'")
         device = backend_options.pop("device", 0)
         T, F = volume.shape
         mesh = ModelMesh()
@@ -182,7 +186,12 @@ class ClearwaterRiverine:
         self._index = {name: k for k, name in enumerate(self.constituents)}
         # update() copies c[t+1] of every constituent straight into row t+1 of its output array; page-locking
         # those arrays lets the copies run at the full PCIe rate with no intermediate host buffer
-        self._pinned = [self.mesh[name] for name in self.constituents if pin_host_array(self.mesh[name])]
+        outputs = [self.mesh[name] for name in self.constituents]
+        if store_mass_flux:
+            for name in self.constituents:
+                c = self.constituent_dict[name]
+                outputs += [c.advection_mass_flux, c.diffusion_mass_flux, c.total_mass_flux]
+        self._pinned = [a for a in outputs if pin_host_array(a)]
         self._row_cache = None
         self._store_flux = bool(store_mass_flux)
         self.solver_info = []
@@ -202,6 +211,8 @@ class ClearwaterRiverine:
         t = self.time_step
         n = self.mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
         if isinstance(update_concentration, dict):
+            if self.output == "pipelined":
+                self.backend.fetch_wait()                    # row t of the host arrays may still be arriving
             for name, values in update_concentration.items():
                 if name not in self.constituent_dict:        # transport.py:223-229
                     print(f"WARNING: {name} is not being used in the model.")
@@ -220,29 +231,37 @@ class ClearwaterRiverine:
                           f"({info.iterations} iterations, relres {info.max_relres:.3e})", SolverWarning)
         if self.stream_hydro:                                 # slice t+2 goes up while c[t+1] comes down (full duplex)
             self._upload_slice(t + 2, overlap=True)
-        if self.output == "eager":
+        if self.output in ("eager", "pipelined"):
             self._fetch(t + 1)
         self.time_step += 1                                   # transport.py:276
 
     def _fetch(self, t1: int):
-        """c[t1] of every constituent in one device->host copy; ghost cells get their BC value where
-        one is set and stay NaN elsewhere (transport.py:252-264)."""
+        """c[t1] of every constituent and the mass fluxes of step t1 - 1 (transport.py:252-273) gathered on the device
+        and copied straight into row t1 / t1 - 1 of the constituents' (T,F) / (T,E) arrays.  output='eager' (default)
+        waits for the copies, as the reference's update() leaves everything in place; output='pipelined' lets them
+        overlap the next update() (two steps' worth can be in flight) -- call sync() before reading the arrays.
+        Ghost cells get their BC value where one is set and stay NaN elsewhere (transport.py:258-264)."""
         n = self.mesh.attrs[NUMBER_OF_REAL_CELLS] + 1
         if self._row_cache is None:       # per constituent: its (T,F) array, ghost-column BC values (NaN where unset)
             self._row_cache = []
             for name in self.constituents:
                 bc = self.constituent_dict[name].input_array[:, n:]
                 self._row_cache.append((self.mesh[name], np.where(bc != 0, bc, np.nan)))
-        self.backend.get_state_rows(t1, [out[t1] for out, _ in self._row_cache])
+        flux = self._store_flux and bool(self.backend.options.mass_flux)
+        cons = [self.constituent_dict[name] for name in self.constituents]
+        self.backend.fetch_async(
+            t1, [out[t1] for out, _ in self._row_cache],
+            [c.advection_mass_flux[t1 - 1] for c in cons] if flux else None,
+            [c.diffusion_mass_flux[t1 - 1] for c in cons] if flux else None,
+            [c.total_mass_flux[t1 - 1] for c in cons] if flux else None)
         for out, ghost in self._row_cache:
-            out[t1, n:] = ghost[t1]
-        if not (self._store_flux and self.backend.options.mass_flux):
-            return
-        for name, k in self._index.items():
-            c = self.constituent_dict[name]
-            if c.total_mass_flux is not None:
-                self.backend.get_mass_flux(k, t1 - 1, c.advection_mass_flux[t1 - 1], c.diffusion_mass_flux[t1 - 1],
-                                           c.total_mass_flux[t1 - 1])
+            out[t1, n:] = ghost[t1]                             # (columns the device copy does not touch)
+        if self.output == "eager":
+            self.backend.fetch_wait()
+
+    def sync(self):
+        """Wait for the output copies of the updates issued so far (output='pipelined')."""
+        self.backend.fetch_wait()
 
     def run(self, n_steps: Optional[int] = None):
         """`n_steps` updates back to back on the device, then one bulk copy of the concentrations
@@ -250,6 +269,7 @@ class ClearwaterRiverine:
         T = len(self.mesh["time"])
         t0 = self.time_step
         t1 = T - 1 if n_steps is None else min(T - 1, t0 + n_steps)
+        self.backend.fetch_wait()
         info = self.backend.run(t0, t1)
         self.time_step = t1
         if self.output == "eager" and self.backend.options.keep_history:
@@ -259,6 +279,7 @@ class ClearwaterRiverine:
         return info
 
     def finalize(self):
+        self.backend.fetch_wait()
         for a in getattr(self, "_pinned", []):
             unpin_host_array(a)
         self._pinned = []

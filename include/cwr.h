@@ -56,7 +56,8 @@ typedef struct {
                                default 1 */
     int precond_steps;      /* m: the preconditioner applies m - 1 sweeps; 1 = diagonal (Jacobi) scaling only;
                                0 (default) = 6 with Gauss-Seidel sweeps on large meshes, 5 on chip (<= 4096 cells), 8 with
-                               Jacobi steps */
+                               Jacobi steps.  Defect-correction solver: 0 = the sweeps of every cycle are planned on the device
+                               from the measured error factor (2..10 in fp32), m > 0 = every cycle does exactly m - 1 */
     int precond_precision;  /* 32 (default): the sweeps and the preconditioned vectors are fp32 (half the bytes;
                                BiCGSTAB itself, its products A p^ / A s^ and its dots stay fp64, so the converged
                                answer is the fp64 one); 64: fp64 sweeps */
@@ -161,6 +162,15 @@ int cwr_get_state_all(cwr_handle* h, int t, double* c_out);
  * caller's (T,F) output array of constituent k; NULL skips k).  One device->host copy per constituent with no
  * intermediate host buffer; at full PCIe rate when the destinations are page-locked (cwr_host_register). */
 int cwr_get_state_rows(cwr_handle* h, int t, double* const* rows);
+/* Asynchronous outputs of a step: c[t] (rows[k] -> (n,) f64, as cwr_get_state_rows) and, optionally, the three mass-flux
+ * arrays of step t - 1 (adv/diff/tot_rows[k] -> (E,) f64, as cwr_get_mass_flux; any of the three arrays of pointers
+ * may be NULL) are gathered into a staging slot on the handle's stream and copied to the host on a separate stream,
+ * so the copies overlap the next cwr_step (two slots: the call only blocks if the copies of the fetch before the last
+ * one are still running).  The destinations must be page-locked (cwr_host_register) for the overlap to be real and must
+ * not be read before cwr_fetch_wait returns.  Replaces the per-step writes of transport.py:252-273. */
+int cwr_fetch_async(cwr_handle* h, int t, double* const* state_rows, double* const* adv_rows, double* const* diff_rows,
+                    double* const* tot_rows);
+int cwr_fetch_wait(cwr_handle* h);
 /* Page-lock / release a caller-owned host array (cudaHostRegister) so that the copies above run asynchronously
  * at full rate.  Optional; no handle needed (a CUDA device must be present). */
 int cwr_host_register(void* p, size_t bytes);

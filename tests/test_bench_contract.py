@@ -1,5 +1,6 @@
 """bench.py's reference arm runs on the host cores only (oracle = reference arithmetic incl. SuperLU) and must
-print the contract's JSON line; checked here on CPU.  (The GPU arm needs a B200 and is exercised by the driver.)"""
+print the contract's JSON line; checked here on CPU with --sample-reference (the 100k-cell sample: the arm's default,
+the 1M-cell headline mesh, takes ~50 s per SuperLU solve).  (The GPU arm needs a B200 and is exercised by the driver.)"""
 import json
 import subprocess
 import sys
@@ -12,7 +13,7 @@ ROOT = Path(__file__).resolve().parents[1]
 
 @pytest.mark.timeout(300)
 def test_reference_arm_json_line():
-    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--sample-reference"],
                          capture_output=True, text=True, timeout=280, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
