@@ -83,8 +83,9 @@ struct cwr_handle {
     cudaStream_t out_stream = nullptr; cudaEvent_t ev_extract[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     double* d_out[2] = {nullptr, nullptr}; size_t out_bytes[2] = {0, 0}; int out_next = 0; bool out_pending[2] = {false, false};
     StepParams* d_sp = nullptr;
-    SolverCtl* h_ctl = nullptr;                                   // pinned
-    double* h_sc = nullptr; int* h_flags = nullptr; int* h_iters = nullptr;   // pinned
+    HostMirror* h_mirror = nullptr; HostMirror* d_mirror = nullptr;   // page-locked, mapped into the device (k_mirror)
+    SolverCtl* h_ctl = nullptr;                                   // = &h_mirror->ctl
+    double* h_sc = nullptr; int* h_flags = nullptr;               // = h_mirror->sc, flags
     int n_state_slots = 0;
     std::vector<double> dt;
     std::vector<int> slot_time;
@@ -393,11 +394,8 @@ void cwr_destroy(cwr_handle* h) {
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (void* p : h->allocs) cudaFree(p);
     if (h->d_stage) cudaFree(h->d_stage);
-    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->h_mirror) cudaFreeHost(h->h_mirror);
     if (h->h_stats) cudaFreeHost(h->h_stats);
-    if (h->h_sc) cudaFreeHost(h->h_sc);
-    if (h->h_flags) cudaFreeHost(h->h_flags);
-    if (h->h_iters) cudaFreeHost(h->h_iters);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -645,10 +643,10 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     M.diffusion_coefficient = D;
     M.max_iter = h->opt.max_iter;
 
-    CK(cudaMallocHost((void**)&h->h_ctl, sizeof(SolverCtl)));
-    CK(cudaMallocHost((void**)&h->h_sc, (size_t)SC_ROWS * K * sizeof(double)));
-    CK(cudaMallocHost((void**)&h->h_flags, K * sizeof(int)));
-    CK(cudaMallocHost((void**)&h->h_iters, K * sizeof(int)));
+    CK(cudaHostAlloc((void**)&h->h_mirror, sizeof(HostMirror), cudaHostAllocMapped));
+    std::memset(h->h_mirror, 0, sizeof(HostMirror));
+    CK(cudaHostGetDevicePointer((void**)&h->d_mirror, h->h_mirror, 0));
+    h->h_ctl = &h->h_mirror->ctl; h->h_sc = h->h_mirror->sc; h->h_flags = h->h_mirror->flags;
     h->dt.assign(T, NAN);
     h->slot_time.assign(h->C, -1);
     h->initial_row.assign(K, std::vector<double>());
@@ -928,8 +926,8 @@ int cwr_set_state_all(cwr_handle* h, int t, const double* c, const uint8_t* mask
 // ------------------------------------------------------------------------------------------------
 // one step
 // ------------------------------------------------------------------------------------------------
-static int poll(cwr_handle* h) {
-    CK(cudaMemcpyAsync(h->h_ctl, h->M.ctl, sizeof(SolverCtl), cudaMemcpyDeviceToHost, h->stream));
+static int poll(cwr_handle* h, int with_columns = 0) {
+    k_mirror<<<1, 128, 0, h->stream>>>(h->M.ctl, h->M.sc, h->M.colflags, h->K, h->d_mirror, with_columns);
     CK(cudaStreamSynchronize(h->stream));
     return CWR_OK;
 }
@@ -1029,9 +1027,7 @@ static int solve(cwr_handle* h, cwr_step_info* info) {
         break;
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h->h_sc, M.sc, (size_t)SC_ROWS * h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_flags, M.colflags, h->K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { int rcp = poll(h, 1); if (rcp) return rcp; }
     h->iterations += total_iter;
     int status = CWR_OK;
     double worst = 0.0;
@@ -1102,9 +1098,7 @@ static int solve_dc(cwr_handle* h, cwr_step_info* info, bool* fell_back) {
         k_fix_flags<<<1, 128, 0, h->stream>>>(M);
         h->launches += 2;
     }
-    CK(cudaMemcpyAsync(h->h_sc, M.sc, (size_t)SC_ROWS * h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_flags, M.colflags, h->K * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { int rcp = poll(h, 1); if (rcp) return rcp; }
     h->iterations += h->h_ctl->iter;
     int status = CWR_OK;
     double worst = 0.0;
@@ -1131,8 +1125,7 @@ static int solve_dc(cwr_handle* h, cwr_step_info* info, bool* fell_back) {
 // device.  Inside cwr_run nothing is read back per step (statistics accumulate in d_stats).
 static int read_small_stats(cwr_handle* h, cwr_step_info* info) {
     CK(cudaMemcpyAsync(h->h_stats, h->d_stats, sizeof(SmallStats), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_ctl, h->M.ctl, sizeof(SolverCtl), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    { int rcp = poll(h); if (rcp) return rcp; }
     const SmallStats& s = *h->h_stats;
     double rel2;
     std::memcpy(&rel2, &s.max_relres2_bits, sizeof rel2);

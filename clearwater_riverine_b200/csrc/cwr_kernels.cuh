@@ -136,6 +136,25 @@ __global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl) {
     ctl->singular = 0; ctl->dc_fail = 0; ctl->dc_slow = 0; ctl->sweeps_done = 0;
 }
 
+// The solver's control block and per-column scalars, written into page-locked host memory that the device maps
+// (zero-copy): the host polls convergence by synchronising the stream and reading its own memory.  A cudaMemcpy
+// would queue behind the bulk device->host copies of the asynchronous output path on the same copy engine.
+struct HostMirror {
+    SolverCtl ctl;
+    double sc[SC_ROWS * kMaxK];
+    int flags[kMaxK];
+};
+__global__ void k_mirror(const SolverCtl* __restrict__ ctl, const double* __restrict__ sc, const int* __restrict__ flags, int K,
+                         HostMirror* __restrict__ dst, int with_columns) {
+    if (with_columns) {
+        for (int q = threadIdx.x; q < SC_ROWS * K; q += blockDim.x) dst->sc[q] = sc[q];
+        for (int q = threadIdx.x; q < K; q += blockDim.x) dst->flags[q] = flags[q];
+    }
+    const int words = (int)(sizeof(SolverCtl) / sizeof(int));
+    for (int q = threadIdx.x; q < words; q += blockDim.x) reinterpret_cast<int*>(&dst->ctl)[q] = reinterpret_cast<const int*>(ctl)[q];
+    __threadfence_system();
+}
+
 // ---------------------------------------------------------------------------------------------
 // upload helpers: reference order -> device order
 // ---------------------------------------------------------------------------------------------

@@ -43,7 +43,8 @@ def main():
     D = 0.1
     ok_all = True
     cases = [dict(), dict(dd_halo_per_colour=1), dict(precond_sweep=0, precond_steps=4),
-             dict(precond_precision=64, precond_steps=3, precond_colors=9)]
+             dict(precond_precision=64, precond_steps=3, precond_colors=9), dict(solver=1), dict(precond_sync=2),
+             dict(solver=1, precond_sync=1), dict(solver=1, precond_sweep=0, precond_steps=5)]
     for ci, opts in enumerate(cases):
         K, T = args.K, args.steps + 1
         plan = synthetic.make_plan(args.side, args.side * 3 // 4, T, dt=30.0, tri_fraction=0.1, dry_fraction=0.02,
