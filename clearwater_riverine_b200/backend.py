@@ -101,6 +101,7 @@ def load_library():
         "cwr_get_mass_flux": ([H, C.c_int, C.c_int, dp, dp, dp], C.c_int),
         "cwr_mass_totals_at": ([H, C.c_int, C.c_int, C.c_int, C.POINTER(CwrMassTotals)], C.c_int),
         "cwr_get_flux_sums": ([H, C.c_int, dp, dp, dp], C.c_int),
+        "cwr_get_volume_sums": ([H, dp, dp, dp], C.c_int),
         "cwr_get_lhs": ([H, C.POINTER(C.c_int64), ip, ip, dp], C.c_int),
         "cwr_get_rhs": ([H, C.c_int, dp], C.c_int),
         "cwr_get_permutation": ([H, ip], C.c_int),
@@ -392,6 +393,11 @@ class TransportBackend:
     def flux_sums(self, k: int):
         outs = [np.empty(self.n_edge) for _ in range(3)]
         self._check(self._lib.cwr_get_flux_sums(self._h, k, *[_ptr(a, C.c_double) for a in outs]))
+        return tuple(outs)
+
+    def volume_sums(self):
+        outs = [np.empty(self.n_edge) for _ in range(3)]
+        self._check(self._lib.cwr_get_volume_sums(self._h, *[_ptr(a, C.c_double) for a in outs]))
         return tuple(outs)
 
     def mass_totals(self, k: int, t_start: int, t_end: int) -> CwrMassTotals:

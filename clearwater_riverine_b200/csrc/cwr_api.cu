@@ -69,15 +69,16 @@ struct cwr_handle {
     int32_t *d_ell_col = nullptr, *d_ell_code = nullptr, *d_f1p = nullptr, *d_f2p = nullptr;
     int32_t *d_bcell = nullptr, *d_bptr = nullptr, *d_bedge = nullptr, *d_eperm = nullptr, *d_einv = nullptr;
     int32_t *d_new_of_old = nullptr, *d_old_of_new = nullptr, *d_f1 = nullptr, *d_f2 = nullptr;
-    float *d_adv = nullptr, *d_velg = nullptr, *d_vol = nullptr;   // (C,E), (C,E_g), (C,n)
+    float *d_adv = nullptr, *d_velg = nullptr, *d_flowg = nullptr, *d_vol = nullptr;   // (C,E), (C,E_g), (C,E_g), (C,n)
     double* d_cdiff = nullptr;                                    // (C,E)
     double* d_bc = nullptr;                                       // (T,G,K)
     double* d_state = nullptr;                                    // (S,n,K)
     double* d_dist = nullptr;                                     // (E) reference order
     void* d_stage = nullptr; size_t stage_bytes = 0;
     // second stream for uploads that overlap the device->host copies of the previous step (cwr_prefetch_hydro_raw)
-    cudaStream_t up_stream = nullptr; cudaEvent_t up_done = nullptr, compute_mark = nullptr;
-    void* d_stage_up = nullptr; size_t stage_up_bytes = 0; bool up_pending = false;
+    cudaStream_t up_stream = nullptr; cudaEvent_t compute_mark = nullptr;
+    std::vector<cudaEvent_t> up_done; std::vector<uint8_t> up_pending;     // per hydro slot: a prefetched slice is on its way
+    void* d_stage_up = nullptr; size_t stage_up_bytes = 0;
     // asynchronous outputs (cwr_fetch_async): c[t+1] and the mass fluxes of a step are gathered into one of two staging
     // slots on the compute stream and copied to the host on a third stream while the next step runs
     cudaStream_t out_stream = nullptr; cudaEvent_t ev_extract[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
@@ -378,7 +379,7 @@ void cwr_destroy(cwr_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->up_stream) { cudaStreamSynchronize(h->up_stream); cudaStreamDestroy(h->up_stream); }
-    if (h->up_done) cudaEventDestroy(h->up_done);
+    for (cudaEvent_t e : h->up_done) if (e) cudaEventDestroy(e);
     if (h->compute_mark) cudaEventDestroy(h->compute_mark);
     if (h->d_stage_up) cudaFree(h->d_stage_up);
     if (h->out_stream) { cudaStreamSynchronize(h->out_stream); cudaStreamDestroy(h->out_stream); }
@@ -568,6 +569,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     const size_t nK = (size_t)n * K;
     CK(dalloc(h, &h->d_adv, (size_t)h->C * E)); CK(dalloc(h, &h->d_cdiff, (size_t)h->C * E));
     CK(dalloc(h, &h->d_velg, (size_t)h->C * std::max(1, tp.E_g))); CK(dalloc(h, &h->d_vol, (size_t)h->C * n));
+    CK(dalloc(h, &h->d_flowg, (size_t)h->C * std::max(1, tp.E_g)));
     CK(dalloc(h, &h->d_bc, (size_t)T * std::max(1, h->G) * K));
     CK(cudaMemsetAsync(h->d_bc, 0, (size_t)T * std::max(1, h->G) * K * sizeof(double), h->stream));
     h->n_state_slots = h->opt.keep_history ? T : 2;
@@ -634,6 +636,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(dalloc(h, &M.flux, (size_t)3 * E * K));
         CK(dalloc(h, &M.bsum, (size_t)3 * std::max(1, tp.E_g) * K));
         CK(cudaMemsetAsync(M.bsum, 0, (size_t)3 * std::max(1, tp.E_g) * K * sizeof(double), h->stream));
+        CK(dalloc(h, &M.vsum, (size_t)3 * std::max(1, tp.E_g)));
+        CK(cudaMemsetAsync(M.vsum, 0, (size_t)3 * std::max(1, tp.E_g) * sizeof(double), h->stream));
     }
     M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
     if (h->dc_fixed) M.dc_smin = M.dc_smax = std::max(1, h->m_steps - 1);   // precond_steps given: every cycle does m - 1 sweeps
@@ -685,7 +689,7 @@ static int check_slices(cwr_handle* h, int t0, int nt) {
     return CWR_OK;
 }
 
-static int join_prefetch(cwr_handle* h);
+static int join_prefetch(cwr_handle* h, int slot = -1);
 
 int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double* cdiff, const float* vel,
                   const float* vol, const double* dt) {
@@ -716,6 +720,9 @@ int cwr_set_hydro(cwr_handle* h, int t0, int nt, const float* adv, const double*
         if (Eg > 0)
             k_gather<float><<<grid_for(Eg, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
                 h->d_velg + (size_t)slot * Eg, (const float*)(st + off_vel), h->d_eperm + Ei, Eg);
+        if (Eg > 0)     // (the raw face flow is not given on this path: advection_coeff = face_flow * sign(|velocity|) stands in)
+            k_gather<float><<<grid_for(Eg, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
+                h->d_flowg + (size_t)slot * Eg, (const float*)st, h->d_eperm + Ei, Eg);
         k_gather<float><<<grid_for(n, kThreads, h->max_grid), kThreads, 0, h->stream>>>(
             h->d_vol + (size_t)slot * n, (const float*)(st + off_vol), h->d_old_of_new, n);
         h->launches += 4;
@@ -764,6 +771,7 @@ static int upload_raw(cwr_handle* h, cudaStream_t stream, char* st, int t0, int 
         CK(cudaMemcpyAsync(st + off_vol, volume + (size_t)s * F, (size_t)F * 4, cudaMemcpyHostToDevice, stream));
         k_derive<<<grid_for(E, kThreads, h->max_grid), kThreads, 0, stream>>>(
             h->d_adv + (size_t)slot * E, h->d_cdiff + (size_t)slot * E, h->d_velg + (size_t)slot * std::max(1, Eg),
+            h->d_flowg + (size_t)slot * std::max(1, Eg),
             (const float*)st, (const float*)(st + off_vel), h->d_dist, h->d_eperm, E, Ei, (float)h->M.diffusion_coefficient);
         k_gather<float><<<grid_for(n, kThreads, h->max_grid), kThreads, 0, stream>>>(
             h->d_vol + (size_t)slot * n, (const float*)(st + off_vol), h->d_old_of_new, n);
@@ -776,10 +784,13 @@ static int upload_raw(cwr_handle* h, cudaStream_t stream, char* st, int t0, int 
 }
 
 // the compute stream must see a prefetched slice before it reads the hydro window again
-static int join_prefetch(cwr_handle* h) {
-    if (!h->up_pending) return CWR_OK;
-    CK(cudaStreamWaitEvent(h->stream, h->up_done, 0));
-    h->up_pending = false;
+// (slot < 0: every slot)
+static int join_prefetch(cwr_handle* h, int slot) {
+    for (int s = 0; s < (int)h->up_pending.size(); ++s) {
+        if ((slot >= 0 && s != slot) || !h->up_pending[s]) continue;
+        CK(cudaStreamWaitEvent(h->stream, h->up_done[s], 0));
+        h->up_pending[s] = 0;
+    }
     return CWR_OK;
 }
 
@@ -810,8 +821,9 @@ int cwr_prefetch_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow
     CK(cudaSetDevice(h->device));
     if (!h->up_stream) {
         CK(cudaStreamCreateWithFlags(&h->up_stream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&h->up_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->compute_mark, cudaEventDisableTiming));
+        h->up_done.assign(h->C, nullptr); h->up_pending.assign(h->C, 0);
+        for (int sl = 0; sl < h->C; ++sl) CK(cudaEventCreateWithFlags(&h->up_done[sl], cudaEventDisableTiming));
     }
     const size_t need = (size_t)h->E * 8 + (size_t)h->F * 4;
     if (need > h->stage_up_bytes) {
@@ -822,10 +834,14 @@ int cwr_prefetch_hydro_raw(cwr_handle* h, int t0, int nt, const float* face_flow
     // the slots being overwritten may still be read by work already queued on the compute stream
     CK(cudaEventRecord(h->compute_mark, h->stream));
     CK(cudaStreamWaitEvent(h->up_stream, h->compute_mark, 0));
-    rc = upload_raw(h, h->up_stream, (char*)h->d_stage_up, t0, nt, face_flow, edge_velocity, volume, dt);
-    if (rc) return rc;
-    CK(cudaEventRecord(h->up_done, h->up_stream));
-    h->up_pending = true;
+    for (int s = 0; s < nt; ++s) {      // one event per slice: a step only waits for the two slices it reads
+        rc = upload_raw(h, h->up_stream, (char*)h->d_stage_up, t0 + s, 1, face_flow + (size_t)s * h->E, edge_velocity + (size_t)s * h->E,
+                        volume + (size_t)s * h->F, dt + s);
+        if (rc) return rc;
+        const int slot = (t0 + s) % h->C;
+        CK(cudaEventRecord(h->up_done[slot], h->up_stream));
+        h->up_pending[slot] = 1;
+    }
     return CWR_OK;
 }
 
@@ -1221,7 +1237,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     const int s0 = find_slot(h, t), s1 = find_slot(h, t + 1);
     if (s0 < 0 || s1 < 0) FAIL(CWR_EINVAL, "hydrodynamic slices t and t+1 are not resident; call cwr_set_hydro");
     CK(cudaSetDevice(h->device));
-    { int rcj = join_prefetch(h); if (rcj) return rcj; }
+    { int rcj = join_prefetch(h, s0); if (rcj) return rcj; rcj = join_prefetch(h, s1); if (rcj) return rcj; }
     const int64_t launches0 = h->launches;
     const int n = h->n, E = h->E, K = h->K, Eg = std::max(1, h->topo.E_g), G = std::max(1, h->G);
     StepParams p;
@@ -1229,6 +1245,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     p.vol_t = h->d_vol + (size_t)s0 * n; p.vol_t1 = h->d_vol + (size_t)s1 * n;
     p.adv_t1 = h->d_adv + (size_t)s1 * E; p.cdiff_t1 = h->d_cdiff + (size_t)s1 * E;
     p.velg_t1 = h->d_velg + (size_t)s1 * Eg;
+    p.flowg_t = h->d_flowg + (size_t)s0 * Eg;
     p.bc_t1 = h->d_bc + (size_t)(t + 1) * G * K;
     p.state_t = state_slot(h, t); p.state_t1 = state_slot(h, t + 1);
     p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
@@ -1496,6 +1513,23 @@ int cwr_get_flux_sums(cwr_handle* h, int k, double* total_sum, double* in_sum, d
     return CWR_OK;
 }
 
+int cwr_get_volume_sums(cwr_handle* h, double* total_sum, double* in_sum, double* out_sum) {
+    if (!h) return CWR_EINVAL;
+    if (!h->M.want_flux) FAIL(CWR_EINVAL, "mass flux disabled (options.mass_flux = 0)");
+    CK(cudaSetDevice(h->device));
+    const int Eg = h->topo.E_g, Ei = h->topo.E_int;
+    std::vector<double> host((size_t)3 * std::max(1, Eg));
+    CK(cudaMemcpyAsync(host.data(), h->M.vsum, host.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    double* outs[3] = {total_sum, in_sum, out_sum};
+    for (int w = 0; w < 3; ++w) {
+        if (!outs[w]) continue;
+        std::fill(outs[w], outs[w] + h->E, 0.0);
+        for (int g = 0; g < Eg; ++g) outs[w][h->topo.eperm[Ei + g]] = host[(size_t)w * Eg + g];
+    }
+    return CWR_OK;
+}
+
 int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_totals* out) {
     if (!h) return CWR_EINVAL;
     if (!out) FAIL(CWR_EINVAL, "NULL output");
@@ -1514,6 +1548,7 @@ int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_to
         if (rc) return rc;
         const int s = find_slot(h, ts[i]);
         if (s < 0) FAIL(CWR_EINVAL, "volume slice not resident for mass totals");
+        { int rcj = join_prefetch(h, s); if (rcj) return rcj; }
         k_mass_total<<<grid_for(h->M.row_hi - h->M.row_lo, kThreads, kMassBlocks), kThreads, 0, h->stream>>>(
             h->d_vol + (size_t)s * h->n, state_slot(h, ts[i]), h->M.row_lo, h->M.row_hi, h->K, k, d_partial, d_ticket, d_out);
         h->launches += 1;

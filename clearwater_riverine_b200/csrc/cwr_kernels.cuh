@@ -34,6 +34,7 @@ struct StepParams {
     const float* adv_t1;     // (E)  advection_coeff[t+1]
     const double* cdiff_t1;  // (E)  coeff_to_diffusion[t+1]
     const float* velg_t1;    // (E_g) edge_velocity[t+1] of ghost edges
+    const float* flowg_t;    // (E_g) face_flow[t] of ghost edges (boundary volume sums, postproc_util.py:93-95)
     const double* bc_t1;     // (G,K) input_array[t+1][ghost cells]
     const double* state_t;   // (n,K) c[t]
     double* state_t1;        // (n,K) c[t+1]  (the solver iterates in place on it)
@@ -123,7 +124,8 @@ struct DeviceModel {
     SolverCtl* ctl;
     const StepParams* sp;
     double* flux;       // (3, E, K) advection / diffusion / total mass flux of the last step
-    double* bsum;       // (3, E_g, K) running total / in / out sums on ghost edges
+    double* bsum;       // (3, E_g, K) running total / in / out sums of the total mass flux on ghost edges
+    double* vsum;       // (3, E_g) running total / in / out sums of face_flow * dt on ghost edges
     double tol2;        // rtol^2
     double diffusion_coefficient;
     int max_iter;
@@ -240,7 +242,7 @@ __global__ void k_extract_flux(double* __restrict__ out, const double* __restric
 //   cdiff = f64(f32(area * D)) / dist
 // input in reference edge order, output in device edge order.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_derive(float* __restrict__ adv, double* __restrict__ cdiff, float* __restrict__ velg,
+__global__ void k_derive(float* __restrict__ adv, double* __restrict__ cdiff, float* __restrict__ velg, float* __restrict__ flowg,
                          const float* __restrict__ flow, const float* __restrict__ vel, const double* __restrict__ dist,
                          const int32_t* __restrict__ eperm, int E, int E_int, float Df) {
     for (int ep = blockIdx.x * blockDim.x + threadIdx.x; ep < E; ep += gridDim.x * blockDim.x) {
@@ -254,7 +256,7 @@ __global__ void k_derive(float* __restrict__ adv, double* __restrict__ cdiff, fl
         float ad = __fmul_rn(area, Df);
         adv[ep] = a;
         cdiff[ep] = (double)ad / dist[e];
-        if (ep >= E_int) velg[ep - E_int] = u;
+        if (ep >= E_int) { velg[ep - E_int] = u; flowg[ep - E_int] = q; }
     }
 }
 
@@ -1720,6 +1722,15 @@ __global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
             const size_t o = (size_t)e * K + c;
             stv<VEC>(M.flux + o, fa); stv<VEC>(M.flux + EK + o, fd); stv<VEC>(M.flux + 2 * EK + o, ft);
             if (e >= M.E_int) {
+                if (c == 0) {       // boundary volumes (postproc_util.py:93-95, 112-134): face_flow * dt, NaN skipped
+                    const double fv = (double)sp.flowg_t[e - M.E_int] * dt;
+                    if (fv == fv) {
+                        const size_t gv = (size_t)(e - M.E_int), Eg = (size_t)M.E_g;
+                        M.vsum[gv] += fv;
+                        M.vsum[Eg + gv] += (fv <= 0.0) ? fv : 0.0;
+                        M.vsum[2 * Eg + gv] += (fv >= 0.0) ? fv : 0.0;
+                    }
+                }
                 const size_t g = (size_t)(e - M.E_int) * K + c;
 #pragma unroll
                 for (int q = 0; q < VEC; ++q) {

@@ -165,7 +165,7 @@ class ClearwaterRiverine:
         # (meshes whose T x E arrays exceed device memory; also what bench.py's end-to-end leg times)
         self.stream_hydro = bool(backend_options.pop("stream_hydro", False))
         if self.stream_hydro:
-            backend_options.setdefault("hydro_capacity", 3)
+            backend_options.setdefault("hydro_capacity", 4)       # t, t+1 in use; t+2, t+3 on their way
         q = mesh[FLOW_ACROSS_FACE]      # Gauss-Seidel colours follow the time-mean flow
         hint = np.nanmean(q[:: max(1, T // 32)], axis=0, dtype=np.float64).astype(np.float32)
         self.backend = TransportBackend(mesh[EDGES_FACE1], mesh[EDGES_FACE2], F, T, len(inputs), D, device=device,
@@ -193,6 +193,7 @@ class ClearwaterRiverine:
                 outputs += [c.advection_mass_flux, c.diffusion_mass_flux, c.total_mass_flux]
         self._pinned = [a for a in outputs if pin_host_array(a)]
         self._row_cache = None
+        self._mass_start: Dict[int, Tuple[float, float]] = {}
         self._store_flux = bool(store_mass_flux)
         self.solver_info = []
 
@@ -224,13 +225,19 @@ class ClearwaterRiverine:
         if self.stream_hydro:
             self._upload_slice(t)
             self._upload_slice(t + 1)
+        if t == 0 and not self._mass_start and self.backend.options.mass_flux:
+            for k in range(len(self.constituents)):           # sum(V c) at the start (postproc_util.py:36-47)
+                m0 = self.backend.mass_totals(k, 0, 0)
+                self._mass_start[k] = (m0.vol_start, m0.mass_start)
         info = self.backend.step(t)
         self.solver_info.append((info.iterations, info.max_relres, info.status))
         if info.status != CWR_OK:
             warnings.warn(f"step {t}: {STATUS_NAMES.get(info.status, info.status)} "
                           f"({info.iterations} iterations, relres {info.max_relres:.3e})", SolverWarning)
-        if self.stream_hydro:                                 # slice t+2 goes up while c[t+1] comes down (full duplex)
-            self._upload_slice(t + 2, overlap=True)
+        if self.stream_hydro:       # slices t+2, t+3 go up while c[t+1] comes down (full duplex); the next update() only
+            self._upload_slice(t + 2, overlap=True)            # waits for t+2, which then has had a whole step to arrive
+            if self.backend.options.hydro_capacity >= 4:
+                self._upload_slice(t + 3, overlap=True)
         if self.output in ("eager", "pipelined"):
             self._fetch(t + 1)
         self.time_step += 1                                   # transport.py:276
@@ -262,6 +269,48 @@ class ClearwaterRiverine:
     def sync(self):
         """Wait for the output copies of the updates issued so far (output='pipelined')."""
         self.backend.fetch_wait()
+
+    def mass_balance(self, constituent_name: str, boundary_faces: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, float]:
+        """Whole-domain mass balance over the steps taken so far, from device reductions (next row N2): the quantities
+        of the reference's `_mass_bal_global` (postproc_util.py:21-166) under the same names -- Vol/Mass at the start and
+        now, per boundary line the water volume and constituent mass that crossed it (total, in <= 0, out >= 0), the
+        totals over all lines and the closure errors.  Nothing of it needs the (T,E) flux history on the host: the
+        per-face running sums are kept by the mass-flux kernel.  boundary_faces: {line name: face (edge) ids}; default:
+        the lines of the HEC-RAS plan the model was built from."""
+        if boundary_faces is None:
+            bd = getattr(self, "boundary_data", None)
+            if bd is None:
+                raise ValueError("boundary_faces is required for a model built from arrays")
+            boundary_faces = {str(nm): np.asarray(grp["Face Index"], dtype=np.int64) for nm, grp in
+                              sorted(bd.groupby("Name"), key=lambda kv: float(np.mean(kv[1]["BC Line ID"])))}
+        k = self._index[constituent_name]
+        self.backend.fetch_wait()
+        now = self.time_step
+        m = self.backend.mass_totals(k, now, now)
+        start = self._mass_start.get(k)
+        if start is None:                                     # no step taken yet
+            start = (m.vol_start, m.mass_start)
+        out = {"Vol_start": start[0], "Mass_start": start[1], "Vol_end": m.vol_end, "Mass_end": m.mass_end}
+        f_tot, f_in, f_out = self.backend.flux_sums(k)
+        v_tot, v_in, v_out = self.backend.volume_sums()
+        tv_in = tv_out = tm_in = tm_out = tv = tm = 0.0
+        for name, faces in boundary_faces.items():
+            faces = np.asarray(faces, dtype=np.int64)
+            out[f"{name}_vol"], out[f"{name}_mass"] = float(v_tot[faces].sum()), float(f_tot[faces].sum())
+            out[f"{name}_in_vol"], out[f"{name}_out_vol"] = float(v_in[faces].sum()), float(v_out[faces].sum())
+            out[f"{name}_in_mass"], out[f"{name}_out_mass"] = float(f_in[faces].sum()), float(f_out[faces].sum())
+            tv += out[f"{name}_vol"]; tm += out[f"{name}_mass"]
+            tv_in += out[f"{name}_in_vol"]; tv_out += out[f"{name}_out_vol"]
+            tm_in += out[f"{name}_in_mass"]; tm_out += out[f"{name}_out_mass"]
+        out["bcTotalVolInOutAll"], out["bcTotalVolInAll"], out["bcTotalVolOutAll"] = tv, tv_in, tv_out
+        out["bcTotalMassInOutAll"], out["bcTotalMassInAll"], out["bcTotalMassOutAll"] = tm, tm_in, tm_out
+        out["vol_end_calc"] = out["Vol_start"] - tv_in - tv_out
+        out["mass_end_calc"] = out["Mass_start"] - tm_in - tm_out
+        out["error_vol"] = out["vol_end_calc"] - out["Vol_end"]
+        out["error_mass"] = out["mass_end_calc"] - out["Mass_end"]
+        out["prct_error_vol"] = out["error_vol"] / tv_in * 100 if tv_in else float("nan")
+        out["prct_error_mass"] = out["error_mass"] / tm_in * 100 if tm_in else float("nan")
+        return out
 
     def run(self, n_steps: Optional[int] = None):
         """`n_steps` updates back to back on the device, then one bulk copy of the concentrations

@@ -189,6 +189,11 @@ int cwr_mass_totals_at(cwr_handle* h, int k, int t_start, int t_end, cwr_mass_to
  * (E,) f64 each, any may be NULL.  Enabled when options.mass_flux != 0. */
 int cwr_get_flux_sums(cwr_handle* h, int k, double* total_sum, double* in_sum, double* out_sum);
 
+/* The same for the water volume across the boundary faces (postproc_util.py:93-95, 112-134): per-edge running sums
+ * of face_flow[t] * dt[t] over the steps taken so far, total / in (<= 0) / out (>= 0), NaN skipped; (E,) f64 each, zero on
+ * internal edges.  (With cwr_set_hydro, which is not given the raw face flow, advection_coeff stands in for it.) */
+int cwr_get_volume_sums(cwr_handle* h, double* total_sum, double* in_sum, double* out_sum);
+
 /* --- domain decomposition over NVLink (BASELINE configs[4]) ----------------------------
  * One process per GPU creates a handle with options.dd_rank / dd_world set, every rank with the SAME mesh,
  * hydrodynamics and inputs (the mesh is replicated, the rows are not: a rank assembles, solves and stores
