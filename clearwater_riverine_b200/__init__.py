@@ -3,5 +3,6 @@ advection-diffusion step (reference: src/clearwater_riverine/transport.py:201-27
 linalg.py) behind the reference's Python stepping API.  CUDA only -- no CPU fallback."""
 from .backend import CwrError, SolverWarning, TransportBackend, load_library  # noqa: F401
 from .transport import ClearwaterRiverine, Constituent, ModelMesh  # noqa: F401
+from .adapter import attach, extract_model_arrays  # noqa: F401
 
 __version__ = "0.1.0"

@@ -327,8 +327,19 @@ class ClearwaterRiverine:
                     self.backend.get_state(k, t, self.mesh[name][t])
         return info
 
-    def finalize(self):
+    def finalize(self, save: Optional[bool] = False, output_filepath: Optional[str] = None):
+        """Reference transport.py:385-395: with save=True the mesh (every variable, the concentrations included) is written
+        to `output_filepath` (.nc NetCDF-3 classic or .npz; io/outputs.py) and the boundary table next to it."""
         self.backend.fetch_wait()
+        if save:
+            from .io.outputs import save_mesh
+            if not output_filepath:
+                raise ValueError("finalize(save=True) needs output_filepath")
+            save_mesh(self.mesh, output_filepath)
+            bd = getattr(self, "boundary_data", None)
+            if bd is not None:
+                p = Path(output_filepath)
+                bd.to_csv(f"{p.parent}/{p.stem}_boundary_data.csv")
         for a in getattr(self, "_pinned", []):
             unpin_host_array(a)
         self._pinned = []

@@ -178,3 +178,78 @@ def test_device_mass_balance_matches_the_oracles(case):
                 tol = 1e-9 * max(scale_m, abs(want["Mass_start"]))
             assert abs(got[key] - w) <= tol, (c, key, got[key], w)
     model.finalize()
+
+
+class _Var:
+    """The slice of an xarray DataArray attach() touches: `.values` backed by one array, `var[t]` a view of it."""
+    def __init__(self, a):
+        self.values = np.asarray(a)
+
+    def __getitem__(self, i):
+        return self.values[i]
+
+
+class _Mesh(dict):
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.attrs = {}
+
+    nreal = property(lambda self: self.attrs["nreal"])
+    diffusion_coefficient = property(lambda self: self.attrs["diffusion_coefficient"])
+
+
+class _Con:
+    pass
+
+
+@pytest.mark.parametrize("case", ["p01_random_two", "p02_uniform100"])
+def test_attach_swaps_update_on_a_reference_shaped_object(case):
+    """attach(model) on an object with the reference's state layout (mesh[name].values, mesh.nreal, constituent_dict[...]
+    .input_array / *_mass_flux, time_step): its update() -- overrides included -- must reproduce the golden run of the
+    unmodified reference: concentrations (rtol 1e-9) and the three mass-flux arrays, in the object's own arrays."""
+    from clearwater_riverine_b200 import attach
+    from tests.helpers import golden_overrides
+    g = load_golden(case)
+    names = [str(c) for c in g["constituents"]]
+    T, F = g["volume"].shape
+    E = len(g["f1"])
+    n = int(g["f1"].max()) + 1
+    mesh = _Mesh({k: _Var(g[v]) for k, v in (("edges_face1", "f1"), ("edges_face2", "f2"), ("advection_coeff", "adv"),
+                                            ("coeff_to_diffusion", "cdiff"), ("edge_velocity", "edge_velocity"),
+                                            ("volume", "volume"), ("dt", "dt"))})
+    mesh.attrs.update({"nreal": n - 1, "diffusion_coefficient": float(g["diffusion_coefficient"])})
+
+    class Model:
+        time_step = 0
+        def update(self, update_concentration=None):
+            raise AssertionError("the reference's own update() must have been replaced")
+    model = Model()
+    model.mesh = mesh
+    model.constituent_dict = {}
+    for c in names:
+        con = _Con()
+        con.input_array = g[f"input_{c}"].copy()
+        con.advection_mass_flux, con.diffusion_mass_flux, con.total_mass_flux = np.zeros((T, E)), np.zeros((T, E)), np.zeros((T, E))
+        model.constituent_dict[c] = con
+        out = np.full((T, F), np.nan); out[0] = 0.0; out[0, :n] = con.input_array[0, :n]       # constituents.py:39-48, 94-98
+        mesh[c] = _Var(out)
+    stepper = attach(model)
+    overrides = golden_overrides(g)
+    steps = min(T - 1, 40)
+    for t in range(steps):
+        upd = {c: _Var(v) for c, v in overrides[t].items()} if t in overrides else None
+        model.update(upd)
+        assert model.time_step == t + 1
+    for c in names:
+        got, want = mesh[c].values, g[f"conc_{c}"]
+        for t in range(steps + 1):
+            close(got[t], want[t], RTOL, f"attach {c} row {t}")
+        con = model.constituent_dict[c]
+        for mine, theirs in ((con.advection_mass_flux, "advflux"), (con.diffusion_mass_flux, "diffflux"), (con.total_mass_flux, "totflux")):
+            w = g[f"{theirs}_{c}"][:steps]
+            fin = ~np.isnan(w)
+            assert np.array_equal(np.isnan(mine[:steps]), ~fin)
+            assert np.abs(mine[:steps][fin] - w[fin]).max() <= 1e-9 * max(np.abs(w[fin]).max(), 1e-300)
+    stepper.detach()
+    with pytest.raises(AssertionError):
+        model.update()
