@@ -60,6 +60,7 @@ struct SolverCtl {
     int finish_half;      // every active column converged at the half step: skip the sweeps on s and t = A s^
     unsigned gs_bar[2]; // k_precond_gs: grid barrier arrivals, exits
     // defect-correction solver (solver = 2): x += GS^S(r), r -= A z, with S planned on the device after every cycle
+    unsigned long long strip_base;   // k_gs_strip: warp arrivals every strip's flag has counted in the launches so far
     int dc_sweeps;        // sweeps of the next cycle
     int dc_fail;          // the sweeps stagnate or diverge (not an M-matrix?): the host falls back to BiCGSTAB
     int dc_slow;          // consecutive cycles that reduced the residual by less than 0.7
@@ -1132,23 +1133,32 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
                 if ((cs[u] & kPrevBit) && !skipped(cs[u], first_sweep)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
         }
     };
+    // Synchronisation is per WARP, not per CTA: strip_flag2[s] counts the warp arrivals of strip s (every warp of a
+    // strip arrives once per step, after its own stores and a fence), and a warp starts step k + 1 when its own strip
+    // and the neighbouring strips show all their warps' arrivals for step k.  No __syncthreads() in the sweep loop:
+    // the warps of a CTA drift apart by up to a step, a slow warp holds up only the warps that read its rows.
+    constexpr unsigned kWarps = kGsThreads / 32;
+    const unsigned long long base = M.ctl->strip_base;
+    const int wl = threadIdx.x & 31;
     auto publish = [&](int step) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
+        (void)step;
+        __syncwarp();
+        if (wl == 0) {
             __threadfence();
-            st_flag(M.strip_flag + vb, (seq << 20) | (unsigned long long)(step + 1));
+            atomicAdd(M.strip_flag + vb, 1ull);
         }
     };
     auto wait_nbrs = [&](int step) {
-        const unsigned long long target = (seq << 20) | (unsigned long long)(step + 1);
-        for (int j = threadIdx.x; j < n_nbr; j += kGsThreads) {
-            const unsigned long long* f = M.strip_flag + (M.strip_nbr[nb0 + j] - M.strip0);
+        const unsigned long long target = base + (unsigned long long)kWarps * (unsigned long long)(step + 1);
+        // lane 0: this strip; lanes 1..: the neighbouring strips (a strip of an RCM band has two or three)
+        for (int j = wl; j <= n_nbr; j += 32) {
+            const unsigned long long* f = M.strip_flag + (j == 0 ? vb : M.strip_nbr[nb0 + j - 1] - M.strip0);
             unsigned spins = 0;
             const unsigned limit = *reinterpret_cast<volatile int*>(&M.ctl->barrier_timeout) ? 0u : (1u << 26);
             while (ld_acquire_u64(f) < target)
-                if (++spins > limit) { M.ctl->barrier_timeout = 1; break; }
+                if (++spins > limit) { M.ctl->barrier_timeout = 1; break; }      // never hang the device
         }
-        __syncthreads();
+        __syncwarp();
     };
     // a row through registers (rows beyond the pipelined ones, ELL blocks beyond the first, further column chunks)
     auto relax_slow = [&](int i, int cc, int w0, Pk<ST, VEC> acc, bool first_sweep) {
@@ -1256,13 +1266,13 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
         issue_early(step + 1);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
-    if (!multi) return;
     __syncthreads();
-    if (threadIdx.x == 0) {        // the last CTA to leave re-arms the grid barrier for the next launch
+    if (threadIdx.x == 0) {        // the last CTA to leave: arrivals every strip has counted, the grid barrier re-armed
         const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
         if (t == (unsigned)nvb - 1) {
             M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
-            M.dd->bar_epoch = e0 + xe;
+            M.ctl->strip_base = base + (unsigned long long)kWarps * (unsigned long long)(n_steps - 1);
+            if (multi) M.dd->bar_epoch = e0 + xe;
             __threadfence();
         }
     }
