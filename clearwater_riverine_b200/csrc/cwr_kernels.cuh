@@ -792,6 +792,12 @@ __device__ __forceinline__ void cp_async_cg16(void* smem_dst, const void* gsrc) 
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// predicated copy: nothing when !pred; `bytes` = 16 copies, 0 fills the slot with zeros without reading the source
+__device__ __forceinline__ void cp_async_cg16_if(void* smem_dst, const void* gsrc, bool pred, int bytes) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %3, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16, %2;\n}"
+                 ::"r"(d), "l"(gsrc), "r"(bytes), "r"((int)pred) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
 // STRIP = false: rows colour-major (color_ptr), lane groups dealt grid-wide, a GRID barrier between colours.
@@ -1099,7 +1105,10 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
             if (i < re) dst[r] = *reinterpret_cast<const int4*>(ecol + (size_t)i * W);
         }
     };
-    // everything of `step` that does not depend on the step before it
+    // everything of `step` that does not depend on the step before it.  Branch-free: every copy is predicated, and a
+    // neighbour that counts as 0 (first sweep: not visited yet / another rank's row) is a zero-filling copy
+    const ST* __restrict__ zc = z + c;
+    const ST* __restrict__ usc = us + c;
     auto issue_early = [&](int step) {
         const int col = step % nc;
         const bool first_sweep = step < nc;
@@ -1107,16 +1116,16 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const int i = rb + group + r * GPB;
-            if (i >= re || !lane_on) continue;
+            const bool act = i < re && lane_on;
             const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (skipped(cs[u], first_sweep)) *slot(r, u) = make_int4(0, 0, 0, 0);
-                else if (!(cs[u] & kPrevBit)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
+                const bool skip = skipped(cs[u], first_sweep);
+                cp_async_cg16_if(slot(r, u), zc + (size_t)(cs[u] & kColMask) * K, act && (skip || !(cs[u] & kPrevBit)), skip ? 0 : 16);
             }
-            cp_async_cg16(slot(r, 4), us + (size_t)i * K + c);
+            cp_async_cg16_if(slot(r, 4), usc + (size_t)i * K, act, 16);
 #pragma unroll
-            for (int v = 0; v < VS; ++v) cp_async_cg16(slot(r, 5 + v), reinterpret_cast<const char*>(eval + (size_t)i * W) + 16 * v);
+            for (int v = 0; v < VS; ++v) cp_async_cg16_if(slot(r, 5 + v), reinterpret_cast<const char*>(eval + (size_t)i * W) + 16 * v, act, 16);
         }
     };
     auto issue_late = [&](int step) {
@@ -1126,14 +1135,14 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const int i = rb + group + r * GPB;
-            if (i >= re || !lane_on) continue;
+            const bool act = i < re && lane_on;
             const int cs[4] = {pc[r].x, pc[r].y, pc[r].z, pc[r].w};
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                if ((cs[u] & kPrevBit) && !skipped(cs[u], first_sweep)) cp_async_cg16(slot(r, u), z + (size_t)(cs[u] & kColMask) * K + c);
+                cp_async_cg16_if(slot(r, u), zc + (size_t)(cs[u] & kColMask) * K, act && (cs[u] & kPrevBit) && !skipped(cs[u], first_sweep), 16);
         }
     };
-    // Synchronisation is per WARP, not per CTA: strip_flag2[s] counts the warp arrivals of strip s (every warp of a
+    // Synchronisation is per WARP, not per CTA: strip_flag[s] counts the warp arrivals of strip s (every warp of a
     // strip arrives once per step, after its own stores and a fence), and a warp starts step k + 1 when its own strip
     // and the neighbouring strips show all their warps' arrivals for step k.  No __syncthreads() in the sweep loop:
     // the warps of a CTA drift apart by up to a step, a slow warp holds up only the warps that read its rows.
