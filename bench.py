@@ -293,7 +293,7 @@ def family_bytes(o, n, nnz, E, K, Wd, sweeps_per_launch):
     pt = sb if sweeps else 8                            # type of the preconditioned vectors the products gather
     S = float(pt) * n * K
     ell = 4.0 * n * Wd                                  # ELL column indices
-    handed = o.solver == 2 and o.precond_sync == 3      # the residual reaches the sweep kernel in the sweep type (M.us)
+    handed = o.solver == 2 and o.precond_sync >= 3     # the residual reaches the sweep kernel in the sweep type (M.us)
     fb = {
         "assemble": 2 * ell + 12.0 * nnz + 4.0 * n + 8.0 * n * Wd + (4.0 * n * Wd if sb == 4 and sweeps else 0) + 8.0 * n,
         "rhs": 3 * V + 12.0 * n,
@@ -312,7 +312,7 @@ def family_bytes(o, n, nnz, E, K, Wd, sweeps_per_launch):
         # one launch = all sweeps of one application / cycle: per sweep indices + values, u, z gathered, z written;
         # the grid-barrier and the plain strip kernel also read u once as the solver's fp64 vector
         per_sweep = ell + sb * n * Wd + 3.0 * sb * n * K
-        fb["precond"] = sweeps_per_launch * per_sweep + (0.0 if o.precond_sync == 3 else 8.0 * n * K)
+        fb["precond"] = sweeps_per_launch * per_sweep + (0.0 if o.precond_sync >= 3 else 8.0 * n * K)
     else:                 # one launch = one Jacobi step
         fb["precond"] = ell + sb * n * Wd + 3.0 * sb * n * K
     return fb
@@ -330,7 +330,9 @@ def precond_kernel_name(o):
     return {1: "k_precond_gs<STRIP=false> (multicolour Gauss-Seidel sweeps of one cycle, persistent, a grid barrier per colour)",
             2: "k_precond_gs<STRIP=true> (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags)",
             3: "k_gs_strip (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags, "
-               "software-pipelined cp.async gathers)"}.get(o.precond_sync, "k_precond_gs")
+               "software-pipelined cp.async gathers)",
+            4: "k_gs_lean (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags, "
+               "software-pipelined predicated cp.async gathers, fp32 x 16 constituents)"}.get(o.precond_sync, "k_precond_gs")
 
 
 def gpu_workload(name, ctx, args, steps, warmup, profile_steps, opts, *, dd=False, want_roofline=True, want_e2e=False,

@@ -106,7 +106,7 @@ def load_library():
         "cwr_get_rhs": ([H, C.c_int, dp], C.c_int),
         "cwr_get_permutation": ([H, ip], C.c_int),
         "cwr_strip_layout": ([C.c_int, C.c_int, C.c_int, ip, ip, C.c_int, fp, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
-                              ip, ip, ip, ip, C.POINTER(C.c_uint8)], C.c_int),
+                              ip, ip, ip, ip, C.POINTER(C.c_uint8), C.c_int], C.c_int),
         "cwr_get_options": ([H, C.POINTER(CwrOptions)], C.c_int),
         "cwr_dd_export": ([H, C.c_void_p], C.c_int),
         "cwr_dd_attach": ([H, C.c_void_p], C.c_int),
@@ -199,7 +199,7 @@ def order_cells(f1, f2, n_face: int, reorder: bool = True, n_colors: int = 0, fl
     return new_of_old, colours, nl.value, part_ptr[: n_parts + 1].copy(), n_send[:n_parts].copy()
 
 
-def strip_layout(f1, f2, n_face: int, n_colors: int, flow_hint, n_strips: int, n_parts: int = 1):
+def strip_layout(f1, f2, n_face: int, n_colors: int, flow_hint, n_strips: int, n_parts: int = 1, strip_cap: int = 0):
     """Host-only: the strips of the neighbour-synchronised sweep kernel (cwr_strip_layout) as a dict of numpy arrays."""
     lib = load_library()
     f1 = _arr(f1, np.int32); f2 = _arr(f2, np.int32, f1.shape, "f2")
@@ -208,14 +208,15 @@ def strip_layout(f1, f2, n_face: int, n_colors: int, flow_hint, n_strips: int, n
     nc, nb = C.c_int(), C.c_int()
     args = (n, int(n_face), len(f1), _ptr(f1, C.c_int32), _ptr(f2, C.c_int32), int(n_colors), _ptr(hint, C.c_float),
             int(n_parts), int(n_strips), C.byref(nc), C.byref(nb))
-    rc = lib.cwr_strip_layout(*args, None, None, None, None, None)
+    rc = lib.cwr_strip_layout(*args, None, None, None, None, None, int(strip_cap))
     if rc != CWR_OK:
         raise CwrError(rc, lib.cwr_last_error(None).decode())
     NS = n_parts * n_strips
     out = {"new_of_old": np.empty(n, np.int32), "strip_cptr": np.empty((NS, nc.value + 1), np.int32),
            "strip_nptr": np.empty(NS + 1, np.int32), "strip_nbr": np.empty(max(1, nb.value), np.int32), "color_of": np.empty(n, np.uint8)}
     rc = lib.cwr_strip_layout(*args, _ptr(out["new_of_old"], C.c_int32), _ptr(out["strip_cptr"], C.c_int32),
-                              _ptr(out["strip_nptr"], C.c_int32), _ptr(out["strip_nbr"], C.c_int32), _ptr(out["color_of"], C.c_uint8))
+                              _ptr(out["strip_nptr"], C.c_int32), _ptr(out["strip_nbr"], C.c_int32), _ptr(out["color_of"], C.c_uint8),
+                              int(strip_cap))
     if rc != CWR_OK:
         raise CwrError(rc, lib.cwr_last_error(None).decode())
     out["strip_nbr"] = out["strip_nbr"][: nb.value]

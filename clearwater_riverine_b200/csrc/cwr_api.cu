@@ -40,6 +40,9 @@ struct cwr_handle {
     bool dc_fixed = false;           // ... with a fixed number of sweeps per cycle (precond_steps given) instead of the device-side plan
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
+    bool lean = false;               // ... its lean form for fp32 sweeps, K = 16, ELL width 4, one rank (k_gs_lean, precond_sync = 4)
+    int gs_debug = 0;                // CWR_GS_DEBUG (development)
+    int strip_cap = 0;               // rows of a (strip, colour) the sweep kernel takes in one pass
     int n_strips = 0;
     int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
     unsigned long long* d_strip_flag = nullptr;
@@ -326,8 +329,9 @@ static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
     for (int e = 0; e < E; ++e) hint[e] = (float)mean[e];
     Topology t2;
     std::string terr = build_topology(h->n, h->F, E, h->f1_ref.data(), h->f2_ref.data(), h->opt.reorder != 0,
-                                      h->opt.precond_colors, hint.data(), h->world, t2, h->strips ? h->n_strips : 0);
+                                      h->opt.precond_colors, hint.data(), h->world, t2, h->strips ? h->n_strips : 0, h->strip_cap);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
+    if (h->lean && t2.max_strip_nbr > 31) return CWR_OK;      // (a strip of an RCM band has two or three neighbours)
     if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
     if (h->attached) return CWR_OK;                 // peers already rely on the current ownership
     h->topo = std::move(t2);
@@ -459,18 +463,30 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->dc_fixed = h->dc && steps_given;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
-    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 3) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 3;
+    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 4) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 4;
     if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
     h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
-    h->pipelined = h->gauss_seidel && h->opt.precond_sync == 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16;
-    if (h->gauss_seidel && h->opt.precond_sync == 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
+    h->pipelined = h->gauss_seidel && h->opt.precond_sync >= 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16;
+    if (h->gauss_seidel && h->opt.precond_sync >= 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
+    // the lean kernel: fp32 sweeps, 4 lanes x 16 bytes per row, one rank (ELL width 4 is checked once the topology is known)
+    h->lean = h->pipelined && h->opt.precond_sync == 4 && h->sweep_f32 && h->SKC == 4 && h->SVEC == 4 && n_const == 16 &&
+              std::max(1, h->opt.dd_world) == 1;
+    if (h->pipelined && !h->lean) h->opt.precond_sync = 3;
     if (h->gauss_seidel) {
         int occ_gs = 0, coop = 0;
         if (h->pipelined) {
             cudaError_t e = cudaSuccess;
             SWEEP_DISPATCH(e = gs3_prepare<ST, SKC, SVEC>(&occ_gs));
             CK(e);
+            if (h->lean) {
+                int occ_lean = 0;
+                CK(cudaFuncSetAttribute(k_gs_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLeanSmemBytes));
+                CK(cudaFuncSetAttribute(k_gs_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLeanSmemBytes));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lean, k_gs_lean<false>, kGsThreads, kLeanSmemBytes));
+                if (const char* e = getenv("CWR_GS_DEBUG")) h->gs_debug = atoi(e);
+                occ_gs = std::min(occ_gs, occ_lean);      // either kernel may run on these strips
+            }
         } else if (h->strips) {
             SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
             SWEEP_DISPATCH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_gs, k_precond_gs<ST, SKC, SVEC, true>, kGsThreads, kGsSmemBytes));
@@ -485,6 +501,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         const int rows_rank = n_real / std::max(1, h->opt.dd_world);
         h->n_strips = std::max(1, std::min(h->grid_gs, rows_rank / 512));
         if (h->strips) h->grid_gs = h->n_strips;
+        if (h->strips) h->strip_cap = kGsRows * (kGsThreads / h->SKC);
     }
     if (h->opt.precond_colors <= 0 && h->strips) {
         // one colour of a strip = one pass of the CTA: kGsRows rows per lane group (the pipelined rows of k_precond_gs)
@@ -506,10 +523,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, h->opt.reorder != 0,
                                       (h->gauss_seidel || h->tiny) ? h->opt.precond_colors : 0,
                                       (h->gauss_seidel || h->tiny) ? flow_hint : nullptr, h->world, h->topo,
-                                      h->strips ? h->n_strips : 0);
+                                      h->strips ? h->n_strips : 0, h->strip_cap);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (flow_hint) h->hint_done = true;
     const Topology& tp = h->topo;
+    if (h->lean && (tp.W != 4 || tp.max_strip_nbr > 31)) { h->lean = false; h->opt.precond_sync = 3; }
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
     h->C = (h->opt.hydro_capacity <= 0 || h->opt.hydro_capacity > T) ? T : std::max(2, h->opt.hydro_capacity);
@@ -554,8 +572,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     CK(dalloc(h, &h->d_send_mask, (size_t)n)); CK(dalloc(h, &h->d_send_rows, (size_t)n));
     if (h->strips) {
         CK(dalloc(h, &h->d_strip_cptr, tp.strip_cptr.size())); CK(dalloc(h, &h->d_strip_nptr, tp.strip_nptr.size()));
-        CK(dalloc(h, &h->d_strip_flag, (size_t)h->n_strips));
-        CK(cudaMemsetAsync(h->d_strip_flag, 0, (size_t)h->n_strips * sizeof(unsigned long long), h->stream));
+        CK(dalloc(h, &h->d_strip_flag, (size_t)h->n_strips * kFlagStride));
+        CK(cudaMemsetAsync(h->d_strip_flag, 0, (size_t)h->n_strips * kFlagStride * sizeof(unsigned long long), h->stream));
     }
     {
         int rc = upload_topology(h);
@@ -968,7 +986,12 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
                 h->launches += 1;
             }
             void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
-            SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream)));
+            if (h->lean && h->gs_debug) {          // development: timing experiments (see k_gs_lean)
+                int packed = sweeps | (h->gs_debug << 16);
+                void* argsd[] = {(void*)&M, (void*)&dst, (void*)&packed};
+                e = cudaLaunchCooperativeKernel((const void*)k_gs_lean<true>, dim3(h->grid_gs), dim3(kGsThreads), argsd, kLeanSmemBytes, h->stream);
+            } else if (h->lean) e = cudaLaunchCooperativeKernel((const void*)k_gs_lean<false>, dim3(h->grid_gs), dim3(kGsThreads), args3, kLeanSmemBytes, h->stream);
+            else SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream)));
         } else
         if (h->strips) { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, true>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
         else { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, false>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
@@ -1696,10 +1719,11 @@ int cwr_dd_layout(cwr_handle* h, cwr_dd_info* out, uint8_t* owned_cells, uint8_t
 
 int cwr_strip_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,
                      int n_parts, int n_strips, int* n_colors_out, int* nbr_total, int32_t* new_of_old, int32_t* strip_cptr,
-                     int32_t* strip_nptr, int32_t* strip_nbr, uint8_t* color_of) {
+                     int32_t* strip_nptr, int32_t* strip_nbr, uint8_t* color_of, int strip_cap) {
     if (!f1 || !f2) return CWR_EINVAL;
     Topology t;
-    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, std::max(1, n_parts), t, n_strips);
+    const std::string terr = build_topology(n_real, n_face, n_edge, f1, f2, true, n_colors, flow_hint, std::max(1, n_parts), t, n_strips,
+                                            std::max(0, strip_cap));
     if (!terr.empty()) { g_create_error = terr; return CWR_EINVAL; }
     if (n_colors_out) *n_colors_out = t.n_colors;
     if (nbr_total) *nbr_total = (int)t.strip_nbr.size();
@@ -1718,7 +1742,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
-    out->precond_sync = h->gauss_seidel ? (h->pipelined ? 3 : (h->strips ? 2 : 1)) : 0;
+    out->precond_sync = h->gauss_seidel ? (h->lean ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
     return CWR_OK;
 }
 

@@ -59,7 +59,7 @@ float hint_threshold() {
 
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
                            bool rcm, int n_colors, const float* hint, int n_parts, Topology& T,
-                           int n_strips) {
+                           int n_strips, int strip_cap) {
     if (n_parts < 1 || n_parts > 8) return "n_parts must be in [1, 8]";
     if (n_strips < 0 || n_strips > 4096) return "n_strips must be in [0, 4096]";
     if (n_strips > 0 && n_colors <= 0) return "strips need colours";
@@ -233,11 +233,38 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             strip.resize(n);
             for (int i = 0; i < n; ++i) strip[i] = (int32_t)(((int64_t)rcm_pos[i] * n_parts * n_strips) / n);
         }
+        std::vector<uint8_t> colr(n);
+        for (int i = 0; i < n; ++i) colr[i] = (uint8_t)(level[i] % nc);
+        // ---- strips: no (strip, colour) above strip_cap rows -------------------------------------------------
+        // The sweep kernel handles strip_cap rows of a colour per pass; the level colours are uneven (1M-cell
+        // benchmark, 16 colours: mean 211 rows, max 307) and the strips march in lock-step with their neighbours,
+        // so one over-full colour slows every strip around it.  The rows an over-full colour holds beyond the cap
+        // (last in RCM order) move to the nearest later colour no neighbour has and that still has room: they are
+        // swept a little later in the sweep than their level asks for -- still after their upstream neighbours.
+        if (n_strips > 0 && strip_cap > 0) {
+            const int NS = n_parts * n_strips;
+            std::vector<int32_t> cnt((size_t)NS * nc, 0);
+            for (int i = 0; i < n; ++i) ++cnt[(size_t)strip[i] * nc + colr[i]];
+            for (int pos = n - 1; pos >= 0; --pos) {
+                const int32_t u = T.old_of_new[pos];
+                int32_t* cs = cnt.data() + (size_t)strip[u] * nc;
+                if (cs[colr[u]] <= strip_cap) continue;
+                uint64_t used = 0;
+                for (int32_t j = aptr[u]; j < aptr[u + 1]; ++j) used |= (uint64_t)1 << colr[adj[j]];
+                for (int d = 1; d < nc; ++d) {
+                    const int c2 = (colr[u] + d) % nc;
+                    if (((used >> c2) & 1) || cs[c2] >= strip_cap) continue;
+                    --cs[colr[u]]; ++cs[c2];
+                    colr[u] = (uint8_t)c2;
+                    break;
+                }
+            }
+        }
         std::vector<uint64_t> key(n);
         for (int i = 0; i < n; ++i)
             key[i] = n_strips > 0
-                ? ((uint64_t)strip[i] << 44) | ((uint64_t)(level[i] % nc) << 38) | (uint32_t)rcm_pos[i]
-                : ((uint64_t)part[i] << 60) | ((uint64_t)(level[i] % nc) << 54) | ((uint64_t)level[i] << 32) | (uint32_t)rcm_pos[i];
+                ? ((uint64_t)strip[i] << 44) | ((uint64_t)colr[i] << 38) | (uint32_t)rcm_pos[i]
+                : ((uint64_t)part[i] << 60) | ((uint64_t)colr[i] << 54) | ((uint64_t)level[i] << 32) | (uint32_t)rcm_pos[i];
         std::sort(key.begin(), key.end());
         std::vector<int32_t> order(n);
         for (int i = 0; i < n; ++i) order[i] = T.old_of_new[(uint32_t)key[i]];       // RCM position -> cell
@@ -247,7 +274,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         T.part_ptr.assign(n_parts + 1, 0);
         {
             std::vector<int32_t> cnt((size_t)n_parts * nc, 0);
-            for (int i = 0; i < n; ++i) ++cnt[(size_t)part[i] * nc + level[i] % nc];
+            for (int i = 0; i < n; ++i) ++cnt[(size_t)part[i] * nc + colr[i]];
             int32_t pos = 0;
             for (int p = 0; p < n_parts; ++p) {
                 T.part_ptr[p] = pos;
@@ -261,7 +288,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         if (n_strips > 0) {        // rows are (strip, colour)-major: the ranges of every strip's colours
             const int NS = n_parts * n_strips;
             std::vector<int32_t> cnt((size_t)NS * nc, 0);
-            for (int i = 0; i < n; ++i) ++cnt[(size_t)strip[i] * nc + level[i] % nc];
+            for (int i = 0; i < n; ++i) ++cnt[(size_t)strip[i] * nc + colr[i]];
             T.strip_cptr.assign((size_t)NS * (nc + 1), 0);
             int32_t pos = 0;
             for (int s = 0; s < NS; ++s) {
@@ -275,7 +302,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         T.old_of_new.swap(order);
         T.n_levels = max_level + 1;
         T.color_of.resize(n);
-        for (int i = 0; i < n; ++i) T.color_of[i] = (uint8_t)(level[T.old_of_new[i]] % nc);       // by new id
+        for (int i = 0; i < n; ++i) T.color_of[i] = colr[T.old_of_new[i]];       // by new id
     } else {
         // no colours: parts are equal chunks of the RCM order
         T.n_colors = 0;

@@ -79,8 +79,9 @@ struct Topology {
 // (may be NULL): one signed flow per edge (reference order, > 0 = out of f1) the colours are aligned with.
 // n_parts: strips of a domain decomposition (1 = none); rows are then ordered part-major.
 // n_strips > 0 (needs n_colors > 0): rows ordered (part, strip, colour, RCM position), see Topology.
+// strip_cap > 0: rows a (strip, colour) holds beyond strip_cap move to another legal colour with room (best effort).
 std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2,
                            bool rcm, int n_colors, const float* hint, int n_parts, Topology& out,
-                           int n_strips = 0);
+                           int n_strips = 0, int strip_cap = 0);
 
 }  // namespace cwr

@@ -80,3 +80,27 @@ def test_neighbour_synchronised_schedule_equals_the_sequential_sweep():
             relax(z, np.arange(cptr[s, c], cptr[s, c + 1]))
             done[s] += 1
         assert np.array_equal(z, zs)
+
+
+def test_strip_cap_moves_overflow_rows_to_legal_colours():
+    """strip_cap: no (strip, colour) above the cap where a legal colour with room exists; colours still separate
+    coupled rows; only rows of over-full colours move."""
+    plan = synthetic.make_plan(120, 90, 6, tri_fraction=0.2, dry_fraction=0.02, seed=9)
+    n = plan.n_real
+    hint = plan.face_flow.mean(0)
+    L0 = strip_layout(plan.f1, plan.f2, plan.n_face, 10, hint, 8)
+    d0 = np.diff(L0["strip_cptr"], axis=1)
+    cap = int(np.ceil(d0.sum(1).max() / 10 * 1.08))
+    assert d0.max() > cap, "the case must have over-full colours"
+    L = strip_layout(plan.f1, plan.f2, plan.n_face, 10, hint, 8, strip_cap=cap)
+    d = np.diff(L["strip_cptr"], axis=1)
+    assert d.max() <= cap and np.array_equal(d.sum(1), d0.sum(1))
+    p, cptr = L["new_of_old"], L["strip_cptr"]
+    assert np.array_equal(np.sort(p), np.arange(n))
+    internal = plan.f2 < n
+    col = L["color_of"].astype(int)
+    a, b = p[plan.f1[internal]], p[plan.f2[internal]]
+    assert np.all(col[a] != col[b])
+    # rows that kept their colour: everything outside the over-full (strip, colour) pairs
+    moved = (L["color_of"][p] != L0["color_of"][L0["new_of_old"]]).sum()
+    assert 0 < moved <= np.maximum(d0 - cap, 0).sum()

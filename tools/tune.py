@@ -38,6 +38,10 @@ def main():
         opts = {}
         for kv in filter(None, spec.split(",")):
             key, val = kv.split("=", 1)
+            if key.startswith("CWR_"):          # development switches read from the environment at create
+                import os
+                os.environ[key] = val
+                continue
             opts[key] = float(val) if key == "rtol" else int(val)
         t_c = time.perf_counter()
         be = TransportBackend(plan.f1, plan.f2, plan.n_face, T, K, bench.DIFFUSION, device=0, mass_flux=0, **opts)
