@@ -41,6 +41,7 @@ struct cwr_handle {
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
     bool lean = false;               // ... its lean form for fp32 sweeps, K = 16, ELL width 4, one rank (k_gs_lean, precond_sync = 4)
+    bool tma = false;                // ... with the TMA-fed operand ring and register gathers (k_gs_tma, precond_sync = 5)
     int gs_debug = 0;                // CWR_GS_DEBUG (development)
     int strip_cap = 0;               // rows of a (strip, colour) the sweep kernel takes in one pass
     int n_strips = 0;
@@ -463,16 +464,17 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->dc_fixed = h->dc && steps_given;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
-    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 4) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 4;
+    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 5) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 4;
     if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
     h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
     h->pipelined = h->gauss_seidel && h->opt.precond_sync >= 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16;
     if (h->gauss_seidel && h->opt.precond_sync >= 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
     // the lean kernel: fp32 sweeps, 4 lanes x 16 bytes per row, one rank (ELL width 4 is checked once the topology is known)
-    h->lean = h->pipelined && h->opt.precond_sync == 4 && h->sweep_f32 && h->SKC == 4 && h->SVEC == 4 && n_const == 16 &&
+    h->lean = h->pipelined && h->opt.precond_sync >= 4 && h->sweep_f32 && h->SKC == 4 && h->SVEC == 4 && n_const == 16 &&
               std::max(1, h->opt.dd_world) == 1;
     if (h->pipelined && !h->lean) h->opt.precond_sync = 3;
+    h->tma = h->lean && h->opt.precond_sync == 5;
     if (h->gauss_seidel) {
         int occ_gs = 0, coop = 0;
         if (h->pipelined) {
@@ -485,6 +487,10 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
                 CK(cudaFuncSetAttribute(k_gs_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLeanSmemBytes));
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lean, k_gs_lean<false>, kGsThreads, kLeanSmemBytes));
                 if (const char* e = getenv("CWR_GS_DEBUG")) h->gs_debug = atoi(e);
+                if (h->tma) {
+                    CK(cudaFuncSetAttribute(k_gs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lean, k_gs_tma, kGsThreads, kTmaSmemBytes));
+                }
                 occ_gs = std::min(occ_gs, occ_lean);      // either kernel may run on these strips
             }
         } else if (h->strips) {
@@ -527,7 +533,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (flow_hint) h->hint_done = true;
     const Topology& tp = h->topo;
-    if (h->lean && (tp.W != 4 || tp.max_strip_nbr > 31)) { h->lean = false; h->opt.precond_sync = 3; }
+    if (h->lean && (tp.W != 4 || tp.max_strip_nbr > 31)) { h->lean = h->tma = false; h->opt.precond_sync = 3; }
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
     h->C = (h->opt.hydro_capacity <= 0 || h->opt.hydro_capacity > T) ? T : std::max(2, h->opt.hydro_capacity);
@@ -986,7 +992,8 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
                 h->launches += 1;
             }
             void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
-            if (h->lean && h->gs_debug) {          // development: timing experiments (see k_gs_lean)
+            if (h->tma) e = cudaLaunchCooperativeKernel((const void*)k_gs_tma, dim3(h->grid_gs), dim3(kGsThreads), args3, kTmaSmemBytes, h->stream);
+            else if (h->lean && h->gs_debug) {          // development: timing experiments (see k_gs_lean)
                 int packed = sweeps | (h->gs_debug << 16);
                 void* argsd[] = {(void*)&M, (void*)&dst, (void*)&packed};
                 e = cudaLaunchCooperativeKernel((const void*)k_gs_lean<true>, dim3(h->grid_gs), dim3(kGsThreads), argsd, kLeanSmemBytes, h->stream);
@@ -1742,7 +1749,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
-    out->precond_sync = h->gauss_seidel ? (h->lean ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
+    out->precond_sync = h->gauss_seidel ? (h->tma ? 5 : h->lean ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
     return CWR_OK;
 }
 

@@ -1508,6 +1508,210 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_lean(DeviceModel M, float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Strip sweep kernel with a TMA-fed operand ring (precond_sync = 5; same case as k_gs_lean: fp32 sweeps, K = 16,
+// ELL width 4, one rank; same schedule, flags and arithmetic -- bitwise the same results).
+// What the ncu counters of k_gs_lean said (profiles/r02_notes.md): its pace is set by (a) two DRAM latencies in
+// series per colour step -- the column indices of step k + 1 are loaded during step k, and only then can the copies
+// of step k + 1 go out, one step ahead of their use -- and (b) L2 -> SM traffic: cp.async.cg (LDGSTS.BYPASS) moves
+// whole 128-byte lines per quarter warp, so a 64-byte row gather, and above all the 16-byte-per-row value and index
+// streams, fetch 1.5 - 4 x the sectors they use (127 M sectors per 6 sweeps against 66 M useful), where ld.global.cg
+// is sector-exact.  Here:
+//  * the three STREAMS of a step (column indices, matrix values, right-hand side u: contiguous per warp, 8 rows per
+//    pass) arrive by cp.async.bulk -- one elected lane, three bulk copies per pass, completion on an mbarrier -- into
+//    a per-warp ring kTmaStages steps deep: no registers, no per-lane address arithmetic, sector-exact, an L2
+//    evict-first policy (they are read once per sweep; z, which every row gathers four times, keeps the L2), and
+//    their DRAM latency is off the step's dependent chain;
+//  * the GATHERS are predicated ld.global.cg into registers: the early ones (every neighbour but those of the
+//    colour swept just before) go out after the step before, the late ones after the neighbour wait.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTmaStages = 4;
+constexpr int kTmaStageBytes = kGsRows * 8 * (16 + 16 + 64);              // per warp and stage: indices | values | u
+constexpr int kTmaSmemBytes = (kGsThreads / 32) * kTmaStages * kTmaStageBytes;
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @!p bra WAIT_%=;\n}"
+                 ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned sdst, const void* gsrc, unsigned bytes, unsigned bar, unsigned long long policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+
+__global__ void __launch_bounds__(kGsThreads, 2) k_gs_tma(DeviceModel M, float* __restrict__ z, int n_sweeps_arg) {
+    constexpr int NR = kGsRows, GPB = kGsThreads / 4, ST = kTmaStages, kWarps = kGsThreads / 32;
+    static_assert(NR == 2, "two rows per lane group");
+    extern __shared__ int4 gs_land[];                    // [warp][stage][ idx[NR][8] | val[NR][8] | u[NR][8][4] ] (16-byte units)
+    __shared__ int s_cp[kMaxColors + 1];
+    __shared__ __align__(8) unsigned long long s_bar[kWarps * ST];
+    if (M.ctl->all_done || M.ctl->finish_half) return;
+    const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
+    const int nc = M.n_colors, vb = blockIdx.x, nvb = gridDim.x;
+    const int lane = threadIdx.x & 3, group = threadIdx.x >> 2, wl = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = group & 7;
+    const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)vb * (nc + 1);
+    for (int q = threadIdx.x; q <= nc; q += kGsThreads) s_cp[q] = cp_src[q];
+    const int nb0 = M.strip_nptr[vb], n_nbr = M.strip_nptr[vb + 1] - nb0;
+    unsigned long long* const own_flag = M.strip_flag + (size_t)vb * kFlagStride;
+    const unsigned long long* const my_flag = wl == 0 ? own_flag : (wl <= n_nbr ? M.strip_flag + (size_t)M.strip_nbr[nb0 + wl - 1] * kFlagStride : nullptr);
+    unsigned long long target = M.ctl->strip_base;
+    const unsigned long long base = target;
+    const unsigned spin_limit = M.ctl->barrier_timeout ? 0u : (1u << 26);
+    const unsigned bar0 = (unsigned)__cvta_generic_to_shared(s_bar + warp * ST);
+    if (wl == 0) {
+#pragma unroll
+        for (int s = 0; s < ST; ++s) mbar_init(bar0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int n_steps = n_sweeps * nc;
+    int4* const ring = gs_land + warp * (ST * kTmaStageBytes / 16);            // this warp's ring
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring);
+    const int4* __restrict__ ecol4 = reinterpret_cast<const int4*>(M.ell_col);
+    const int4* __restrict__ val4 = reinterpret_cast<const int4*>(M.valf);
+    int4* const zq = reinterpret_cast<int4*>(z);                               // pack 4 * row + lane
+    const int4* __restrict__ usq = reinterpret_cast<const int4*>(M.us);
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    auto nbr_ptr = [&](int cs) { return zq + (((unsigned)cs << 2) + (unsigned)lane); };
+    auto row_pack = [&](int i) { return ((unsigned)i << 2) + (unsigned)lane; };
+    // the streams of `step` into its stage (one elected lane): rows rb + 128 r + 8 warp + [0, 8) of the step's colour
+    auto fill = [&](int step, int col) {
+        const int stage = step % ST;
+        const int b = s_cp[col], e = s_cp[col + 1];
+        const unsigned sbase = ring_s + stage * kTmaStageBytes, bar = bar0 + 8 * stage;
+        int cnt[NR];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) cnt[r] = max(0, min(8, e - (b + r * GPB + 8 * warp)));
+        mbar_expect_tx(bar, 96u * (unsigned)(cnt[0] + cnt[1]));
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            if (cnt[r] <= 0) continue;
+            const int row0 = b + r * GPB + 8 * warp;
+            bulk_g2s(sbase + r * 128, ecol4 + row0, 16u * cnt[r], bar, policy);
+            bulk_g2s(sbase + NR * 128 + r * 128, val4 + row0, 16u * cnt[r], bar, policy);
+            bulk_g2s(sbase + 2 * NR * 128 + r * 512, usq + (size_t)row0 * 4, 64u * cnt[r], bar, policy);
+        }
+    };
+    float4 x[NR][4];
+    int act[NR];
+    // early gathers of `step` (its indices have landed): everything but the neighbours of the colour swept just before
+    auto gather_early = [&](int step, int b, int e) {
+        const int4* st = ring + (step % ST) * (kTmaStageBytes / 16);
+        const int emask = step < nc ? (int)(kLaterBit | kPrevBit) : (int)kPrevBit;
+        const int zmask = step < nc ? (int)kLaterBit : 0;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            act[r] = b + group + r * GPB < e;
+            const int4 c4 = st[r * 8 + gl];
+            const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                x[r][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (act[r] && (cs[u] & emask) != kPrevBit && !(cs[u] & zmask)) x[r][u] = __ldcg(reinterpret_cast<const float4*>(nbr_ptr(cs[u])));
+            }
+        }
+    };
+    auto gather_late = [&](int step) {
+        const int4* st = ring + (step % ST) * (kTmaStageBytes / 16);
+        const int emask = step < nc ? (int)(kLaterBit | kPrevBit) : (int)kPrevBit;
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const int4 c4 = st[r * 8 + gl];
+            const int cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (act[r] && (cs[u] & emask) == kPrevBit) x[r][u] = __ldcg(reinterpret_cast<const float4*>(nbr_ptr(cs[u])));
+        }
+    };
+
+    // prologue: the streams of the first ST steps, the early gathers of step 0
+    if (wl == 0)
+        for (int s = 0, c = 0; s < ST && s < n_steps; ++s) { fill(s, c); c = c + 1 == nc ? 0 : c + 1; }
+    int rb = s_cp[0], re = s_cp[1];
+    int col = 0, col_fill = ST % nc;              // colour of the step the next refill is for (step + ST - 1 at the top of `step`)
+    mbar_wait(bar0, 0);
+    gather_early(0, rb, re);
+    for (int step = 0; step < n_steps; ++step) {
+        const bool last_step = step + 1 == n_steps;
+        const int stage = step % ST;
+        const int coln = col + 1 == nc ? 0 : col + 1;
+        const int rbn = s_cp[coln], ren = s_cp[coln + 1];
+        if (step > 0) {
+            // the stage of step - 1 is free (every lane has used it): the streams of step - 1 + ST go there
+            __syncwarp();
+            if (wl == 0 && step - 1 + ST < n_steps) fill(step - 1 + ST, col_fill);
+            col_fill = col_fill + 1 == nc ? 0 : col_fill + 1;
+            // every warp of this strip and of the neighbouring strips has finished step - 1
+            if (my_flag) {
+                unsigned spins = 0;
+                while (ld_relaxed_u64(my_flag) < target) {
+                    if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; break; }      // never hang the device
+                    __nanosleep(64);
+                }
+            }
+            __syncwarp();
+        }
+        gather_late(step);
+        const int4* st = ring + stage * (kTmaStageBytes / 16);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const float4 v = *reinterpret_cast<const float4*>(st + NR * 8 + r * 8 + gl);
+            const float4 own = *reinterpret_cast<const float4*>(st + 2 * NR * 8 + r * 32 + gl * 4 + lane);
+            const float4 x0 = x[r][0], x1 = x[r][1], x2 = x[r][2], x3 = x[r][3];
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            o.x += v.x * x0.x; o.y += v.x * x0.y; o.z += v.x * x0.z; o.w += v.x * x0.w;
+            o.x += v.y * x1.x; o.y += v.y * x1.y; o.z += v.y * x1.z; o.w += v.y * x1.w;
+            o.x += v.z * x2.x; o.y += v.z * x2.y; o.z += v.z * x2.z; o.w += v.z * x2.w;
+            o.x += v.w * x3.x; o.y += v.w * x3.y; o.z += v.w * x3.z; o.w += v.w * x3.w;
+            o.x = own.x - o.x; o.y = own.y - o.y; o.z = own.z - o.z; o.w = own.w - o.w;
+            const int i = rb + group + r * GPB;
+            if (act[r]) *reinterpret_cast<float4*>(zq + row_pack(i)) = o;
+        }
+        // rows beyond one pass of the CTA (rare: strip_cap): through registers, all gathers after the wait
+#pragma unroll 1
+        for (int i = rb + group + NR * GPB; i < re; i += GPB) {
+            const int4 d4 = __ldg(ecol4 + i);
+            const float4 wv = __ldg(reinterpret_cast<const float4*>(val4) + i);
+            const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (step < nc && ds[u] < 0) continue;
+                const float4 y = __ldcg(reinterpret_cast<const float4*>(nbr_ptr(ds[u])));
+                o.x += ws[u] * y.x; o.y += ws[u] * y.y; o.z += ws[u] * y.z; o.w += ws[u] * y.w;
+            }
+            const float4 own = __ldcg(reinterpret_cast<const float4*>(usq + row_pack(i)));
+            o.x = own.x - o.x; o.y = own.y - o.y; o.z = own.z - o.z; o.w = own.w - o.w;
+            *reinterpret_cast<float4*>(zq + row_pack(i)) = o;
+        }
+        if (last_step) break;
+        // publish this warp's step: its lanes' stores, then one release per warp
+        __syncwarp();
+        if (wl == 0) red_release_add1(own_flag);
+        target += kWarps;
+        rb = rbn; re = ren; col = coln;
+        mbar_wait(bar0 + 8 * ((step + 1) % ST), ((step + 1) / ST) & 1);
+        gather_early(step + 1, rb, re);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
+    __syncthreads();
+    if (threadIdx.x == 0) {        // the last CTA to leave: arrivals every strip has counted
+        const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
+        if (t == (unsigned)nvb - 1) {
+            M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
+            M.ctl->strip_base = base + (unsigned long long)kWarps * (unsigned long long)(n_steps - 1);
+            __threadfence();
+        }
+    }
+}
+
 // u (fp64) -> the sweep type, own rows (the BiCGSTAB path in front of k_gs_strip: its vectors are fp64)
 template <typename ST>
 __global__ void __launch_bounds__(kThreads) k_to_sweep_type(DeviceModel M, const double* __restrict__ u, ST* __restrict__ out) {
