@@ -331,8 +331,9 @@ def precond_kernel_name(o):
             2: "k_precond_gs<STRIP=true> (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags)",
             3: "k_gs_strip (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags, "
                "software-pipelined cp.async gathers)",
-            4: "k_gs_lean (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags, "
-               "software-pipelined predicated cp.async gathers, fp32 x 16 constituents)"}.get(o.precond_sync, "k_precond_gs")
+            4: "k_gs_tma (multicolour Gauss-Seidel sweeps of one cycle, persistent, one strip per CTA, neighbour flags; index / "
+               "value / right-hand-side streams by cp.async.bulk + mbarrier into a per-warp ring, predicated ld.global.cg "
+               "gathers in registers; fp32 x 16 constituents)"}.get(o.precond_sync, "k_precond_gs")
 
 
 def gpu_workload(name, ctx, args, steps, warmup, profile_steps, opts, *, dd=False, want_roofline=True, want_e2e=False,

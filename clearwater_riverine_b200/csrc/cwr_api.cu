@@ -40,8 +40,8 @@ struct cwr_handle {
     bool dc_fixed = false;           // ... with a fixed number of sweeps per cycle (precond_steps given) instead of the device-side plan
     bool strips = false;             // neighbour-synchronised sweep kernel: one strip of rows per CTA (precond_sync = 2, 3)
     bool pipelined = false;          // ... software-pipelined across the synchronisation (k_gs_strip, precond_sync = 3)
-    bool lean = false;               // ... its lean form for fp32 sweeps, K = 16, ELL width 4, one rank (k_gs_lean, precond_sync = 4)
-    bool tma = false;                // ... with the TMA-fed operand ring and register gathers (k_gs_tma, precond_sync = 5)
+    bool tma = false;                // ... with a TMA-fed operand ring and register gathers: fp32 sweeps, K = 16, ELL width 4, one rank
+                                     // (k_gs_tma, precond_sync = 4)
     int gs_debug = 0;                // CWR_GS_DEBUG (development)
     int strip_cap = 0;               // rows of a (strip, colour) the sweep kernel takes in one pass
     int n_strips = 0;
@@ -332,7 +332,7 @@ static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
     std::string terr = build_topology(h->n, h->F, E, h->f1_ref.data(), h->f2_ref.data(), h->opt.reorder != 0,
                                       h->opt.precond_colors, hint.data(), h->world, t2, h->strips ? h->n_strips : 0, h->strip_cap);
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
-    if (h->lean && t2.max_strip_nbr > 31) return CWR_OK;      // (a strip of an RCM band has two or three neighbours)
+    if (h->tma && t2.max_strip_nbr > 31) return CWR_OK;      // (a strip of an RCM band has two or three neighbours)
     if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
     if (h->attached) return CWR_OK;                 // peers already rely on the current ownership
     h->topo = std::move(t2);
@@ -464,34 +464,29 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->dc_fixed = h->dc && steps_given;
     if (h->opt.solver == 2 && !h->dc) h->opt.solver = 1;
     // sweep kernel: one strip of rows per resident CTA, synchronised with its neighbour strips only
-    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 5) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 4;
+    if (h->opt.precond_sync < 1 || h->opt.precond_sync > 4) h->opt.precond_sync = h->opt.dd_halo_per_colour ? 1 : 4;
     if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
     h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
     h->pipelined = h->gauss_seidel && h->opt.precond_sync >= 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16;
     if (h->gauss_seidel && h->opt.precond_sync >= 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
-    // the lean kernel: fp32 sweeps, 4 lanes x 16 bytes per row, one rank (ELL width 4 is checked once the topology is known)
-    h->lean = h->pipelined && h->opt.precond_sync >= 4 && h->sweep_f32 && h->SKC == 4 && h->SVEC == 4 && n_const == 16 &&
-              std::max(1, h->opt.dd_world) == 1;
-    if (h->pipelined && !h->lean) h->opt.precond_sync = 3;
-    h->tma = h->lean && h->opt.precond_sync == 5;
+    // k_gs_tma: fp32 sweeps, 4 lanes x 16 bytes per row, one rank (ELL width 4 is checked once the topology is known)
+    h->tma = h->pipelined && h->opt.precond_sync == 4 && h->sweep_f32 && h->SKC == 4 && h->SVEC == 4 && n_const == 16 &&
+             std::max(1, h->opt.dd_world) == 1;
+    if (h->pipelined && !h->tma) h->opt.precond_sync = 3;
     if (h->gauss_seidel) {
         int occ_gs = 0, coop = 0;
         if (h->pipelined) {
             cudaError_t e = cudaSuccess;
             SWEEP_DISPATCH(e = gs3_prepare<ST, SKC, SVEC>(&occ_gs));
             CK(e);
-            if (h->lean) {
-                int occ_lean = 0;
-                CK(cudaFuncSetAttribute(k_gs_lean<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLeanSmemBytes));
-                CK(cudaFuncSetAttribute(k_gs_lean<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kLeanSmemBytes));
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lean, k_gs_lean<false>, kGsThreads, kLeanSmemBytes));
+            if (h->tma) {
+                int occ_tma = 0;
+                CK(cudaFuncSetAttribute(k_gs_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+                CK(cudaFuncSetAttribute(k_gs_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_tma, k_gs_tma<false>, kGsThreads, kTmaSmemBytes));
                 if (const char* e = getenv("CWR_GS_DEBUG")) h->gs_debug = atoi(e);
-                if (h->tma) {
-                    CK(cudaFuncSetAttribute(k_gs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemBytes));
-                    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_lean, k_gs_tma, kGsThreads, kTmaSmemBytes));
-                }
-                occ_gs = std::min(occ_gs, occ_lean);      // either kernel may run on these strips
+                occ_gs = std::min(occ_gs, occ_tma);       // either kernel may run on these strips
             }
         } else if (h->strips) {
             SWEEP_DISPATCH(cudaFuncSetAttribute(k_precond_gs<ST, SKC, SVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGsSmemBytes));
@@ -512,8 +507,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->opt.precond_colors <= 0 && h->strips) {
         // one colour of a strip = one pass of the CTA: kGsRows rows per lane group (the pipelined rows of k_precond_gs)
         const double rows_strip = (double)n_real / std::max(1, h->opt.dd_world) / h->n_strips;
-        const int per_pass = kGsRows * (kGsThreads / h->SKC);
-        h->opt.precond_colors = (int)std::min(48.0, std::max(8.0, std::ceil(rows_strip * 1.15 / per_pass)));
+        const int per_pass = h->strip_cap;          // (build_topology moves the rows a colour would hold beyond one pass)
+        h->opt.precond_colors = (int)std::min(48.0, std::max(8.0, std::ceil(rows_strip * 1.1 / per_pass)));
     }
     if (h->opt.precond_colors <= 0) {
         // auto: a colour should move ~20 MB (well above the ~4 us a grid barrier + gather latency cost):
@@ -533,7 +528,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (!terr.empty()) FAIL(CWR_EINVAL, terr);
     if (flow_hint) h->hint_done = true;
     const Topology& tp = h->topo;
-    if (h->lean && (tp.W != 4 || tp.max_strip_nbr > 31)) { h->lean = h->tma = false; h->opt.precond_sync = 3; }
+    if (h->tma && (tp.W != 4 || tp.max_strip_nbr > 31)) { h->tma = false; h->opt.precond_sync = 3; }
     h->n = tp.n; h->F = tp.F; h->E = tp.E; h->G = tp.G; h->K = n_const; h->T = n_time;
     const int n = h->n, E = h->E, K = h->K, T = h->T;
     h->C = (h->opt.hydro_capacity <= 0 || h->opt.hydro_capacity > T) ? T : std::max(2, h->opt.hydro_capacity);
@@ -992,12 +987,11 @@ static const void* precondition(cwr_handle* h, const double* u, void* dst, void*
                 h->launches += 1;
             }
             void* args3[] = {(void*)&M, (void*)&dst, (void*)&sweeps, (void*)&seq};
-            if (h->tma) e = cudaLaunchCooperativeKernel((const void*)k_gs_tma, dim3(h->grid_gs), dim3(kGsThreads), args3, kTmaSmemBytes, h->stream);
-            else if (h->lean && h->gs_debug) {          // development: timing experiments (see k_gs_lean)
+            if (h->tma && h->gs_debug) {          // development: timing experiments (see k_gs_tma)
                 int packed = sweeps | (h->gs_debug << 16);
                 void* argsd[] = {(void*)&M, (void*)&dst, (void*)&packed};
-                e = cudaLaunchCooperativeKernel((const void*)k_gs_lean<true>, dim3(h->grid_gs), dim3(kGsThreads), argsd, kLeanSmemBytes, h->stream);
-            } else if (h->lean) e = cudaLaunchCooperativeKernel((const void*)k_gs_lean<false>, dim3(h->grid_gs), dim3(kGsThreads), args3, kLeanSmemBytes, h->stream);
+                e = cudaLaunchCooperativeKernel((const void*)k_gs_tma<true>, dim3(h->grid_gs), dim3(kGsThreads), argsd, kTmaSmemBytes, h->stream);
+            } else if (h->tma) e = cudaLaunchCooperativeKernel((const void*)k_gs_tma<false>, dim3(h->grid_gs), dim3(kGsThreads), args3, kTmaSmemBytes, h->stream);
             else SWEEP_DISPATCH(e = (gs3_launch<ST, SKC, SVEC>(h->grid_gs, args3, h->stream)));
         } else
         if (h->strips) { SWEEP_DISPATCH(e = cudaLaunchCooperativeKernel((const void*)k_precond_gs<ST, SKC, SVEC, true>, dim3(h->grid_gs), dim3(kGsThreads), args, kGsSmemBytes, h->stream)); }
@@ -1749,7 +1743,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
     out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
-    out->precond_sync = h->gauss_seidel ? (h->tma ? 5 : h->lean ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
+    out->precond_sync = h->gauss_seidel ? (h->tma ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
     return CWR_OK;
 }
 

@@ -1289,50 +1289,6 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// Lean strip sweep kernel (precond_sync = 4): k_gs_strip's schedule, flags and arithmetic (bitwise the same
-// results), written for the one case the large benchmark runs -- fp32 sweeps, K = 16 (4 lanes x 16 bytes per row),
-// ELL width 4, one rank -- with the instruction count as the design constraint.  ncu on k_gs_strip (r02): 870 warp
-// instructions per warp and colour step for 2 rows per lane group, issue slots 55 % busy, 35 % of the warp samples
-// in the fence / poll chain: the schedulers, not the memory system, set its pace.  Here:
-//  * early / late / zero-filling copies are one predicated cp.async each, the predicates made inside the asm block
-//    from the two flag bits of the column index and two step-uniform masks (first sweep from z = 0: not-yet-visited
-//    neighbours are zero-filled through the ignore-src operand) -- no branches in the step body;
-//  * shared-memory and global addresses are base + immediate; one IMAD.WIDE per gathered row;
-//  * the poll is a relaxed load per lane (lane 0: own strip, lanes 1..: neighbour strips); the data it guards is
-//    read by cp.async.cg (L2) after the dependent branch, so no L1 invalidate and no fence on the acquire side;
-//    the release side is one red.release.gpu per warp;
-//  * the time-out flag is read once per launch, not once per step (it was a dependent global load in front of
-//    every poll: 9 % of the samples).
-// Rows a (strip, colour) holds beyond one pass (build_topology's strip_cap keeps that from happening) take a
-// plain register path after the pipelined rows.
-// ---------------------------------------------------------------------------------------------
-constexpr int kLeanSlots = 6;                                        // 4 gathers | u | values
-constexpr int kLeanSmemBytes = kGsRows * kLeanSlots * 16 * kGsThreads;
-constexpr int kLeanPlane = 16 * kGsThreads;                          // bytes between two slots of a thread
-
-// (`act`: the lane group has a row in this pass)
-template <int OFF>
-__device__ __forceinline__ void lean_cp(unsigned sdst, const void* gsrc, int act) {
-    asm volatile("{\n .reg .pred a;\n setp.ne.b32 a, %3, 0;\n @a cp.async.cg.shared.global [%0+%2], [%1], 16;\n}"
-                 ::"r"(sdst), "l"(gsrc), "n"(OFF), "r"(act) : "memory");
-}
-// early: unless the neighbour is exactly "previous colour, already visited"; zero-filled (source ignored) where zmask hits
-template <int OFF>
-__device__ __forceinline__ void lean_cp_early(unsigned sdst, const void* gsrc, int cs, int emask, int zmask, int act) {
-    asm volatile("{\n .reg .pred p, q, a;\n .reg .b32 t, s;\n"
-                 " and.b32 t, %2, %3;\n setp.ne.b32 a, %6, 0;\n setp.ne.and.b32 p, t, 0x40000000, a;\n"
-                 " and.b32 s, %2, %4;\n setp.ne.b32 q, s, 0;\n"
-                 " @p cp.async.cg.shared.global [%0+%5], [%1], 16, q;\n}"
-                 ::"r"(sdst), "l"(gsrc), "r"(cs), "r"(emask), "r"(zmask), "n"(OFF), "r"(act) : "memory");
-}
-template <int OFF>
-__device__ __forceinline__ void lean_cp_late(unsigned sdst, const void* gsrc, int cs, int emask, int act) {
-    asm volatile("{\n .reg .pred p, a;\n .reg .b32 t;\n"
-                 " and.b32 t, %2, %3;\n setp.ne.b32 a, %5, 0;\n setp.eq.and.b32 p, t, 0x40000000, a;\n"
-                 " @p cp.async.cg.shared.global [%0+%4], [%1], 16;\n}"
-                 ::"r"(sdst), "l"(gsrc), "r"(cs), "r"(emask), "n"(OFF), "r"(act) : "memory");
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1342,176 +1298,10 @@ __device__ __forceinline__ void red_release_add1(unsigned long long* p) {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(p) : "memory");
 }
 
-// DBG (development, CWR_GS_DEBUG=bits): timing experiments that break the sweep's semantics -- 1: no neighbour wait,
-// 2: no publish, 4: no late copies, 8: no __nanosleep between polls, 16: acquire polls (L1 invalidate per poll),
-// 64: no u / value copies, 128: no early gathers,
-// 32: every row through the register path (ld.global.cg gathers; combine with 4 to drop the cp.async gathers)
-template <bool DBG>
-__global__ void __launch_bounds__(kGsThreads, 2) k_gs_lean(DeviceModel M, float* __restrict__ z, int n_sweeps_arg) {
-    constexpr int NR = kGsRows, NS = kLeanSlots, GPB = kGsThreads / 4, PL = kLeanPlane;
-    const int dbg = DBG ? n_sweeps_arg >> 16 : 0;
-    n_sweeps_arg &= 0xffff;
-    static_assert(NR == 2, "the copies below are written out for two rows per lane group");
-    extern __shared__ int4 gs_land[];          // [NR rows][4 gathers | u | values][kGsThreads]
-    __shared__ int s_cp[kMaxColors + 1];
-    if (M.ctl->all_done || M.ctl->finish_half) return;
-    const int n_sweeps = n_sweeps_arg > 0 ? n_sweeps_arg : M.ctl->dc_sweeps;
-    const int nc = M.n_colors, vb = blockIdx.x, nvb = gridDim.x;
-    const int lane = threadIdx.x & 3, group = threadIdx.x >> 2, wl = threadIdx.x & 31;
-    const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)vb * (nc + 1);
-    for (int q = threadIdx.x; q <= nc; q += kGsThreads) s_cp[q] = cp_src[q];
-    const int nb0 = M.strip_nptr[vb], n_nbr = M.strip_nptr[vb + 1] - nb0;
-    unsigned long long* const own_flag = M.strip_flag + (size_t)vb * kFlagStride;
-    const unsigned long long* const my_flag = wl == 0 ? own_flag : (wl <= n_nbr ? M.strip_flag + (size_t)M.strip_nbr[nb0 + wl - 1] * kFlagStride : nullptr);
-    constexpr unsigned kWarps = kGsThreads / 32;
-    unsigned long long target = M.ctl->strip_base;
-    const unsigned long long base = target;
-    const unsigned spin_limit = M.ctl->barrier_timeout ? 0u : (1u << 26);
-    __syncthreads();
-    const int n_steps = n_sweeps * nc;
-    const unsigned sl = (unsigned)__cvta_generic_to_shared(gs_land) + threadIdx.x * 16;
-    const int4* __restrict__ ecol4 = reinterpret_cast<const int4*>(M.ell_col);
-    const int4* __restrict__ val4 = reinterpret_cast<const int4*>(M.valf);
-    int4* const zq = reinterpret_cast<int4*>(z);                               // pack 4 * row + lane
-    const int4* __restrict__ usq = reinterpret_cast<const int4*>(M.us);
-
-    int rb = s_cp[0], re = s_cp[1];
-    int4 pc[NR], pcn[NR];
-    int ic[NR], icn[NR], act[NR];
-    auto clamp_row = [&](int i, int e) { return max(min(i, e - 1), 0); };
-    auto load_idx = [&](int4 (&dst)[NR], int (&rows)[NR], int b, int e) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            rows[r] = clamp_row(b + group + r * GPB, e);       // (a valid address for the index load of an idle lane group)
-            dst[r] = __ldg(ecol4 + rows[r]);
-        }
-    };
-    auto set_act = [&](int b, int e) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) act[r] = b + group + r * GPB < e;
-    };
-    // pack of this lane in the neighbour's row: the shift drops the two flag bits (n < 2^30 rows)
-    auto nbr_ptr = [&](int cs) { return zq + (((unsigned)cs << 2) + (unsigned)lane); };
-    auto row_pack = [&](int i) { return ((unsigned)i << 2) + (unsigned)lane; };
-    auto issue_early = [&](int emask, int zmask) {
-        if (!(DBG && (dbg & 128))) {
-        lean_cp_early<(0 * NS + 0) * PL>(sl, nbr_ptr(pc[0].x), pc[0].x, emask, zmask, act[0]);
-        lean_cp_early<(0 * NS + 1) * PL>(sl, nbr_ptr(pc[0].y), pc[0].y, emask, zmask, act[0]);
-        lean_cp_early<(0 * NS + 2) * PL>(sl, nbr_ptr(pc[0].z), pc[0].z, emask, zmask, act[0]);
-        lean_cp_early<(0 * NS + 3) * PL>(sl, nbr_ptr(pc[0].w), pc[0].w, emask, zmask, act[0]);
-        lean_cp_early<(1 * NS + 0) * PL>(sl, nbr_ptr(pc[1].x), pc[1].x, emask, zmask, act[1]);
-        lean_cp_early<(1 * NS + 1) * PL>(sl, nbr_ptr(pc[1].y), pc[1].y, emask, zmask, act[1]);
-        lean_cp_early<(1 * NS + 2) * PL>(sl, nbr_ptr(pc[1].z), pc[1].z, emask, zmask, act[1]);
-        lean_cp_early<(1 * NS + 3) * PL>(sl, nbr_ptr(pc[1].w), pc[1].w, emask, zmask, act[1]);
-        }
-        if (!(DBG && (dbg & 64))) {
-        lean_cp<(0 * NS + 4) * PL>(sl, usq + row_pack(ic[0]), act[0]);
-        lean_cp<(0 * NS + 5) * PL>(sl, val4 + (unsigned)ic[0], act[0]);
-        lean_cp<(1 * NS + 4) * PL>(sl, usq + row_pack(ic[1]), act[1]);
-        lean_cp<(1 * NS + 5) * PL>(sl, val4 + (unsigned)ic[1], act[1]);
-        }
-    };
-    auto issue_late = [&](int emask) {
-        lean_cp_late<(0 * NS + 0) * PL>(sl, nbr_ptr(pc[0].x), pc[0].x, emask, act[0]);
-        lean_cp_late<(0 * NS + 1) * PL>(sl, nbr_ptr(pc[0].y), pc[0].y, emask, act[0]);
-        lean_cp_late<(0 * NS + 2) * PL>(sl, nbr_ptr(pc[0].z), pc[0].z, emask, act[0]);
-        lean_cp_late<(0 * NS + 3) * PL>(sl, nbr_ptr(pc[0].w), pc[0].w, emask, act[0]);
-        lean_cp_late<(1 * NS + 0) * PL>(sl, nbr_ptr(pc[1].x), pc[1].x, emask, act[1]);
-        lean_cp_late<(1 * NS + 1) * PL>(sl, nbr_ptr(pc[1].y), pc[1].y, emask, act[1]);
-        lean_cp_late<(1 * NS + 2) * PL>(sl, nbr_ptr(pc[1].z), pc[1].z, emask, act[1]);
-        lean_cp_late<(1 * NS + 3) * PL>(sl, nbr_ptr(pc[1].w), pc[1].w, emask, act[1]);
-    };
-    // masks of a step: in the first sweep (from z = 0) a neighbour visited later counts as 0 -- zero-filled early,
-    // whatever its colour; afterwards only "previous colour" matters
-    auto emask_of = [&](int step) { return step < nc ? (int)(kLaterBit | kPrevBit) : (int)kPrevBit; };
-    auto zmask_of = [&](int step) { return step < nc ? (int)kLaterBit : 0; };
-
-    load_idx(pc, ic, rb, re);
-    set_act(rb, re);
-    issue_early(emask_of(0), zmask_of(0));
-    int col = 0;
-    for (int step = 0; step < n_steps; ++step) {
-        const bool last_step = step + 1 == n_steps;
-        const int coln = col + 1 == nc ? 0 : col + 1;
-        const int rbn = s_cp[coln], ren = s_cp[coln + 1];
-        if (!last_step) load_idx(pcn, icn, rbn, ren);            // indices of the next step, in flight across this one
-        if (step > 0) {
-            // every warp of this strip and of the neighbouring strips has finished step - 1
-            if (my_flag && !(dbg & 1)) {
-                unsigned spins = 0;
-                while ((DBG && (dbg & 16) ? ld_acquire_u64(my_flag) : ld_relaxed_u64(my_flag)) < target) {
-                    if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; break; }      // never hang the device
-                    if (!(DBG && (dbg & 8))) __nanosleep(64);      // (measured: 527 -> 507 us per 6 sweeps)
-                }
-            }
-            __syncwarp();
-        }
-        if (!(dbg & 4)) issue_late(emask_of(step));
-        cp_async_wait_all();
-        if (!(DBG && (dbg & 32)))
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const int4* s = gs_land + (r * NS) * kGsThreads + threadIdx.x;
-            const float4 v = *reinterpret_cast<const float4*>(s + 5 * kGsThreads);
-            const float4 x0 = *reinterpret_cast<const float4*>(s);
-            const float4 x1 = *reinterpret_cast<const float4*>(s + kGsThreads);
-            const float4 x2 = *reinterpret_cast<const float4*>(s + 2 * kGsThreads);
-            const float4 x3 = *reinterpret_cast<const float4*>(s + 3 * kGsThreads);
-            const float4 own = *reinterpret_cast<const float4*>(s + 4 * kGsThreads);
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            o.x += v.x * x0.x; o.y += v.x * x0.y; o.z += v.x * x0.z; o.w += v.x * x0.w;
-            o.x += v.y * x1.x; o.y += v.y * x1.y; o.z += v.y * x1.z; o.w += v.y * x1.w;
-            o.x += v.z * x2.x; o.y += v.z * x2.y; o.z += v.z * x2.z; o.w += v.z * x2.w;
-            o.x += v.w * x3.x; o.y += v.w * x3.y; o.z += v.w * x3.z; o.w += v.w * x3.w;
-            o.x = own.x - o.x; o.y = own.y - o.y; o.z = own.z - o.z; o.w = own.w - o.w;
-            const int i = rb + group + r * GPB;
-            if (i < re) *reinterpret_cast<float4*>(zq + row_pack(i)) = o;
-        }
-        // rows beyond one pass of the CTA (rare: strip_cap): through registers, all gathers after the wait
-#pragma unroll 1
-        for (int i = rb + group + (DBG && (dbg & 32) ? 0 : NR * GPB); i < re; i += GPB) {
-            const int4 d4 = __ldg(ecol4 + i);
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(val4) + i);
-            const int ds[4] = {d4.x, d4.y, d4.z, d4.w};
-            const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (step < nc && ds[u] < 0) continue;
-                const float4 y = __ldcg(reinterpret_cast<const float4*>(nbr_ptr(ds[u])));
-                o.x += ws[u] * y.x; o.y += ws[u] * y.y; o.z += ws[u] * y.z; o.w += ws[u] * y.w;
-            }
-            const float4 own = __ldcg(reinterpret_cast<const float4*>(usq + row_pack(i)));
-            o.x = own.x - o.x; o.y = own.y - o.y; o.z = own.z - o.z; o.w = own.w - o.w;
-            *reinterpret_cast<float4*>(zq + row_pack(i)) = o;
-        }
-        if (last_step) break;
-        // publish this warp's step: its lanes' stores, then one release per warp
-        __syncwarp();
-        if (wl == 0 && !(dbg & 2)) red_release_add1(own_flag);
-        target += kWarps;
-#pragma unroll
-        for (int r = 0; r < NR; ++r) { pc[r] = pcn[r]; ic[r] = icn[r]; }
-        rb = rbn; re = ren; col = coln;
-        set_act(rb, re);
-        issue_early(emask_of(step + 1), zmask_of(step + 1));
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
-    __syncthreads();
-    if (threadIdx.x == 0) {        // the last CTA to leave: arrivals every strip has counted
-        const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
-        if (t == (unsigned)nvb - 1) {
-            M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
-            M.ctl->strip_base = DBG && (dbg & 2) ? base : base + (unsigned long long)kWarps * (unsigned long long)(n_steps - 1);
-            __threadfence();
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
-// Strip sweep kernel with a TMA-fed operand ring (precond_sync = 5; same case as k_gs_lean: fp32 sweeps, K = 16,
+// Strip sweep kernel with a TMA-fed operand ring (precond_sync = 4: fp32 sweeps, K = 16 -- 4 lanes x 16 bytes per row --,
 // ELL width 4, one rank; same schedule, flags and arithmetic -- bitwise the same results).
-// What the ncu counters of k_gs_lean said (profiles/r02_notes.md): its pace is set by (a) two DRAM latencies in
+// What the ncu counters of k_gs_strip and of a leaner cp.async form of it said (profiles/r02_notes.md): the pace is set by (a) two DRAM latencies in
 // series per colour step -- the column indices of step k + 1 are loaded during step k, and only then can the copies
 // of step k + 1 go out, one step ahead of their use -- and (b) L2 -> SM traffic: cp.async.cg (LDGSTS.BYPASS) moves
 // whole 128-byte lines per quarter warp, so a 64-byte row gather, and above all the 16-byte-per-row value and index
@@ -1544,8 +1334,13 @@ __device__ __forceinline__ void bulk_g2s(unsigned sdst, const void* gsrc, unsign
                  ::"r"(sdst), "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(kGsThreads, 2) k_gs_tma(DeviceModel M, float* __restrict__ z, int n_sweeps_arg) {
     constexpr int NR = kGsRows, GPB = kGsThreads / 4, ST = kTmaStages, kWarps = kGsThreads / 32;
+    // DBG (development, CWR_GS_DEBUG = bits): timing experiments, some of which break the sweep's semantics -- 1: no neighbour
+    // wait, 2: no publish (no release fence), 8: no __nanosleep between polls, 16: streams without the evict-first policy
+    const int dbg = DBG ? n_sweeps_arg >> 16 : 0;
+    n_sweeps_arg &= 0xffff;
     static_assert(NR == 2, "two rows per lane group");
     extern __shared__ int4 gs_land[];                    // [warp][stage][ idx[NR][8] | val[NR][8] | u[NR][8][4] ] (16-byte units)
     __shared__ int s_cp[kMaxColors + 1];
@@ -1578,6 +1373,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_tma(DeviceModel M, float* 
     const int4* __restrict__ usq = reinterpret_cast<const int4*>(M.us);
     unsigned long long policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (DBG && (dbg & 16)) asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(policy));
     auto nbr_ptr = [&](int cs) { return zq + (((unsigned)cs << 2) + (unsigned)lane); };
     auto row_pack = [&](int i) { return ((unsigned)i << 2) + (unsigned)lane; };
     // the streams of `step` into its stage (one elected lane): rows rb + 128 r + 8 warp + [0, 8) of the step's colour
@@ -1648,11 +1444,11 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_tma(DeviceModel M, float* 
             if (wl == 0 && step - 1 + ST < n_steps) fill(step - 1 + ST, col_fill);
             col_fill = col_fill + 1 == nc ? 0 : col_fill + 1;
             // every warp of this strip and of the neighbouring strips has finished step - 1
-            if (my_flag) {
+            if (my_flag && !(dbg & 1)) {
                 unsigned spins = 0;
                 while (ld_relaxed_u64(my_flag) < target) {
                     if (++spins > spin_limit) { M.ctl->barrier_timeout = 1; break; }      // never hang the device
-                    __nanosleep(64);
+                    if (!(dbg & 8)) __nanosleep(DBG && (dbg & 32) ? 20 : 64);
                 }
             }
             __syncwarp();
@@ -1692,13 +1488,18 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_tma(DeviceModel M, float* 
             *reinterpret_cast<float4*>(zq + row_pack(i)) = o;
         }
         if (last_step) break;
-        // publish this warp's step: its lanes' stores, then one release per warp
-        __syncwarp();
-        if (wl == 0) red_release_add1(own_flag);
-        target += kWarps;
+        // The early gathers of the next step go out BEFORE this step is published: the release fence waits for the
+        // warp's outstanding stores (~1 us: ncu, 90 of 373 us per 6 sweeps), and gathers issued behind it would
+        // start a store latency late in every step.  They are safe here: the neighbouring strips have finished
+        // step - 1 and cannot start step + 1 before this strip publishes, so all they may be writing is this
+        // step's colour -- which is exactly what a step's early gathers leave out.
         rb = rbn; re = ren; col = coln;
         mbar_wait(bar0 + 8 * ((step + 1) % ST), ((step + 1) / ST) & 1);
         gather_early(step + 1, rb, re);
+        // publish this warp's step: its lanes' stores, then one release per warp
+        __syncwarp();
+        if (wl == 0 && !(dbg & 2)) red_release_add1(own_flag);
+        target += kWarps;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
     __syncthreads();
@@ -1706,7 +1507,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_tma(DeviceModel M, float* 
         const unsigned t = atomicAdd(&M.ctl->gs_bar[1], 1u);
         if (t == (unsigned)nvb - 1) {
             M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
-            M.ctl->strip_base = base + (unsigned long long)kWarps * (unsigned long long)(n_steps - 1);
+            M.ctl->strip_base = DBG && (dbg & 2) ? base : base + (unsigned long long)kWarps * (unsigned long long)(n_steps - 1);
             __threadfence();
         }
     }

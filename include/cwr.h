@@ -81,8 +81,14 @@ typedef struct {
                                3 = the same strips, software-pipelined across that wait: everything a colour reads except the
                                values of the colour swept just before it is fetched (cp.async into shared memory) BEFORE the
                                wait, so the dependent latency overlaps the streaming (16-byte packs: K a multiple of 4 with
-                               fp32 sweeps; otherwise 2 is used).  Same arithmetic in all three; 0 (default) = 3 unless
-                               dd_halo_per_colour */
+                               fp32 sweeps; otherwise 2 is used);
+                               4 = the schedule of 3 with the operands arriving the Blackwell way: the contiguous streams of a
+                               colour step (column indices, matrix values, right-hand side) by cp.async.bulk + mbarrier into a
+                               per-warp ring four steps deep (L2 evict-first), the neighbour gathers as predicated
+                               ld.global.cg into registers (sector-exact where cp.async.cg fetches whole lines).  Written for
+                               fp32 sweeps over 16 constituents, ELL width 4, one rank; otherwise 3 is used.
+                               Same arithmetic in all four (bitwise equal results for the same colours);
+                               0 (default) = 4 unless dd_halo_per_colour */
 } cwr_options;
 
 typedef struct {

@@ -198,9 +198,7 @@ SOLVER_VARIANTS = [dict(solver=1, precond_sync=1), dict(solver=1, precond_sync=2
                    dict(solver=2, precond_sync=2, precond_colors=5), dict(solver=2, precond_sweep=0, precond_steps=6),
                    dict(solver=2, precond_sync=3, precond_colors=40),
                    dict(solver=2, precond_sync=4), dict(solver=1, precond_sync=4), dict(solver=2, precond_sync=4, precond_colors=5),
-                   dict(solver=2, precond_sync=4, precond_colors=40),
-                   dict(solver=2, precond_sync=5), dict(solver=1, precond_sync=5), dict(solver=2, precond_sync=5, precond_colors=5),
-                   dict(solver=2, precond_sync=5, precond_colors=40)]
+                   dict(solver=2, precond_sync=4, precond_colors=40)]
 
 
 @pytest.mark.parametrize("K", [1, 3, 16])
@@ -214,8 +212,8 @@ def test_solver_and_sweep_kernel_variants(K, opts):
     assert be.options.solver == opts["solver"]
     if opts.get("precond_sweep", 1) == 1:
         sync = opts["precond_sync"]
-        if sync >= 4 and not (K == 16 and opts.get("precond_precision", 32) == 32):
-            sync = 3               # the lean / TMA-ring kernels are written for fp32 sweeps over 16 constituents
+        if sync == 4 and not (K == 16 and opts.get("precond_precision", 32) == 32):
+            sync = 3               # the TMA-ring kernel is written for fp32 sweeps over 16 constituents
         if sync >= 3 and (K * (4 if opts.get("precond_precision", 32) == 32 else 8)) % 16 != 0:
             sync = 2               # the pipelined kernel moves 16-byte packs
         assert be.options.precond_sync == sync
@@ -249,18 +247,16 @@ def test_strip_kernel_with_every_cta_and_sync_variants_agree():
         close(outs[1][k], oracle.constituent_dict[f"c{k}"].concentration[3][:mesh.n], RTOL, f"170k cells k{k}")
 
 
-DEFAULT_SYNC_K16 = 4       # sweep kernel cwr_create picks for fp32 sweeps over 16 constituents on one rank
-
-
-def test_lean_strip_kernel_is_bitwise_the_pipelined_one():
-    """170k cells x 16 constituents, one strip per resident CTA: k_gs_lean (precond_sync = 4, the default for fp32 sweeps
-    over 16 constituents) runs k_gs_strip's schedule and arithmetic with a third of the instructions -- same bits, same
-    sweep counts; and the colour balancing (no strip colour above one pass of the CTA) leaves no overflow rows."""
+def test_tma_ring_strip_kernel_is_bitwise_the_pipelined_one():
+    """170k cells x 16 constituents, one strip per resident CTA: k_gs_tma (precond_sync = 4, the default for fp32 sweeps
+    over 16 constituents on one rank: operand streams by cp.async.bulk into a per-warp ring, gathers in registers) runs
+    k_gs_strip's schedule and arithmetic -- same bits, same sweep counts; and the colour balancing (no strip colour above
+    one pass of the CTA) leaves no overflow rows."""
     _, mesh, inputs = synthetic_case(410, 380, 4, 16, seed=78, dry_fraction=0.02)
     outs, sweeps = [], []
-    for sync in (3, 4, 5, 0):
+    for sync in (3, 4, 0):
         be = make_backend(mesh, list(inputs), solver_path=1, solver=2, precond_sync=sync)
-        assert be.options.precond_sync == (sync or DEFAULT_SYNC_K16)
+        assert be.options.precond_sync == (sync or 4)
         for t in range(3):
             info = be.step(t)
             assert info.status == 0 and info.max_relres <= 1e-13 and info.sweeps > 0
@@ -268,12 +264,12 @@ def test_lean_strip_kernel_is_bitwise_the_pipelined_one():
         sweeps.append(be.solver_stats()[0])
         assert be.solver_stats()[2] >= 148 and be.solver_stats()[1] == 0
         be.close()
-    assert all(np.array_equal(o, outs[0]) for o in outs[1:])
-    assert len(set(sweeps)) == 1, sweeps
+    assert np.array_equal(outs[1], outs[0]) and np.array_equal(outs[2], outs[0])
+    assert sweeps[0] == sweeps[1] == sweeps[2], sweeps
     oracle = ref.OracleRiverine(mesh, {"c0": inputs[0]})
     for _ in range(3):
         oracle.update()
-    close(outs[1][0], oracle.constituent_dict["c0"].concentration[3][:mesh.n], RTOL, "170k cells x 16, lean kernel, k0")
+    close(outs[1][0], oracle.constituent_dict["c0"].concentration[3][:mesh.n], RTOL, "170k cells x 16, TMA-ring kernel, k0")
 
 
 def test_defect_correction_falls_back_to_bicgstab_when_the_sweeps_diverge():
