@@ -658,7 +658,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(dalloc(h, &M.vsum, (size_t)3 * std::max(1, tp.E_g)));
         CK(cudaMemsetAsync(M.vsum, 0, (size_t)3 * std::max(1, tp.E_g) * sizeof(double), h->stream));
     }
-    M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 10 : 24; M.dc_floor = h->sweep_f32 ? 3e5 : 1e12;
+    // what one cycle in the sweep precision can gain: measured on the 1M x 16 benchmark, fp32 cycles of 9 - 10 sweeps still
+    // gain their full 0.2^S (3e5 / 10 planned three cycles of ~6 sweeps: 1.81 ms per step; 1e7 / 12 two of 9 - 10: 1.67)
+    M.dc_smin = 2; M.dc_smax = h->sweep_f32 ? 12 : 24; M.dc_floor = h->sweep_f32 ? 1e7 : 1e12;
     if (h->dc_fixed) M.dc_smin = M.dc_smax = std::max(1, h->m_steps - 1);   // precond_steps given: every cycle does m - 1 sweeps
     M.sweep_f32 = h->sweep_f32 ? 1 : 0;
     M.us_from_producer = (h->dc && h->pipelined) ? 1 : 0;

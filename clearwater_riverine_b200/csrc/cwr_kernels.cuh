@@ -1536,7 +1536,7 @@ enum SpmmMode { MODE_INIT = 0, MODE_AV = 1, MODE_AT = 2, MODE_PLAIN = 4, MODE_IN
 
 // Sweeps of the next defect-correction cycle: `worst` = how far the worst column is from the tolerance
 // ((||r||/||b||)/rtol > 1), `rate` = measured error factor per sweep.  A cycle in the sweep precision cannot
-// reduce the residual by more than ~1/floor_gain (fp32: a few 1e-6), so longer cycles would be wasted; the last
+// reduce the residual by more than ~1/floor_gain (fp32: ~1e-7), so longer cycles would be wasted; the last
 // cycle gets one sweep of margin (another cycle costs about four sweeps of memory traffic).
 __device__ __forceinline__ int dc_plan(double worst, double rate, int smin, int smax, double floor_gain) {
     rate = fmin(fmax(rate, 0.02), 0.97);

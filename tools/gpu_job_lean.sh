@@ -1,4 +1,3 @@
-TAG=${1:-r02w}
+TAG=${1:-r02y}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "solver_and_sweep_kernel_variants or tma_ring or strip_kernel_with_every" > gpurun_out/${TAG}_tests.log 2>&1; tail -3 gpurun_out/${TAG}_tests.log
-timeout 1200 python tools/tune.py --steps 8 "precond_sync=0" "precond_sync=3"  > gpurun_out/${TAG}_tune.log 2>&1; grep -v "ms/step by" gpurun_out/${TAG}_tune.log
+timeout 1200 python tools/tune.py --steps 10 "CWR_DC_FLOOR=3e5,CWR_DC_SMAX=10" "CWR_DC_FLOOR=1e6,CWR_DC_SMAX=12" "CWR_DC_FLOOR=3e6,CWR_DC_SMAX=12" "CWR_DC_FLOOR=1e7,CWR_DC_SMAX=12" "CWR_DC_FLOOR=3e7,CWR_DC_SMAX=14" > gpurun_out/${TAG}_tune.log 2>&1; cat gpurun_out/${TAG}_tune.log
