@@ -47,6 +47,7 @@ struct cwr_handle {
     int n_strips = 0;
     int32_t *d_strip_cptr = nullptr, *d_strip_nptr = nullptr, *d_strip_nbr = nullptr; size_t strip_nbr_cap = 0;
     unsigned long long* d_strip_flag = nullptr;
+    uint8_t* d_strip_peers = nullptr;
     unsigned long long gs_seq = 0;   // launches of the sweep kernel so far (epoch of the strip flags)
     int last_cycles = 0;             // cycles of the previous defect-correction solve (launch-ahead prediction)
     double* cur_x = nullptr;         // c[t+1] slot of the step being solved (the iterate)
@@ -288,6 +289,7 @@ static int upload_topology(cwr_handle* h) {
             CK(cudaMalloc((void**)&h->d_strip_nbr, h->strip_nbr_cap * sizeof(int32_t)));
         }
         CK(put(h, h->d_strip_nbr, tp.strip_nbr));
+        CK(put(h, h->d_strip_peers, tp.strip_peers));
     }
     CK(cudaStreamSynchronize(h->stream));
     return CWR_OK;
@@ -304,7 +306,10 @@ static void set_owned_ranges(cwr_handle* h) {
     M.b_lo = tp.bcell_ptr[r]; M.b_hi = tp.bcell_ptr[r + 1];
     M.n_colors = tp.n_colors;
     M.color_ptr = h->d_color_ptr + (size_t)r * (tp.n_colors + 1);
-    M.strip_cptr = h->d_strip_cptr; M.strip_nptr = h->d_strip_nptr; M.strip_nbr = h->d_strip_nbr; M.strip_flag = h->d_strip_flag;
+    M.strip_cptr = h->d_strip_cptr; M.strip_nptr = h->d_strip_nptr; M.strip_nbr = h->d_strip_nbr; M.strip_peers = h->d_strip_peers;
+    // one rank: the flags of its strips; several: the flags of ALL strips in the symmetric slab (the ranks that read rows of
+    // a strip hold a mirror of its flag, written by the strip's owner over NVLink)
+    M.strip_flag = h->world > 1 ? reinterpret_cast<unsigned long long*>(h->d_slab + kDdFlagOffset) : h->d_strip_flag;
     M.n_strips = h->strips ? h->n_strips : 0; M.strip0 = r * M.n_strips;
     unsigned nbr = 0;
     for (int32_t j = tp.send_ptr[r]; j < tp.send_ptr[r + 1]; ++j) nbr |= tp.send_mask[tp.send_rows[j]];
@@ -468,8 +473,8 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     if (h->opt.precond_sync != 1 && h->opt.dd_halo_per_colour)
         FAIL(CWR_EINVAL, "dd_halo_per_colour needs the grid-barrier sweep kernel (precond_sync = 1)");
     h->strips = h->gauss_seidel && h->opt.precond_sync >= 2;
-    h->pipelined = h->gauss_seidel && h->opt.precond_sync >= 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16;
-    if (h->gauss_seidel && h->opt.precond_sync >= 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes
+    h->pipelined = h->gauss_seidel && h->opt.precond_sync >= 3 && (h->sweep_f32 ? 4 : 8) * h->SVEC == 16 && std::max(1, h->opt.dd_world) == 1;
+    if (h->gauss_seidel && h->opt.precond_sync >= 3 && !h->pipelined) h->opt.precond_sync = 2;     // packs narrower than 16 bytes / several ranks
     // k_gs_tma: fp32 sweeps, 4 lanes x 16 bytes per row, one rank (ELL width 4 is checked once the topology is known)
     h->tma = h->pipelined && h->opt.precond_sync == 4 && h->sweep_f32 && h->SKC == 4 && h->SVEC == 4 && n_const == 16 &&
              std::max(1, h->opt.dd_world) == 1;
@@ -575,6 +580,9 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(dalloc(h, &h->d_strip_cptr, tp.strip_cptr.size())); CK(dalloc(h, &h->d_strip_nptr, tp.strip_nptr.size()));
         CK(dalloc(h, &h->d_strip_flag, (size_t)h->n_strips * kFlagStride));
         CK(cudaMemsetAsync(h->d_strip_flag, 0, (size_t)h->n_strips * kFlagStride * sizeof(unsigned long long), h->stream));
+        CK(dalloc(h, &h->d_strip_peers, tp.strip_peers.size()));
+        if ((size_t)h->world * h->n_strips * kFlagStride * sizeof(unsigned long long) > kDdCtlBytes - kDdFlagOffset)
+            FAIL(CWR_EINVAL, "too many strips for the flag mirrors of a domain decomposition");
     }
     {
         int rc = upload_topology(h);
@@ -1276,7 +1284,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     p.state_t = state_slot(h, t); p.state_t1 = state_slot(h, t + 1);
     p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
     DeviceModel& M = h->M;
-    k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl);
+    k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl, h->world > 1 ? M.dd : nullptr);
     h->cur_x = p.state_t1;
     mark(h, CWR_FAM_ASSEMBLE);
     if (h->world > 1 && !h->attached) FAIL(CWR_EINVAL, "domain-decomposed handle: call cwr_dd_attach before stepping");

@@ -82,7 +82,8 @@ struct DdCtl {
     double dot_inbox[2][kMaxRanks][kMaxDots * kMaxK];   // [epoch parity][from rank][dot * K + k]
 };
 constexpr int kFlagStride = 16;                // strip flags: one per 128-byte line
-constexpr size_t kDdCtlBytes = 128 << 10;     // room reserved for DdCtl at the head of the slab
+constexpr size_t kDdCtlBytes = 1 << 20;       // room reserved at the head of the slab: DdCtl, and from kDdFlagOffset the strip flags
+constexpr size_t kDdFlagOffset = 512 << 10;   // (several ranks: a strip's flag is mirrored into the ranks that read its rows)
 
 struct DeviceModel {
     int n, K, E, E_int, E_g, G, nb, W;     // W = ELL width (multiple of 4)
@@ -103,7 +104,8 @@ struct DeviceModel {
     const int32_t* color_ptr; int n_colors;   // (n_colors+1) row ranges of the Gauss-Seidel colours
     // strips of the neighbour-synchronised Gauss-Seidel kernel (cwr_topology.h): CTA b owns strip strip0 + b
     const int32_t* strip_cptr; const int32_t* strip_nptr; const int32_t* strip_nbr;
-    unsigned long long* strip_flag;   // (n_strips x kFlagStride: one 128-byte line per strip -- the polls of 48 warps per flag would
+    const uint8_t* strip_peers;       // (all strips, global ids) bit q: rank q reads rows of the strip
+    unsigned long long* strip_flag;   // (all strips, global ids; x kFlagStride: one 128-byte line per strip -- the polls of 48 warps per flag would
                                       // otherwise queue at the one L2 slice that owns 16 flags) progress of a strip, see the sweep kernels
     int n_strips, strip0;
     int us_from_producer;             // the kernels that produce the residual also write it in the sweep type to M.us (k_gs_strip)
@@ -135,8 +137,9 @@ struct DeviceModel {
     int want_flux;
 };
 
-__global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl) {
+__global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl, DdCtl* dd) {
     *dst = p;
+    if (dd) dd->timeout = 0;            // (a peer that was slow in an earlier step is waited for again)
     ctl->all_done = 0; ctl->iter = 0; ctl->flags_or = 0; ctl->hit_max_iter = 0; ctl->finish_half = 0;
     ctl->singular = 0; ctl->dc_fail = 0; ctl->dc_slow = 0; ctl->sweeps_done = 0;
 }
@@ -546,9 +549,17 @@ __device__ __forceinline__ bool dd_arrived(const DeviceModel& M, bool dots, unsi
 }
 __device__ __forceinline__ void dd_wait(const DeviceModel& M, bool dots, unsigned long long e, unsigned mask) {
     unsigned spins = 0;
-    if (*reinterpret_cast<volatile int*>(&M.dd->timeout)) return;     // a peer already went missing: fail fast
-    while (!dd_arrived(M, dots, e, mask))
-        if (++spins > (1u << 22)) { M.dd->timeout = 1; break; }       // never hang the device (seconds)
+    if (*reinterpret_cast<volatile int*>(&M.dd->timeout)) return;     // a peer already went missing in this step: fail fast
+    // never hang the device, but ordinary rank skew (a host stall, a slow first step on one rank) must not fail the
+    // handle: the bound is wall time (30 s on %globaltimer, looked at every 4096 polls), and cwr_step re-arms it
+    unsigned long long t0 = 0;
+    while (!dd_arrived(M, dots, e, mask)) {
+        if ((++spins & 4095u) != 0) continue;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 30000000000ull) { M.dd->timeout = 1; break; }
+    }
     // The rows / totals the peer announced were performed at system scope before its flag store (its
     // fence.sys), they live in THIS device's memory and are read through L2 (ld.cg / cp.async.cg / the next
     // kernel): a device-scope fence orders those reads after the flag read.  (fence.sys costs 1.75 us on
@@ -852,14 +863,20 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     // boundary rows cross once at the end of each sweep: within a sweep the neighbours' rows are one sweep old (zero
     // in the first sweep) -- Gauss-Seidel inside a rank's rows, Jacobi across ranks -- and only one barrier per sweep
     // waits for NVLink.
-    const bool per_sweep = multi && (STRIP || M.halo_per_sweep), per_colour = multi && !per_sweep;
+    // STRIP with several ranks (xs): EXACT Gauss-Seidel across the cut -- a finished row that another rank reads goes
+    // there at once (peer store), the strip's flag is mirrored into those ranks after a system-scope fence, and a
+    // boundary strip waits for the strips of the neighbouring rank exactly as for its local neighbours: no halo barrier,
+    // no sweep of lag (the sweep-lagged halo cost 25 sweeps against 13 on the 16M-cell mesh).
+    const bool xs = multi && STRIP;
+    const bool per_sweep = multi && !STRIP && M.halo_per_sweep, per_colour = multi && !STRIP && !per_sweep;
+    const unsigned my_peers = xs ? (unsigned)M.strip_peers[sid] & ~(1u << M.rank) : 0u;
     const int row_lo = M.row_lo, row_hi = M.row_hi;
     const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;     // halo epochs continue where the last kernel stopped
     unsigned long long xe = 0;                                         // halo barriers of this launch
     // a finished row also goes to the ranks that read it (NVLink peer stores)
     bool pushed = false;
     auto push = [&](int i, int cc, const Pk<ST, VEC>& o) {
-        if (!per_colour) return;
+        if (!(per_colour || xs)) return;
         unsigned m = M.send_mask[i];
         pushed |= m != 0;
         while (m) {
@@ -896,14 +913,19 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
     auto publish = [&](int step) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence();
-            st_flag(M.strip_flag + (size_t)vb * kFlagStride, (seq << 20) | (unsigned long long)(step + 1));
+            const unsigned long long v = (seq << 20) | (unsigned long long)(step + 1);
+            if (my_peers) {              // rows of this strip went into other ranks: their mirrors of the flag, after a system-scope fence
+                __threadfence_system();
+                for (unsigned m = my_peers; m; m &= m - 1)
+                    st_flag(peer_ptr(M, __ffs(m) - 1, M.strip_flag) + (size_t)sid * kFlagStride, v);
+            } else __threadfence();
+            st_flag(M.strip_flag + (size_t)sid * kFlagStride, v);
         }
     };
     auto wait_nbrs = [&](int step) {
         const unsigned long long target = (seq << 20) | (unsigned long long)(step + 1);
         for (int j = threadIdx.x; j < n_nbr; j += kGsThreads) {
-            const unsigned long long* f = M.strip_flag + (size_t)(M.strip_nbr[nb0 + j] - M.strip0) * kFlagStride;
+            const unsigned long long* f = M.strip_flag + (size_t)M.strip_nbr[nb0 + j] * kFlagStride;
             unsigned spins = 0;
             const unsigned limit = *reinterpret_cast<volatile int*>(&M.ctl->barrier_timeout) ? 0u : (1u << 26);
             while (ld_acquire_u64(f) < target)
@@ -996,7 +1018,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             for (int cc = c; cc < c_end; cc += KC * VEC)
                 relax_tail(i, cc, 0, zero, load_own(i, cc, first_sweep), first_sweep);
         const bool last_step = step + 1 == n_steps;
-        if (STRIP && !last_step) publish(step);
+        if (STRIP && (!last_step || xs)) publish(step);
         if (per_sweep && col == nc - 1) {
             // end of a sweep: once the last colour is complete on this device, the rank's boundary rows go to
             // the ranks that read them, and the next barrier also waits for theirs
@@ -1021,6 +1043,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
             pushed = false;
         } else if (STRIP) {
             if (!last_step) { prefetch(step + 1); wait_nbrs(step); }
+            else if (xs) wait_nbrs(step);      // the products that follow gather the neighbouring ranks' last colour too
         } else if (!last_step) {
             prefetch(step + 1);
             ++epoch;
@@ -1033,7 +1056,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_precond_gs(DeviceModel M, con
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) M.ctl->sweeps_done += n_sweeps;
-    if (STRIP && !multi) return;           // no grid barrier was used: nothing to re-arm
+    if (STRIP) return;                     // no grid barrier was used: nothing to re-arm
     // the last CTA to leave re-arms the barrier for the next launch
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1079,7 +1102,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
     const int32_t* __restrict__ ecol = M.ell_col;
     const ST* __restrict__ eval = sizeof(ST) == 4 ? reinterpret_cast<const ST*>(M.valf) : reinterpret_cast<const ST*>(M.val);
     const ST* __restrict__ us = reinterpret_cast<const ST*>(M.us);
-    const int sid = M.strip0 + vb;
+    const int sid = vb;                        // (one rank: several ranks run k_precond_gs<STRIP>)
     const int32_t* __restrict__ cp_src = M.strip_cptr + (size_t)sid * (nc + 1);
     for (int q = threadIdx.x; q <= nc; q += kGsThreads) s_cp[q] = cp_src[q];
     const int nb0 = M.strip_nptr[sid], n_nbr = M.strip_nptr[sid + 1] - nb0;
@@ -1087,16 +1110,8 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
     const int c = lane * VEC;
     const bool lane_on = c < K;
     const int n_steps = n_sweeps * nc;
-    const bool multi = M.world > 1;           // several ranks: boundary rows cross NVLink once per sweep (see k_precond_gs)
-    const int row_lo = M.row_lo, row_hi = M.row_hi;
-    const unsigned long long e0 = multi ? M.dd->bar_epoch : 0ull;
-    unsigned long long xe = 0;
-    unsigned epoch = 0;
     auto slot = [&](int r, int s) { return gs_land + (r * NS + s) * kGsThreads + threadIdx.x; };
-    auto skipped = [&](int cj, bool first_sweep) {     // first sweep from z = 0: not visited yet / another rank's row
-        const int j = cj & kColMask;
-        return first_sweep && (cj < 0 || (multi && (j < row_lo || j >= row_hi)));
-    };
+    auto skipped = [&](int cj, bool first_sweep) { return first_sweep && cj < 0; };     // first sweep from z = 0: not visited yet
     int4 pc[NR], pcn[NR];
     auto load_idx = [&](int4 (&dst)[NR], int step) {
         const int col = step % nc;
@@ -1163,7 +1178,7 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
         const unsigned long long target = base + (unsigned long long)kWarps * (unsigned long long)(step + 1);
         // lane 0: this strip; lanes 1..: the neighbouring strips (a strip of an RCM band has two or three)
         for (int j = wl; j <= n_nbr; j += 32) {
-            const unsigned long long* f = M.strip_flag + (size_t)(j == 0 ? vb : M.strip_nbr[nb0 + j - 1] - M.strip0) * kFlagStride;
+            const unsigned long long* f = M.strip_flag + (size_t)(j == 0 ? vb : M.strip_nbr[nb0 + j - 1]) * kFlagStride;
             unsigned spins = 0;
             const unsigned limit = *reinterpret_cast<volatile int*>(&M.ctl->barrier_timeout) ? 0u : (1u << 26);
             while (ld_acquire_u64(f) < target)
@@ -1248,30 +1263,8 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
 #pragma unroll 1
         for (int i = rb + group + NR * GPB; i < re; i += GPB)
             for (int cc = c; cc < K; cc += KC * VEC) relax_slow(i, cc, 0, zero, first_sweep);
-        if (last_step && !(multi && col == nc - 1)) break;
-        if (!last_step) publish(step);
-        if (multi && col == nc - 1) {
-            // end of a sweep: this rank's boundary rows go to the ranks that read them (see k_precond_gs)
-            bool pushed = false;
-            ++epoch;
-            grid_barrier(M, epoch * nvb, 0, false, false);
-            const int packs = (K + VEC - 1) / VEC;
-            for (int q = blockIdx.x * kGsThreads + threadIdx.x; q < M.n_send * packs; q += gridDim.x * kGsThreads) {
-                const int i = M.send_rows[q / packs], cc = (q % packs) * VEC;
-                if (cc + VEC > K) continue;
-                const Pk<ST, VEC> o = ldk_cg<ST, VEC>(z + (size_t)i * K + cc);
-                unsigned m = M.send_mask[i];
-                pushed |= m != 0;
-                while (m) {
-                    const int r = __ffs(m) - 1;
-                    m &= m - 1;
-                    stk<ST, VEC>(peer_ptr(M, r, z) + (size_t)i * K + cc, o);
-                }
-            }
-            ++epoch; ++xe;
-            grid_barrier(M, epoch * nvb, e0 + xe, pushed, true);
-            if (last_step) break;
-        }
+        if (last_step) break;
+        publish(step);
 #pragma unroll
         for (int r = 0; r < NR; ++r) pc[r] = pcn[r];
         issue_early(step + 1);
@@ -1283,7 +1276,6 @@ __global__ void __launch_bounds__(kGsThreads, 2) k_gs_strip(DeviceModel M, ST* z
         if (t == (unsigned)nvb - 1) {
             M.ctl->gs_bar[0] = 0; M.ctl->gs_bar[1] = 0;
             M.ctl->strip_base = base + (unsigned long long)kWarps * (unsigned long long)(n_steps - 1);
-            if (multi) M.dd->bar_epoch = e0 + xe;
             __threadfence();
         }
     }

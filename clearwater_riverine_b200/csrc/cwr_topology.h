@@ -66,7 +66,8 @@ struct Topology {
     int n_strips = 0;                      // strips per part
     std::vector<int32_t> strip_cptr;       // (n_parts * n_strips, n_colors+1) absolute row ranges of a strip's colours
     std::vector<int32_t> strip_nptr;       // (n_parts * n_strips + 1) ranges into strip_nbr
-    std::vector<int32_t> strip_nbr;        // strips OF THE SAME PART (global strip ids) a strip shares an edge with
+    std::vector<int32_t> strip_nbr;        // strips (global strip ids, other parts included) a strip shares an edge with
+    std::vector<uint8_t> strip_peers;      // (n_parts * n_strips) bit q: part q reads rows of this strip
     int max_strip_nbr = 0;
     std::vector<int32_t> iedge_ptr, gedge_ptr, bcell_ptr;   // (n_parts+1) owned internal edges / ghost edges (index into the
                                       // ghost block) / boundary cells: an internal edge belongs to the part of its lower cell

@@ -65,6 +65,9 @@ class DomainDecomposedBackend(TransportBackend):
         handles = exchange_ipc_handles(self.dd_export(), self.rank, self.world, self.group)
         self.dd_attach(handles)
         self.info, self._owned_cells, self._owned_edges = self.dd_layout()
+        import torch.distributed as dist
+        if dist.is_initialized():        # no rank steps (and stores into a peer's slab) before every rank has mapped it
+            dist.barrier(group=self.group)
         return self.info
 
     # -- merged outputs (collective) ---------------------------------------------------------------

@@ -248,7 +248,7 @@ int cwr_order_cells(int n_real, int n_face, int n_edge, const int32_t* f1, const
  * cut into n_strips equal chunks of the RCM order, rows ordered (part, strip, colour, RCM position).  Call once with the
  * array pointers NULL for the sizes (n_colors_out, nbr_total), then with arrays: new_of_old (n_real), strip_cptr
  * (n_parts * n_strips, n_colors + 1: absolute row ranges of a strip's colours), strip_nptr (n_parts * n_strips + 1) and
- * strip_nbr (nbr_total): the strips of the same part a strip shares an edge with, color_of (n_real, new numbering).
+ * strip_nbr (nbr_total): the strips (global ids, other parts included) a strip shares an edge with, color_of (n_real, new numbering).
  * strip_cap > 0: the rows a (strip, colour) would hold beyond strip_cap (one pass of the sweep kernel's CTA: 256 at
  * K = 16) are moved to the nearest later colour that no neighbour has and that has room; 0 = colours as levelled. */
 int cwr_strip_layout(int n_real, int n_face, int n_edge, const int32_t* f1, const int32_t* f2, int n_colors, const float* flow_hint,

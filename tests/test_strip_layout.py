@@ -34,14 +34,17 @@ def test_strips_partition_the_rows_and_list_their_neighbours(n_parts, n_strips, 
     internal = plan.f2 < n
     a, b = p[plan.f1[internal]], p[plan.f2[internal]]
     assert np.all(col_pos[a] != col_pos[b])
-    # neighbour lists: symmetric, same part only, and complete for every internal edge inside a part
+    # neighbour lists: symmetric, global strip ids (strips of other parts included: the sweep kernel synchronises with
+    # them through flag mirrors in peer memory), and complete for every internal edge
     nptr, nbr = L["strip_nptr"], L["strip_nbr"]
     pairs = {(s, int(q)) for s in range(NS) for q in nbr[nptr[s]:nptr[s + 1]]}
     assert all((q, s) in pairs for (s, q) in pairs)
-    assert all(s // n_strips == q // n_strips and s != q for (s, q) in pairs)
+    assert all(s != q for (s, q) in pairs)
     sa, sb = strip_of[a], strip_of[b]
-    cross = (sa != sb) & (sa // n_strips == sb // n_strips)
+    cross = sa != sb
     assert {(int(x), int(y)) for x, y in zip(sa[cross], sb[cross])} <= pairs
+    if n_parts > 1:
+        assert any(s // n_strips != q // n_strips for (s, q) in pairs), "the parts are coupled through their boundary strips"
     assert len(pairs) == 2 * len({(min(x, y), max(x, y)) for x, y in zip(sa[cross].tolist(), sb[cross].tolist())})
 
 
@@ -90,7 +93,7 @@ def test_strip_cap_moves_overflow_rows_to_legal_colours():
     hint = plan.face_flow.mean(0)
     L0 = strip_layout(plan.f1, plan.f2, plan.n_face, 10, hint, 8)
     d0 = np.diff(L0["strip_cptr"], axis=1)
-    cap = int(np.ceil(d0.sum(1).max() / 10 * 1.08))
+    cap = int(np.ceil(d0.sum(1).max() / 10 * 1.09))        # (a cap the strips cannot meet with 8 % to spare is relaxed)
     assert d0.max() > cap, "the case must have over-full colours"
     L = strip_layout(plan.f1, plan.f2, plan.n_face, 10, hint, 8, strip_cap=cap)
     d = np.diff(L["strip_cptr"], axis=1)

@@ -1,16 +1,13 @@
-# 2-GPU regression check: domain-decomposition parity (tools/dd_check.py), the multi-GPU pytest, the default bench at N = 2
-TAG=${1:-r02n2}
+# 2-GPU check of the domain-decomposed path: parity (tools/dd_check.py), the multi-GPU pytest, the 16M-cell mesh
+TAG=${1:-r02n2}; N=${2:-2}
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512"
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512"
 timeout 600 $TR tools/dd_check.py --steps 3 > gpurun_out/${TAG}_dd_check.jsonl 2> gpurun_out/${TAG}_dd_check.err
+tail -3 gpurun_out/${TAG}_dd_check.err
 grep '"ok"' gpurun_out/${TAG}_dd_check.jsonl | python -c "
 import sys,json
-for l in sys.stdin: d=json.loads(l); print(d['case'], d['ok'], d['max_rel_diff_vs_oracle'])"
+for l in sys.stdin: d=json.loads(l); print(d['case'], d['ok'], d['max_rel_diff_vs_oracle'], d.get('iterations_per_step'), d.get('single_gpu_iterations_last_step'))"
 timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -x -q 2>&1 | tail -2
-timeout 1200 $TR bench.py --gpus 2 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -c 600 gpurun_out/${TAG}_bench.err
-python - <<PY
-import json
-d=json.loads(open("gpurun_out/${TAG}_bench.json").read().strip().splitlines()[-1])
-print("N=2 ms/step", d["ms_per_step"], "value", d["value"], "e2e", {k:v for k,v in (d.get("e2e") or {}).items() if k in ("value","ms_per_step")}, "lean", {k:v for k,v in ((d.get("e2e") or {}).get("lean") or {}).items() if k in ("value","ms_per_step")})
-print("extra", json.dumps(d.get("extra"))[:3000])
-PY
+show='import sys,json; d=json.loads(sys.stdin.read()); print(sys.argv[1], round(d["ms_per_step"],3), "ms/step", d["solver"], {k:(round(v["ms_per_step"],3), round(v["ms_per_launch"]*1e3,1)) for k,v in d["roofline"]["kernels"].items()}, "setup", d.get("setup_seconds"))'
+timeout 900 $TR bench.py --gpus $N --workload 16m --steps 5 --warmup 3 --profile-steps 1 --no-e2e --no-cpu --no-extras 2> gpurun_out/${TAG}_16m.err | tail -1 > gpurun_out/${TAG}_16m.json
+python -c "$show" "16m N=$N" < gpurun_out/${TAG}_16m.json || tail -5 gpurun_out/${TAG}_16m.err
