@@ -14,6 +14,7 @@ independent units, no data-path collective; NCCL only reduces the mass-balance s
 The same JSON line carries the other BASELINE configurations under "extra" (bounded, inside the same run):
   extra.ohio   configs[1]  Ohio-River-shaped mesh, 1 constituent             (N = 1 only)
   extra.ens64  configs[3]  64 boundary-condition scenarios sharded over the N ranks (strong scaling)
+  extra.ens_weak           128 scenarios per rank on the same mesh (weak scaling: the ensemble grows with the GPUs)
   extra.dd16m  configs[4]  16M-cell mesh as ONE model cut into N strips with NVLink halo exchange
                            (strong scaling; N = 1 is the single-GPU point of the curve), plus a small-mesh
                            parity figure of the decomposed path against the single-GPU answer (N > 1)
@@ -47,6 +48,7 @@ WORKLOAD_NAMES = {
     "1m16": "synthetic 1M-cell unstructured mesh, 16 constituents batched (BASELINE configs[2])",
     "ohio": "Ohio-River-shaped synthetic mesh (2943 cells), 1 constituent (BASELINE configs[1])",
     "ens64": "64 boundary-condition scenarios on the Ohio-shaped mesh (BASELINE configs[3])",
+    "ensw": "128 boundary-condition scenarios PER GPU on the Ohio-shaped mesh (the ensemble of configs[3] grown with the GPUs: weak scaling)",
     "16m": "synthetic 16M-cell mesh, 1 constituent (BASELINE configs[4])",
 }
 
@@ -63,6 +65,8 @@ def workload_plan(name: str, n_time: int, seed: int, scale: float = 1.0):
         return synthetic.ohio_like(n_time, seed=seed), 1
     if name == "ens64":
         return synthetic.ohio_like(n_time, seed=seed), 64
+    if name == "ensw":
+        return synthetic.ohio_like(n_time, seed=seed), 128
     if name == "16m":
         side = max(8, int(round(3814 * scale)))
         plan = synthetic.make_plan(side, side, n_time, dt=30.0, tri_fraction=0.1, dry_fraction=0.02, courant=1.5,
@@ -351,8 +355,8 @@ def gpu_workload(name, ctx, args, steps, warmup, profile_steps, opts, *, dd=Fals
     n_units = K * world                      # weak scaling: every rank brings its own K constituents
     if dd:
         n_units = K                          # one model cut into strips: total work fixed (strong scaling)
-    if name == "ens64":                      # 64 scenarios sharded over the ranks (total work fixed)
-        n_units = 64
+    if name in ("ens64", "ensw"):            # ens64: 64 scenarios sharded over the ranks (total work fixed); ensw: 128 per rank
+        n_units = 64 if name == "ens64" else 128 * world
         mine = ensemble.shard_units(n_units, world, rank)
         K = len(mine)
         scales = np.exp(np.random.default_rng(100).normal(0.0, 0.5, size=n_units))      # same table on every rank
@@ -603,7 +607,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="1m16", choices=["1m16", "ohio", "ens64", "16m"])
+    ap.add_argument("--workload", default="1m16", choices=["1m16", "ohio", "ens64", "ensw", "16m"])
     ap.add_argument("--scale", type=float, default=1.0, help="mesh side scale (debugging only; 1.0 = the named size)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -661,6 +665,8 @@ def main():
             extra["ohio"] = leg(lambda: slim(gpu_workload("ohio", ctx, args, 200, 3, 2, opts, want_e2e=False, want_clocks=False)))
         if within_budget():
             extra["ens64"] = leg(lambda: slim(gpu_workload("ens64", ctx, args, 200, 3, 2, opts, want_e2e=False, want_clocks=False)))
+        if within_budget():
+            extra["ens_weak"] = leg(lambda: slim(gpu_workload("ensw", ctx, args, 200, 3, 2, opts, want_e2e=False, want_clocks=False)))
         if world > 1 and within_budget():
             extra["dd_small_parity"] = leg(lambda: dd_small_parity(ctx, opts))
         if within_budget():
@@ -712,7 +718,7 @@ def slim(res):
     fam = {f: {"ms_per_launch": v["ms_per_launch"], "launches_per_step": v["launches_per_step"], "ms_per_step": v["ms_per_step"],
                "frac": v["frac"]} for f, v in (r.get("kernels") or {}).items()}
     return {"value": res["value"], "unit": UNIT, "ms_per_step": res["ms_per_step"], "steps": res["steps"],
-            "scaling": "strong" if res["workload"] in ("ens64", "16m") else "n/a", "solver": res["solver"],
+            "scaling": "strong" if res["workload"] in ("ens64", "16m") else ("weak" if res["workload"] == "ensw" else "n/a"), "solver": res["solver"],
             "dominant_kernel": {"kernel": r.get("kernel"), "frac": r.get("frac"), "ms_per_launch": r.get("ms_per_launch"),
                                 "share_of_step": r.get("share_of_step")},
             "families": fam, "config": {k: res["config"][k] for k in ("workload", "cells", "constituents_per_gpu", "precond_colors",

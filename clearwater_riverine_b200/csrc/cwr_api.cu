@@ -66,6 +66,8 @@ struct cwr_handle {
     bool small_path = false;         // one-CTA-per-column in-kernel solve (small meshes)
     bool tiny = false;               // ... entirely on chip (k_solve_tiny: matrix in shared memory, Gauss-Seidel sweeps)
     int tiny_rpt = 1;                // rows per thread of k_solve_tiny
+    int max_optin_smem = 0;
+    int chip_ns = 0;                 // > 0: k_solve_chip with this many colour slots per thread (ELL width 4, colours of <= 256 rows)
     bool in_run = false;             // inside cwr_run: the small path does not synchronise per step
     SmallStats* d_stats = nullptr; SmallStats* h_stats = nullptr;
     int num_sms = 148, grid_rows = 0, grid_edges = 0, grid_b = 0, max_grid = 0, grid_spmm = 0, grid_at = 0, grid_xrp = 0;
@@ -233,8 +235,9 @@ static int ensure_stage(cwr_handle* h, size_t bytes) {
     switch (h->tiny_rpt) {                                         \
         case 1: { constexpr int RPT = 1; __VA_ARGS__; break; }     \
         case 2: { constexpr int RPT = 2; __VA_ARGS__; break; }     \
-        case 3: { constexpr int RPT = 3; __VA_ARGS__; break; }     \
-        default: { constexpr int RPT = 4; __VA_ARGS__; break; }    \
+        case 3: case 4: { constexpr int RPT = 4; __VA_ARGS__; break; }     \
+        case 5: case 6: { constexpr int RPT = 6; __VA_ARGS__; break; }     \
+        default: { constexpr int RPT = 8; __VA_ARGS__; break; }    \
     }
 #define TINY_DISPATCH(...)                                                     \
     if (h->topo.W == 4) { constexpr bool W4 = true; TINY_RPT_CASES(__VA_ARGS__) } \
@@ -319,6 +322,22 @@ static void set_owned_ranges(cwr_handle* h) {
     M.halo_per_sweep = h->opt.dd_halo_per_colour ? 0 : 1;
 }
 
+// k_solve_chip (one row of every colour per thread) where the colours allow it: ELL width 4, at most 14 colours of at most
+// 256 rows, everything in shared memory.  CWR_TINY_KERNEL=1 keeps k_solve_tiny (for comparisons).
+static void choose_chip(cwr_handle* h) {
+    const Topology& tp = h->topo;
+    h->chip_ns = 0;
+    if (!h->tiny) return;
+    const char* ev = std::getenv("CWR_TINY_KERNEL");
+    if (ev && std::atoi(ev) == 1) return;
+    if (tp.W != 4 || tp.n_colors < 1 || tp.n_colors > 14) return;
+    int widest = 0;
+    for (int c = 0; c < tp.n_colors; ++c) widest = std::max(widest, tp.color_ptr[c + 1] - tp.color_ptr[c]);
+    const int ns = tp.n_colors <= 8 ? 8 : (tp.n_colors <= 12 ? 12 : 14);
+    if (widest > kChipThreads || chip_smem_bytes(tp.n, ns) + kTinyStaticSmem > (size_t)h->max_optin_smem) return;
+    h->chip_ns = ns;
+}
+
 // Gauss-Seidel colours follow the flow: the first hydrodynamic slices the caller uploads give the
 // direction (time mean of the face flows over the call's slices).  Only possible while nothing that
 // depends on the cell order is on the device yet (no inputs, no hydro slices, no steps).
@@ -341,6 +360,7 @@ static int align_colours_with_flow(cwr_handle* h, const float* flow, int nt) {
     if (t2.W != h->topo.W || t2.color_ptr.size() != h->topo.color_ptr.size()) return CWR_OK;   // cannot happen: same graph
     if (h->attached) return CWR_OK;                 // peers already rely on the current ownership
     h->topo = std::move(t2);
+    choose_chip(h);
     int rc = upload_topology(h);                    // (may move the strip neighbour list)
     set_owned_ranges(h);
     return rc;
@@ -424,10 +444,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     // tiny meshes (<= 4096 cells, the Ohio River model): the whole solve on chip with Gauss-Seidel sweeps
     const bool tiny = small && h->opt.precond_sweep == 1 && h->opt.precond_steps != 1 && n_real <= kTinyThreads * kTinyMaxRows;
     // auto: 5 Gauss-Seidel sweeps per application on large meshes (about two BiCGSTAB iterations per step on the
-    // 1M x 16 benchmark; with the half-step exit, 5..11 sweeps all land within a few % of each other), 4 on chip,
+    // 1M x 16 benchmark; with the half-step exit, 5..11 sweeps all land within a few % of each other), 8 on chip
+    // (Ohio-shaped mesh, k_solve_chip: 4 / 6 / 8 / 10 sweeps per application 0.077 / 0.074 / 0.072 / 0.077 ms per step),
     // 7 Jacobi steps
     const bool steps_given = h->opt.precond_steps > 0;
-    if (h->opt.precond_steps <= 0) h->opt.precond_steps = h->opt.precond_sweep == 1 ? (tiny ? 5 : (!small ? 6 : 8)) : 8;
+    if (h->opt.precond_steps <= 0) h->opt.precond_steps = h->opt.precond_sweep == 1 ? (tiny ? 9 : (!small ? 6 : 8)) : 8;
     h->m_steps = std::min(h->opt.precond_steps, 64);
     if (h->opt.precond_precision != 64) h->opt.precond_precision = 32;
     h->sweep_f32 = h->opt.precond_precision == 32;
@@ -521,8 +542,11 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         const double bytes = (double)n_real / std::max(1, h->opt.dd_world) * (32.0 + 3.0 * n_const * (h->sweep_f32 ? 4 : 8));
         // (a colour's barrier also waits for the neighbour ranks of a domain decomposition: ~10 us, so 40 MB there)
         h->opt.precond_colors = (int)std::lround(std::min(48.0, std::max(8.0, bytes / (h->opt.dd_world > 1 ? 40e6 : 20e6))));
-        if (tiny) h->opt.precond_colors = 12;       // on chip a colour costs a __syncthreads(): measured optimum on the Ohio-shaped mesh
+        // on chip a colour costs a CTA barrier: 12 measured best on the Ohio-shaped mesh; one or two more where that lets
+        // every colour fit one pass of k_solve_chip (256 rows)
+        if (tiny) h->opt.precond_colors = std::max(12, std::min(14, (int)std::ceil(n_real * 1.03 / kChipThreads)));
     }
+    if (tiny && !h->strips) h->strip_cap = kChipThreads;      // colours balanced towards <= 256 rows (build_topology)
     h->opt.precond_colors = std::min(h->opt.precond_colors, 64);
 
     h->f1_ref.assign(f1, f1 + n_edge); h->f2_ref.assign(f2, f2 + n_edge);
@@ -556,12 +580,17 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         const size_t need = tiny_smem_bytes(n, tp.W);
         int max_optin = 0;
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-        if (need + 1024 > (size_t)max_optin) h->tiny = false;      // falls back to k_solve_small (Jacobi steps, any row order)
+        if (need + kTinyStaticSmem > (size_t)max_optin) h->tiny = false;      // falls back to k_solve_small (Jacobi steps, any row order)
         else {
             h->tiny_rpt = (n + kTinyThreads - 1) / kTinyThreads;
             cudaError_t e = cudaSuccess;
             TINY_DISPATCH(e = cudaFuncSetAttribute(k_solve_tiny<RPT, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             CK(e);
+            CK(cudaFuncSetAttribute(k_solve_chip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            h->max_optin_smem = max_optin;
+            choose_chip(h);
         }
     }
     h->grid_rows = grid_for(tp.part_ptr[h->rank + 1] - tp.part_ptr[h->rank], kThreads / kc, h->max_grid);
@@ -1191,7 +1220,13 @@ static int read_small_stats(cwr_handle* h, cwr_step_info* info) {
 static int solve_small(cwr_handle* h, cwr_step_info* info) {
     if (!h->in_run) CK(cudaMemsetAsync(h->d_stats, 0, sizeof(SmallStats), h->stream));
     mark(h, CWR_FAM_SOLVE_SMALL);
-    if (h->tiny) {
+    if (h->tiny && h->chip_ns > 0) {
+        const size_t sm = chip_smem_bytes(h->n, h->chip_ns);
+        const int sweeps = h->m_steps - 1;
+        if (h->chip_ns == 8) k_solve_chip<8><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats);
+        else if (h->chip_ns == 12) k_solve_chip<12><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats);
+        else k_solve_chip<14><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats);
+    } else if (h->tiny) {
         const size_t sm = tiny_smem_bytes(h->n, h->topo.W);
         const int sweeps = h->m_steps - 1;
         TINY_DISPATCH((k_solve_tiny<RPT, W4><<<h->K, kTinyThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats)));
@@ -1751,7 +1786,7 @@ int cwr_get_options(const cwr_handle* h, cwr_options* out) {
     *out = h->opt;
     out->precond_colors = (h->gauss_seidel || h->tiny) ? h->topo.n_colors : 0;
     out->precond_sweep = (h->gauss_seidel || h->tiny) ? 1 : 0;
-    out->solver_path = h->tiny ? 3 : (h->small_path ? 2 : 1);
+    out->solver_path = h->tiny ? (h->chip_ns > 0 ? 4 : 3) : (h->small_path ? 2 : 1);
     out->solver = h->dc ? 2 : 1;
     out->precond_sync = h->gauss_seidel ? (h->tma ? 4 : (h->pipelined ? 3 : (h->strips ? 2 : 1))) : 0;
     return CWR_OK;

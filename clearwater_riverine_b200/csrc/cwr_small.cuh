@@ -194,20 +194,53 @@ __global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M,
 // ---------------------------------------------------------------------------------------------
 // Tiny meshes (the Ohio River model: 2,943 cells): the whole solve of one column ON CHIP.
 // One CTA per constituent / scenario; the matrix (column-major ELL: fp64 values + 16-bit column
-// indices), the gathered vector z, b and rhat live in shared memory (<= 227 KB), the other BiCGSTAB
-// vectors (x, r, p, v, t, p^) in registers -- a thread owns rows tid, tid + 1024, ...  A pass over the
-// matrix then costs shared-memory bandwidth (~80 B per row) instead of L2 latency, and the
-// preconditioner is the same flow-aligned multicolour Gauss-Seidel as on large meshes, with
-// __syncthreads() between colours: a sweep moves the bytes of one Jacobi step and carries information
-// several cells downstream.  Same recurrences, stopping test, restart and NaN / zero-rhs rules as
-// k_solve_small.
+// indices), the gathered vector z and the preconditioner's input u live in shared memory (<= 227 KB),
+// the BiCGSTAB vectors (x, r, p, v, t, p^) in registers -- a thread owns rows tid, tid + 512, ... --
+// and the shadow residual in a column-contiguous scratch only its owner thread touches.  The
+// preconditioner is the same flow-aligned multicolour Gauss-Seidel as on large meshes with a CTA barrier
+// between colours.
+//
+// A solve is ~250 barrier-separated phases (information travels one flow level per colour step, and
+// ~100 levels matter at Courant 2.5), so the cost of a PHASE is what counts, not bytes:
+//  * a colour's rows (a contiguous range, ~n / colours of them) are taken by the first warps of the CTA,
+//    row = first row of the colour + thread id; the other warps go straight to the barrier.  (The first
+//    version walked every thread's own rows with a colour predicate: 32 warps x ~60 instructions per
+//    phase, issue-bound at ~900 cycles per phase.)
+//  * 512 threads: half the warps at every barrier;
+//  * dot products cost ONE barrier: per-warp partials into a double-buffered array, every warp adds the
+//    partials itself in the same order (bitwise identical totals in all warps).
+// Same recurrences, stopping test, restart and NaN / zero-rhs rules as k_solve_small.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTinyThreads = 1024;
-constexpr int kTinyMaxRows = 4;          // rows per thread: n <= 4096
+constexpr int kTinyThreads = 512;
+constexpr int kTinyMaxRows = 8;          // rows per thread: n <= 4096 (and the shared-memory limit)
+constexpr int kTinyStaticSmem = 4096;    // red[] + colour pointers, rounded up
 
 __host__ __device__ inline size_t tiny_smem_bytes(int n, int W) {
-    // val (n*W f64) | z, b, rhat (n f64 each) | idx (n*W u16)
-    return (size_t)n * W * 8 + (size_t)3 * n * 8 + (((size_t)n * W * 2 + 15) & ~(size_t)15);
+    // val (n*W f64) | z, u (n f64 each) | idx (n*W u16)
+    return (size_t)n * W * 8 + (size_t)2 * n * 8 + (((size_t)n * W * 2 + 15) & ~(size_t)15);
+}
+
+// one barrier: totals of ND partial sums, identical bits in every thread; `red` is [2][ND][32], `parity` alternates
+template <int ND, int NWARPS = kTinyThreads / 32>
+__device__ __forceinline__ void tiny_sum(double (&v)[ND], double* red, int& parity) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) v[d] += __shfl_xor_sync(0xffffffffu, v[d], off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* buf = red + parity * (4 * 32);
+    parity ^= 1;
+    if (lane == 0)
+#pragma unroll
+        for (int d = 0; d < ND; ++d) buf[d * 32 + warp] = v[d];
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        double s = lane < NWARPS ? buf[d * 32 + lane] : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        v[d] = s;
+    }
 }
 
 // W4: ELL width 4 (quad / triangle meshes): a row's four values are two 16-byte shared loads, its four
@@ -215,17 +248,19 @@ __host__ __device__ inline size_t tiny_smem_bytes(int n, int W) {
 template <int RPT, bool W4>
 __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, int n_sweeps, SmallStats* stats) {
     extern __shared__ double tiny_smem[];
-    __shared__ double red[4 * 32];
+    __shared__ double red[2 * 4 * 32];
+    __shared__ int cptr[65];
     const int k = blockIdx.x, n = M.n, K = M.K, W = M.W, nc = M.n_colors;
     double* sval = tiny_smem;                       // [W][n]   (W4: double2 [2][n])
     double* z = sval + (size_t)n * W;               // [n] the gathered vector
-    double* sb = z + n;                             // [n] b
-    double* srh = sb + n;                           // [n] rhat
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(srh + n);   // [W][n] (W4: [n][4]), bit 15 = visited later in a sweep
+    double* su = z + n;                             // [n] what the sweeps are applied to
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(su + n);   // [W][n] (W4: [n][4]), bit 15 = visited later in a sweep
     double* __restrict__ xg = M.sp->state_t1 + k;   // stride K
     const double* __restrict__ bg = M.b + k;
+    double* __restrict__ rhat = M.rhat + (size_t)k * n;   // element i only ever touched by the thread that owns row i
+    int parity = 0;
 
-    // ---- matrix -> shared memory (column-major), b ------------------------------------------------
+    // ---- matrix -> shared memory (column-major) ------------------------------------------------------
     for (int q = threadIdx.x; q < n * W; q += kTinyThreads) {
         const int i = q / W, w = q % W;
         const int32_t cj = M.ell_col[q];
@@ -233,16 +268,14 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
         if (W4) { sval[((size_t)(w >> 1) * n + i) * 2 + (w & 1)] = M.val[q]; sidx[(size_t)i * 4 + w] = packed; }
         else { sval[(size_t)w * n + i] = M.val[q]; sidx[(size_t)w * n + i] = packed; }
     }
-    int row[RPT]; bool on[RPT]; int colr[RPT];
+    if (threadIdx.x <= nc) cptr[threadIdx.x] = M.color_ptr[threadIdx.x];
+    int row[RPT]; bool on[RPT];
     double x[RPT], r[RPT], p[RPT], v[RPT], t[RPT], ph[RPT];
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
         row[q] = threadIdx.x + q * kTinyThreads; on[q] = row[q] < n;
         x[q] = on[q] ? xg[(size_t)row[q] * K] : 0.0;
-        if (on[q]) sb[row[q]] = bg[(size_t)row[q] * K];
         r[q] = p[q] = v[q] = t[q] = ph[q] = 0.0;
-        colr[q] = 0;
-        if (on[q]) for (int c = 0; c < nc; ++c) if (row[q] >= M.color_ptr[c + 1]) colr[q] = c + 1;
     }
     __syncthreads();
 
@@ -263,19 +296,18 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
         }
         return s;
     };
-    // z = M^-1 u (u in registers): n_sweeps multicolour Gauss-Seidel sweeps from z = 0; ends synchronised
-    auto precondition = [&](const double (&u)[RPT]) {
+    // z = M^-1 su (su complete and synchronised): n_sweeps multicolour Gauss-Seidel sweeps from z = 0; ends synchronised
+    auto precondition = [&]() {
         if (n_sweeps <= 0) {
 #pragma unroll
-            for (int q = 0; q < RPT; ++q) if (on[q]) z[row[q]] = u[q];
+            for (int q = 0; q < RPT; ++q) if (on[q]) z[row[q]] = su[row[q]];
             __syncthreads();
             return;
         }
         for (int s = 0; s < n_sweeps; ++s)
             for (int c = 0; c < nc; ++c) {
-#pragma unroll
-                for (int q = 0; q < RPT; ++q)
-                    if (on[q] && colr[q] == c) z[row[q]] = u[q] - row_dot(row[q], s == 0);
+                const int hi = cptr[c + 1];
+                for (int i = cptr[c] + (int)threadIdx.x; i < hi; i += kTinyThreads) z[i] = su[i] - row_dot(i, s == 0);
                 __syncthreads();
             }
     };
@@ -298,11 +330,11 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
 #pragma unroll
         for (int q = 0; q < RPT; ++q)
             if (on[q]) {
-                const double bi = sb[row[q]];
-                r[q] = bi - ax[q]; p[q] = r[q]; srh[row[q]] = r[q];
+                const double bi = bg[(size_t)row[q] * K];
+                r[q] = bi - ax[q]; p[q] = r[q]; rhat[row[q]] = r[q]; su[row[q]] = r[q];
                 d2[0] = fma(r[q], r[q], d2[0]); d2[1] = fma(bi, bi, d2[1]);
             }
-        cta_sum<2>(d2, red);
+        tiny_sum<2>(d2, red, parity);                    // its barrier also publishes su = p and retires the reads of z
         rr = d2[0]; bb = d2[1];
         if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) {
             flags |= FL_NAN;
@@ -321,40 +353,43 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
         double rho = rr;
         bool breakdown = false;
         while (iters < M.max_iter) {
-            precondition(p);
+            precondition();                              // z = p^
 #pragma unroll
             for (int q = 0; q < RPT; ++q) ph[q] = on[q] ? z[row[q]] : 0.0;
             product(v);
             double d1[1] = {0.0};
 #pragma unroll
-            for (int q = 0; q < RPT; ++q) if (on[q]) d1[0] = fma(srh[row[q]], v[q], d1[0]);
-            cta_sum<1>(d1, red);
+            for (int q = 0; q < RPT; ++q) if (on[q]) d1[0] = fma(rhat[row[q]], v[q], d1[0]);
+            tiny_sum<1>(d1, red, parity);                // (all reads of z and su are behind this barrier)
             if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
             const double alpha = rho / d1[0];
             double dh[1] = {0.0};
 #pragma unroll
-            for (int q = 0; q < RPT; ++q) { r[q] = fma(-alpha, v[q], r[q]); if (on[q]) dh[0] = fma(r[q], r[q], dh[0]); }      // s
-            cta_sum<1>(dh, red);
+            for (int q = 0; q < RPT; ++q) {
+                r[q] = fma(-alpha, v[q], r[q]);                                                                // s
+                if (on[q]) { dh[0] = fma(r[q], r[q], dh[0]); su[row[q]] = r[q]; }
+            }
+            tiny_sum<1>(dh, red, parity);                // publishes su = s
             if (dh[0] <= M.tol2 * bb) {                      // converged at the half step: x += alpha p^
 #pragma unroll
                 for (int q = 0; q < RPT; ++q) x[q] = fma(alpha, ph[q], x[q]);
                 rr = dh[0]; ++iters; flags |= FL_CONVERGED;
                 break;
             }
-            precondition(r);
-            double sh[RPT];
-#pragma unroll
-            for (int q = 0; q < RPT; ++q) sh[q] = on[q] ? z[row[q]] : 0.0;
+            precondition();                              // z = s^
             product(t);
             double d4[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int q = 0; q < RPT; ++q)
                 if (on[q]) {
-                    const double rh = srh[row[q]];
+                    const double rh = rhat[row[q]];
                     d4[0] = fma(t[q], r[q], d4[0]); d4[1] = fma(t[q], t[q], d4[1]);
                     d4[2] = fma(rh, t[q], d4[2]); d4[3] = fma(rh, r[q], d4[3]);
                 }
-            cta_sum<4>(d4, red);
+            double shq[RPT];                             // s^ of the own rows, read before the barrier that frees z
+#pragma unroll
+            for (int q = 0; q < RPT; ++q) shq[q] = on[q] ? z[row[q]] : 0.0;
+            tiny_sum<4>(d4, red, parity);
             const double omega = d4[1] > 0.0 ? d4[0] / d4[1] : 0.0;
             const double rho_new = d4[3] - omega * d4[2];
             double beta = 0.0;
@@ -366,13 +401,14 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
 #pragma unroll
             for (int q = 0; q < RPT; ++q)
                 if (on[q]) {
-                    x[q] = fma(omega, sh[q], fma(alpha, ph[q], x[q]));
+                    x[q] = fma(omega, shq[q], fma(alpha, ph[q], x[q]));
                     const double rn = fma(-omega, t[q], r[q]);
                     r[q] = rn;
                     p[q] = fma(beta, fma(-omega, v[q], p[q]), rn);
+                    su[row[q]] = p[q];
                     dr[0] = fma(rn, rn, dr[0]);
                 }
-            cta_sum<1>(dr, red);
+            tiny_sum<1>(dr, red, parity);                // publishes su = p
             rr = dr[0];
             ++iters;
             rho = rho_new;
@@ -381,12 +417,256 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
             if (stagnated) { breakdown = true; break; }
         }
         if ((flags & (FL_CONVERGED | FL_NAN)) || iters >= M.max_iter) break;
-        if (breakdown && restarts < 3) { ++restarts; continue; }     // new shadow residual from the current iterate
+        if (breakdown && restarts < 3) { ++restarts; __syncthreads(); continue; }     // new shadow residual from the current iterate
         if (breakdown) flags |= FL_BREAKDOWN;
         break;
     }
 #pragma unroll
     for (int q = 0; q < RPT; ++q) if (on[q]) xg[(size_t)row[q] * K] = x[q];
+    if (threadIdx.x == 0) {
+        M.colflags[k] = flags; M.coliters[k] = iters;
+        M.sc[SC_BNORM2 * K + k] = bb; M.sc[SC_RNORM2 * K + k] = rr;
+        atomicMax(&stats->max_iterations, iters);
+        atomicAdd(&stats->sum_iterations, (unsigned long long)iters);
+        atomicOr(&stats->flags_or, flags & (FL_BREAKDOWN | FL_NAN));
+        atomicMax(&stats->restarts, restarts);
+        if (!(flags & FL_CONVERGED)) atomicAdd(&stats->not_converged, 1);
+        const double rel2 = bb > 0.0 ? rr / bb : (rr > 0.0 ? __longlong_as_double(0x7ff0000000000000LL) : 0.0);
+        if (rel2 == rel2) atomicMax(&stats->max_relres2_bits, (unsigned long long)__double_as_longlong(rel2));
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_solve_chip: the on-chip solve again, organised around the COLOUR STEP.
+//
+// ncu of k_solve_tiny on the Ohio-shaped mesh (profiles/r02tiny1_*): 240 colour steps + ~20 vector phases
+// in 194 k cycles = ~800 cycles per colour step, and the step is one dependent chain of ~65 instructions
+// (colour pointer -> row -> index word -> unpack -> gathers -> 4 chained DFMA -> store -> barrier) issued at one
+// instruction per ~11 cycles; bytes and flops are irrelevant.  So this kernel takes everything that does not depend
+// on z out of the chain:
+//  * thread t owns row (first row of colour c) + t of EVERY colour c -- the rows it sweeps are the rows whose
+//    BiCGSTAB vectors it keeps: the right-hand side of a sweep (p or r) is a register, nothing is published for it;
+//  * its rows' matrix values (4 x fp64) and neighbour indices (4 x 16 bit) stay in REGISTERS for the whole solve
+//    (10 per colour); a colour step loads nothing but the four gathered z (shared-memory wavefronts are the
+//    second limit after latency: 8 warps x 4 x 64-bit gathers ~ 90 per step);
+//  * the vectors a step does not need (x, p^, v, t, r^) live in private shared-memory columns [colour][thread]
+//    (conflict-free), touched only in the vector phases;
+//  * the four products are summed as a tree (two DFMA chains of depth 2 + one add);
+//  * z starts at zero (zeroed by its owners behind a barrier that is there anyway), so the first sweep
+//    needs no "not visited yet" predicates;
+//  * 256 threads = the rows of a colour (n / colours <= 256): 8 warps at every barrier;
+//  * the global loads of the set-up (matrix, x, b: ~40 per thread) are issued in batches, not one per dependent
+//    use (the first version spent 27 % of its cycles there).
+// Needs ELL width 4, <= NS colours of <= 256 rows; anything else takes k_solve_tiny.  Same recurrences,
+// stopping test, restart and NaN / zero-rhs rules as k_solve_small.
+// ---------------------------------------------------------------------------------------------
+constexpr int kChipThreads = 256;
+
+__host__ __device__ inline size_t chip_smem_bytes(int n, int NS) {
+    // x, p^, v, t, r^ [NS][256] f64 | z [n] f64
+    return (size_t)NS * kChipThreads * 40 + (size_t)n * 8;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, int n_sweeps, SmallStats* stats) {
+    extern __shared__ double chip_smem[];
+    __shared__ double red[2 * 4 * 32];
+    __shared__ int cptr[NS + 1];
+    constexpr int NT = kChipThreads, NW = kChipThreads / 32;
+    const int tid = threadIdx.x, k = blockIdx.x, n = M.n, K = M.K, nc = M.n_colors;
+    double* sx = chip_smem + tid;                               // [NS][NT] private columns: element c at [c * NT]
+    double* sph = sx + NS * NT;
+    double* sv = sph + NS * NT;
+    double* st = sv + NS * NT;
+    double* srh = st + NS * NT;
+    double* z = chip_smem + 5 * NS * NT;                        // [n] the gathered vector
+    double* __restrict__ xg = M.sp->state_t1 + k;               // stride K
+    const double* __restrict__ bg = M.b + k;
+    int parity = 0;
+
+    if (tid <= NS) cptr[tid] = M.color_ptr[tid < nc ? tid : nc];
+    __syncthreads();
+#define CHIP_ROW(c) (cptr[c] + tid)
+#define CHIP_ON(c) ((on >> (c)) & 1u)
+    unsigned on = 0;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) if (c < nc && CHIP_ROW(c) < cptr[c + 1]) on |= 1u << c;
+    double2 va[NS], vb[NS]; uint2 nb[NS];
+    double r[NS], p[NS];
+    // ---- the thread's rows: matrix values and indices -> registers, x -> its column (loads issued four rows at a time)
+#pragma unroll
+    for (int c0 = 0; c0 < NS; c0 += 4) {
+        int4 cj[4]; double xq[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q;
+            if (c < NS) {
+                const size_t row = CHIP_ON(c) ? CHIP_ROW(c) : 0;
+                cj[q] = __ldg(reinterpret_cast<const int4*>(M.ell_col + row * 4));
+                va[c] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
+                vb[c] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
+                xq[q] = xg[row * K];
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q;
+            if (c < NS) {
+                nb[c].x = (unsigned)(cj[q].x & 0x7fff) | ((unsigned)(cj[q].y & 0x7fff) << 16);
+                nb[c].y = (unsigned)(cj[q].z & 0x7fff) | ((unsigned)(cj[q].w & 0x7fff) << 16);
+                if (!CHIP_ON(c)) { nb[c] = make_uint2(0u, 0u); va[c] = make_double2(0.0, 0.0); vb[c] = va[c]; xq[q] = 0.0; }
+                sx[c * NT] = xq[q];
+                sph[c * NT] = 0.0; sv[c * NT] = 0.0; st[c * NT] = 0.0; srh[c * NT] = 0.0;
+                r[c] = p[c] = 0.0;
+            }
+        }
+    }
+
+    // (L z) of the thread's row of colour c
+    auto dot4 = [&](int c) {
+        const double z0 = z[nb[c].x & 0xffffu], z1 = z[nb[c].x >> 16], z2 = z[nb[c].y & 0xffffu], z3 = z[nb[c].y >> 16];
+        return fma(va[c].y, z1, va[c].x * z0) + fma(vb[c].y, z3, vb[c].x * z2);
+    };
+    // z = M^-1 u: n_sweeps multicolour Gauss-Seidel sweeps; z is ZERO and synchronised on entry, complete and synchronised on exit
+    auto precondition = [&](const double (&u)[NS]) {
+        if (n_sweeps <= 0) {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = u[c];
+            __syncthreads();
+            return;
+        }
+        for (int s = 0; s < n_sweeps; ++s) {
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                if (c < nc) {
+                    const double zi = u[c] - dot4(c);
+                    if (CHIP_ON(c)) z[CHIP_ROW(c)] = zi;
+                    __syncthreads();
+                }
+            }
+        }
+    };
+    auto zero_z = [&]() {
+#pragma unroll
+        for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = 0.0;
+    };
+
+    int flags = 0, iters = 0, restarts = 0;
+    double bb = 0.0, rr = 0.0;
+    for (;;) {
+        // r = b - A x ; rhat = p = r
+        double d2[2] = {0.0, 0.0};
+        {
+            double bq[NS];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) bq[c] = bg[(size_t)(CHIP_ON(c) ? CHIP_ROW(c) : 0) * K];
+#pragma unroll
+            for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = sx[c * NT];
+            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                const double bi = CHIP_ON(c) ? bq[c] : 0.0;
+                const double ri = CHIP_ON(c) ? bi - (z[CHIP_ROW(c)] + dot4(c)) : 0.0;
+                r[c] = ri; p[c] = ri; srh[c * NT] = ri;
+                d2[0] = fma(ri, ri, d2[0]); d2[1] = fma(bi, bi, d2[1]);
+            }
+        }
+        tiny_sum<2, NW>(d2, red, parity);                // (every read of z is behind this barrier)
+        rr = d2[0]; bb = d2[1];
+        if (!(rr == rr) || !(bb == bb) || isinf(rr) || isinf(bb)) {
+            flags |= FL_NAN;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) sx[c * NT] = qnan();
+            break;
+        }
+        if (bb == 0.0 && rr != 0.0) {                    // b == 0  =>  x = 0
+            flags |= FL_ZERO_RHS | FL_CONVERGED;
+#pragma unroll
+            for (int c = 0; c < NS; ++c) sx[c * NT] = 0.0;
+            rr = 0.0;
+            break;
+        }
+        if (rr <= M.tol2 * bb) { flags |= FL_CONVERGED; break; }
+        zero_z();
+        __syncthreads();
+        double rho = rr;
+        bool breakdown = false;
+        while (iters < M.max_iter) {
+            precondition(p);                             // z = p^
+            double d1[1] = {0.0};
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                const double zi = CHIP_ON(c) ? z[CHIP_ROW(c)] : 0.0;
+                const double vi = CHIP_ON(c) ? zi + dot4(c) : 0.0;
+                sph[c * NT] = zi; sv[c * NT] = vi;
+                d1[0] = fma(srh[c * NT], vi, d1[0]);
+            }
+            tiny_sum<1, NW>(d1, red, parity);            // (all reads of z are behind this barrier)
+            if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
+            const double alpha = rho / d1[0];
+            double dh[1] = {0.0};
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                r[c] = fma(-alpha, sv[c * NT], r[c]);                                                          // s
+                dh[0] = fma(r[c], r[c], dh[0]);
+            }
+            zero_z();
+            tiny_sum<1, NW>(dh, red, parity);            // publishes z = 0
+            if (dh[0] <= M.tol2 * bb) {                      // converged at the half step: x += alpha p^
+#pragma unroll
+                for (int c = 0; c < NS; ++c) sx[c * NT] = fma(alpha, sph[c * NT], sx[c * NT]);
+                rr = dh[0]; ++iters; flags |= FL_CONVERGED;
+                break;
+            }
+            precondition(r);                             // z = s^
+            double d4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                const double zi = CHIP_ON(c) ? z[CHIP_ROW(c)] : 0.0;          // s^ of the own row
+                const double ti = CHIP_ON(c) ? zi + dot4(c) : 0.0;
+                st[c * NT] = ti;
+                sx[c * NT] = fma(alpha, sph[c * NT], sx[c * NT]);             // x += alpha p^ now, + omega s^ below
+                sph[c * NT] = zi;                                             // (p^ is done with: the column keeps s^)
+                const double rh = srh[c * NT];
+                d4[0] = fma(ti, r[c], d4[0]); d4[1] = fma(ti, ti, d4[1]);
+                d4[2] = fma(rh, ti, d4[2]); d4[3] = fma(rh, r[c], d4[3]);
+            }
+            tiny_sum<4, NW>(d4, red, parity);
+            const double omega = d4[1] > 0.0 ? d4[0] / d4[1] : 0.0;
+            const double rho_new = d4[3] - omega * d4[2];
+            double beta = 0.0;
+            bool stagnated = false;
+            if (omega != 0.0 && rho != 0.0) beta = (rho_new / rho) * (alpha / omega);
+            else if (d4[1] > 0.0) stagnated = true;
+            if (!(beta == beta) || isinf(beta)) { beta = 0.0; stagnated = true; }
+            double dr[1] = {0.0};
+#pragma unroll
+            for (int c = 0; c < NS; ++c) {
+                sx[c * NT] = fma(omega, sph[c * NT], sx[c * NT]);
+                const double rn = fma(-omega, st[c * NT], r[c]);
+                r[c] = rn;
+                p[c] = fma(beta, fma(-omega, sv[c * NT], p[c]), rn);
+                dr[0] = fma(rn, rn, dr[0]);
+            }
+            zero_z();
+            tiny_sum<1, NW>(dr, red, parity);            // publishes z = 0
+            rr = dr[0];
+            ++iters;
+            rho = rho_new;
+            if (!(rr == rr) || isinf(rr)) { flags |= FL_NAN; break; }
+            if (rr <= M.tol2 * bb) { flags |= FL_CONVERGED; break; }
+            if (stagnated) { breakdown = true; break; }
+        }
+        if ((flags & (FL_CONVERGED | FL_NAN)) || iters >= M.max_iter) break;
+        if (breakdown && restarts < 3) { ++restarts; __syncthreads(); continue; }     // new shadow residual from the current iterate
+        if (breakdown) flags |= FL_BREAKDOWN;
+        break;
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) xg[(size_t)CHIP_ROW(c) * K] = sx[c * NT];
+#undef CHIP_ON
+#undef CHIP_ROW
     if (threadIdx.x == 0) {
         M.colflags[k] = flags; M.coliters[k] = iters;
         M.sc[SC_BNORM2 * K + k] = bb; M.sc[SC_RNORM2 * K + k] = rr;

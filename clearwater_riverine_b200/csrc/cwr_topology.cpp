@@ -241,8 +241,12 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         // so one over-full colour slows every strip around it.  The rows an over-full colour holds beyond the cap
         // (last in RCM order) move to the nearest later colour no neighbour has and that still has room: they are
         // swept a little later in the sweep than their level asks for -- still after their upstream neighbours.
-        if (n_strips > 0 && strip_cap > 0) {
-            const int NS = n_parts * n_strips;
+        // (without strips, on one part: the whole mesh is the one strip -- the on-chip solver k_solve_chip takes a colour
+        // in one pass of its CTA)
+        const bool one_strip = n_strips == 0 && n_parts == 1 && strip_cap > 0;
+        if (one_strip) strip.assign(n, 0);
+        if ((n_strips > 0 || one_strip) && strip_cap > 0) {
+            const int NS = one_strip ? 1 : n_parts * n_strips;
             std::vector<int32_t> cnt((size_t)NS * nc, 0);
             for (int i = 0; i < n; ++i) ++cnt[(size_t)strip[i] * nc + colr[i]];
             // (a strip whose rows do not fit n_colors passes with 8 % to spare is balanced towards 1.25 x its mean colour
@@ -252,7 +256,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 std::vector<int64_t> rows(NS, 0);
                 for (int i = 0; i < n; ++i) ++rows[strip[i]];
                 for (int sidx = 0; sidx < NS; ++sidx)
-                    if ((int64_t)nc * strip_cap * 100 < rows[sidx] * 108)
+                    if ((int64_t)nc * strip_cap * 100 < rows[sidx] * (one_strip ? 103 : 108))      // (on chip 3 % to spare will do)
                         cap_of[sidx] = std::max<int64_t>(strip_cap, (rows[sidx] * 5 + 4 * nc - 1) / (4 * nc));
             }
             for (int pos = n - 1; pos >= 0; --pos) {
@@ -271,6 +275,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 }
             }
         }
+        if (one_strip) std::vector<int32_t>().swap(strip);
         std::vector<uint64_t> key(n);
         for (int i = 0; i < n; ++i)
             key[i] = n_strips > 0

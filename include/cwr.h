@@ -45,7 +45,8 @@ typedef struct {
     int mass_flux;          /* 1 = compute the three per-edge mass-flux arrays every step (default, as the
                                reference does, transport.py:267-273), 0 = skip */
     int solver_path;        /* 0 = auto, 1 = multi-CTA kernels, 2 = one CTA per constituent runs the whole solve (small meshes;
-                               <= 4096 cells with Gauss-Seidel sweeps: entirely on chip -- cwr_get_options reports 3) */
+                               <= 4096 cells with Gauss-Seidel sweeps: entirely on chip -- cwr_get_options reports 3, or 4 where a
+                               thread keeps one row of every colour: quad / triangle meshes with colours of <= 256 rows) */
     int solver;             /* large meshes (solver_path 1): 1 = right-preconditioned BiCGSTAB; 2 = defect correction with the
                                preconditioner sweeps themselves: x += M^-1 r, r -= A (M^-1 r) in fp64, no Krylov vectors -- with
                                flow-aligned Gauss-Seidel sweeps the sweeps ARE the solver (18-19 of them reach 1e-13 where

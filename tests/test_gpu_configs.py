@@ -29,7 +29,7 @@ def test_ohio_preset_through_update_matches_oracle_every_step():
     inputs = synthetic.make_inputs(plan, 1, seed=2)
     model = ClearwaterRiverine.from_arrays(plan.f1, plan.f2, plan.face_x, plan.face_y, plan.time_seconds, plan.face_flow,
                                            plan.edge_velocity, plan.volume, D, {"ecoli": inputs[0]})
-    assert model.backend.options.solver_path == 3
+    assert model.backend.options.solver_path == 4          # k_solve_chip
     oracle = ref.OracleRiverine(_oracle_mesh(plan), {"ecoli": inputs[0]})
     con = oracle.constituent_dict["ecoli"]
     for t in range(60):

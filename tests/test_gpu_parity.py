@@ -330,6 +330,47 @@ def test_small_mesh_paths(shape, opts):
     run_against_oracle(mesh, inputs, 5, solver_path=2, **opts)
 
 
+def test_on_chip_kernels_against_the_oracle_and_each_other(monkeypatch):
+    """k_solve_chip (a thread keeps one row of every colour: solver_path 4) and k_solve_tiny (rows dealt by thread id:
+    3) solve the same systems: both within rtol of the oracle, each bitwise repeatable; the wider mesh (colours of more than
+    256 rows) can only take k_solve_tiny; NaN boundary values and an all-zero right-hand side behave alike."""
+    _, mesh, inputs = synthetic_case(40, 25, 6, 3, seed=33, dry_fraction=0.02)
+    inputs = [a.copy() for a in inputs]
+    inputs[1][:] = 0.0                                   # zero initial state, zero boundary: b == 0
+    states = {}
+    for env, want_path in ((None, 4), ("1", 3)):
+        if env is None:
+            monkeypatch.delenv("CWR_TINY_KERNEL", raising=False)
+        else:
+            monkeypatch.setenv("CWR_TINY_KERNEL", env)
+        for rep in range(2):
+            be = make_backend(mesh, list(inputs), solver_path=2)
+            assert be.options.solver_path == want_path
+            oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(3)})
+            for t in range(5):
+                assert be.step(t).status == 0
+                oracle.update()
+                for k in range(3):
+                    close(be.get_state(k, t + 1), oracle.constituent_dict[f"c{k}"].concentration[t + 1], RTOL, f"path {want_path} t{t} k{k}")
+            final = be.get_state_all(5)
+            be.close()
+            if rep == 0:
+                states[want_path] = final
+            else:
+                assert np.array_equal(final, states[want_path], equal_nan=True), "not bitwise repeatable"
+    close(states[4], states[3], 1e-11, "chip vs tiny")
+    monkeypatch.delenv("CWR_TINY_KERNEL", raising=False)
+    _, wide, winputs = synthetic_case(70, 50, 4, 2, seed=34)
+    be = make_backend(wide, list(winputs), solver_path=2)
+    assert be.options.solver_path == 3
+    be.close()
+    for colours, want_path in ((5, 4), (8, 4), (13, 4), (16, 3)):          # 8 / 12 / 14 colour slots per thread; too many colours
+        be = make_backend(mesh, list(inputs), solver_path=2, precond_colors=colours)
+        assert be.options.solver_path == want_path, (colours, be.options.solver_path)
+        be.close()
+        run_against_oracle(mesh, inputs, 4, solver_path=2, precond_colors=colours)
+
+
 def test_gauss_seidel_is_deterministic_and_hint_independent():
     """Same inputs, with and without the flow hint (different row orders): both within rtol of the oracle;
     two runs with the same order are bitwise identical."""
