@@ -1,4 +1,6 @@
 #include "cwr_topology.h"
+#include <chrono>
+#include <cstdio>
 
 #include <algorithm>
 #include <cmath>
@@ -65,6 +67,15 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     if (n_strips > 0 && n_colors <= 0) return "strips need colours";
     if (n_real <= 0 || n_face < n_real || n_edge <= 0) return "n_real, n_face, n_edge must be positive and n_face >= n_real";
     const int n = n_real, F = n_face, E = n_edge;
+    // CWR_TOPO_TIMING=1: seconds per section on stderr (set-up is host work: 16M cells take tens of seconds)
+    const bool timing = std::getenv("CWR_TOPO_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto tick = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[cwr topology] %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     int32_t max_f1 = -1;
     int E_int = 0;
     for (int e = 0; e < E; ++e) {
@@ -92,6 +103,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             if (f2[e] < n) { adj[fill[f1[e]]++] = f2[e]; adj[fill[f2[e]]++] = f1[e]; }
     }
 
+    tick("adjacency");
     // ---- reverse Cuthill-McKee -------------------------------------------------------------------
     T.old_of_new.resize(n);
     T.new_of_old.resize(n);
@@ -137,6 +149,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         }
         for (int i = 0; i < n; ++i) T.old_of_new[i] = order[n - 1 - i];
     }
+    tick("reverse Cuthill-McKee");
     // ---- flow-aligned multicolouring (for the Gauss-Seidel preconditioner) -------------------------------
     // A sweep visits the colours in order and updates the rows of one colour in parallel, so colours
     // must separate coupled rows.  Upwind advection makes the matrix nearly triangular in the downstream
@@ -220,6 +233,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 if (--indeg[v] == 0 && !queued[v]) { queued[v] = 1; queue.push_back(v); }
             }
         }
+        tick("levels / colours");
         // ---- partition into n_parts strips (domain decomposition), then colour-major inside a part ------
         // Parts are equal chunks of the RCM order (strips of the RCM band: breadth-first wavefronts, so a
         // part only couples to its two neighbouring strips and the cut is a smooth front).  Final order:
@@ -276,15 +290,26 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             }
         }
         if (one_strip) std::vector<int32_t>().swap(strip);
-        std::vector<uint64_t> key(n);
-        for (int i = 0; i < n; ++i)
-            key[i] = n_strips > 0
-                ? ((uint64_t)strip[i] << 44) | ((uint64_t)colr[i] << 38) | (uint32_t)rcm_pos[i]
-                : ((uint64_t)part[i] << 60) | ((uint64_t)colr[i] << 54) | ((uint64_t)level[i] << 32) | (uint32_t)rcm_pos[i];
-        std::sort(key.begin(), key.end());
+        // (stable counting sorts over the RCM order instead of one comparison sort of n 64-bit keys: the row order is
+        // most of the set-up's sorting at 16M cells)
         std::vector<int32_t> order(n);
-        for (int i = 0; i < n; ++i) order[i] = T.old_of_new[(uint32_t)key[i]];       // RCM position -> cell
-        std::vector<uint64_t>().swap(key);
+        {
+            const bool by_strip = n_strips > 0;
+            std::vector<int32_t> seq(n);               // cells in RCM order, then (non-strip mode) stably by level
+            if (by_strip) seq = T.old_of_new;
+            else {
+                std::vector<int32_t> lptr((size_t)max_level + 2, 0);
+                for (int i = 0; i < n; ++i) ++lptr[level[i] + 1];
+                for (int l = 0; l <= max_level; ++l) lptr[l + 1] += lptr[l];
+                for (int pos = 0; pos < n; ++pos) { const int32_t u = T.old_of_new[pos]; seq[lptr[level[u]]++] = u; }
+            }
+            const size_t nb = (size_t)(by_strip ? n_parts * n_strips : n_parts) * nc;
+            std::vector<int32_t> bptr(nb + 1, 0);
+            auto bucket = [&](int32_t u) { return (size_t)(by_strip ? strip[u] : part[u]) * nc + colr[u]; };
+            for (int i = 0; i < n; ++i) ++bptr[bucket(i) + 1];
+            for (size_t b = 0; b < nb; ++b) bptr[b + 1] += bptr[b];
+            for (int q = 0; q < n; ++q) { const int32_t u = seq[q]; order[bptr[bucket(u)]++] = u; }
+        }
         T.n_colors = nc;
         T.color_ptr.assign((size_t)n_parts * (nc + 1), 0);
         T.part_ptr.assign(n_parts + 1, 0);
@@ -329,24 +354,40 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     }
     for (int i = 0; i < n; ++i) T.new_of_old[T.old_of_new[i]] = i;
 
+    tick("strip balancing / row order");
     // ---- edge renumbering ---------------------------------------------------------------------------
     // internal edges: sort by (min new cell, max new cell, original id); ghost edges: by (new cell, original id)
     std::vector<int32_t> internal, ghost;
-    internal.reserve(E_int); ghost.reserve(T.E_g);
     {
-        std::vector<std::pair<uint64_t, int32_t>> ik; ik.reserve(E_int);
-        std::vector<uint64_t> gk; gk.reserve(T.E_g);
+        // counting sort by the lower new cell (edges scattered in original order: ties keep ascending ids), then the
+        // handful of edges of a cell by (higher cell, id)
+        std::vector<int32_t> iptr(n + 1, 0), gptr(n + 1, 0);
         for (int e = 0; e < E; ++e) {
             const int32_t a = T.new_of_old[f1[e]];
-            if (f2[e] < n) {
-                const int32_t b = T.new_of_old[f2[e]];
-                ik.emplace_back(((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b), e);
-            } else gk.push_back(((uint64_t)(uint32_t)a << 32) | (uint32_t)e);
+            if (f2[e] < n) ++iptr[std::min(a, T.new_of_old[f2[e]]) + 1];
+            else ++gptr[a + 1];
         }
-        std::sort(ik.begin(), ik.end());
-        std::sort(gk.begin(), gk.end());
-        for (auto& pr : ik) internal.push_back(pr.second);
-        for (uint64_t k : gk) ghost.push_back((int32_t)(uint32_t)k);
+        for (int i = 0; i < n; ++i) { iptr[i + 1] += iptr[i]; gptr[i + 1] += gptr[i]; }
+        internal.resize(E_int); ghost.resize(T.E_g);
+        std::vector<int32_t> hi(E_int);
+        {
+            std::vector<int32_t> ifill(iptr.begin(), iptr.end() - 1), gfill(gptr.begin(), gptr.end() - 1);
+            for (int e = 0; e < E; ++e) {
+                const int32_t a = T.new_of_old[f1[e]];
+                if (f2[e] < n) {
+                    const int32_t b = T.new_of_old[f2[e]];
+                    const int32_t o = ifill[std::min(a, b)]++;
+                    internal[o] = e; hi[o] = std::max(a, b);
+                } else ghost[gfill[a]++] = e;
+            }
+        }
+        for (int i = 0; i < n; ++i)
+            for (int32_t j = iptr[i] + 1; j < iptr[i + 1]; ++j) {          // insertion sort, stable
+                const int32_t e = internal[j], h = hi[j];
+                int32_t q = j;
+                while (q > iptr[i] && hi[q - 1] > h) { internal[q] = internal[q - 1]; hi[q] = hi[q - 1]; --q; }
+                internal[q] = e; hi[q] = h;
+            }
     }
     T.eperm.resize(E); T.f1p.resize(E); T.f2p.resize(E);
     for (int i = 0; i < E_int; ++i) T.eperm[i] = internal[i];
@@ -357,6 +398,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         T.f2p[ep] = f2[e] < n ? T.new_of_old[f2[e]] : f2[e];   // ghost cells keep their id (>= n)
     }
 
+    tick("edge renumbering");
     // ---- off-diagonal CSR with slot -> (edge, side) --------------------------------------------------
     T.rowptr.assign(n + 1, 0);
     for (int ep = 0; ep < E_int; ++ep) { ++T.rowptr[T.f1p[ep] + 1]; ++T.rowptr[T.f2p[ep] + 1]; }
@@ -385,6 +427,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         }
     }
 
+    tick("CSR pattern");
     // ---- row-major ELL copy of the pattern (what the kernels read) ------------------------------------
     T.W = std::max(4, (T.max_row_len + 3) / 4 * 4);
     T.ell_col.assign((size_t)n * T.W, 0);
@@ -398,6 +441,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         }
     }
 
+    tick("ELL pattern");
     // ---- boundary cells ----------------------------------------------------------------------------------
     T.bcell.clear(); T.bptr.clear(); T.bedge.resize(T.E_g);
     for (int i = 0; i < T.E_g; ++i) {
@@ -419,6 +463,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 if (cn == (ci + T.n_colors - 1) % T.n_colors && cn != ci) cj |= kPrevBit;
             }
 
+    tick("boundary cells / sweep flags");
     // ---- strips: which strips a strip's rows are coupled to (global strip ids; strips of other parts included:
     // the sweep kernel synchronises with them through flag mirrors in peer memory) ---------------------------
     T.strip_nptr.clear(); T.strip_nbr.clear(); T.max_strip_nbr = 0;
@@ -446,6 +491,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         for (uint64_t pr : pairs) T.strip_nbr.push_back((int32_t)(uint32_t)pr);
     }
 
+    tick("strip neighbours");
     // ---- domain decomposition: who reads whose rows, which edges / boundary cells a part owns ----------
     const int P = n_parts;
     auto part_of = [&](int32_t row) { return (int)(std::upper_bound(T.part_ptr.begin(), T.part_ptr.end(), row) - T.part_ptr.begin()) - 1; };
