@@ -107,3 +107,28 @@ def test_strip_cap_moves_overflow_rows_to_legal_colours():
     # rows that kept their colour: everything outside the over-full (strip, colour) pairs
     moved = (L["color_of"][p] != L0["color_of"][L0["new_of_old"]]).sum()
     assert 0 < moved <= np.maximum(d0 - cap, 0).sum()
+
+
+@pytest.mark.parametrize("hinted", [False, True])
+def test_whole_mesh_as_one_strip_balances_the_colours_for_the_on_chip_solver(hinted):
+    """Without strips a cap makes the whole mesh the one strip (what create passes for meshes of <= 4096 cells): on the
+    Ohio-shaped mesh every one of the 12 colours ends at <= 256 rows -- one pass of k_solve_chip's 256 threads -- with
+    or without a flow hint (the unhinted greedy colouring starts at 1468 rows in its first colour); colours still
+    separate coupled rows, and colour-major row ranges stay contiguous."""
+    plan = synthetic.ohio_like(12, seed=2)
+    n = plan.n_real
+    hint = plan.face_flow.mean(0) if hinted else None
+    L0 = strip_layout(plan.f1, plan.f2, plan.n_face, 12, hint, 0)
+    L = strip_layout(plan.f1, plan.f2, plan.n_face, 12, hint, 0, strip_cap=256)
+    assert L["n_colors"] == 12
+    cnt0 = np.bincount(L0["color_of"], minlength=12)
+    cnt = np.bincount(L["color_of"], minlength=12)
+    assert cnt.sum() == n and cnt.max() <= 256
+    if not hinted:
+        assert cnt0.max() > 256, "the case must need balancing"
+    p = L["new_of_old"]
+    assert np.array_equal(np.sort(p), np.arange(n))
+    internal = plan.f2 < n
+    col = L["color_of"].astype(int)                  # by new id
+    assert np.all(col[p[plan.f1[internal]]] != col[p[plan.f2[internal]]])
+    assert np.all(np.diff(col) >= 0), "rows are colour-major"
