@@ -586,9 +586,12 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
             cudaError_t e = cudaSuccess;
             TINY_DISPATCH(e = cudaFuncSetAttribute(k_solve_tiny<RPT, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             CK(e);
-            CK(cudaFuncSetAttribute(k_solve_chip<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
             h->max_optin_smem = max_optin;
             choose_chip(h);
         }
@@ -1223,9 +1226,13 @@ static int solve_small(cwr_handle* h, cwr_step_info* info) {
     if (h->tiny && h->chip_ns > 0) {
         const size_t sm = chip_smem_bytes(h->n, h->chip_ns);
         const int sweeps = h->m_steps - 1;
-        if (h->chip_ns == 8) k_solve_chip<8><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats);
-        else if (h->chip_ns == 12) k_solve_chip<12><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats);
-        else k_solve_chip<14><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats);
+#define CHIP_LAUNCH(NS) do { \
+            if (h->sweep_f32) k_solve_chip<NS, true><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats); \
+            else k_solve_chip<NS, false><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats); } while (0)
+        if (h->chip_ns == 8) CHIP_LAUNCH(8);
+        else if (h->chip_ns == 12) CHIP_LAUNCH(12);
+        else CHIP_LAUNCH(14);
+#undef CHIP_LAUNCH
     } else if (h->tiny) {
         const size_t sm = tiny_smem_bytes(h->n, h->topo.W);
         const int sweeps = h->m_steps - 1;

@@ -464,12 +464,23 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
 constexpr int kChipThreads = 256;
 
 __host__ __device__ inline size_t chip_smem_bytes(int n, int NS) {
-    // x, p^, v, t, r^ [NS][256] f64 | z [n] f64
-    return (size_t)NS * kChipThreads * 40 + (size_t)n * 8;
+    // x, p^, v, t, r^, p [NS][256] f64 | z [n] f64 | zf [n] f32 (p and zf: only the kernel with fp32 sweeps uses them)
+    return (size_t)NS * kChipThreads * 48 + (size_t)n * 8 + (size_t)n * 4;
 }
 
-template <int NS>
+// F32: the sweeps run in fp32 (options.precond_precision = 32, the default): the gathered vector is 4 bytes per row
+// (half the shared-memory wavefronts of a colour step) and the chain of a step is FMUL/FFMA/FADD.  What the sweeps are
+// given (p or r) is scaled by a power of two near 1 / ||r|| first, so the fp32 range never matters; p^ / s^ = the fp32
+// result widened exactly, and v = A p^, t = A s^, every dot product and the recurrences stay fp64 with the fp64 matrix
+// values: the converged answer is the fp64 one, as on the large path.
+// The registers then hold fp32 copies of the matrix values (and p moves to a private shared-memory column); the fp64 values
+// are re-read from global memory (L2) in the few vector phases that need them (v = A p^, t = A s^, r = b - A x).
+// Measured on the Ohio-shaped mesh (profiles/r02chip1_*): fp64 sweeps 0.071 ms per step, fp32 0.069 (64 scenarios 0.080 / 0.078),
+// same iteration counts; keeping the fp64 values in registers and narrowing them inside the colour step (4 F2F per step, off
+// the dependent chain) was slower than fp64 (0.073) and is gone.
+template <int NS, bool F32>
 __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, int n_sweeps, SmallStats* stats) {
+    constexpr bool REG64 = !F32;                 // fp64 matrix values in registers
     extern __shared__ double chip_smem[];
     __shared__ double red[2 * 4 * 32];
     __shared__ int cptr[NS + 1];
@@ -480,7 +491,9 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     double* sv = sph + NS * NT;
     double* st = sv + NS * NT;
     double* srh = st + NS * NT;
-    double* z = chip_smem + 5 * NS * NT;                        // [n] the gathered vector
+    double* spp = srh + NS * NT;                                // (fp32 sweeps: p lives here, its registers go to the compiler)
+    double* z = chip_smem + 6 * NS * NT;                        // [n] the gathered vector
+    float* zf = reinterpret_cast<float*>(z + n);                // [n] ... of the fp32 sweeps
     double* __restrict__ xg = M.sp->state_t1 + k;               // stride K
     const double* __restrict__ bg = M.b + k;
     int parity = 0;
@@ -492,20 +505,23 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     unsigned on = 0;
 #pragma unroll
     for (int c = 0; c < NS; ++c) if (c < nc && CHIP_ROW(c) < cptr[c + 1]) on |= 1u << c;
-    double2 va[NS], vb[NS]; uint2 nb[NS];
-    double r[NS], p[NS];
+    double2 va[REG64 ? NS : 1], vb[REG64 ? NS : 1]; uint2 nb[NS];
+    float4 vf[REG64 ? 1 : NS];
+    double r[NS], p[F32 ? 1 : NS];
+    auto getp = [&](int c) -> double { if constexpr (F32) return spp[c * NT]; else return p[c]; };
+    auto setp = [&](int c, double v) { if constexpr (F32) spp[c * NT] = v; else p[c] = v; };
     // ---- the thread's rows: matrix values and indices -> registers, x -> its column (loads issued four rows at a time)
 #pragma unroll
     for (int c0 = 0; c0 < NS; c0 += 4) {
-        int4 cj[4]; double xq[4];
+        int4 cj[4]; double xq[4]; double2 ta[4], tb[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = c0 + q;
             if (c < NS) {
                 const size_t row = CHIP_ON(c) ? CHIP_ROW(c) : 0;
                 cj[q] = __ldg(reinterpret_cast<const int4*>(M.ell_col + row * 4));
-                va[c] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
-                vb[c] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
+                ta[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
+                tb[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
                 xq[q] = xg[row * K];
             }
         }
@@ -515,41 +531,108 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
             if (c < NS) {
                 nb[c].x = (unsigned)(cj[q].x & 0x7fff) | ((unsigned)(cj[q].y & 0x7fff) << 16);
                 nb[c].y = (unsigned)(cj[q].z & 0x7fff) | ((unsigned)(cj[q].w & 0x7fff) << 16);
-                if (!CHIP_ON(c)) { nb[c] = make_uint2(0u, 0u); va[c] = make_double2(0.0, 0.0); vb[c] = va[c]; xq[q] = 0.0; }
+                if (!CHIP_ON(c)) { nb[c] = make_uint2(0u, 0u); ta[q] = make_double2(0.0, 0.0); tb[q] = ta[q]; xq[q] = 0.0; }
+                if constexpr (REG64) { va[c] = ta[q]; vb[c] = tb[q]; }
+                else vf[c] = make_float4((float)ta[q].x, (float)ta[q].y, (float)tb[q].x, (float)tb[q].y);
                 sx[c * NT] = xq[q];
                 sph[c * NT] = 0.0; sv[c * NT] = 0.0; st[c * NT] = 0.0; srh[c * NT] = 0.0;
-                r[c] = p[c] = 0.0;
+                r[c] = 0.0; setp(c, 0.0);
             }
         }
     }
 
-    // (L z) of the thread's row of colour c
-    auto dot4 = [&](int c) {
+    // the fp64 matrix values of the thread's row of colour c (rows that are off: whatever row 0 holds, the callers discard it)
+    auto mat = [&](int c, double2& a, double2& b) {
+        if constexpr (REG64) { a = va[c]; b = vb[c]; }
+        else {
+            const size_t row = CHIP_ON(c) ? CHIP_ROW(c) : 0;
+            a = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
+            b = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
+        }
+    };
+    // the vector phases walk the colours four at a time: the matrix values of four rows are requested together (with
+    // fp32 sweeps they come from L2; one colour at a time the phase paid a round trip per colour, 7 of the solve's 67 us)
+    auto batched = [&](auto body) {
+#pragma unroll
+        for (int c0 = 0; c0 < NS; c0 += 4) {
+            double2 a[4], b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (c0 + q < NS) mat(c0 + q, a[q], b[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (c0 + q < NS) body(c0 + q, a[q], b[q]);
+        }
+    };
+    // (L z) of the thread's row of colour c, fp64 vector
+    auto dot4 = [&](int c, const double2& a, const double2& b) {
         const double z0 = z[nb[c].x & 0xffffu], z1 = z[nb[c].x >> 16], z2 = z[nb[c].y & 0xffffu], z3 = z[nb[c].y >> 16];
-        return fma(va[c].y, z1, va[c].x * z0) + fma(vb[c].y, z3, vb[c].x * z2);
+        return fma(a.y, z1, a.x * z0) + fma(b.y, z3, b.x * z2);
+    };
+    // the preconditioned vector after the sweeps: own row / (L .) of the row, in fp64 whatever the sweeps ran in
+    double unscale = 1.0;                       // fp32 sweeps: 2^h, undoes the scaling of what the sweeps were given
+    auto zrow = [&](int c) -> double {
+        if constexpr (F32) return (double)zf[CHIP_ROW(c)] * unscale;
+        else return z[CHIP_ROW(c)];
+    };
+    auto dot4z = [&](int c, const double2& a, const double2& b) -> double {
+        if constexpr (F32) {
+            const double z0 = (double)zf[nb[c].x & 0xffffu], z1 = (double)zf[nb[c].x >> 16];
+            const double z2 = (double)zf[nb[c].y & 0xffffu], z3 = (double)zf[nb[c].y >> 16];
+            return (fma(a.y, z1, a.x * z0) + fma(b.y, z3, b.x * z2)) * unscale;    // (power of two: exact)
+        } else return dot4(c, a, b);
     };
     // z = M^-1 u: n_sweeps multicolour Gauss-Seidel sweeps; z is ZERO and synchronised on entry, complete and synchronised on exit
-    auto precondition = [&](const double (&u)[NS]) {
-        if (n_sweeps <= 0) {
+    // (norm2: a squared norm of the size of u's, for the fp32 scaling)
+    auto precondition = [&](auto u, double norm2) {
+        if constexpr (F32) {
+            // scale = 2^-h with h = half the exponent of norm2: u * scale is O(1) whatever the units of the system
+            const int e = ((__double2hiint(norm2) >> 20) & 0x7ff) - 1023;
+            const int hh = e / 2;
+            const double scale = __hiloint2double((1023 - hh) << 20, 0);
+            unscale = __hiloint2double((1023 + hh) << 20, 0);
+            float uf[NS];
 #pragma unroll
-            for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = u[c];
-            __syncthreads();
-            return;
-        }
-        for (int s = 0; s < n_sweeps; ++s) {
+            for (int c = 0; c < NS; ++c) uf[c] = (float)(u(c) * scale);
+            if (n_sweeps <= 0) {
 #pragma unroll
-            for (int c = 0; c < NS; ++c) {
-                if (c < nc) {
-                    const double zi = u[c] - dot4(c);
-                    if (CHIP_ON(c)) z[CHIP_ROW(c)] = zi;
-                    __syncthreads();
+                for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) zf[CHIP_ROW(c)] = uf[c];
+                __syncthreads();
+                return;
+            }
+            for (int s = 0; s < n_sweeps; ++s) {
+#pragma unroll
+                for (int c = 0; c < NS; ++c) {
+                    if (c < nc) {
+                        const float a0 = vf[c].x, a1 = vf[c].y, a2 = vf[c].z, a3 = vf[c].w;
+                        const float z0 = zf[nb[c].x & 0xffffu], z1 = zf[nb[c].x >> 16], z2 = zf[nb[c].y & 0xffffu], z3 = zf[nb[c].y >> 16];
+                        const float zi = uf[c] - (fmaf(a1, z1, a0 * z0) + fmaf(a3, z3, a2 * z2));
+                        if (CHIP_ON(c)) zf[CHIP_ROW(c)] = zi;
+                        __syncthreads();
+                    }
+                }
+            }
+        } else {
+            if (n_sweeps <= 0) {
+#pragma unroll
+                for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = u(c);
+                __syncthreads();
+                return;
+            }
+            for (int s = 0; s < n_sweeps; ++s) {
+#pragma unroll
+                for (int c = 0; c < NS; ++c) {
+                    if (c < nc) {
+                        const double zi = u(c) - dot4(c, va[c], vb[c]);
+                        if (CHIP_ON(c)) z[CHIP_ROW(c)] = zi;
+                        __syncthreads();
+                    }
                 }
             }
         }
     };
     auto zero_z = [&]() {
 #pragma unroll
-        for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = 0.0;
+        for (int c = 0; c < NS; ++c)
+            if (CHIP_ON(c)) { if constexpr (F32) zf[CHIP_ROW(c)] = 0.f; else z[CHIP_ROW(c)] = 0.0; }
     };
 
     int flags = 0, iters = 0, restarts = 0;
@@ -564,13 +647,12 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
 #pragma unroll
             for (int c = 0; c < NS; ++c) if (CHIP_ON(c)) z[CHIP_ROW(c)] = sx[c * NT];
             __syncthreads();
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {
+            batched([&](int c, const double2& a, const double2& b) {
                 const double bi = CHIP_ON(c) ? bq[c] : 0.0;
-                const double ri = CHIP_ON(c) ? bi - (z[CHIP_ROW(c)] + dot4(c)) : 0.0;
-                r[c] = ri; p[c] = ri; srh[c * NT] = ri;
+                const double ri = CHIP_ON(c) ? bi - (z[CHIP_ROW(c)] + dot4(c, a, b)) : 0.0;
+                r[c] = ri; setp(c, ri); srh[c * NT] = ri;
                 d2[0] = fma(ri, ri, d2[0]); d2[1] = fma(bi, bi, d2[1]);
-            }
+            });
         }
         tiny_sum<2, NW>(d2, red, parity);                // (every read of z is behind this barrier)
         rr = d2[0]; bb = d2[1];
@@ -593,15 +675,14 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
         double rho = rr;
         bool breakdown = false;
         while (iters < M.max_iter) {
-            precondition(p);                             // z = p^
+            precondition(getp, rr);                      // z = p^
             double d1[1] = {0.0};
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {
-                const double zi = CHIP_ON(c) ? z[CHIP_ROW(c)] : 0.0;
-                const double vi = CHIP_ON(c) ? zi + dot4(c) : 0.0;
+            batched([&](int c, const double2& a, const double2& b) {
+                const double zi = CHIP_ON(c) ? zrow(c) : 0.0;
+                const double vi = CHIP_ON(c) ? zi + dot4z(c, a, b) : 0.0;
                 sph[c * NT] = zi; sv[c * NT] = vi;
                 d1[0] = fma(srh[c * NT], vi, d1[0]);
-            }
+            });
             tiny_sum<1, NW>(d1, red, parity);            // (all reads of z are behind this barrier)
             if (d1[0] == 0.0 || !(d1[0] == d1[0])) { breakdown = true; break; }
             const double alpha = rho / d1[0];
@@ -619,19 +700,18 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
                 rr = dh[0]; ++iters; flags |= FL_CONVERGED;
                 break;
             }
-            precondition(r);                             // z = s^
+            precondition([&](int c) { return r[c]; }, dh[0]);        // z = s^
             double d4[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int c = 0; c < NS; ++c) {
-                const double zi = CHIP_ON(c) ? z[CHIP_ROW(c)] : 0.0;          // s^ of the own row
-                const double ti = CHIP_ON(c) ? zi + dot4(c) : 0.0;
+            batched([&](int c, const double2& a, const double2& b) {
+                const double zi = CHIP_ON(c) ? zrow(c) : 0.0;                 // s^ of the own row
+                const double ti = CHIP_ON(c) ? zi + dot4z(c, a, b) : 0.0;
                 st[c * NT] = ti;
                 sx[c * NT] = fma(alpha, sph[c * NT], sx[c * NT]);             // x += alpha p^ now, + omega s^ below
                 sph[c * NT] = zi;                                             // (p^ is done with: the column keeps s^)
                 const double rh = srh[c * NT];
                 d4[0] = fma(ti, r[c], d4[0]); d4[1] = fma(ti, ti, d4[1]);
                 d4[2] = fma(rh, ti, d4[2]); d4[3] = fma(rh, r[c], d4[3]);
-            }
+            });
             tiny_sum<4, NW>(d4, red, parity);
             const double omega = d4[1] > 0.0 ? d4[0] / d4[1] : 0.0;
             const double rho_new = d4[3] - omega * d4[2];
@@ -646,7 +726,7 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
                 sx[c * NT] = fma(omega, sph[c * NT], sx[c * NT]);
                 const double rn = fma(-omega, st[c * NT], r[c]);
                 r[c] = rn;
-                p[c] = fma(beta, fma(-omega, sv[c * NT], p[c]), rn);
+                setp(c, fma(beta, fma(-omega, sv[c * NT], getp(c)), rn));
                 dr[0] = fma(rn, rn, dr[0]);
             }
             zero_z();

@@ -371,6 +371,31 @@ def test_on_chip_kernels_against_the_oracle_and_each_other(monkeypatch):
         run_against_oracle(mesh, inputs, 4, solver_path=2, precond_colors=colours)
 
 
+@pytest.mark.parametrize("precision", [32, 64])
+def test_on_chip_kernel_sweep_precisions(precision):
+    """k_solve_chip with fp32 sweeps inside the fp64 BiCGSTAB (precond_precision = 32, the default) and with fp64 sweeps:
+    within rtol of the oracle at 8 / 12 / 14 colour slots and with few sweeps, in units 1e-20 and 1e+20 (the fp32 sweeps
+    scale what they are given); bitwise repeatable."""
+    _, mesh, inputs = synthetic_case(40, 25, 6, 3, seed=35, dry_fraction=0.02)
+    inputs = [a.copy() for a in inputs]
+    inputs[1] *= 1e-20                                   # tiny units: the fp32 sweeps scale what they are given
+    inputs[2] *= 1e+20
+    finals = []
+    for colours in (5, 12, 13, 12):
+        be = make_backend(mesh, list(inputs), solver_path=2, precond_colors=colours, precond_precision=precision)
+        assert be.options.solver_path == 4 and be.options.precond_precision == precision
+        oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(3)})
+        for t in range(5):
+            assert be.step(t).status == 0
+            oracle.update()
+            for k in range(3):
+                close(be.get_state(k, t + 1), oracle.constituent_dict[f"c{k}"].concentration[t + 1], RTOL, f"fp{precision} colours {colours} t{t} k{k}")
+        finals.append(be.get_state_all(5))
+        be.close()
+    assert np.array_equal(finals[1], finals[3], equal_nan=True), "not bitwise repeatable"
+    run_against_oracle(mesh, inputs, 4, solver_path=2, precond_steps=3, precond_precision=precision)
+
+
 def test_gauss_seidel_is_deterministic_and_hint_independent():
     """Same inputs, with and without the flow hint (different row orders): both within rtol of the oracle;
     two runs with the same order are bitwise identical."""
