@@ -67,6 +67,7 @@ struct cwr_handle {
     bool tiny = false;               // ... entirely on chip (k_solve_tiny: matrix in shared memory, Gauss-Seidel sweeps)
     int tiny_rpt = 1;                // rows per thread of k_solve_tiny
     int max_optin_smem = 0;
+    bool pdl = false;                // small-mesh path: the step's kernels are launched with programmatic stream serialization
     int chip_ns = 0;                 // > 0: k_solve_chip with this many colour slots per thread (ELL width 4, colours of <= 256 rows)
     bool in_run = false;             // inside cwr_run: the small path does not synchronise per step
     SmallStats* d_stats = nullptr; SmallStats* h_stats = nullptr;
@@ -322,6 +323,19 @@ static void set_owned_ranges(cwr_handle* h) {
     M.halo_per_sweep = h->opt.dd_halo_per_colour ? 0 : 1;
 }
 
+// Launch of a kernel of the small-mesh step chain: with programmatic stream serialization when h->pdl (every kernel
+// launched through here starts with pdl_enter()).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(cwr_handle* h, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = h->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 // k_solve_chip (one row of every colour per thread) where the colours allow it: ELL width 4, at most 14 colours of at most
 // 256 rows, everything in shared memory.  CWR_TINY_KERNEL=1 keeps k_solve_tiny (for comparisons).
 static void choose_chip(cwr_handle* h) {
@@ -454,6 +468,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
     h->sweep_f32 = h->opt.precond_precision == 32;
     // solver path: small meshes run the whole solve of a column inside one CTA (cwr_small.cuh)
     h->small_path = small;
+    h->pdl = small && !std::getenv("CWR_NO_PDL");
     h->world = std::max(1, h->opt.dd_world); h->rank = h->opt.dd_rank;
     if (h->world > kMaxRanks || h->rank < 0 || h->rank >= h->world) FAIL(CWR_EINVAL, "dd_rank / dd_world out of range (at most 8 ranks)");
     if (h->world > 1 && (small || h->m_steps < 2))
@@ -1227,8 +1242,8 @@ static int solve_small(cwr_handle* h, cwr_step_info* info) {
         const size_t sm = chip_smem_bytes(h->n, h->chip_ns);
         const int sweeps = h->m_steps - 1;
 #define CHIP_LAUNCH(NS) do { \
-            if (h->sweep_f32) k_solve_chip<NS, true><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats); \
-            else k_solve_chip<NS, false><<<h->K, kChipThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats); } while (0)
+            if (h->sweep_f32) CK(launch_chain(h, k_solve_chip<NS, true>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); \
+            else CK(launch_chain(h, k_solve_chip<NS, false>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); } while (0)
         if (h->chip_ns == 8) CHIP_LAUNCH(8);
         else if (h->chip_ns == 12) CHIP_LAUNCH(12);
         else CHIP_LAUNCH(14);
@@ -1236,9 +1251,9 @@ static int solve_small(cwr_handle* h, cwr_step_info* info) {
     } else if (h->tiny) {
         const size_t sm = tiny_smem_bytes(h->n, h->topo.W);
         const int sweeps = h->m_steps - 1;
-        TINY_DISPATCH((k_solve_tiny<RPT, W4><<<h->K, kTinyThreads, sm, h->stream>>>(h->M, sweeps, h->d_stats)));
+        TINY_DISPATCH((launch_chain(h, k_solve_tiny<RPT, W4>, h->K, kTinyThreads, sm, h->M, sweeps, h->d_stats)));
     } else
-    k_solve_small<<<h->K, kSmallThreads, 0, h->stream>>>(h->M, h->m_steps, h->d_stats);
+    CK(launch_chain(h, k_solve_small, h->K, kSmallThreads, 0, h->M, h->m_steps, h->d_stats));
     h->launches += 1;
     CK(cudaGetLastError());
     if (h->in_run) {
@@ -1282,7 +1297,7 @@ static int patch_real_cells(cwr_handle* h, int t, int before_solve) {
     // pageable sources: the copies have left the host vectors when the calls return
     CK(cudaMemcpyAsync(h->d_ov_idx, h->ov_idx.data(), cnt * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_ov_val, h->ov_val.data(), cnt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    k_patch_rows<<<grid_for((int64_t)cnt, kThreads, 64), kThreads, 0, h->stream>>>(M, h->d_ov_idx, h->d_ov_val, (int)cnt, before_solve);
+    CK(launch_chain(h, k_patch_rows, grid_for((int64_t)cnt, kThreads, 64), kThreads, 0, M, (const long long*)h->d_ov_idx, (const double*)h->d_ov_val, (int)cnt, before_solve));
     h->launches += 1;
     return CWR_OK;
 }
@@ -1292,12 +1307,12 @@ static int patch_real_cells(cwr_handle* h, int t, int before_solve) {
 static int build_rhs(cwr_handle* h, int t) {
     DeviceModel& M = h->M;
     mark(h, CWR_FAM_RHS);
-    KC_DISPATCH(h->KC, (k_rhs<KC, VEC><<<h->grid_rows, kThreads, 0, h->stream>>>(M)));
+    KC_DISPATCH(h->KC, (launch_chain(h, k_rhs<KC, VEC>, h->grid_rows, kThreads, 0, M)));
     h->launches += 1;
     int rc = patch_real_cells(h, t, 1);
     if (rc) return rc;
     if (M.b_hi - M.b_lo > 0) {
-        k_boundary_rhs<<<h->grid_b, kThreads, 0, h->stream>>>(M);
+        CK(launch_chain(h, k_boundary_rhs, h->grid_b, kThreads, 0, M));
         h->launches += 1;
     }
     return halo_push(h, h->cur_x);      // x0 = c~: the first residual gathers the neighbours' rows
@@ -1326,13 +1341,13 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     p.state_t = state_slot(h, t); p.state_t1 = state_slot(h, t + 1);
     p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
     DeviceModel& M = h->M;
-    k_set_step<<<1, 1, 0, h->stream>>>(p, h->d_sp, M.ctl, h->world > 1 ? M.dd : nullptr);
+    CK(launch_chain(h, k_set_step, 1, 1, 0, p, h->d_sp, M.ctl, h->world > 1 ? M.dd : (DdCtl*)nullptr));
     h->cur_x = p.state_t1;
     mark(h, CWR_FAM_ASSEMBLE);
     if (h->world > 1 && !h->attached) FAIL(CWR_EINVAL, "domain-decomposed handle: call cwr_dd_attach before stepping");
     const int nb_own = M.b_hi - M.b_lo;
-    if (nb_own > 0) k_boundary_diag<<<grid_for(nb_own, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
-    k_assemble<<<grid_for(M.row_hi - M.row_lo, kThreads, h->max_grid), kThreads, 0, h->stream>>>(M);
+    if (nb_own > 0) CK(launch_chain(h, k_boundary_diag, grid_for(nb_own, kThreads, h->max_grid), kThreads, 0, M));
+    CK(launch_chain(h, k_assemble, grid_for(M.row_hi - M.row_lo, kThreads, h->max_grid), kThreads, 0, M));
     h->launches += 2 + (nb_own > 0);
     h->lhs_step = t;
     { int rc = build_rhs(h, t); if (rc) return rc; }
@@ -1362,7 +1377,7 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     { int rc = halo_push(h, p.state_t1); if (rc) return rc; }
     if (M.want_flux) {
         mark(h, CWR_FAM_MASS_FLUX);
-        KC_DISPATCH(h->KC, (k_mass_flux<KC, VEC><<<h->grid_edges, kThreads, 0, h->stream>>>(M)));
+        KC_DISPATCH(h->KC, (launch_chain(h, k_mass_flux<KC, VEC>, h->grid_edges, kThreads, 0, M)));
         h->launches += 1;
         h->flux_step = t;
     }

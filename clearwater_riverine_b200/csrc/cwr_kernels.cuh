@@ -137,7 +137,17 @@ struct DeviceModel {
     int want_flux;
 };
 
+// Programmatic dependent launch (small-mesh path: a step is a chain of 6 - 8 launches of a few microseconds each, so the
+// gaps between them count).  The host launches these kernels with programmaticStreamSerialization; each lets its successor
+// be scheduled at once and waits for its predecessor's memory before it touches anything.  Launched without the attribute
+// (the large path) both instructions do nothing.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl, DdCtl* dd) {
+    pdl_enter();
     *dst = p;
     if (dd) dd->timeout = 0;            // (a peer that was slow in an earlier step is waited for again)
     ctl->all_done = 0; ctl->iter = 0; ctl->flags_or = 0; ctl->hit_max_iter = 0; ctl->finish_half = 0;
@@ -280,6 +290,7 @@ __global__ void k_dist(double* __restrict__ dist, const double* __restrict__ fx,
 // ghost-edge diagonal terms: sum over a boundary cell's ghost edges of cdiff + max(adv, 0)
 // (linalg.py:92-97 and 113-115 applied to ghost edges).
 __global__ void k_boundary_diag(DeviceModel M) {
+    pdl_enter();
     const StepParams& sp = *M.sp;
     for (int b = M.b_lo + blockIdx.x * blockDim.x + threadIdx.x; b < M.b_hi; b += gridDim.x * blockDim.x) {
         double s = 0.0;
@@ -298,6 +309,7 @@ __global__ void k_boundary_diag(DeviceModel M) {
 //     A[P,P] += d + max(a,0)   A[N,N] += d - min(a,0)
 //   A[i,i] += vol[t+1,i]/dt[t]  (+1 if vol[t+1,i] == 0, linalg.py:66,77-81)
 __global__ void __launch_bounds__(kThreads) k_assemble(DeviceModel M) {
+    pdl_enter();
     const StepParams& sp = *M.sp;
     const double dt = sp.dt;
     const int W = M.W;
@@ -384,6 +396,7 @@ __device__ __forceinline__ void stv(double* p, const Vd<VEC>& v) {
 // RHS  (reference linalg.py:177-275), K constituents at once, row-scaled by 1/D; warm start x0 = c~
 template <int KC, int VEC>
 __global__ void __launch_bounds__(kThreads) k_rhs(DeviceModel M) {
+    pdl_enter();
     const StepParams& sp = *M.sp;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const double dt = sp.dt;
@@ -409,6 +422,7 @@ __global__ void __launch_bounds__(kThreads) k_rhs(DeviceModel M) {
 // (linalg.py:199-200: state and load term recomputed; k_boundary_rhs, which runs afterwards, adds the ghost terms),
 // after it they are re-imposed on the stored row (transport.py:258-264).  idx = row * K + column, device order.
 __global__ void k_patch_rows(DeviceModel M, const long long* __restrict__ idx, const double* __restrict__ val, int count, int before_solve) {
+    pdl_enter();
     const StepParams& sp = *M.sp;
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < count; q += gridDim.x * blockDim.x) {
         const long long i = idx[q];
@@ -421,6 +435,7 @@ __global__ void k_patch_rows(DeviceModel M, const long long* __restrict__ idx, c
 // Boundary cells: b_i = load + ghost_in + ghost_out with the reference's selection and
 // last-edge-wins assignment (linalg.py:349-351, 372-378, 390).  One lane per (cell, column).
 __global__ void __launch_bounds__(kThreads) k_boundary_rhs(DeviceModel M) {
+    pdl_enter();
     const StepParams& sp = *M.sp;
     const int K = M.K;
     const double dt = sp.dt;
@@ -1930,6 +1945,7 @@ __global__ void __launch_bounds__(kThreads) k_update_xrp(DeviceModel M, const PT
 // ---------------------------------------------------------------------------------------------
 template <int KC, int VEC>
 __global__ void __launch_bounds__(kThreads) k_mass_flux(DeviceModel M) {
+    pdl_enter();
     const StepParams& sp = *M.sp;
     const int K = M.K, lane = threadIdx.x % KC, group = threadIdx.x / KC, GPB = kThreads / KC;
     const double dt = sp.dt;

@@ -80,6 +80,7 @@ __device__ __forceinline__ const double* small_precondition(const DeviceModel& M
 
 __global__ void __launch_bounds__(kSmallThreads, 1) k_solve_small(DeviceModel M, int m_steps, SmallStats* stats) {
     __shared__ double red[4 * 32];
+    pdl_enter();
     const int k = blockIdx.x, n = M.n, K = M.K;
     double* __restrict__ x = M.sp->state_t1 + k;          // stride K
     const double* __restrict__ b = M.b + k;               // stride K
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
     extern __shared__ double tiny_smem[];
     __shared__ double red[2 * 4 * 32];
     __shared__ int cptr[65];
+    pdl_enter();
     const int k = blockIdx.x, n = M.n, K = M.K, W = M.W, nc = M.n_colors;
     double* sval = tiny_smem;                       // [W][n]   (W4: double2 [2][n])
     double* z = sval + (size_t)n * W;               // [n] the gathered vector
@@ -485,6 +487,7 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     __shared__ double red[2 * 4 * 32];
     __shared__ int cptr[NS + 1];
     constexpr int NT = kChipThreads, NW = kChipThreads / 32;
+    pdl_enter();
     const int tid = threadIdx.x, k = blockIdx.x, n = M.n, K = M.K, nc = M.n_colors;
     double* sx = chip_smem + tid;                               // [NS][NT] private columns: element c at [c * NT]
     double* sph = sx + NS * NT;
