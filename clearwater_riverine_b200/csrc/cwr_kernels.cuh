@@ -141,9 +141,11 @@ struct DeviceModel {
 // gaps between them count).  The host launches these kernels with programmaticStreamSerialization; each lets its successor
 // be scheduled at once and waits for its predecessor's memory before it touches anything.  Launched without the attribute
 // (the large path) both instructions do nothing.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    pdl_launch_dependents();
+    pdl_wait();
 }
 
 __global__ void k_set_step(StepParams p, StepParams* dst, SolverCtl* ctl, DdCtl* dd) {

@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     __shared__ double red[2 * 4 * 32];
     __shared__ int cptr[NS + 1];
     constexpr int NT = kChipThreads, NW = kChipThreads / 32;
-    pdl_enter();
+    pdl_launch_dependents();
     const int tid = threadIdx.x, k = blockIdx.x, n = M.n, K = M.K, nc = M.n_colors;
     double* sx = chip_smem + tid;                               // [NS][NT] private columns: element c at [c * NT]
     double* sph = sx + NS * NT;
@@ -497,10 +497,11 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     double* spp = srh + NS * NT;                                // (fp32 sweeps: p lives here, its registers go to the compiler)
     double* z = chip_smem + 6 * NS * NT;                        // [n] the gathered vector
     float* zf = reinterpret_cast<float*>(z + n);                // [n] ... of the fp32 sweeps
-    double* __restrict__ xg = M.sp->state_t1 + k;               // stride K
     const double* __restrict__ bg = M.b + k;
     int parity = 0;
 
+    // (what follows down to pdl_wait() reads the mesh only -- colour pointers and neighbour indices, written at set-up: it
+    // runs while the kernels that build this step's matrix and right-hand side are still at work)
     if (tid <= NS) cptr[tid] = M.color_ptr[tid < nc ? tid : nc];
     __syncthreads();
 #define CHIP_ROW(c) (cptr[c] + tid)
@@ -513,16 +514,34 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     double r[NS], p[F32 ? 1 : NS];
     auto getp = [&](int c) -> double { if constexpr (F32) return spp[c * NT]; else return p[c]; };
     auto setp = [&](int c, double v) { if constexpr (F32) spp[c * NT] = v; else p[c] = v; };
-    // ---- the thread's rows: matrix values and indices -> registers, x -> its column (loads issued four rows at a time)
+    // ---- the thread's rows: neighbour indices -> registers
 #pragma unroll
     for (int c0 = 0; c0 < NS; c0 += 4) {
-        int4 cj[4]; double xq[4]; double2 ta[4], tb[4];
+        int4 cj[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (c0 + q < NS) cj[q] = __ldg(reinterpret_cast<const int4*>(M.ell_col + (size_t)(CHIP_ON(c0 + q) ? CHIP_ROW(c0 + q) : 0) * 4));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + q;
+            if (c < NS) {
+                nb[c].x = (unsigned)(cj[q].x & 0x7fff) | ((unsigned)(cj[q].y & 0x7fff) << 16);
+                nb[c].y = (unsigned)(cj[q].z & 0x7fff) | ((unsigned)(cj[q].w & 0x7fff) << 16);
+                if (!CHIP_ON(c)) nb[c] = make_uint2(0u, 0u);
+            }
+        }
+    }
+    pdl_wait();
+    double* __restrict__ xg = M.sp->state_t1 + k;               // stride K
+    // ---- matrix values -> registers, x -> its column (loads issued four rows at a time)
+#pragma unroll
+    for (int c0 = 0; c0 < NS; c0 += 4) {
+        double xq[4]; double2 ta[4], tb[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = c0 + q;
             if (c < NS) {
                 const size_t row = CHIP_ON(c) ? CHIP_ROW(c) : 0;
-                cj[q] = __ldg(reinterpret_cast<const int4*>(M.ell_col + row * 4));
                 ta[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
                 tb[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
                 xq[q] = xg[row * K];
@@ -532,9 +551,7 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
         for (int q = 0; q < 4; ++q) {
             const int c = c0 + q;
             if (c < NS) {
-                nb[c].x = (unsigned)(cj[q].x & 0x7fff) | ((unsigned)(cj[q].y & 0x7fff) << 16);
-                nb[c].y = (unsigned)(cj[q].z & 0x7fff) | ((unsigned)(cj[q].w & 0x7fff) << 16);
-                if (!CHIP_ON(c)) { nb[c] = make_uint2(0u, 0u); ta[q] = make_double2(0.0, 0.0); tb[q] = ta[q]; xq[q] = 0.0; }
+                if (!CHIP_ON(c)) { ta[q] = make_double2(0.0, 0.0); tb[q] = ta[q]; xq[q] = 0.0; }
                 if constexpr (REG64) { va[c] = ta[q]; vb[c] = tb[q]; }
                 else vf[c] = make_float4((float)ta[q].x, (float)ta[q].y, (float)tb[q].x, (float)tb[q].y);
                 sx[c * NT] = xq[q];
