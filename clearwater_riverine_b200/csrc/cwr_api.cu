@@ -601,12 +601,18 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
             cudaError_t e = cudaSuccess;
             TINY_DISPATCH(e = cudaFuncSetAttribute(k_solve_tiny<RPT, W4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
             CK(e);
-            CK(cudaFuncSetAttribute(k_solve_chip<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<14, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
-            CK(cudaFuncSetAttribute(k_solve_chip<14, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<8, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<8, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<8, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<8, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<12, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
+            CK(cudaFuncSetAttribute(k_solve_chip<14, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_optin - kTinyStaticSmem));
             h->max_optin_smem = max_optin;
             choose_chip(h);
         }
@@ -1242,8 +1248,11 @@ static int solve_small(cwr_handle* h, cwr_step_info* info) {
         const size_t sm = chip_smem_bytes(h->n, h->chip_ns);
         const int sweeps = h->m_steps - 1;
 #define CHIP_LAUNCH(NS) do { \
-            if (h->sweep_f32) CK(launch_chain(h, k_solve_chip<NS, true>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); \
-            else CK(launch_chain(h, k_solve_chip<NS, false>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); } while (0)
+            const bool full = h->topo.n_colors == NS; \
+            if (h->sweep_f32 && full) CK(launch_chain(h, k_solve_chip<NS, true, true>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); \
+            else if (h->sweep_f32) CK(launch_chain(h, k_solve_chip<NS, true, false>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); \
+            else if (full) CK(launch_chain(h, k_solve_chip<NS, false, true>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); \
+            else CK(launch_chain(h, k_solve_chip<NS, false, false>, h->K, kChipThreads, sm, h->M, sweeps, h->d_stats)); } while (0)
         if (h->chip_ns == 8) CHIP_LAUNCH(8);
         else if (h->chip_ns == 12) CHIP_LAUNCH(12);
         else CHIP_LAUNCH(14);

@@ -466,8 +466,9 @@ __global__ void __launch_bounds__(kTinyThreads, 1) k_solve_tiny(DeviceModel M, i
 constexpr int kChipThreads = 256;
 
 __host__ __device__ inline size_t chip_smem_bytes(int n, int NS) {
-    // x, p^, v, t, r^, p [NS][256] f64 | z [n] f64 | zf [n] f32 (p and zf: only the kernel with fp32 sweeps uses them)
-    return (size_t)NS * kChipThreads * 48 + (size_t)n * 8 + (size_t)n * 4;
+    // x, p^, v, t, r^, p [NS][256] f64 | z [n + 1] f64 | zf [n + 2] f32 (p and zf: only the kernel with fp32 sweeps uses them;
+    // element n of z / zf takes the stores of threads without a row in the colour)
+    return (size_t)NS * kChipThreads * 48 + (size_t)(n + 1) * 8 + (size_t)(n + 2) * 4;
 }
 
 // F32: the sweeps run in fp32 (options.precond_precision = 32, the default): the gathered vector is 4 bytes per row
@@ -480,7 +481,10 @@ __host__ __device__ inline size_t chip_smem_bytes(int n, int NS) {
 // Measured on the Ohio-shaped mesh (profiles/r02chip1_*): fp64 sweeps 0.071 ms per step, fp32 0.069 (64 scenarios 0.080 / 0.078),
 // same iteration counts; keeping the fp64 values in registers and narrowing them inside the colour step (4 F2F per step, off
 // the dependent chain) was slower than fp64 (0.073) and is gone.
-template <int NS, bool F32>
+// FULL: the mesh has exactly NS colours (no "is there a colour c" test in the colour step).  A colour step has no branch:
+// threads without a row in the colour compute on row 0's neighbours with zero values and store into a spare element
+// (ncu, profiles/r02chip2_*: the two test-and-branch pairs at the head of a step held 40 % of its stall samples).
+template <int NS, bool F32, bool FULL>
 __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, int n_sweeps, SmallStats* stats) {
     constexpr bool REG64 = !F32;                 // fp64 matrix values in registers
     extern __shared__ double chip_smem[];
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     double* srh = st + NS * NT;
     double* spp = srh + NS * NT;                                // (fp32 sweeps: p lives here, its registers go to the compiler)
     double* z = chip_smem + 6 * NS * NT;                        // [n] the gathered vector
-    float* zf = reinterpret_cast<float*>(z + n);                // [n] ... of the fp32 sweeps
+    float* zf = reinterpret_cast<float*>(z + n + 1);            // [n] ... of the fp32 sweeps
     const double* __restrict__ bg = M.b + k;
     int parity = 0;
 
@@ -621,11 +625,11 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
             for (int s = 0; s < n_sweeps; ++s) {
 #pragma unroll
                 for (int c = 0; c < NS; ++c) {
-                    if (c < nc) {
+                    if (FULL || c < nc) {
                         const float a0 = vf[c].x, a1 = vf[c].y, a2 = vf[c].z, a3 = vf[c].w;
                         const float z0 = zf[nb[c].x & 0xffffu], z1 = zf[nb[c].x >> 16], z2 = zf[nb[c].y & 0xffffu], z3 = zf[nb[c].y >> 16];
                         const float zi = uf[c] - (fmaf(a1, z1, a0 * z0) + fmaf(a3, z3, a2 * z2));
-                        if (CHIP_ON(c)) zf[CHIP_ROW(c)] = zi;
+                        zf[CHIP_ON(c) ? CHIP_ROW(c) : n] = zi;
                         __syncthreads();
                     }
                 }
@@ -640,9 +644,9 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
             for (int s = 0; s < n_sweeps; ++s) {
 #pragma unroll
                 for (int c = 0; c < NS; ++c) {
-                    if (c < nc) {
+                    if (FULL || c < nc) {
                         const double zi = u(c) - dot4(c, va[c], vb[c]);
-                        if (CHIP_ON(c)) z[CHIP_ROW(c)] = zi;
+                        z[CHIP_ON(c) ? CHIP_ROW(c) : n] = zi;
                         __syncthreads();
                     }
                 }
