@@ -92,6 +92,10 @@ struct cwr_handle {
     cudaStream_t out_stream = nullptr; cudaEvent_t ev_extract[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     double* d_out[2] = {nullptr, nullptr}; size_t out_bytes[2] = {0, 0}; int out_next = 0; bool out_pending[2] = {false, false};
     StepParams* d_sp = nullptr;
+    // cwr_run on the small-mesh path: the parameters of every step of the run are uploaded at once and a step's kernels are
+    // given their element (no k_set_step launch per step)
+    StepParams* d_sp_ring = nullptr; size_t sp_ring_cap = 0; std::vector<StepParams> sp_host;
+    const StepParams* sp_ready = nullptr;      // != nullptr inside such a run: the device copy of the current step's parameters
     HostMirror* h_mirror = nullptr; HostMirror* d_mirror = nullptr;   // page-locked, mapped into the device (k_mirror)
     SolverCtl* h_ctl = nullptr;                                   // = &h_mirror->ctl
     double* h_sc = nullptr; int* h_flags = nullptr;               // = h_mirror->sc, flags
@@ -434,6 +438,7 @@ void cwr_destroy(cwr_handle* h) {
     }
     if (h->d_strip_nbr) cudaFree(h->d_strip_nbr);
     if (h->d_ov_idx) cudaFree(h->d_ov_idx);
+    if (h->d_sp_ring) cudaFree(h->d_sp_ring);
     if (h->d_ov_val) cudaFree(h->d_ov_val);
     for (void* p : h->peer_maps) cudaIpcCloseMemHandle(p);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
@@ -695,7 +700,7 @@ static int create_impl(cwr_handle* h, int device, int n_real, int n_face, int n_
         CK(cudaMemsetAsync(us, 0, nK * sizeof(double), h->stream));
         M.ph = h->d_slab + kDdCtlBytes; M.sh = h->d_slab + kDdCtlBytes + vec_bytes; M.tmp = h->d_slab + kDdCtlBytes + 2 * vec_bytes;
         M.us = us;
-        if (h->sweep_f32 && !h->small_path) CK(dalloc(h, &M.valf, (size_t)n * tp.W));
+        if (h->sweep_f32 && (!h->small_path || h->tiny)) CK(dalloc(h, &M.valf, (size_t)n * tp.W));     // (on chip: k_solve_chip's fp32 sweeps)
     }
     if (h->small_path) {
         CK(dalloc(h, &M.xc, nK));
@@ -1327,6 +1332,21 @@ static int build_rhs(cwr_handle* h, int t) {
     return halo_push(h, h->cur_x);      // x0 = c~: the first residual gathers the neighbours' rows
 }
 
+// pointers and scalars of step t (hydrodynamic slices t / t + 1 in slots s0 / s1)
+static StepParams step_params(cwr_handle* h, int t, int s0, int s1) {
+    const int n = h->n, E = h->E, K = h->K, Eg = std::max(1, h->topo.E_g), G = std::max(1, h->G);
+    StepParams p;
+    p.adv_t = h->d_adv + (size_t)s0 * E; p.cdiff_t = h->d_cdiff + (size_t)s0 * E;
+    p.vol_t = h->d_vol + (size_t)s0 * n; p.vol_t1 = h->d_vol + (size_t)s1 * n;
+    p.adv_t1 = h->d_adv + (size_t)s1 * E; p.cdiff_t1 = h->d_cdiff + (size_t)s1 * E;
+    p.velg_t1 = h->d_velg + (size_t)s1 * Eg;
+    p.flowg_t = h->d_flowg + (size_t)s0 * Eg;
+    p.bc_t1 = h->d_bc + (size_t)(t + 1) * G * K;
+    p.state_t = state_slot(h, t); p.state_t1 = state_slot(h, t + 1);
+    p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
+    return p;
+}
+
 int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     if (!h) return CWR_EINVAL;
     if (t < 0 || t + 1 >= h->T) FAIL(CWR_EINVAL, "cwr_step: t must satisfy 0 <= t < n_time - 1 (dt[n_time-1] is NaN)");
@@ -1339,18 +1359,10 @@ int cwr_step(cwr_handle* h, int t, cwr_step_info* info) {
     CK(cudaSetDevice(h->device));
     { int rcj = join_prefetch(h, s0); if (rcj) return rcj; rcj = join_prefetch(h, s1); if (rcj) return rcj; }
     const int64_t launches0 = h->launches;
-    const int n = h->n, E = h->E, K = h->K, Eg = std::max(1, h->topo.E_g), G = std::max(1, h->G);
-    StepParams p;
-    p.adv_t = h->d_adv + (size_t)s0 * E; p.cdiff_t = h->d_cdiff + (size_t)s0 * E;
-    p.vol_t = h->d_vol + (size_t)s0 * n; p.vol_t1 = h->d_vol + (size_t)s1 * n;
-    p.adv_t1 = h->d_adv + (size_t)s1 * E; p.cdiff_t1 = h->d_cdiff + (size_t)s1 * E;
-    p.velg_t1 = h->d_velg + (size_t)s1 * Eg;
-    p.flowg_t = h->d_flowg + (size_t)s0 * Eg;
-    p.bc_t1 = h->d_bc + (size_t)(t + 1) * G * K;
-    p.state_t = state_slot(h, t); p.state_t1 = state_slot(h, t + 1);
-    p.dt = h->dt[t]; p.t = t; p.apply_ic = (t == 0);
+    const StepParams p = step_params(h, t, s0, s1);
     DeviceModel& M = h->M;
-    CK(launch_chain(h, k_set_step, 1, 1, 0, p, h->d_sp, M.ctl, h->world > 1 ? M.dd : (DdCtl*)nullptr));
+    if (h->sp_ready) M.sp = const_cast<StepParams*>(h->sp_ready);      // (cwr_run, small-mesh path: uploaded with the run's other steps)
+    else CK(launch_chain(h, k_set_step, 1, 1, 0, p, h->d_sp, M.ctl, h->world > 1 ? M.dd : (DdCtl*)nullptr));
     h->cur_x = p.state_t1;
     mark(h, CWR_FAM_ASSEMBLE);
     if (h->world > 1 && !h->attached) FAIL(CWR_EINVAL, "domain-decomposed handle: call cwr_dd_attach before stepping");
@@ -1414,14 +1426,42 @@ int cwr_run(cwr_handle* h, int t_begin, int t_end, cwr_step_info* worst) {
         // of them, synchronise once, report the worst solver statistics over the run
         CK(cudaSetDevice(h->device));
         CK(cudaMemsetAsync(h->d_stats, 0, sizeof(SmallStats), h->stream));
+        // the parameters of all the steps in one upload (their hydrodynamic slices are resident for the whole call: nothing
+        // is uploaded in between); k_set_step once, for the control block
+        bool ring = t_end > t_begin && t_begin >= 0 && t_end < h->T && !std::getenv("CWR_NO_SP_RING");
+        h->sp_host.clear();
+        for (int t = t_begin; ring && t < t_end; ++t) {
+            const int s0 = find_slot(h, t), s1 = find_slot(h, t + 1);
+            if (s0 < 0 || s1 < 0) ring = false;
+            else h->sp_host.push_back(step_params(h, t, s0, s1));
+        }
+        if (ring) {
+            const size_t cnt = h->sp_host.size();
+            if (cnt > h->sp_ring_cap) {
+                CK(cudaStreamSynchronize(h->stream));
+                if (h->d_sp_ring) CK(cudaFree(h->d_sp_ring));
+                h->d_sp_ring = nullptr; h->sp_ring_cap = 0;
+                CK(cudaMalloc((void**)&h->d_sp_ring, (cnt + cnt / 2 + 16) * sizeof(StepParams)));
+                h->sp_ring_cap = cnt + cnt / 2 + 16;
+            }
+            // (pageable source: the copy has left the host vector when the call returns)
+            CK(cudaMemcpyAsync(h->d_sp_ring, h->sp_host.data(), cnt * sizeof(StepParams), cudaMemcpyHostToDevice, h->stream));
+            CK(launch_chain(h, k_set_step, 1, 1, 0, h->sp_host[0], h->d_sp, h->M.ctl, (DdCtl*)nullptr));
+            h->launches += 1;
+        }
         h->in_run = true;
         int rc = CWR_OK;
         for (int t = t_begin; t < t_end && rc == CWR_OK; ++t) {
             cwr_step_info i{};
+            h->sp_ready = ring ? h->d_sp_ring + (t - t_begin) : nullptr;
             rc = cwr_step(h, t, &i);
             w.n_launches += i.n_launches;
         }
         h->in_run = false;
+        h->sp_ready = nullptr;
+        h->M.sp = h->d_sp;
+        if (ring && rc == CWR_OK)     // what a later call reads through M.sp (cwr_get_lhs / cwr_get_rhs): the last step's parameters
+            CK(cudaMemcpyAsync(h->d_sp, h->d_sp_ring + (t_end - 1 - t_begin), sizeof(StepParams), cudaMemcpyDeviceToDevice, h->stream));
         if (rc != CWR_OK) return rc;
         const int n_launches = w.n_launches;
         rc = read_small_stats(h, &w);

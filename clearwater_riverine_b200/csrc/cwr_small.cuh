@@ -540,14 +540,16 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
     // ---- matrix values -> registers, x -> its column (loads issued four rows at a time)
 #pragma unroll
     for (int c0 = 0; c0 < NS; c0 += 4) {
-        double xq[4]; double2 ta[4], tb[4];
+        double xq[4]; double2 ta[4], tb[4]; float4 tf[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int c = c0 + q;
             if (c < NS) {
                 const size_t row = CHIP_ON(c) ? CHIP_ROW(c) : 0;
-                ta[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
-                tb[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
+                if constexpr (REG64) {
+                    ta[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4));
+                    tb[q] = __ldg(reinterpret_cast<const double2*>(M.val + row * 4 + 2));
+                } else tf[q] = __ldg(reinterpret_cast<const float4*>(M.valf + row * 4));     // (k_assemble's fp32 copy: same rounding)
                 xq[q] = xg[row * K];
             }
         }
@@ -555,9 +557,9 @@ __global__ void __launch_bounds__(kChipThreads, 1) k_solve_chip(DeviceModel M, i
         for (int q = 0; q < 4; ++q) {
             const int c = c0 + q;
             if (c < NS) {
-                if (!CHIP_ON(c)) { ta[q] = make_double2(0.0, 0.0); tb[q] = ta[q]; xq[q] = 0.0; }
+                if (!CHIP_ON(c)) { ta[q] = make_double2(0.0, 0.0); tb[q] = ta[q]; tf[q] = make_float4(0.f, 0.f, 0.f, 0.f); xq[q] = 0.0; }
                 if constexpr (REG64) { va[c] = ta[q]; vb[c] = tb[q]; }
-                else vf[c] = make_float4((float)ta[q].x, (float)ta[q].y, (float)tb[q].x, (float)tb[q].y);
+                else vf[c] = tf[q];
                 sx[c * NT] = xq[q];
                 sph[c * NT] = 0.0; sv[c * NT] = 0.0; st[c * NT] = 0.0; srh[c * NT] = 0.0;
                 r[c] = 0.0; setp(c, 0.0);
