@@ -325,7 +325,7 @@ def family_bytes(o, n, nnz, E, K, Wd, sweeps_per_launch):
 KERNEL_NAMES = {
     "spmm_t": "k_spmm<AT> (t = A s^ fused with four dot products)", "spmm_v": "k_spmm<AV> (v = A p^ fused with (rhat, v))",
     "update_xrp": "k_update_xrp", "dc_update": "k_spmm<DC> (r -= A z, x += z fused with (r, r) and the plan of the next cycle)",
-    "solve_small": "k_solve_tiny / k_solve_small (whole solve of a constituent in one CTA, on chip up to 4096 cells)"}
+    "solve_small": "k_solve_chip / k_solve_tiny / k_solve_small (whole solve of a constituent in one CTA, on chip up to 4096 cells; k_solve_chip: fp32 sweeps inside the fp64 BiCGSTAB, branch-free colour step)"}
 
 
 def precond_kernel_name(o):
