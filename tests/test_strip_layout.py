@@ -132,3 +132,89 @@ def test_whole_mesh_as_one_strip_balances_the_colours_for_the_on_chip_solver(hin
     col = L["color_of"].astype(int)                  # by new id
     assert np.all(col[p[plan.f1[internal]]] != col[p[plan.f2[internal]]])
     assert np.all(np.diff(col) >= 0), "rows are colour-major"
+
+
+def _chip_emulation(A, b, x0, col, n_sweeps, rtol=1e-13, f32=True, max_iter=50):
+    """numpy restatement of k_solve_chip (cwr_small.cuh): right-preconditioned BiCGSTAB in fp64 on the row-scaled system,
+    the preconditioner = n_sweeps multicolour Gauss-Seidel sweeps from zero -- in fp32 on fp32 copies of the values, applied to
+    the input scaled by 2^-h (h = half the exponent of the squared norm handed over), the result widened and scaled back."""
+    d = A.diagonal()
+    As = sp.diags(1.0 / d) @ A
+    L = (As - sp.identity(A.shape[0])).tocsr()              # unit diagonal implied
+    bs = b / d
+    L32 = L.astype(np.float32)
+    rows_of = [np.nonzero(col == c)[0] for c in range(col.max() + 1)]
+
+    def precondition(u, norm2):
+        if not f32:
+            z = np.zeros_like(u)
+            for _ in range(n_sweeps):
+                for rows in rows_of:
+                    z[rows] = u[rows] - L[rows] @ z
+            return z
+        h = int(np.trunc((np.frexp(norm2)[1] - 1) / 2))    # exponent field - 1023, halved towards zero
+        uf = (u * np.ldexp(1.0, -h)).astype(np.float32)
+        z = np.zeros_like(uf)
+        for _ in range(n_sweeps):
+            for rows in rows_of:
+                z[rows] = uf[rows] - L32[rows] @ z
+        assert z.dtype == np.float32
+        return z.astype(np.float64) * np.ldexp(1.0, h)
+
+    x = x0.copy()
+    r = bs - (x + L @ x)
+    rhat, p = r.copy(), r.copy()
+    bb, rr = bs @ bs, r @ r
+    rho, its = rr, 0
+    while rr > rtol * rtol * bb and its < max_iter:
+        ph = precondition(p, rr)
+        v = ph + L @ ph
+        alpha = rho / (rhat @ v)
+        s = r - alpha * v
+        ss = s @ s
+        if ss <= rtol * rtol * bb:
+            x += alpha * ph
+            its += 1
+            rr = ss
+            break
+        sh = precondition(s, ss)
+        t = sh + L @ sh
+        omega = (t @ s) / (t @ t)
+        rho_new = rhat @ s - omega * (rhat @ t)
+        x += alpha * ph + omega * sh
+        r = s - omega * t
+        beta = (rho_new / rho) * (alpha / omega)
+        p = r + beta * (p - omega * v)
+        rho, rr = rho_new, r @ r
+        its += 1
+    return x, its, np.sqrt(rr / bb)
+
+
+@pytest.mark.parametrize("units", [1.0, 1e-20, 1e+20])
+def test_fp32_sweeps_inside_fp64_bicgstab_reach_the_fp64_answer_in_any_units(units):
+    """What k_solve_chip does with precond_precision = 32, restated in numpy on the oracle's own system of the Ohio-shaped
+    mesh: same iteration count as with fp64 sweeps, relative residual <= 1e-13, answer within 1e-9 of spsolve -- also when
+    the concentrations are 1e-20 or 1e+20 (the power-of-two scaling keeps the fp32 sweeps in range)."""
+    import scipy.sparse.linalg as spla
+    from oracle import reference_step as ref
+    plan = synthetic.ohio_like(4, seed=2)
+    n = plan.n_real
+    adv, _, _, cdiff, dt = ref.derive_coefficients(plan.face_flow, plan.edge_velocity, plan.face_x, plan.face_y,
+                                                   plan.f1, plan.f2, 0.1, plan.time_seconds)
+    mesh = ref.HydroMesh(plan.f1, plan.f2, plan.n_face, adv, cdiff, plan.edge_velocity, plan.volume, dt, 0.1)
+    inputs = synthetic.make_inputs(plan, 1, seed=2)[0] * units
+    lhs = ref.LHS(mesh); lhs.update_values(mesh, 1)
+    A = lhs.to_csr(); A.sum_duplicates()
+    rhs = ref.RHS(mesh, inputs)
+    x0 = inputs[0][:n].copy()
+    rhs.update_values(x0.copy(), mesh, 1)
+    b = np.asarray(rhs.vals, dtype=np.float64)
+    Lay = strip_layout(plan.f1, plan.f2, plan.n_face, 12, plan.face_flow.mean(0), 0, strip_cap=256)
+    col = Lay["color_of"].astype(int)[Lay["new_of_old"]]                  # colour by original cell id
+    want = spla.spsolve(A.tocsc(), b)
+    x64, its64, rel64 = _chip_emulation(A, b, x0, col, 8, f32=False)
+    x32, its32, rel32 = _chip_emulation(A, b, x0, col, 8, f32=True)
+    assert its32 == its64 and its32 <= 3
+    assert rel32 <= 1e-13 and rel64 <= 1e-13
+    scale = np.abs(want).max()
+    assert np.abs(x32 - want).max() <= 1e-9 * scale and np.abs(x64 - want).max() <= 1e-9 * scale
