@@ -433,6 +433,34 @@ def test_run_many_steps_without_host_round_trips():
     be.close()
 
 
+def test_run_step_run_sequences_and_the_system_after_a_run():
+    """cwr_run on the small path hands every step its parameters from one upload; cwr_step writes them per step.  Mixed
+    sequences (run, step, run; a run of one step; a run over the rest) stay within rtol of the oracle at every time index,
+    and the system read back after a run (cwr_get_lhs / cwr_get_rhs) is the last step's, equal to the oracle's."""
+    _, mesh, inputs = synthetic_case(30, 20, 12, 2, seed=29, dry_fraction=0.02)
+    be = make_backend(mesh, list(inputs), solver_path=2)
+    oracle = ref.OracleRiverine(mesh, {f"c{k}": inputs[k] for k in range(2)})
+    assert be.run(0, 4).status == 0
+    assert be.step(4).status == 0
+    assert be.run(5, 6).status == 0
+    assert be.run(6, 11).status == 0
+    n = mesh.n
+    for t in range(11):
+        oracle.update()
+    for k in range(2):
+        for t in range(1, 12):
+            close(be.get_state(k, t), oracle.constituent_dict[f"c{k}"].concentration[t], RTOL, f"k{k} t{t}")
+    lhs = ref.LHS(mesh); lhs.update_values(mesh, 10)
+    A = lhs.to_csr(); A.sum_duplicates(); A.sort_indices()
+    got = be.get_lhs(); got.sort_indices()
+    assert np.array_equal(got.indptr, A.indptr) and np.array_equal(got.indices, A.indices)
+    close(got.data, A.data, 1e-13, "LHS after the run")
+    rhs = ref.RHS(mesh, inputs[1])
+    rhs.update_values(oracle.constituent_dict["c1"].concentration[10][:n].copy(), mesh, 10)
+    close(be.get_rhs(1), np.asarray(rhs.vals, dtype=np.float64), RTOL, "RHS after the run")
+    be.close()
+
+
 @pytest.mark.parametrize("opts", [dict(reorder=0), dict(keep_history=0), dict(solver_path=1, check_every=3),
                                   dict(hydro_capacity=2)])
 def test_option_variants(opts):
