@@ -32,6 +32,14 @@ struct Bfs {
             size_t level_end = queue.size();
             level_begin = head;
             for (; head < level_end; ++head) {
+                // (the walk is a chain of cache misses -- row pointer, neighbour list, stamps: the queue says which cells
+                // come next, so their lines are requested a few cells ahead)
+                if (head + 16 < queue.size()) __builtin_prefetch(&ptr[queue[head + 16]]);
+                if (head + 8 < queue.size()) __builtin_prefetch(&adj[ptr[queue[head + 8]]]);
+                if (head + 4 < queue.size()) {
+                    const int32_t w = queue[head + 4];
+                    for (int32_t j = ptr[w]; j < ptr[w + 1]; ++j) __builtin_prefetch(&stamp[adj[j]]);
+                }
                 int32_t u = queue[head];
                 for (int32_t j = ptr[u]; j < ptr[u + 1]; ++j) {
                     int32_t v = adj[j];
@@ -94,13 +102,20 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
 
     // ---- adjacency of real cells (both directions of every internal edge) --------------------
     std::vector<int32_t> aptr(n + 1, 0), adj(T.nnz);
-    for (int e = 0; e < E; ++e)
+    // (edge loops touch their two cells' entries at random: the lines are requested kPF edges ahead)
+    constexpr int kPF = 16;
+    for (int e = 0; e < E; ++e) {
+        if (e + kPF < E) { __builtin_prefetch(&aptr[f1[e + kPF] + 1], 1); if (f2[e + kPF] < n) __builtin_prefetch(&aptr[f2[e + kPF] + 1], 1); }
         if (f2[e] < n) { ++aptr[f1[e] + 1]; ++aptr[f2[e] + 1]; }
+    }
     for (int i = 0; i < n; ++i) aptr[i + 1] += aptr[i];
     {
         std::vector<int32_t> fill(aptr.begin(), aptr.end() - 1);
-        for (int e = 0; e < E; ++e)
+        for (int e = 0; e < E; ++e) {
+            if (e + kPF < E) { __builtin_prefetch(&fill[f1[e + kPF]], 1); if (f2[e + kPF] < n) __builtin_prefetch(&fill[f2[e + kPF]], 1); }
+            if (e + kPF / 2 < E && f2[e + kPF / 2] < n) { __builtin_prefetch(&adj[fill[f1[e + kPF / 2]]], 1); __builtin_prefetch(&adj[fill[f2[e + kPF / 2]]], 1); }
             if (f2[e] < n) { adj[fill[f1[e]]++] = f2[e]; adj[fill[f2[e]]++] = f1[e]; }
+        }
     }
 
     tick("adjacency");
@@ -110,10 +125,17 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     if (!rcm) {
         std::iota(T.old_of_new.begin(), T.old_of_new.end(), 0);
     } else {
+        // cells by (degree, id): a stable counting sort (a comparison sort of 16M cells was ~2 s of the set-up)
         std::vector<int32_t> by_degree(n);
-        std::iota(by_degree.begin(), by_degree.end(), 0);
         auto deg = [&](int32_t u) { return aptr[u + 1] - aptr[u]; };
-        std::stable_sort(by_degree.begin(), by_degree.end(), [&](int32_t a, int32_t b) { return deg(a) < deg(b); });
+        {
+            int max_deg = 0;
+            for (int i = 0; i < n; ++i) max_deg = std::max(max_deg, deg(i));
+            std::vector<int32_t> dptr((size_t)max_deg + 2, 0);
+            for (int i = 0; i < n; ++i) ++dptr[deg(i) + 1];
+            for (int d = 0; d <= max_deg; ++d) dptr[d + 1] += dptr[d];
+            for (int i = 0; i < n; ++i) by_degree[dptr[deg(i)]++] = i;
+        }
         std::vector<uint8_t> visited(n, 0);
         std::vector<int32_t> order;
         order.reserve(n);
@@ -134,6 +156,12 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             order.push_back(start);
             visited[start] = 1;
             while (head < order.size()) {
+                if (head + 16 < order.size()) __builtin_prefetch(&aptr[order[head + 16]]);
+                if (head + 8 < order.size()) __builtin_prefetch(&adj[aptr[order[head + 8]]]);
+                if (head + 4 < order.size()) {
+                    const int32_t w = order[head + 4];
+                    for (int32_t j = aptr[w]; j < aptr[w + 1]; ++j) { __builtin_prefetch(&visited[adj[j]]); __builtin_prefetch(&aptr[adj[j]]); }
+                }
                 int32_t u = order[head++];
                 nbrs.clear();
                 for (int32_t j = aptr[u]; j < aptr[u + 1]; ++j) {
@@ -180,6 +208,7 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             std::vector<float> cellmax(n, 0.f);
             if (tau > 0.f)
                 for (int e = 0; e < E; ++e) {
+                    if (e + kPF < E) { __builtin_prefetch(&cellmax[f1[e + kPF]], 1); if (f2[e + kPF] < n) __builtin_prefetch(&cellmax[f2[e + kPF]], 1); }
                     const float q = std::fabs(hint[e]);
                     if (!(q == q)) continue;
                     cellmax[f1[e]] = std::max(cellmax[f1[e]], q);
@@ -189,17 +218,26 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) return false;
                 return tau <= 0.f || std::fabs(hint[e]) >= tau * std::max(cellmax[f1[e]], cellmax[f2[e]]);
             };
+            // (classified once: 0 = undirected, 1 = f1 -> f2, 2 = f2 -> f1)
+            std::vector<uint8_t> dir(E);
             for (int e = 0; e < E; ++e) {
-                if (!directed(e)) continue;
-                const int32_t up = hint[e] > 0.f ? f1[e] : f2[e], down = hint[e] > 0.f ? f2[e] : f1[e];
+                if (e + kPF < E && f2[e + kPF] < n) { __builtin_prefetch(&cellmax[f1[e + kPF]]); __builtin_prefetch(&cellmax[f2[e + kPF]]); }
+                dir[e] = !directed(e) ? 0 : (hint[e] > 0.f ? 1 : 2);
+            }
+            for (int e = 0; e < E; ++e) {
+                if (e + kPF < E && dir[e + kPF]) { __builtin_prefetch(&optr[f1[e + kPF] + 1], 1); __builtin_prefetch(&optr[f2[e + kPF] + 1], 1);
+                                                   __builtin_prefetch(&indeg[f1[e + kPF]], 1); __builtin_prefetch(&indeg[f2[e + kPF]], 1); }
+                if (!dir[e]) continue;
+                const int32_t up = dir[e] == 1 ? f1[e] : f2[e], down = dir[e] == 1 ? f2[e] : f1[e];
                 ++optr[up + 1]; ++indeg[down];
             }
             for (int i = 0; i < n; ++i) optr[i + 1] += optr[i];
             oadj.resize(optr[n]);
             std::vector<int32_t> fill(optr.begin(), optr.end() - 1);
             for (int e = 0; e < E; ++e) {
-                if (!directed(e)) continue;
-                const int32_t up = hint[e] > 0.f ? f1[e] : f2[e], down = hint[e] > 0.f ? f2[e] : f1[e];
+                if (e + kPF < E && dir[e + kPF]) { __builtin_prefetch(&fill[f1[e + kPF]], 1); __builtin_prefetch(&fill[f2[e + kPF]], 1); }
+                if (!dir[e]) continue;
+                const int32_t up = dir[e] == 1 ? f1[e] : f2[e], down = dir[e] == 1 ? f2[e] : f1[e];
                 oadj[fill[up]++] = down;
             }
         }
@@ -216,6 +254,18 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
                 while (queued[T.old_of_new[scan]]) ++scan;
                 const int32_t u = T.old_of_new[scan];
                 queued[u] = 1; queue.push_back(u);
+            }
+            if (head + 16 < queue.size()) { __builtin_prefetch(&aptr[queue[head + 16]]); __builtin_prefetch(&optr[queue[head + 16]]); }
+            if (head + 8 < queue.size()) {
+                const int32_t w = queue[head + 8];
+                __builtin_prefetch(&adj[aptr[w]]);
+                if (!oadj.empty()) __builtin_prefetch(&oadj[std::min<size_t>(optr[w], oadj.size() - 1)]);
+                __builtin_prefetch(&tentative[w]);
+            }
+            if (head + 4 < queue.size()) {
+                const int32_t w = queue[head + 4];
+                for (int32_t j = aptr[w]; j < aptr[w + 1]; ++j) __builtin_prefetch(&level[adj[j]]);
+                for (int32_t j = optr[w]; j < optr[w + 1]; ++j) { __builtin_prefetch(&tentative[oadj[j]]); __builtin_prefetch(&indeg[oadj[j]]); }
             }
             const int32_t u = queue[head++];
             uint64_t used = 0;
@@ -357,15 +407,18 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     tick("strip balancing / row order");
     // ---- edge renumbering ---------------------------------------------------------------------------
     // internal edges: sort by (min new cell, max new cell, original id); ghost edges: by (new cell, original id)
-    std::vector<int32_t> internal, ghost;
+    std::vector<int32_t> internal, ghost, ea(E), eb(E);       // ea / eb: new ids of an edge's cells (eb = -1: ghost cell)
     {
         // counting sort by the lower new cell (edges scattered in original order: ties keep ascending ids), then the
         // handful of edges of a cell by (higher cell, id)
+        // (the new ids of an edge's cells are random reads of new_of_old: looked up once, kept for the second pass)
         std::vector<int32_t> iptr(n + 1, 0), gptr(n + 1, 0);
         for (int e = 0; e < E; ++e) {
+            if (e + kPF < E) { __builtin_prefetch(&T.new_of_old[f1[e + kPF]]); if (f2[e + kPF] < n) __builtin_prefetch(&T.new_of_old[f2[e + kPF]]); }
             const int32_t a = T.new_of_old[f1[e]];
-            if (f2[e] < n) ++iptr[std::min(a, T.new_of_old[f2[e]]) + 1];
-            else ++gptr[a + 1];
+            ea[e] = a;
+            if (f2[e] < n) { eb[e] = T.new_of_old[f2[e]]; ++iptr[std::min(a, eb[e]) + 1]; }
+            else { eb[e] = -1; ++gptr[a + 1]; }
         }
         for (int i = 0; i < n; ++i) { iptr[i + 1] += iptr[i]; gptr[i + 1] += gptr[i]; }
         internal.resize(E_int); ghost.resize(T.E_g);
@@ -373,9 +426,8 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         {
             std::vector<int32_t> ifill(iptr.begin(), iptr.end() - 1), gfill(gptr.begin(), gptr.end() - 1);
             for (int e = 0; e < E; ++e) {
-                const int32_t a = T.new_of_old[f1[e]];
-                if (f2[e] < n) {
-                    const int32_t b = T.new_of_old[f2[e]];
+                const int32_t a = ea[e], b = eb[e];
+                if (b >= 0) {
                     const int32_t o = ifill[std::min(a, b)]++;
                     internal[o] = e; hi[o] = std::max(a, b);
                 } else ghost[gfill[a]++] = e;
@@ -394,8 +446,8 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     for (int i = 0; i < T.E_g; ++i) T.eperm[E_int + i] = ghost[i];
     for (int ep = 0; ep < E; ++ep) {
         int32_t e = T.eperm[ep];
-        T.f1p[ep] = T.new_of_old[f1[e]];
-        T.f2p[ep] = f2[e] < n ? T.new_of_old[f2[e]] : f2[e];   // ghost cells keep their id (>= n)
+        T.f1p[ep] = ea[e];
+        T.f2p[ep] = eb[e] >= 0 ? eb[e] : f2[e];                // ghost cells keep their id (>= n)
     }
 
     tick("edge renumbering");
