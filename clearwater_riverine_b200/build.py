@@ -12,7 +12,7 @@ LIB = PKG / "libcwr_b200.so"
 SOURCES = [CSRC / "cwr_api.cu", CSRC / "cwr_topology.cpp"]
 DEPS = SOURCES + [CSRC / "cwr_kernels.cuh", CSRC / "cwr_small.cuh", CSRC / "cwr_topology.h", PKG.parent / "include" / "cwr.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
 
 
 def nvcc_path() -> str:

@@ -5,7 +5,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <numeric>
+#include <thread>
 
 namespace cwr {
 namespace {
@@ -58,6 +60,38 @@ struct Bfs {
     }
 };
 
+// Host threads for the loops of the set-up whose result does not depend on the order of their iterations (counts and
+// maxima through atomics, element-wise maps): CWR_TOPO_THREADS, default min(4, hardware threads) -- several ranks of one
+// node build their topologies at the same time.  The order-dependent passes (breadth-first walks, stable scatters) stay
+// on one thread, so the topology is the same bit for bit with any thread count.
+int topo_threads(int64_t work) {
+    if (work < (1 << 18)) return 1;
+    if (const char* ev = std::getenv("CWR_TOPO_THREADS")) return std::max(1, std::min(64, std::atoi(ev)));
+    return (int)std::max(1u, std::min(4u, std::thread::hardware_concurrency()));
+}
+template <typename F>
+void parallel_chunks(int64_t count, F body) {          // body(begin, end) over [0, count) cut into one chunk per thread
+    const int T = topo_threads(count);
+    if (T <= 1) { body((int64_t)0, count); return; }
+    std::vector<std::thread> pool;
+    const int64_t per = (count + T - 1) / T;
+    bool failed = false;
+    int64_t done = 0;
+    for (int t = 0; t < T - 1 && !failed; ++t) {
+        const int64_t lo = t * per, hi = std::min(count, lo + per);
+        try { pool.emplace_back([=, &body] { body(lo, hi); }); done = hi; } catch (...) { failed = true; }
+    }
+    body(done, count);                                  // (the caller's thread takes the rest: all of it if no thread started)
+    for (auto& th : pool) th.join();
+}
+inline void atomic_inc(int32_t& x) { __atomic_fetch_add(&x, 1, __ATOMIC_RELAXED); }
+inline void atomic_max_nonneg(float& x, float q) {      // q >= 0: the bit patterns of non-negative floats order like integers
+    int32_t* px = reinterpret_cast<int32_t*>(&x);
+    int32_t qi; std::memcpy(&qi, &q, 4);
+    int32_t cur = __atomic_load_n(px, __ATOMIC_RELAXED);
+    while (cur < qi && !__atomic_compare_exchange_n(px, &cur, qi, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+}
+
 // fraction of a cell's strongest face flow below which an edge does not direct the colouring (0 = every edge
 // does); CWR_HINT_TAU overrides it for experiments
 float hint_threshold() {
@@ -104,10 +138,12 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     std::vector<int32_t> aptr(n + 1, 0), adj(T.nnz);
     // (edge loops touch their two cells' entries at random: the lines are requested kPF edges ahead)
     constexpr int kPF = 16;
-    for (int e = 0; e < E; ++e) {
-        if (e + kPF < E) { __builtin_prefetch(&aptr[f1[e + kPF] + 1], 1); if (f2[e + kPF] < n) __builtin_prefetch(&aptr[f2[e + kPF] + 1], 1); }
-        if (f2[e] < n) { ++aptr[f1[e] + 1]; ++aptr[f2[e] + 1]; }
-    }
+    parallel_chunks(E, [&](int64_t lo, int64_t hi) {
+        for (int64_t e = lo; e < hi; ++e) {
+            if (e + kPF < hi) { __builtin_prefetch(&aptr[f1[e + kPF] + 1], 1); if (f2[e + kPF] < n) __builtin_prefetch(&aptr[f2[e + kPF] + 1], 1); }
+            if (f2[e] < n) { atomic_inc(aptr[f1[e] + 1]); atomic_inc(aptr[f2[e] + 1]); }
+        }
+    });
     for (int i = 0; i < n; ++i) aptr[i + 1] += aptr[i];
     {
         std::vector<int32_t> fill(aptr.begin(), aptr.end() - 1);
@@ -207,30 +243,34 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             const float tau = hint_threshold();
             std::vector<float> cellmax(n, 0.f);
             if (tau > 0.f)
-                for (int e = 0; e < E; ++e) {
-                    if (e + kPF < E) { __builtin_prefetch(&cellmax[f1[e + kPF]], 1); if (f2[e + kPF] < n) __builtin_prefetch(&cellmax[f2[e + kPF]], 1); }
-                    const float q = std::fabs(hint[e]);
-                    if (!(q == q)) continue;
-                    cellmax[f1[e]] = std::max(cellmax[f1[e]], q);
-                    if (f2[e] < n) cellmax[f2[e]] = std::max(cellmax[f2[e]], q);
-                }
+                parallel_chunks(E, [&](int64_t lo, int64_t hi) {
+                    for (int64_t e = lo; e < hi; ++e) {
+                        if (e + kPF < hi) { __builtin_prefetch(&cellmax[f1[e + kPF]], 1); if (f2[e + kPF] < n) __builtin_prefetch(&cellmax[f2[e + kPF]], 1); }
+                        const float q = std::fabs(hint[e]);
+                        if (!(q == q)) continue;
+                        atomic_max_nonneg(cellmax[f1[e]], q);
+                        if (f2[e] < n) atomic_max_nonneg(cellmax[f2[e]], q);
+                    }
+                });
             auto directed = [&](int e) {
                 if (f2[e] >= n || !(hint[e] != 0.f) || hint[e] != hint[e]) return false;
                 return tau <= 0.f || std::fabs(hint[e]) >= tau * std::max(cellmax[f1[e]], cellmax[f2[e]]);
             };
             // (classified once: 0 = undirected, 1 = f1 -> f2, 2 = f2 -> f1)
             std::vector<uint8_t> dir(E);
-            for (int e = 0; e < E; ++e) {
-                if (e + kPF < E && f2[e + kPF] < n) { __builtin_prefetch(&cellmax[f1[e + kPF]]); __builtin_prefetch(&cellmax[f2[e + kPF]]); }
-                dir[e] = !directed(e) ? 0 : (hint[e] > 0.f ? 1 : 2);
-            }
-            for (int e = 0; e < E; ++e) {
-                if (e + kPF < E && dir[e + kPF]) { __builtin_prefetch(&optr[f1[e + kPF] + 1], 1); __builtin_prefetch(&optr[f2[e + kPF] + 1], 1);
-                                                   __builtin_prefetch(&indeg[f1[e + kPF]], 1); __builtin_prefetch(&indeg[f2[e + kPF]], 1); }
-                if (!dir[e]) continue;
-                const int32_t up = dir[e] == 1 ? f1[e] : f2[e], down = dir[e] == 1 ? f2[e] : f1[e];
-                ++optr[up + 1]; ++indeg[down];
-            }
+            parallel_chunks(E, [&](int64_t lo, int64_t hi) {
+                for (int64_t e = lo; e < hi; ++e) {
+                    if (e + kPF < hi && f2[e + kPF] < n) { __builtin_prefetch(&cellmax[f1[e + kPF]]); __builtin_prefetch(&cellmax[f2[e + kPF]]); }
+                    dir[e] = !directed((int)e) ? 0 : (hint[e] > 0.f ? 1 : 2);
+                }
+                for (int64_t e = lo; e < hi; ++e) {
+                    if (e + kPF < hi && dir[e + kPF]) { __builtin_prefetch(&optr[f1[e + kPF] + 1], 1); __builtin_prefetch(&optr[f2[e + kPF] + 1], 1);
+                                                        __builtin_prefetch(&indeg[f1[e + kPF]], 1); __builtin_prefetch(&indeg[f2[e + kPF]], 1); }
+                    if (!dir[e]) continue;
+                    const int32_t up = dir[e] == 1 ? f1[e] : f2[e], down = dir[e] == 1 ? f2[e] : f1[e];
+                    atomic_inc(optr[up + 1]); atomic_inc(indeg[down]);
+                }
+            });
             for (int i = 0; i < n; ++i) optr[i + 1] += optr[i];
             oadj.resize(optr[n]);
             std::vector<int32_t> fill(optr.begin(), optr.end() - 1);
@@ -413,19 +453,26 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
         // handful of edges of a cell by (higher cell, id)
         // (the new ids of an edge's cells are random reads of new_of_old: looked up once, kept for the second pass)
         std::vector<int32_t> iptr(n + 1, 0), gptr(n + 1, 0);
-        for (int e = 0; e < E; ++e) {
-            if (e + kPF < E) { __builtin_prefetch(&T.new_of_old[f1[e + kPF]]); if (f2[e + kPF] < n) __builtin_prefetch(&T.new_of_old[f2[e + kPF]]); }
-            const int32_t a = T.new_of_old[f1[e]];
-            ea[e] = a;
-            if (f2[e] < n) { eb[e] = T.new_of_old[f2[e]]; ++iptr[std::min(a, eb[e]) + 1]; }
-            else { eb[e] = -1; ++gptr[a + 1]; }
-        }
+        parallel_chunks(E, [&](int64_t lo, int64_t hi) {
+            for (int64_t e = lo; e < hi; ++e) {
+                if (e + kPF < hi) { __builtin_prefetch(&T.new_of_old[f1[e + kPF]]); if (f2[e + kPF] < n) __builtin_prefetch(&T.new_of_old[f2[e + kPF]]); }
+                const int32_t a = T.new_of_old[f1[e]];
+                ea[e] = a;
+                if (f2[e] < n) { eb[e] = T.new_of_old[f2[e]]; atomic_inc(iptr[std::min(a, eb[e]) + 1]); }
+                else { eb[e] = -1; atomic_inc(gptr[a + 1]); }
+            }
+        });
         for (int i = 0; i < n; ++i) { iptr[i + 1] += iptr[i]; gptr[i + 1] += gptr[i]; }
         internal.resize(E_int); ghost.resize(T.E_g);
         std::vector<int32_t> hi(E_int);
         {
             std::vector<int32_t> ifill(iptr.begin(), iptr.end() - 1), gfill(gptr.begin(), gptr.end() - 1);
             for (int e = 0; e < E; ++e) {
+                if (e + kPF < E) __builtin_prefetch(&ifill[eb[e + kPF] >= 0 ? std::min(ea[e + kPF], eb[e + kPF]) : 0], 1);
+                if (e + kPF / 2 < E && eb[e + kPF / 2] >= 0) {
+                    const int32_t o = ifill[std::min(ea[e + kPF / 2], eb[e + kPF / 2])];
+                    __builtin_prefetch(&internal[std::min(o, E_int - 1)], 1); __builtin_prefetch(&hi[std::min(o, E_int - 1)], 1);
+                }
                 const int32_t a = ea[e], b = eb[e];
                 if (b >= 0) {
                     const int32_t o = ifill[std::min(a, b)]++;
@@ -444,11 +491,14 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     T.eperm.resize(E); T.f1p.resize(E); T.f2p.resize(E);
     for (int i = 0; i < E_int; ++i) T.eperm[i] = internal[i];
     for (int i = 0; i < T.E_g; ++i) T.eperm[E_int + i] = ghost[i];
-    for (int ep = 0; ep < E; ++ep) {
-        int32_t e = T.eperm[ep];
-        T.f1p[ep] = ea[e];
-        T.f2p[ep] = eb[e] >= 0 ? eb[e] : f2[e];                // ghost cells keep their id (>= n)
-    }
+    parallel_chunks(E, [&](int64_t lo, int64_t hi) {
+        for (int64_t ep = lo; ep < hi; ++ep) {
+            if (ep + kPF < hi) { __builtin_prefetch(&ea[T.eperm[ep + kPF]]); __builtin_prefetch(&eb[T.eperm[ep + kPF]]); }
+            const int32_t e = T.eperm[ep];
+            T.f1p[ep] = ea[e];
+            T.f2p[ep] = eb[e] >= 0 ? eb[e] : f2[e];            // ghost cells keep their id (>= n)
+        }
+    });
 
     tick("edge renumbering");
     // ---- off-diagonal CSR with slot -> (edge, side) --------------------------------------------------
@@ -464,19 +514,29 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
             int32_t a = fill[P]++; T.col[a] = N; T.slot_edge[a] = (ep << 1) | 0;   // A[P,N]
             int32_t b = fill[N]++; T.col[b] = P; T.slot_edge[b] = (ep << 1) | 1;   // A[N,P]
         }
-        std::vector<std::pair<int32_t, int32_t>> tmp;
         T.max_row_len = 0; T.bandwidth = 0;
-        for (int i = 0; i < n; ++i) {
-            int32_t s = T.rowptr[i], e = T.rowptr[i + 1];
-            T.max_row_len = std::max(T.max_row_len, e - s);
-            tmp.clear();
-            for (int32_t j = s; j < e; ++j) tmp.emplace_back(T.col[j], T.slot_edge[j]);
-            std::sort(tmp.begin(), tmp.end());
-            for (int32_t j = s; j < e; ++j) {
-                T.col[j] = tmp[j - s].first; T.slot_edge[j] = tmp[j - s].second;
-                T.bandwidth = std::max<int64_t>(T.bandwidth, std::abs((int64_t)T.col[j] - i));
+        const int NT = topo_threads(n);
+        std::vector<int32_t> len_of(NT + 1, 0);
+        std::vector<int64_t> band_of(NT + 1, 0);
+        const int64_t per = ((int64_t)n + NT - 1) / NT;
+        parallel_chunks(n, [&](int64_t lo, int64_t hi) {        // rows are independent; maxima per chunk, merged below
+            std::vector<std::pair<int32_t, int32_t>> tmp;
+            int32_t len = 0; int64_t band = 0;
+            for (int64_t i = lo; i < hi; ++i) {
+                int32_t s = T.rowptr[i], e = T.rowptr[i + 1];
+                len = std::max(len, e - s);
+                tmp.clear();
+                for (int32_t j = s; j < e; ++j) tmp.emplace_back(T.col[j], T.slot_edge[j]);
+                std::sort(tmp.begin(), tmp.end());
+                for (int32_t j = s; j < e; ++j) {
+                    T.col[j] = tmp[j - s].first; T.slot_edge[j] = tmp[j - s].second;
+                    band = std::max<int64_t>(band, std::abs((int64_t)T.col[j] - i));
+                }
             }
-        }
+            const int slot = (int)std::min<int64_t>(NT, lo / std::max<int64_t>(1, per));   // (chunks start at multiples of per, or at 0)
+            len_of[slot] = std::max(len_of[slot], len); band_of[slot] = std::max(band_of[slot], band);
+        });
+        for (int t = 0; t <= NT; ++t) { T.max_row_len = std::max(T.max_row_len, len_of[t]); T.bandwidth = std::max(T.bandwidth, band_of[t]); }
     }
 
     tick("CSR pattern");
@@ -484,14 +544,16 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     T.W = std::max(4, (T.max_row_len + 3) / 4 * 4);
     T.ell_col.assign((size_t)n * T.W, 0);
     T.ell_code.assign((size_t)n * T.W, -1);
-    for (int i = 0; i < n; ++i) {
-        const int32_t s = T.rowptr[i], e = T.rowptr[i + 1];
-        for (int w = 0; w < T.W; ++w) {
-            const size_t o = (size_t)i * T.W + w;
-            if (s + w < e) { T.ell_col[o] = T.col[s + w]; T.ell_code[o] = T.slot_edge[s + w]; }
-            else T.ell_col[o] = i;
+    parallel_chunks(n, [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            const int32_t s = T.rowptr[i], e = T.rowptr[i + 1];
+            for (int w = 0; w < T.W; ++w) {
+                const size_t o = (size_t)i * T.W + w;
+                if (s + w < e) { T.ell_col[o] = T.col[s + w]; T.ell_code[o] = T.slot_edge[s + w]; }
+                else T.ell_col[o] = (int32_t)i;
+            }
         }
-    }
+    });
 
     tick("ELL pattern");
     // ---- boundary cells ----------------------------------------------------------------------------------
@@ -507,13 +569,15 @@ std::string build_topology(int n_real, int n_face, int n_edge, const int32_t* f1
     // (colour >= the row's colour; padding points at the row itself).  During the first sweep from z = 0
     // those neighbours still hold 0.  Bit 31 of ell_col; every kernel masks it off.
     if (T.n_colors > 0)
-        for (int i = 0; i < n; ++i)
-            for (int w = 0; w < T.W; ++w) {
-                int32_t& cj = T.ell_col[(size_t)i * T.W + w];
-                const int ci = T.color_of[i], cn = T.color_of[cj];
-                if (cn >= ci) cj |= kLaterBit;
-                if (cn == (ci + T.n_colors - 1) % T.n_colors && cn != ci) cj |= kPrevBit;
-            }
+        parallel_chunks(n, [&](int64_t lo, int64_t hi) {
+            for (int64_t i = lo; i < hi; ++i)
+                for (int w = 0; w < T.W; ++w) {
+                    int32_t& cj = T.ell_col[(size_t)i * T.W + w];
+                    const int ci = T.color_of[i], cn = T.color_of[cj];
+                    if (cn >= ci) cj |= kLaterBit;
+                    if (cn == (ci + T.n_colors - 1) % T.n_colors && cn != ci) cj |= kPrevBit;
+                }
+        });
 
     tick("boundary cells / sweep flags");
     // ---- strips: which strips a strip's rows are coupled to (global strip ids; strips of other parts included:
