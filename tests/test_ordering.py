@@ -92,3 +92,21 @@ def test_domain_decomposition_strips(n_parts, n_colors):
             inv = np.empty(n, np.int64)
             colour[np.isin(p, rows)] = colour_of_row[p[np.isin(p, rows)] - part_ptr[q]]
         assert np.all(colour[a] != colour[b]), "coupled rows share a colour"
+
+
+def test_topology_does_not_depend_on_the_host_thread_count(monkeypatch):
+    """build_topology runs its order-independent loops on host threads (meshes of >= 2^18 cells): rows, colours, strips and
+    strip neighbours are identical with 1, 3 and 5 threads."""
+    from clearwater_riverine_b200 import synthetic
+    from clearwater_riverine_b200.backend import strip_layout
+    plan = synthetic.make_plan(530, 520, 3, tri_fraction=0.1, dry_fraction=0.02, seed=4)
+    assert plan.n_real >= 1 << 18
+    hint = plan.face_flow.mean(0)
+    outs = []
+    for threads in ("1", "3", "5"):
+        monkeypatch.setenv("CWR_TOPO_THREADS", threads)
+        outs.append(strip_layout(plan.f1, plan.f2, plan.n_face, 12, hint, 37, 2, strip_cap=256))
+    for other in outs[1:]:
+        assert set(other) == set(outs[0])
+        for key, val in outs[0].items():
+            assert np.array_equal(np.asarray(val), np.asarray(other[key])), key
